@@ -1,0 +1,149 @@
+/* pir_b200.h — C ABI of the B200-native PIR server answer path.
+ *
+ * Drop-in boundary for OpenMined/PIR's server side.  The reference has no FFI layer; its boundary is the
+ * public C++ API of pir::PIRServer / pir::PIRDatabase (pir/cpp/server.h:43-131, pir/cpp/database.h:47-127).
+ * Each entry point below cites the reference interface it replaces.  All ciphertext / plaintext / key
+ * arguments are raw RNS limbs, uint64, values in [0, q_j), laid out exactly as SEAL lays them out in
+ * Ciphertext::data(i) (the reference relies on that layout directly: server.cpp:94-100,
+ * ct_reencoder.cpp:58-63):
+ *
+ *   ciphertext  [2][k][N]            poly-major, then RNS modulus, then coefficient        (ct_limbs = 2kN)
+ *   plaintext   [N] coefficients < t (coefficient form)   or   [k][N] (NTT form)           (pt_limbs = kN)
+ *   Galois key  [k][2][k+1][N]       digit J, component c, key-level modulus I, NTT form    (key_limbs)
+ *               == seal::KSwitchKeys::data()[index][J].data().data(c)[I*N + n]
+ *
+ * NTT form uses SEAL's ordering (minimal primitive 2N-th root, bit-reversed output) so keys and
+ * preprocessed databases produced by SEAL can be loaded unchanged.
+ *
+ * Status codes follow absl::StatusCode as the reference uses it: 0 OK, 3 InvalidArgument, 13 Internal.
+ * pirb_last_error() returns the message of the last failure on the calling thread.
+ * A context may be used from one host thread at a time; batching is explicit (n_queries).
+ * There is NO CPU fallback: every entry point that computes fails with 13 if CUDA is unavailable.
+ */
+#ifndef PIR_B200_H_
+#define PIR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIRB_OK 0
+#define PIRB_INVALID_ARGUMENT 3
+#define PIRB_INTERNAL 13
+
+#define PIRB_MAX_MODULI 9
+#define PIRB_MAX_DIMS 8
+
+typedef struct pirb_ctx pirb_ctx;   /* owns device tables, the HBM-resident database shard, workspaces, a stream */
+typedef struct pirb_keys pirb_keys; /* one client's Galois keys, resident in HBM */
+
+/* What PIRContext::Create / PIRParameters carry for this path (pir/cpp/context.cpp:37-50,
+ * pir/proto/payload.proto:45-69), with the SEAL EncryptionParameters unpacked. */
+typedef struct {
+  uint32_t poly_modulus_degree;               /* N, power of two, 2048..16384 */
+  uint32_t n_moduli;                          /* k+1: data-level primes q_0..q_{k-1}, then the special prime P */
+  uint64_t coeff_modulus[PIRB_MAX_MODULI];
+  uint64_t plain_modulus;                     /* t */
+  uint32_t n_dims;                            /* d */
+  uint32_t dims[PIRB_MAX_DIMS];               /* PIRParameters.dimensions */
+  uint64_t num_pt;                            /* PIRParameters.num_pt (whole database, all shards) */
+  int32_t device;                             /* CUDA device ordinal */
+  uint32_t shard_index;                       /* row shard of dims[0] owned by this context ... */
+  uint32_t shard_count;                       /* ... out of shard_count (1 = whole database) */
+} pirb_params;
+
+const char* pirb_last_error(void);
+
+/* PIRServer::Create + PIRContext::Create (server.cpp:35-42, context.cpp:37-50). */
+int pirb_ctx_create(const pirb_params* params, pirb_ctx** out);
+void pirb_ctx_destroy(pirb_ctx* ctx);
+
+/* shape queries */
+uint64_t pirb_ct_limbs(const pirb_ctx* ctx);
+uint64_t pirb_pt_limbs(const pirb_ctx* ctx);
+uint64_t pirb_key_limbs(const pirb_ctx* ctx);
+uint32_t pirb_expansion_ratio(const pirb_ctx* ctx);      /* CiphertextReencoder::ExpansionRatio (ct_reencoder.cpp:29-38) */
+uint64_t pirb_reply_cts(const pirb_ctx* ctx);            /* (2*ER)^(d-1)  (database.cpp:215, client.cpp:224-226) */
+uint64_t pirb_dim_sum(const pirb_ctx* ctx);              /* PIRContext::DimensionsSum (context.h:59-62) */
+uint64_t pirb_query_cts(const pirb_ctx* ctx);            /* dim_sum / N + 1 (client.cpp:109, server.cpp:154-158) */
+uint64_t pirb_shard_pt_begin(const pirb_ctx* ctx);       /* first plaintext index held by this shard */
+uint64_t pirb_shard_pt_count(const pirb_ctx* ctx);
+uint64_t pirb_db_size(const pirb_ctx* ctx);              /* PIRDatabase::size(): plaintexts loaded so far (database.h:94) */
+
+/* PIRDatabase::populate (database.cpp:84-110) after StringEncoder/IntegerEncoder packing:
+ * coeffs[count][N] < t, plaintext indices are GLOBAL; the shard keeps the ones it owns.
+ * The centred lift + NTT (transform_to_ntt_inplace(pt, first_parms_id), database.cpp:103-106) run on the GPU. */
+int pirb_db_load_coeff(pirb_ctx* ctx, const uint64_t* coeffs, uint64_t first_pt, uint64_t count);
+/* Same, for a database already in NTT form (SEAL ordering): limbs[count][k][N]. */
+int pirb_db_load_ntt(pirb_ctx* ctx, const uint64_t* limbs, uint64_t first_pt, uint64_t count);
+/* Read back NTT-form plaintexts (persistence / tests): out[count][k][N]. */
+int pirb_db_read_ntt(const pirb_ctx* ctx, uint64_t* out, uint64_t first_pt, uint64_t count);
+/* Synthetic database for benchmarks: uniform limbs in [0,q_j), generated on the device (scan cost is data-independent). */
+int pirb_db_fill_random(pirb_ctx* ctx, uint64_t seed);
+
+/* seal::GaloisKeys as deserialized by ProcessRequest (server.cpp:46-48): n keys, elts[i] = Galois element. */
+int pirb_keys_load(pirb_ctx* ctx, const uint32_t* elts, uint32_t n_elts, const uint64_t* limbs, pirb_keys** out);
+void pirb_keys_destroy(pirb_keys* keys);
+
+/* PIRServer::substitute_power_x_inplace (server.cpp:67-76): ct(x) -> ct(x^power), in place. 13 if the key is missing. */
+int pirb_substitute(pirb_ctx* ctx, const pirb_keys* keys, uint64_t* ct, uint32_t power);
+/* PIRServer::multiply_inverse_power_of_x (server.cpp:78-103). */
+int pirb_mul_inv_pow_x(pirb_ctx* ctx, const uint64_t* ct_in, uint32_t k, uint64_t* ct_out);
+/* PIRServer::oblivious_expansion: single != 0 -> the one-ciphertext overload (server.cpp:105-146), else the
+ * vector overload (server.cpp:148-171).  out[total_items][2][k][N].  3 on the reference's argument errors. */
+int pirb_expand(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* cts, uint64_t n_ct, uint64_t total_items,
+                int single, uint64_t* out);
+/* PIRDatabase::multiply (database.cpp:290-316), re-encoder path.  sv[n_sv][2][k][N] in coefficient form is
+ * transformed to NTT form IN PLACE like the reference does (database.cpp:190,222).  out[(2*ER)^(d-1)][2][k][N].
+ * 3 if n_sv != dim_sum. */
+int pirb_db_multiply(pirb_ctx* ctx, uint64_t* sv, uint64_t n_sv, uint64_t* out, uint64_t out_cap_cts,
+                     uint64_t* out_count);
+/* PIRServer::processQuery for every query of a request (server.cpp:60-63, 173-195): expansion + multiply.
+ * queries[n_queries][n_ct][2][k][N] -> replies[n_queries][reply_cts][2][k][N].  Host buffers. */
+int pirb_answer(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* queries, uint32_t n_queries, uint64_t n_ct,
+                uint64_t* replies);
+
+/* Device-resident variants (pointers are CUDA device pointers on ctx's device; stream = cudaStream_t or NULL
+ * for the context's own stream).  pirb_answer_dev writes final replies (shard_count == 1).  With shards, each rank
+ * calls pirb_answer_partial_dev -> partial[n_queries][reply_cts][2][k][N] in NTT form (sum over its rows), the
+ * partials are exchanged (NCCL all-gather or peer pointers) and pirb_reduce_finish_* adds them mod q and
+ * applies the final inverse NTT (database.cpp:250-254).  A plain integer sum is never used. */
+int pirb_answer_dev(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries,
+                    uint64_t n_ct, uint64_t* d_replies, void* stream);
+int pirb_answer_partial_dev(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries,
+                            uint64_t n_ct, uint64_t* d_partial, void* stream);
+int pirb_reduce_finish_dev(pirb_ctx* ctx, const uint64_t* d_partials, uint32_t n_parts, uint64_t part_stride_limbs,
+                           uint32_t n_queries, uint64_t* d_replies, void* stream);
+int pirb_reduce_finish_peers_dev(pirb_ctx* ctx, const uint64_t* const* d_peer_ptrs, uint32_t n_parts,
+                                 uint32_t n_queries, uint64_t* d_replies, void* stream);
+/* Scan only (the HBM-bound kernel): d_sv_ntt[n_queries][dims[d-1]][2][k][N] NTT form -> rows in NTT form.
+ * Used by the bench to time the scan in isolation.  d_rows may be NULL (internal scratch). */
+int pirb_scan_dev(pirb_ctx* ctx, const uint64_t* d_sv_ntt, uint32_t n_queries, uint64_t* d_rows, void* stream);
+int pirb_sync(pirb_ctx* ctx);
+
+/* Per-stage device times of the last pirb_answer* call, measured with CUDA events on the launching stream
+ * when profiling is enabled.  stage: 0 expand, 1 sv NTT, 2 scan, 3 row INTT, 4 upper dims, 5 total. */
+#define PIRB_N_STAGES 6
+int pirb_set_profiling(pirb_ctx* ctx, int enabled);
+int pirb_get_stage_ms(pirb_ctx* ctx, float* out_ms /*[PIRB_N_STAGES]*/);
+/* kernels launched by the last pirb_answer* call, and algorithmic scan bytes of one scan launch. */
+uint64_t pirb_last_launch_count(const pirb_ctx* ctx);
+uint64_t pirb_scan_bytes(const pirb_ctx* ctx, uint32_t n_queries);
+
+/* Host-side shape math of the reference, exported so bindings need not re-implement it:
+ * PIRDatabase::calculate_dimensions (database.cpp:334-342), next_power_two / ceil_log2 / log2 (utils.h:29-37,
+ * utils.cpp:16-44), PlainModulus::Batching and CoeffModulus::BFVDefault as used by GenerateEncryptionParams
+ * (parameters.cpp:33-54). */
+void pirb_calculate_dimensions(uint32_t db_size, uint32_t n_dims, uint32_t* out);
+uint64_t pirb_next_power_two(uint64_t v);
+uint32_t pirb_ceil_log2(uint32_t v);
+uint32_t pirb_log2(uint32_t v);
+uint64_t pirb_plain_modulus_batching(uint32_t poly_modulus_degree, uint32_t bit_size);
+int pirb_bfv_default_coeff_modulus(uint32_t poly_modulus_degree, uint64_t* out, uint32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIR_B200_H_ */

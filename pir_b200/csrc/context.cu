@@ -1,0 +1,811 @@
+// context.cu — host side of the C ABI (include/pir_b200.h): context, HBM-resident database shard, Galois key
+// handles, expansion plans, workspaces and the orchestration of the kernels in kernels_*.cu.
+//
+// Reference call stack this file replaces:
+//   PIRServer::processQuery (server.cpp:173-195) -> oblivious_expansion (server.cpp:105-171)
+//   -> PIRDatabase::multiply / DatabaseMultiplier::multiply (database.cpp:170-258, 290-316)
+//   -> CiphertextReencoder::Encode (ct_reencoder.cpp:40-71)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pir_b200.h"
+#include "host_math.h"
+#include "kernels.cuh"
+
+using namespace pirb;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(x)                                                                                     \
+  do {                                                                                            \
+    cudaError_t e_ = (x);                                                                         \
+    if (e_ != cudaSuccess) return fail(PIRB_INTERNAL, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+#define RC(x)             \
+  do {                    \
+    int rc_ = (x);        \
+    if (rc_) return rc_;  \
+  } while (0)
+
+struct DevBuf {
+  u64* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int ensure(size_t b) {
+    if (b <= bytes) return 0;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    cudaError_t e = cudaMalloc(&p, b);
+    if (e != cudaSuccess) {
+      return fail(PIRB_INTERNAL, "cudaMalloc(" + std::to_string(b) + " bytes): " + cudaGetErrorString(e));
+    }
+    bytes = b;
+    return 0;
+  }
+};
+
+// One oblivious-expansion job: every query ciphertext is the root of a binary tree (server.cpp:105-146);
+// trees of all ciphertexts (server.cpp:148-171) and of all queries of a batch run level by level.
+struct ExpandPlan {
+  u64 total_items = 0;
+  int n_trees = 0;
+  std::vector<u64> items, base;  // per tree: outputs kept, first ct index in S
+  std::vector<int> logm;
+  u64 cap = 0;  // ciphertext slots in S (and in T)
+  int max_logm = 0;
+  u64 max_nodes = 0;  // per query, max over levels
+  DevBuf d_off;       // [root_off | per level: src_off, dst_off]
+  std::vector<int> lvl_ntrees;
+  std::vector<size_t> lvl_src, lvl_dst;  // element positions inside d_off
+};
+
+}  // namespace
+
+struct pirb_keys {
+  std::vector<u32> elts;
+  DevBuf d;  // [n][k][2][k+1][N]
+  u64 key_limbs = 0;
+  int device = 0;
+  const u64* find(u32 g) const {
+    for (size_t i = 0; i < elts.size(); ++i)
+      if (elts[i] == g) return d.p + i * key_limbs;
+    return nullptr;
+  }
+};
+
+struct pirb_ctx {
+  pirb_params prm;
+  DevParams P;
+  int device = 0, sm_count = 148;
+  u32 N = 0;
+  int k = 0, logn = 0, d = 0;
+  u64 ctL = 0, ptL = 0;
+  u32 two_er = 0;
+  std::vector<u32> dims;
+  u64 dim_sum = 0, reply_cts = 1, rest = 1;  // rest = prod dims[1..]
+  u32 top_lo = 0, top_hi = 0;                // owned slice of dims[0]
+  u64 pt_begin = 0, pt_count = 0;            // owned plaintexts (global indices)
+  u64 loaded = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<DevBuf> tables;
+  DevBuf db, stage, work, dig, acc, part, bufA[2], pts, qbuf, rbuf, svbuf;
+  std::map<std::pair<u64, int>, std::unique_ptr<ExpandPlan>> plans;
+  bool profiling = false;
+  cudaEvent_t ev[PIRB_N_STAGES + 1] = {};
+  bool ev_valid = false;
+  u64 launches = 0;
+  int scan_split = 1;
+};
+
+namespace {
+
+#define LAUNCH(ctx, call)                                                                            \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    ++(ctx)->launches;                                                                               \
+    if (e_ != cudaSuccess) return fail(PIRB_INTERNAL, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// uint64_t (unsigned long) <-> u64 (unsigned long long): same representation on LP64
+inline u64* U(uint64_t* p) { return reinterpret_cast<u64*>(p); }
+inline const u64* U(const uint64_t* p) { return reinterpret_cast<const u64*>(p); }
+static_assert(sizeof(u64) == sizeof(uint64_t), "u64 must be 64 bits");
+
+u32 inv_mod_2n(u32 g, u32 N) {
+  // g odd; inverse modulo 2N (power of two) by Newton iteration
+  u32 x = g;
+  for (int i = 0; i < 5; ++i) x *= 2 - g * x;
+  return x & (2 * N - 1);
+}
+
+ExpandPlan* get_plan(pirb_ctx* c, u64 total_items, int single, int* rc) {
+  *rc = 0;
+  auto key = std::make_pair(total_items, single);
+  auto it = c->plans.find(key);
+  if (it != c->plans.end()) return it->second.get();
+  auto pl = std::make_unique<ExpandPlan>();
+  const u64 N = c->N;
+  pl->total_items = total_items;
+  pl->n_trees = single ? 1 : (int)(total_items / N + 1);
+  u64 remaining = total_items;
+  for (int t = 0; t < pl->n_trees; ++t) {
+    u64 it_ = single ? total_items : (remaining < N ? remaining : N);
+    pl->items.push_back(it_);
+    pl->logm.push_back((int)hm::ceil_log2((uint32_t)it_));
+    pl->base.push_back((u64)t * N);
+    pl->max_logm = std::max(pl->max_logm, pl->logm.back());
+    remaining = remaining >= N ? remaining - N : 0;
+  }
+  pl->cap = pl->base.back() + hm::next_power_two(pl->items.back());
+  const u64 Soff = 0, Toff = pl->cap * c->ctL;
+  std::vector<u64> h;
+  for (int t = 0; t < pl->n_trees; ++t) h.push_back(((pl->logm[t] & 1) ? Toff : Soff) + pl->base[t] * c->ctL);
+  for (int j = 0; j < pl->max_logm; ++j) {
+    std::vector<u64> src, dst;
+    for (int t = 0; t < pl->n_trees; ++t) {
+      if (pl->logm[t] <= j) continue;
+      const bool src_in_S = ((pl->logm[t] - j) % 2) == 0;
+      src.push_back((src_in_S ? Soff : Toff) + pl->base[t] * c->ctL);
+      dst.push_back((src_in_S ? Toff : Soff) + pl->base[t] * c->ctL);
+    }
+    pl->lvl_ntrees.push_back((int)src.size());
+    pl->lvl_src.push_back(h.size());
+    h.insert(h.end(), src.begin(), src.end());
+    pl->lvl_dst.push_back(h.size());
+    h.insert(h.end(), dst.begin(), dst.end());
+    pl->max_nodes = std::max(pl->max_nodes, (u64)src.size() << j);
+  }
+  if (pl->d_off.ensure(h.size() * sizeof(u64))) { *rc = PIRB_INTERNAL; return nullptr; }
+  if (cudaMemcpy(pl->d_off.p, h.data(), h.size() * sizeof(u64), cudaMemcpyHostToDevice) != cudaSuccess) {
+    *rc = fail(PIRB_INTERNAL, "plan upload failed");
+    return nullptr;
+  }
+  ExpandPlan* raw = pl.get();
+  c->plans[key] = std::move(pl);
+  return raw;
+}
+
+// Expansion of n_queries x n_trees root ciphertexts (contiguous at d_query) into c->work.
+// Result: work[qi*q_stride + i*ctL] for i < total_items (S region), coefficient form.
+int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_query, int n_queries,
+               cudaStream_t st) {
+  const u64 q_stride = 2 * pl->cap * c->ctL;
+  RC(c->work.ensure((size_t)n_queries * q_stride * sizeof(u64)));
+  const u64 nodes = pl->max_nodes * n_queries;
+  RC(c->dig.ensure((size_t)std::max<u64>(nodes, 1) * (c->k + 1) * c->k * c->N * sizeof(u64)));
+  RC(c->acc.ensure((size_t)std::max<u64>(nodes, 1) * 2 * (c->k + 1) * c->N * sizeof(u64)));
+  LAUNCH(c, launch_place_roots(c->P, d_query, c->work.p, pl->d_off.p, pl->n_trees, n_queries, q_stride, st));
+  for (int j = 0; j < pl->max_logm; ++j) {
+    const u32 g = (c->N >> j) + 1;
+    if (!keys) return fail(PIRB_INTERNAL, "Galois keys required");
+    const u64* key = keys->find(g);
+    if (!key) return fail(PIRB_INTERNAL, "Galois key not present for element " + std::to_string(g));
+    LevelArgs L;
+    L.src_off = pl->d_off.p + pl->lvl_src[j];
+    L.dst_off = pl->d_off.p + pl->lvl_dst[j];
+    L.n_trees = pl->lvl_ntrees[j];
+    L.j = j;
+    L.ginv = inv_mod_2n(g, c->N);
+    L.q_stride = q_stride;
+    L.n_queries = n_queries;
+    const int n_nodes = (n_queries * L.n_trees) << j;
+    LAUNCH(c, launch_ks_digits(c->P, c->work.p, L, c->dig.p, st));
+    LAUNCH(c, launch_ks_mac_intt(c->P, c->dig.p, key, c->acc.p, n_nodes, st));
+    LAUNCH(c, launch_ks_combine(c->P, c->work.p, L, c->acc.p, 0, st));
+  }
+  return 0;
+}
+
+int choose_split(u64 base_ctas, u32 len, int sm_count) {
+  const u64 want = (u64)sm_count * 4;
+  int s = 1;
+  if (base_ctas < want) s = (int)((want + base_ctas - 1) / base_ctas);
+  const int max_split = (int)((len + 3) / 4);
+  if (s > max_split) s = max_split;
+  return s < 1 ? 1 : s;
+}
+
+// DatabaseMultiplier::multiply on the device.  d_sv: [n_queries] x (sv_qstride limbs apart) x [dim_sum][2][k][N]
+// coefficient form; transformed to NTT form in place.  d_out: [n_queries][reply_cts][2][k][N]; coefficient form,
+// or (partial != 0) the NTT-form sum over this shard's rows, to be reduced across shards.
+int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_out, int partial, cudaStream_t st) {
+  const int d = c->d, k = c->k;
+  const u64 ctL = c->ctL;
+  const DevParams& P = c->P;
+  if (c->profiling) cudaEventRecord(c->ev[1], st);
+  LAUNCH(c, launch_ntt_fwd(P, d_sv, d_sv, (int)(c->dim_sum * 2 * k), k, 0, n_queries, sv_qstride, sv_qstride, st));
+  if (c->profiling) cudaEventRecord(c->ev[2], st);
+
+  const u64 out_cts = c->reply_cts;
+  if (c->pt_count == 0 || c->loaded == 0) {
+    // empty shard: contributes the additive identity
+    CU(cudaMemsetAsync(d_out, 0, (size_t)n_queries * out_cts * ctL * sizeof(u64), st));
+    if (c->profiling) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
+    return 0;
+  }
+  // ---- last dimension: scan against the database ----
+  u32 dimL, n_rows;
+  const u64* sv_last;
+  if (d == 1) {
+    dimL = c->top_hi - c->top_lo;
+    n_rows = 1;
+    sv_last = d_sv + (u64)c->top_lo * ctL;
+  } else {
+    dimL = c->dims[d - 1];
+    n_rows = (u32)((c->pt_count + dimL - 1) / dimL);
+    u64 off = 0;
+    for (int e = 0; e < d - 1; ++e) off += c->dims[e];
+    sv_last = d_sv + off * ctL;
+  }
+  int n_split;
+  scan_config(P, dimL, n_rows, n_queries, c->sm_count, &n_split);
+  c->scan_split = n_split;
+  RC(c->part.ensure((size_t)n_queries * n_split * n_rows * ctL * sizeof(u64)));
+  LAUNCH(c, launch_scan(P, c->db.p, c->pt_count, dimL, n_rows, sv_last, sv_qstride, n_queries, n_split, c->part.p, st));
+  if (c->profiling) cudaEventRecord(c->ev[3], st);
+  if (d == 1) {
+    if (partial) {
+      for (int qi = 0; qi < n_queries; ++qi)
+        LAUNCH(c, launch_modadd_reduce(P, c->part.p + (u64)qi * n_split * ctL, ctL, n_split, d_out + qi * ctL, 1, st));
+    } else {
+      LAUNCH(c, launch_ntt_inv(P, c->part.p, d_out, 2 * k, k, 0, n_split, (u64)n_rows * ctL, n_queries,
+                               (u64)n_split * n_rows * ctL, ctL, st));
+    }
+    if (c->profiling) { cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
+    return 0;
+  }
+  // rows -> coefficient form (database.cpp:250-254)
+  RC(c->bufA[0].ensure((size_t)n_queries * n_rows * ctL * sizeof(u64)));
+  LAUNCH(c, launch_ntt_inv(P, c->part.p, c->bufA[0].p, (int)(n_rows * 2 * k), k, 0, n_split, (u64)n_rows * ctL,
+                           n_queries, (u64)n_split * n_rows * ctL, (u64)n_rows * ctL, st));
+  if (c->profiling) cudaEventRecord(c->ev[4], st);
+  // ---- upper dimensions (database.cpp:196-235) ----
+  u32 n_entries = n_rows;
+  u32 w = 1;
+  int cur = 0;
+  for (int l = d - 2; l >= 0; --l) {
+    const u32 dim = (l == 0) ? (c->top_hi - c->top_lo) : c->dims[l];
+    const u32 n_groups = (n_entries + dim - 1) / dim;
+    const u32 w_out = w * c->two_er;
+    u64 sv_off = (l == 0) ? c->top_lo : 0;
+    for (int e = 0; e < l; ++e) sv_off += c->dims[e];
+    const u64 n_cts_in = (u64)n_entries * w;  // per query, contiguous
+    RC(c->pts.ensure((size_t)n_queries * n_cts_in * c->two_er * c->ptL * sizeof(u64)));
+    LAUNCH(c, launch_reencode_ntt(P, c->bufA[cur].p, c->pts.p, (int)(n_queries * n_cts_in), st));
+    const u32 slices = (u32)(c->ptL / 256);
+    const int ns = choose_split((u64)slices * w_out * n_groups * n_queries, dim, c->sm_count);
+    RC(c->part.ensure((size_t)n_queries * ns * n_groups * w_out * ctL * sizeof(u64)));
+    LAUNCH(c, launch_dim_mac(P, c->pts.p, n_cts_in * c->two_er * c->ptL, d_sv + sv_off * ctL, sv_qstride, n_queries, dim,
+                             n_entries, n_groups, w_out, ns, c->part.p, st));
+    const u64 lvl_cts = (u64)n_groups * w_out;  // per query
+    if (l == 0 && partial) {
+      for (int qi = 0; qi < n_queries; ++qi)
+        LAUNCH(c, launch_modadd_reduce(P, c->part.p + (u64)qi * ns * lvl_cts * ctL, lvl_cts * ctL, ns,
+                                       d_out + (u64)qi * lvl_cts * ctL, lvl_cts, st));
+    } else {
+      u64* dst = d_out;
+      if (l != 0) {
+        RC(c->bufA[cur ^ 1].ensure((size_t)n_queries * lvl_cts * ctL * sizeof(u64)));
+        dst = c->bufA[cur ^ 1].p;
+      }
+      LAUNCH(c, launch_ntt_inv(P, c->part.p, dst, (int)(lvl_cts * 2 * k), k, 0, ns, lvl_cts * ctL, n_queries,
+                               (u64)ns * lvl_cts * ctL, lvl_cts * ctL, st));
+    }
+    n_entries = n_groups;
+    w = w_out;
+    cur ^= 1;
+  }
+  if (c->profiling) cudaEventRecord(c->ev[5], st);
+  return 0;
+}
+
+int run_answer(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u32 n_queries, u64 n_ct, u64* d_out,
+               int partial, cudaStream_t st) {
+  if (!n_queries) return 0;
+  if (n_ct != c->dim_sum / c->N + 1) {  // server.cpp:154-158
+    return fail(PIRB_INVALID_ARGUMENT,
+                "Number of ciphertexts doesn't match number of items for oblivious expansion.");
+  }
+  if (c->loaded != c->pt_count) return fail(PIRB_INVALID_ARGUMENT, "database size mismatch");  // server.cpp:37-39
+  int rc;
+  ExpandPlan* pl = get_plan(c, c->dim_sum, 0, &rc);
+  if (!pl) return rc;
+  c->launches = 0;
+  if (c->profiling) cudaEventRecord(c->ev[0], st);
+  RC(run_expand(c, keys, pl, d_queries, (int)n_queries, st));
+  RC(run_multiply(c, c->work.p, 2 * pl->cap * c->ctL, (int)n_queries, d_out, partial, st));
+  c->ev_valid = c->profiling;
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* pirb_last_error(void) { return g_err.c_str(); }
+
+int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
+  if (!prm || !out) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  const u32 N = prm->poly_modulus_degree;
+  int logn = 0;
+  while ((1u << logn) < N) ++logn;
+  if ((1u << logn) != N || logn < 11 || logn > 14)
+    return fail(PIRB_INVALID_ARGUMENT, "poly_modulus_degree must be a power of two in [2048, 16384]");
+  if (prm->n_moduli < 2 || prm->n_moduli > PIRB_MAX_MODULI)
+    return fail(PIRB_INVALID_ARGUMENT, "need 1..8 data moduli plus the special prime");
+  if (prm->n_dims < 1 || prm->n_dims > PIRB_MAX_DIMS) return fail(PIRB_INVALID_ARGUMENT, "bad number of dimensions");
+  for (u32 i = 0; i < prm->n_moduli; ++i) {
+    const u64 q = prm->coeff_modulus[i];
+    if (q >> 61) return fail(PIRB_INVALID_ARGUMENT, "coefficient moduli must be below 2^61");
+    if (!hm::is_prime(q) || (q - 1) % (2ull * N)) return fail(PIRB_INVALID_ARGUMENT, "coefficient modulus is not an NTT prime");
+    for (u32 j = 0; j < i; ++j)
+      if (prm->coeff_modulus[j] == q) return fail(PIRB_INVALID_ARGUMENT, "coefficient moduli must be distinct");
+  }
+  const u64 t = prm->plain_modulus;
+  if (t < 2 || t >> 32) return fail(PIRB_INVALID_ARGUMENT, "plain modulus out of range");
+  for (u32 i = 0; i + 1 < prm->n_moduli; ++i)
+    if (t >= prm->coeff_modulus[i]) return fail(PIRB_INVALID_ARGUMENT, "plain modulus must be below every data modulus");
+  for (u32 i = 0; i < prm->n_dims; ++i)
+    if (!prm->dims[i]) return fail(PIRB_INVALID_ARGUMENT, "zero dimension");
+  if (prm->shard_count == 0 || prm->shard_index >= prm->shard_count)
+    return fail(PIRB_INVALID_ARGUMENT, "bad shard index/count");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PIRB_INTERNAL, "no CUDA device available (this library has no CPU fallback)");
+  if (prm->device < 0 || prm->device >= ndev) return fail(PIRB_INVALID_ARGUMENT, "bad device ordinal");
+  CU(cudaSetDevice(prm->device));
+
+  std::unique_ptr<pirb_ctx> c(new pirb_ctx());
+  c->prm = *prm;
+  c->device = prm->device;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, prm->device);
+  c->N = N;
+  c->logn = logn;
+  c->k = (int)prm->n_moduli - 1;
+  c->d = (int)prm->n_dims;
+  c->ctL = 2ull * c->k * N;
+  c->ptL = (u64)c->k * N;
+  c->dims.assign(prm->dims, prm->dims + prm->n_dims);
+  for (u32 v : c->dims) c->dim_sum += v;
+  for (int i = 1; i < c->d; ++i) c->rest *= c->dims[i];
+
+  DevParams& P = c->P;
+  memset(&P, 0, sizeof(P));
+  P.logn = logn;
+  P.k = c->k;
+  P.N = N;
+  P.t = t;
+  P.thr = (t + 1) >> 1;
+  P.ptb = hm::trunc_log2((uint32_t)t);
+  if (P.ptb == 0) return fail(PIRB_INVALID_ARGUMENT, "plain modulus too small");
+  const u64 Pq = prm->coeff_modulus[c->k];
+  P.half_P = Pq >> 1;
+  c->tables.resize(prm->n_moduli);
+  for (u32 i = 0; i < prm->n_moduli; ++i) {
+    const u64 q = prm->coeff_modulus[i];
+    hm::Tables T = hm::build_tables(q, logn);
+    RC(c->tables[i].ensure(4ull * N * sizeof(u64)));
+    u64* base = c->tables[i].p;
+    CU(cudaMemcpy(base, T.rp.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + N, T.rps.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + 2ull * N, T.irp.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + 3ull * N, T.irps.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
+    ModC& m = P.m[i];
+    m.q = q;
+    hm::barrett_ratio(q, &m.ratio_hi, &m.ratio_lo);
+    m.inv_n = T.inv_n;
+    m.inv_n_s = T.inv_n_s;
+    m.rp = base;
+    m.rps = base + N;
+    m.irp = base + 2ull * N;
+    m.irps = base + 3ull * N;
+    if ((int)i < c->k) {
+      P.inv_P[i] = hm::invmod_prime(Pq % q, q);
+      P.inv_P_s[i] = hm::shoup(P.inv_P[i], q);
+      P.half_P_mod[i] = P.half_P % q;
+    }
+  }
+  // re-encode chunk table (ct_reencoder.cpp:29-71: double log2, ceil)
+  u32 e = 0;
+  for (int poly = 0; poly < 2; ++poly)
+    for (int j = 0; j < c->k; ++j) {
+      const u32 le = (u32)std::ceil(std::log2((double)prm->coeff_modulus[j]) / P.ptb);
+      for (u32 i = 0; i < le; ++i, ++e) {
+        if (e >= PIRB_MAX_REENC) return fail(PIRB_INVALID_ARGUMENT, "expansion ratio too large");
+        P.re_poly[e] = (u8)poly;
+        P.re_mod[e] = (u8)j;
+        P.re_shift[e] = (u8)(i * P.ptb);
+      }
+    }
+  P.two_er = (int)e;
+  c->two_er = e;
+  for (int i = 1; i < c->d; ++i) c->reply_cts *= e;
+
+  // row shard of the first dimension
+  const u32 d0 = c->dims[0];
+  const u32 per = (d0 + prm->shard_count - 1) / prm->shard_count;
+  c->top_lo = std::min<u64>(d0, (u64)per * prm->shard_index);
+  c->top_hi = std::min<u64>(d0, (u64)c->top_lo + per);
+  const u64 lo = std::min<u64>(prm->num_pt, (u64)c->top_lo * c->rest);
+  const u64 hi = std::min<u64>(prm->num_pt, (u64)c->top_hi * c->rest);
+  c->pt_begin = lo;
+  c->pt_count = hi - lo;
+  RC(c->db.ensure(std::max<size_t>(c->pt_count * c->ptL * sizeof(u64), 256)));
+
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
+  *out = c.release();
+  return 0;
+}
+
+void pirb_ctx_destroy(pirb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+uint64_t pirb_ct_limbs(const pirb_ctx* c) { return c->ctL; }
+uint64_t pirb_pt_limbs(const pirb_ctx* c) { return c->ptL; }
+uint64_t pirb_key_limbs(const pirb_ctx* c) { return (u64)c->k * 2 * (c->k + 1) * c->N; }
+uint32_t pirb_expansion_ratio(const pirb_ctx* c) { return c->two_er / 2; }
+uint64_t pirb_reply_cts(const pirb_ctx* c) { return c->reply_cts; }
+uint64_t pirb_dim_sum(const pirb_ctx* c) { return c->dim_sum; }
+uint64_t pirb_query_cts(const pirb_ctx* c) { return c->dim_sum / c->N + 1; }
+uint64_t pirb_shard_pt_begin(const pirb_ctx* c) { return c->pt_begin; }
+uint64_t pirb_shard_pt_count(const pirb_ctx* c) { return c->pt_count; }
+uint64_t pirb_db_size(const pirb_ctx* c) { return c->loaded; }
+
+static int clip_to_shard(const pirb_ctx* c, uint64_t first, uint64_t count, u64* lo, u64* hi) {
+  if (first + count > c->prm.num_pt) return fail(PIRB_INVALID_ARGUMENT, "plaintext index beyond num_pt");
+  *lo = std::max<u64>(first, c->pt_begin);
+  *hi = std::min<u64>(first + count, c->pt_begin + c->pt_count);
+  return 0;
+}
+
+int pirb_db_load_coeff(pirb_ctx* c, const uint64_t* coeffs, uint64_t first, uint64_t count) {
+  if (!c || !coeffs) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  u64 lo, hi;
+  RC(clip_to_shard(c, first, count, &lo, &hi));
+  const u64 chunk_max = std::max<u64>(1, (64ull << 20) / (c->N * sizeof(u64)));
+  for (u64 p = lo; p < hi;) {
+    const u64 n = std::min(chunk_max, hi - p);
+    RC(c->stage.ensure(n * c->N * sizeof(u64)));
+    CU(cudaMemcpyAsync(c->stage.p, coeffs + (p - first) * c->N, n * c->N * sizeof(u64), cudaMemcpyHostToDevice,
+                       c->stream));
+    LAUNCH(c, launch_db_preprocess(c->P, c->stage.p, c->db.p + (p - c->pt_begin) * c->ptL, n, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->loaded += n;
+    p += n;
+  }
+  return 0;
+}
+
+int pirb_db_load_ntt(pirb_ctx* c, const uint64_t* limbs, uint64_t first, uint64_t count) {
+  if (!c || !limbs) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  u64 lo, hi;
+  RC(clip_to_shard(c, first, count, &lo, &hi));
+  if (hi > lo) {
+    CU(cudaMemcpy(c->db.p + (lo - c->pt_begin) * c->ptL, limbs + (lo - first) * c->ptL, (hi - lo) * c->ptL * sizeof(u64),
+                  cudaMemcpyHostToDevice));
+    c->loaded += hi - lo;
+  }
+  return 0;
+}
+
+int pirb_db_read_ntt(const pirb_ctx* c, uint64_t* out, uint64_t first, uint64_t count) {
+  if (!c || !out) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (first < c->pt_begin || first + count > c->pt_begin + c->pt_count)
+    return fail(PIRB_INVALID_ARGUMENT, "range outside this shard");
+  CU(cudaMemcpy(out, c->db.p + (first - c->pt_begin) * c->ptL, count * c->ptL * sizeof(u64), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int pirb_db_fill_random(pirb_ctx* c, uint64_t seed) {
+  if (!c) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  LAUNCH(c, launch_fill_random(c->P, c->db.p, c->pt_count * (u64)c->k, c->k, 0, seed + c->pt_begin, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->loaded = c->pt_count;
+  return 0;
+}
+
+int pirb_keys_load(pirb_ctx* c, const uint32_t* elts, uint32_t n, const uint64_t* limbs, pirb_keys** out) {
+  if (!c || !out || (n && (!elts || !limbs))) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  std::unique_ptr<pirb_keys> kz(new pirb_keys());
+  kz->elts.assign(elts, elts + n);
+  kz->key_limbs = pirb_key_limbs(c);
+  kz->device = c->device;
+  for (u32 i = 0; i < n; ++i)
+    if (!(elts[i] & 1) || elts[i] >= 2 * c->N) return fail(PIRB_INVALID_ARGUMENT, "Galois element must be odd and < 2N");
+  RC(kz->d.ensure(std::max<size_t>((size_t)n * kz->key_limbs * sizeof(u64), 256)));
+  if (n) CU(cudaMemcpy(kz->d.p, limbs, (size_t)n * kz->key_limbs * sizeof(u64), cudaMemcpyHostToDevice));
+  *out = kz.release();
+  return 0;
+}
+void pirb_keys_destroy(pirb_keys* kz) {
+  if (!kz) return;
+  cudaSetDevice(kz->device);
+  delete kz;
+}
+
+int pirb_substitute(pirb_ctx* c, const pirb_keys* keys, uint64_t* ct, uint32_t power) {
+  if (!c || !keys || !ct) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  const u64* key = keys->find(power);
+  if (!key) return fail(PIRB_INTERNAL, "Galois key not present");  // SEAL throws; server.cpp:72-74 -> InternalError
+  cudaStream_t st = c->stream;
+  RC(c->work.ensure(2 * c->ctL * sizeof(u64)));
+  RC(c->dig.ensure((size_t)(c->k + 1) * c->k * c->N * sizeof(u64)));
+  RC(c->acc.ensure((size_t)2 * (c->k + 1) * c->N * sizeof(u64)));
+  RC(c->stage.ensure(2 * sizeof(u64)));
+  const u64 offs[2] = {0, c->ctL};
+  CU(cudaMemcpyAsync(c->stage.p, offs, sizeof(offs), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c->work.p, ct, c->ctL * sizeof(u64), cudaMemcpyHostToDevice, st));
+  LevelArgs L;
+  L.src_off = c->stage.p;
+  L.dst_off = c->stage.p + 1;
+  L.n_trees = 1;
+  L.j = 0;
+  L.ginv = inv_mod_2n(power, c->N);
+  L.q_stride = 0;
+  L.n_queries = 1;
+  LAUNCH(c, launch_ks_digits(c->P, c->work.p, L, c->dig.p, st));
+  LAUNCH(c, launch_ks_mac_intt(c->P, c->dig.p, key, c->acc.p, 1, st));
+  LAUNCH(c, launch_ks_combine(c->P, c->work.p, L, c->acc.p, 1, st));
+  CU(cudaMemcpyAsync(ct, c->work.p + c->ctL, c->ctL * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pirb_mul_inv_pow_x(pirb_ctx* c, const uint64_t* in, uint32_t kpow, uint64_t* out) {
+  if (!c || !in || !out) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  RC(c->work.ensure(2 * c->ctL * sizeof(u64)));
+  CU(cudaMemcpyAsync(c->work.p, in, c->ctL * sizeof(u64), cudaMemcpyHostToDevice, st));
+  LAUNCH(c, launch_mul_inv_pow_x(c->P, c->work.p, c->work.p + c->ctL, kpow, 1, st));
+  CU(cudaMemcpyAsync(out, c->work.p + c->ctL, c->ctL * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pirb_expand(pirb_ctx* c, const pirb_keys* keys, const uint64_t* cts, uint64_t n_ct, uint64_t total_items,
+                int single, uint64_t* out) {
+  if (!c || !cts || (!out && total_items)) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (single) {
+    if (total_items > c->N)  // server.cpp:111-114
+      return fail(PIRB_INVALID_ARGUMENT, "Cannot expand more items from a CT than poly modulus degree");
+    n_ct = 1;
+  } else if (n_ct != total_items / c->N + 1) {  // server.cpp:154-158
+    return fail(PIRB_INVALID_ARGUMENT,
+                "Number of ciphertexts doesn't match number of items for oblivious expansion.");
+  }
+  int rc;
+  ExpandPlan* pl = get_plan(c, total_items, single ? 1 : 0, &rc);
+  if (!pl) return rc;
+  cudaStream_t st = c->stream;
+  RC(c->qbuf.ensure(n_ct * c->ctL * sizeof(u64)));
+  CU(cudaMemcpyAsync(c->qbuf.p, cts, n_ct * c->ctL * sizeof(u64), cudaMemcpyHostToDevice, st));
+  RC(run_expand(c, keys, pl, c->qbuf.p, 1, st));
+  if (total_items)
+    CU(cudaMemcpyAsync(out, c->work.p, total_items * c->ctL * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pirb_db_multiply(pirb_ctx* c, uint64_t* sv, uint64_t n_sv, uint64_t* out, uint64_t out_cap, uint64_t* out_count) {
+  if (!c || !sv || !out) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (n_sv != c->dim_sum)  // database.cpp:297-300
+    return fail(PIRB_INVALID_ARGUMENT, "Selection vector size does not match dimensions");
+  if (c->prm.shard_count != 1) return fail(PIRB_INVALID_ARGUMENT, "pirb_db_multiply needs an unsharded context");
+  if (out_cap < c->reply_cts) return fail(PIRB_INVALID_ARGUMENT, "output buffer too small");
+  cudaStream_t st = c->stream;
+  RC(c->svbuf.ensure(n_sv * c->ctL * sizeof(u64)));
+  RC(c->rbuf.ensure(c->reply_cts * c->ctL * sizeof(u64)));
+  CU(cudaMemcpyAsync(c->svbuf.p, sv, n_sv * c->ctL * sizeof(u64), cudaMemcpyHostToDevice, st));
+  c->launches = 0;
+  RC(run_multiply(c, c->svbuf.p, n_sv * c->ctL, 1, c->rbuf.p, 0, st));
+  if (c->loaded == 0) {
+    // empty database: the reference returns an empty result vector (database.cpp:181-183)
+    CU(cudaStreamSynchronize(st));
+    if (out_count) *out_count = 0;
+    return 0;
+  }
+  CU(cudaMemcpyAsync(out, c->rbuf.p, c->reply_cts * c->ctL * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  // mirror the in-place NTT of the selection vector entries the reference touches (database.cpp:190,222)
+  u64 off = 0;
+  u64 entries_below = 0;  // entries produced by the level below (n_rows for the level above the scan)
+  std::vector<u64> used(c->d);
+  for (int l = c->d - 1; l >= 0; --l) {
+    if (l == c->d - 1) {
+      used[l] = std::min<u64>(c->dims[l], c->loaded);
+      entries_below = (c->loaded + c->dims[l] - 1) / c->dims[l];
+    } else {
+      used[l] = std::min<u64>(c->dims[l], entries_below);
+      entries_below = (entries_below + c->dims[l] - 1) / c->dims[l];
+    }
+  }
+  for (int l = 0; l < c->d; ++l) {
+    if (used[l])
+      CU(cudaMemcpyAsync(sv + off * c->ctL, c->svbuf.p + off * c->ctL, used[l] * c->ctL * sizeof(u64),
+                         cudaMemcpyDeviceToHost, st));
+    off += c->dims[l];
+  }
+  CU(cudaStreamSynchronize(st));
+  if (out_count) *out_count = c->reply_cts;
+  return 0;
+}
+
+int pirb_answer(pirb_ctx* c, const pirb_keys* keys, const uint64_t* queries, uint32_t n_queries, uint64_t n_ct,
+                uint64_t* replies) {
+  if (!c || !queries || !replies) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (c->prm.shard_count != 1) return fail(PIRB_INVALID_ARGUMENT, "pirb_answer needs an unsharded context");
+  cudaStream_t st = c->stream;
+  const size_t qbytes = (size_t)n_queries * n_ct * c->ctL * sizeof(u64);
+  const size_t rbytes = (size_t)n_queries * c->reply_cts * c->ctL * sizeof(u64);
+  RC(c->qbuf.ensure(std::max<size_t>(qbytes, 256)));
+  RC(c->rbuf.ensure(std::max<size_t>(rbytes, 256)));
+  CU(cudaMemcpyAsync(c->qbuf.p, queries, qbytes, cudaMemcpyHostToDevice, st));
+  RC(run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, 0, st));
+  CU(cudaMemcpyAsync(replies, c->rbuf.p, rbytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pirb_answer_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries, uint64_t n_ct,
+                    uint64_t* d_replies, void* stream) {
+  if (!c || !d_queries || !d_replies) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (c->prm.shard_count != 1) return fail(PIRB_INVALID_ARGUMENT, "use pirb_answer_partial_dev on a sharded context");
+  return run_answer(c, keys, U(d_queries), n_queries, n_ct, U(d_replies), 0, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int pirb_answer_partial_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries,
+                            uint64_t n_ct, uint64_t* d_partial, void* stream) {
+  if (!c || !d_queries || !d_partial) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  return run_answer(c, keys, U(d_queries), n_queries, n_ct, U(d_partial), 1, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int pirb_reduce_finish_dev(pirb_ctx* c, const uint64_t* d_partials, uint32_t n_parts, uint64_t part_stride,
+                           uint32_t n_queries, uint64_t* d_replies, void* stream) {
+  if (!c || !d_partials || !d_replies || !n_parts) return fail(PIRB_INVALID_ARGUMENT, "bad argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const u64 cts = (u64)n_queries * c->reply_cts;
+  // the mod-q add of the partials is fused into the load side of the final inverse NTT
+  LAUNCH(c, launch_ntt_inv(c->P, U(d_partials), U(d_replies), (int)(cts * 2 * c->k), c->k, 0, (int)n_parts, part_stride, 1, 0,
+                           0, st));
+  return 0;
+}
+
+int pirb_reduce_finish_peers_dev(pirb_ctx* c, const uint64_t* const* d_peer_ptrs, uint32_t n_parts,
+                                 uint32_t n_queries, uint64_t* d_replies, void* stream) {
+  if (!c || !d_peer_ptrs || !d_replies || !n_parts) return fail(PIRB_INVALID_ARGUMENT, "bad argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const u64 cts = (u64)n_queries * c->reply_cts;
+  RC(c->rbuf.ensure(cts * c->ctL * sizeof(u64)));
+  LAUNCH(c, launch_modadd_reduce_ptrs(c->P, reinterpret_cast<const u64* const*>(d_peer_ptrs), (int)n_parts, c->rbuf.p, cts, st));
+  LAUNCH(c, launch_ntt_inv(c->P, c->rbuf.p, U(d_replies), (int)(cts * 2 * c->k), c->k, 0, 1, 0, 1, 0, 0, st));
+  return 0;
+}
+
+int pirb_scan_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_queries, uint64_t* d_rows, void* stream) {
+  if (!c || !d_sv_ntt) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  if (!c->pt_count) return 0;
+  const u32 dimL = c->d == 1 ? (c->top_hi - c->top_lo) : c->dims[c->d - 1];
+  const u32 n_rows = c->d == 1 ? 1 : (u32)((c->pt_count + dimL - 1) / dimL);
+  int n_split;
+  scan_config(c->P, dimL, n_rows, (int)n_queries, c->sm_count, &n_split);
+  c->scan_split = n_split;
+  u64* dst = U(d_rows);
+  if (!dst || n_split != 1) {
+    RC(c->part.ensure((size_t)n_queries * n_split * n_rows * c->ctL * sizeof(u64)));
+    dst = c->part.p;
+  }
+  LAUNCH(c, launch_scan(c->P, c->db.p, c->pt_count, dimL, n_rows, U(d_sv_ntt), (u64)dimL * c->ctL, (int)n_queries, n_split,
+                        dst, st));
+  if (d_rows && n_split != 1) {
+    for (u32 qi = 0; qi < n_queries; ++qi)
+      LAUNCH(c, launch_modadd_reduce(c->P, c->part.p + (u64)qi * n_split * n_rows * c->ctL, (u64)n_rows * c->ctL,
+                                     n_split, U(d_rows) + (u64)qi * n_rows * c->ctL, n_rows, st));
+  }
+  return 0;
+}
+
+int pirb_sync(pirb_ctx* c) {
+  if (!c) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int pirb_set_profiling(pirb_ctx* c, int enabled) {
+  if (!c) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  c->profiling = enabled != 0;
+  c->ev_valid = false;
+  return 0;
+}
+int pirb_get_stage_ms(pirb_ctx* c, float* out) {
+  if (!c || !out) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  if (!c->ev_valid) return fail(PIRB_INVALID_ARGUMENT, "no profiled call recorded");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->ev[5]));
+  for (int i = 0; i < 5; ++i) CU(cudaEventElapsedTime(out + i, c->ev[i], c->ev[i + 1]));
+  CU(cudaEventElapsedTime(out + 5, c->ev[0], c->ev[5]));
+  return 0;
+}
+uint64_t pirb_last_launch_count(const pirb_ctx* c) { return c ? c->launches : 0; }
+uint64_t pirb_scan_bytes(const pirb_ctx* c, uint32_t n_queries) {
+  // DB read once + last-dimension selection cts read once + row results written once
+  if (!c || !c->pt_count) return 0;
+  const u32 dimL = c->d == 1 ? (c->top_hi - c->top_lo) : c->dims[c->d - 1];
+  const u64 n_rows = c->d == 1 ? 1 : (c->pt_count + dimL - 1) / dimL;
+  return (c->pt_count * c->ptL + (u64)n_queries * dimL * c->ctL + (u64)n_queries * n_rows * c->ctL) * sizeof(u64);
+}
+
+void pirb_calculate_dimensions(uint32_t db_size, uint32_t nd, uint32_t* out) {
+  auto v = hm::calculate_dimensions(db_size, nd);
+  for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+}
+uint64_t pirb_next_power_two(uint64_t v) { return hm::next_power_two(v); }
+uint32_t pirb_ceil_log2(uint32_t v) { return hm::ceil_log2(v); }
+uint32_t pirb_log2(uint32_t v) { return hm::trunc_log2(v); }
+uint64_t pirb_plain_modulus_batching(uint32_t N, uint32_t bits) {
+  if (bits < 2 || bits > 60) return 0;
+  const u64 factor = 2ull * N;
+  u64 value = (1ull << bits) - factor + 1;
+  const u64 lower = 1ull << (bits - 1);
+  while (value > lower) {
+    if (hm::is_prime(value)) return value;
+    value -= factor;
+  }
+  return 0;
+}
+int pirb_bfv_default_coeff_modulus(uint32_t N, uint64_t* out, uint32_t cap) {
+  // SEAL CoeffModulus::BFVDefault (128-bit security) tables for the degrees this library supports
+  static const u64 m4096[] = {0xffffee001ULL, 0xffffc4001ULL, 0x1ffffe0001ULL};
+  static const u64 m8192[] = {0x7fffffd8001ULL, 0x7fffffc8001ULL, 0xfffffffc001ULL, 0xffffff6c001ULL, 0xfffffebc001ULL};
+  static const u64 m16384[] = {0xfffffffd8001ULL, 0xfffffffa0001ULL, 0xfffffff00001ULL, 0x1fffffff68001ULL,
+                               0x1fffffff50001ULL, 0x1ffffffee8001ULL, 0x1ffffffea0001ULL, 0x1ffffffe88001ULL,
+                               0x1ffffffe48001ULL};
+  const u64* src;
+  u32 n;
+  switch (N) {
+    case 4096: src = m4096; n = 3; break;
+    case 8192: src = m8192; n = 5; break;
+    case 16384: src = m16384; n = 9; break;
+    default: return -1;
+  }
+  if (n > cap) return -1;
+  for (u32 i = 0; i < n; ++i) out[i] = src[i];
+  return (int)n;
+}
+
+}  // extern "C"

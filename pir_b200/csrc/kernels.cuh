@@ -1,0 +1,73 @@
+// kernels.cuh — launch wrappers of the sm_100a kernels of the PIR answer path (implemented in kernels_*.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pirb_common.h"
+
+namespace pirb {
+
+// One expansion level over a batch of trees (SURVEY §3.1 HOT LOOP 1).  Node z of the launch maps to
+// (query qi, tree ti, node kk) with z = (qi * n_trees + ti) << j | kk; its source ciphertext is
+// work + qi*q_stride + src_off[ti] + kk*ctL and its two outputs go to dst_off[ti] + {kk, kk + 2^j}*ctL.
+struct LevelArgs {
+  const u64* src_off;  // device, [n_trees] limb offsets
+  const u64* dst_off;  // device, [n_trees]
+  int n_trees;
+  int j;         // tree level; 2^j nodes per tree
+  u32 ginv;      // inverse of the Galois element (N>>j)+1 modulo 2N
+  u64 q_stride;  // limbs between consecutive queries' workspaces
+  int n_queries;
+};
+
+// generic batched transforms on [n_polys][N] arrays; modulus of poly p is m[(p % cycle) + off].
+// inverse sums n_parts partial inputs (stride part_stride limbs) mod q before transforming.
+cudaError_t launch_ntt_fwd(const DevParams& P, const u64* in, u64* out, int n_polys, int cycle, int off,
+                           int n_batch, u64 in_bstride, u64 out_bstride, cudaStream_t st);
+cudaError_t launch_ntt_inv(const DevParams& P, const u64* in, u64* out, int n_polys, int cycle, int off, int n_parts,
+                           u64 part_stride, int n_batch, u64 in_bstride, u64 out_bstride, cudaStream_t st);
+
+// plaintext coefficients (< t, [n_pt][N]) -> centred lift -> NTT per data modulus -> [n_pt][k][N]
+cudaError_t launch_db_preprocess(const DevParams& P, const u64* coeffs, u64* out, u64 n_pt, cudaStream_t st);
+
+// key switching, step 1: sigma_g(c1) digit J re-reduced mod m_I and forward-transformed -> dig[z][I][J][N]
+cudaError_t launch_ks_digits(const DevParams& P, const u64* work, const LevelArgs& L, u64* dig, cudaStream_t st);
+// step 2: acc[z][c][I] = INTT_I( sum_J dig[z][I][J] (.) key[J][c][I] )
+cudaError_t launch_ks_mac_intt(const DevParams& P, const u64* dig, const u64* key, u64* acc, int n_nodes,
+                               cudaStream_t st);
+// step 3: mod-down by P with rounding + (mode 0) SealPIR expansion combine / (mode 1) plain substitution result
+cudaError_t launch_ks_combine(const DevParams& P, u64* work, const LevelArgs& L, const u64* acc, int mode,
+                              cudaStream_t st);
+
+// ct * x^{-kpow}  (server.cpp:78-103)
+cudaError_t launch_mul_inv_pow_x(const DevParams& P, const u64* in, u64* out, u32 kpow, int n_cts, cudaStream_t st);
+
+// last-dimension inner product against the HBM-resident database (SURVEY §3.1 HOT LOOP 2)
+// part[qi][split][row][2][k][N] = sum over the split's share of i1 of sv[qi][i1] (.) db[row*dimL + i1]   (mod q)
+cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL, u32 n_rows, const u64* sv,
+                        u64 sv_qstride, int n_queries, int n_split, u64* part, cudaStream_t st);
+void scan_config(const DevParams& P, u32 dimL, u32 n_rows, int n_queries, int sm_count, int* n_split);
+
+// re-encode (ct_reencoder.cpp:40-71) + centred lift + forward NTT: cts [n_cts][2][k][N] -> pts [n_cts][2ER][k][N]
+cudaError_t launch_reencode_ntt(const DevParams& P, const u64* cts, u64* pts, int n_cts, cudaStream_t st);
+
+// upper-dimension MAC (SURVEY §3.1 HOT LOOP 3):
+// part[qi][split][g][x][2][k][N] = sum_{i in split, i < cnt(g)} sv[qi][i][c] (.) pts[qi][(g*dim+i)][x]
+cudaError_t launch_dim_mac(const DevParams& P, const u64* pts, u64 pts_qstride, const u64* sv, u64 sv_qstride,
+                           int n_queries, u32 dim, u32 n_entries_in, u32 n_groups, u32 w_out, int n_split, u64* part,
+                           cudaStream_t st);
+
+// out[i] = sum_g in[g*stride + i] mod q_j(i)   for [n_cts][2][k][N] arrays (cross-GPU partial combine)
+cudaError_t launch_modadd_reduce(const DevParams& P, const u64* in, u64 stride, int n_parts, u64* out, u64 n_cts,
+                                 cudaStream_t st);
+// out[i] = sum over peers of *(peers[g] + i) mod q: same, reading each partial through its own (peer) pointer
+cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peers_dev, int n_parts, u64* out,
+                                      u64 n_cts, cudaStream_t st);
+
+// copy root ciphertexts of every tree into place: work[qi*q_stride + root_off[t]] = query[qi][t]
+cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64* work, const u64* root_off, int n_trees,
+                               int n_queries, u64 q_stride, cudaStream_t st);
+
+// synthetic data: out[p][N] uniform in [0, q_{(p % cycle) + off}) from a counter-based generator
+cudaError_t launch_fill_random(const DevParams& P, u64* out, u64 n_polys, int cycle, int off, u64 seed, cudaStream_t st);
+
+}  // namespace pirb

@@ -1,0 +1,265 @@
+// kernels_ntt.cu — every kernel built around the shared-memory NTT core:
+//   k_ntt_fwd / k_ntt_inv     Evaluator::transform_to/from_ntt_inplace (database.cpp:190,222,252)
+//   k_db_preprocess           PIRDatabase::populate's transform_to_ntt_inplace(pt, first_parms_id) (database.cpp:103-106)
+//   k_ks_digits / k_ks_mac_intt   Evaluator::apply_galois_inplace -> switch_key_inplace (server.cpp:71)
+//   k_reencode_ntt            CiphertextReencoder::Encode + plaintext NTT (ct_reencoder.cpp:40-71, database.cpp:217-228)
+// One CTA owns one size-N transform; the polynomial lives in (swizzled) shared memory between
+// a fused load-side transform and a fused store-side transform.
+#include "kernels.cuh"
+#include "pirb_device.cuh"
+
+namespace pirb {
+
+template <int LOGN>
+struct Cfg {
+  static constexpr int N = 1 << LOGN;
+  static constexpr int NT = (N / 8 < 512) ? N / 8 : 512;
+  static constexpr size_t SMEM = sizeof(u64) * N;
+};
+
+// ---------------------------------------------------------------------------------------------
+template <int LOGN>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+k_ntt_fwd(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* __restrict__ out, int cycle, int off,
+          u64 in_bstride, u64 out_bstride) {
+  constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
+  extern __shared__ u64 s[];
+  const int tid = threadIdx.x;
+  const int p = blockIdx.x;
+  const ModC& m = P.m[(p % cycle) + off];
+  const u64* src = in + blockIdx.y * in_bstride + (u64)p * N;
+  u64* dst = out + blockIdx.y * out_bstride + (u64)p * N;
+#pragma unroll
+  for (int i = tid; i < N; i += NT) s[swz(i)] = src[i];
+  __syncthreads();
+  ntt_forward_smem<LOGN, NT>(s, m, tid);
+#pragma unroll
+  for (int i = tid; i < N; i += NT) dst[i] = canon4(s[swz(i)], m.q);
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+k_ntt_inv(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* __restrict__ out, int cycle, int off,
+          int n_parts, u64 part_stride, u64 in_bstride, u64 out_bstride) {
+  constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
+  extern __shared__ u64 s[];
+  const int tid = threadIdx.x;
+  const int p = blockIdx.x;
+  const ModC& m = P.m[(p % cycle) + off];
+  const u64* src = in + blockIdx.y * in_bstride + (u64)p * N;
+  u64* dst = out + blockIdx.y * out_bstride + (u64)p * N;
+#pragma unroll
+  for (int i = tid; i < N; i += NT) {
+    u64 v = src[i];
+    for (int g = 1; g < n_parts; ++g) v = addmod(v, src[g * part_stride + i], m.q);
+    s[swz(i)] = v;
+  }
+  __syncthreads();
+  ntt_inverse_smem<LOGN, NT>(s, m, tid);
+#pragma unroll
+  for (int i = tid; i < N; i += NT) dst[i] = inv_finish(s[swz(i)], m);
+}
+
+// plaintext coefficient c (< t) -> c >= (t+1)/2 ? c + (q_j - t) : c   (SURVEY A.7), then NTT mod q_j
+template <int LOGN>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+k_db_preprocess(const __grid_constant__ DevParams P, const u64* __restrict__ coeffs, u64* __restrict__ out) {
+  constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
+  extern __shared__ u64 s[];
+  const int tid = threadIdx.x;
+  const int j = blockIdx.y;
+  const u64 pt = blockIdx.x;
+  const ModC& m = P.m[j];
+  const u64* src = coeffs + pt * N;
+  u64* dst = out + (pt * P.k + j) * N;
+  const u64 inc = m.q - P.t;
+#pragma unroll
+  for (int i = tid; i < N; i += NT) {
+    u64 c = src[i];
+    s[swz(i)] = c >= P.thr ? c + inc : c;
+  }
+  __syncthreads();
+  ntt_forward_smem<LOGN, NT>(s, m, tid);
+#pragma unroll
+  for (int i = tid; i < N; i += NT) dst[i] = canon4(s[swz(i)], m.q);
+}
+
+// grid (z = node, I = key-level modulus, J = RNS digit)
+template <int LOGN>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+k_ks_digits(const __grid_constant__ DevParams P, const u64* __restrict__ work, const LevelArgs L,
+            u64* __restrict__ dig) {
+  constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
+  extern __shared__ u64 s[];
+  const int tid = threadIdx.x;
+  const int I = blockIdx.y, J = blockIdx.z;
+  const u32 z = blockIdx.x;
+  const u32 kk = z & ((1u << L.j) - 1);
+  const u32 tq = z >> L.j;
+  const u32 ti = tq % L.n_trees, qi = tq / L.n_trees;
+  const int k = P.k;
+  const u64 ctL = (u64)2 * k * N;
+  const u64* c1 = work + qi * L.q_stride + L.src_off[ti] + kk * ctL + (u64)(k + J) * N;
+  const ModC& mI = P.m[I];
+  const u64 qJ = P.m[J].q;
+  const bool need_reduce = qJ > mI.q;
+#pragma unroll
+  for (int i = tid; i < N; i += NT) {
+    u64 v = galois_gather(c1, i, L.ginv, N, qJ);
+    if (need_reduce) v = barrett64(v, mI.q, mI.ratio_hi);
+    s[swz(i)] = v;
+  }
+  __syncthreads();
+  ntt_forward_smem<LOGN, NT>(s, mI, tid);
+  u64* dst = dig + (((u64)z * (k + 1) + I) * k + J) * N;
+#pragma unroll
+  for (int i = tid; i < N; i += NT) dst[i] = canon4(s[swz(i)], mI.q);
+}
+
+// grid (z = node, I, c = key component)
+template <int LOGN>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+k_ks_mac_intt(const __grid_constant__ DevParams P, const u64* __restrict__ dig, const u64* __restrict__ key,
+              u64* __restrict__ acc) {
+  constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
+  extern __shared__ u64 s[];
+  const int tid = threadIdx.x;
+  const int I = blockIdx.y, c = blockIdx.z;
+  const u32 z = blockIdx.x;
+  const int k = P.k;
+  const ModC& mI = P.m[I];
+  const u64* d = dig + ((u64)z * (k + 1) + I) * k * N;
+#pragma unroll
+  for (int i = tid; i < N; i += NT) {
+    u64 lo = 0, hi = 0;
+    for (int J = 0; J < k; ++J) {
+      const u64 kv = __ldg(key + ((u64)(J * 2 + c) * (k + 1) + I) * N + i);
+      mac128(lo, hi, d[(u64)J * N + i], kv);
+    }
+    s[swz(i)] = barrett128(lo, hi, mI.q, mI.ratio_hi, mI.ratio_lo);
+  }
+  __syncthreads();
+  ntt_inverse_smem<LOGN, NT>(s, mI, tid);
+  u64* dst = acc + (((u64)z * 2 + c) * (k + 1) + I) * N;
+#pragma unroll
+  for (int i = tid; i < N; i += NT) dst[i] = inv_finish(s[swz(i)], mI);
+}
+
+// grid (x = ciphertext, e = chunk, j' = target data modulus)
+template <int LOGN>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+k_reencode_ntt(const __grid_constant__ DevParams P, const u64* __restrict__ cts, u64* __restrict__ pts) {
+  constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
+  extern __shared__ u64 s[];
+  const int tid = threadIdx.x;
+  const int jp = blockIdx.z, e = blockIdx.y;
+  const u64 x = blockIdx.x;
+  const int k = P.k;
+  const ModC& m = P.m[jp];
+  const u64* src = cts + (x * 2 * k + (u64)P.re_poly[e] * k + P.re_mod[e]) * N;
+  const u32 shift = P.re_shift[e];
+  const u64 mask = (u64)((1u << P.ptb) - 1);
+  const u64 inc = m.q - P.t;
+#pragma unroll
+  for (int i = tid; i < N; i += NT) {
+    u64 c = (src[i] >> shift) & mask;
+    s[swz(i)] = c >= P.thr ? c + inc : c;
+  }
+  __syncthreads();
+  ntt_forward_smem<LOGN, NT>(s, m, tid);
+  u64* dst = pts + ((x * P.two_er + e) * k + jp) * N;
+#pragma unroll
+  for (int i = tid; i < N; i += NT) dst[i] = canon4(s[swz(i)], m.q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side dispatch on log2(N)
+// ---------------------------------------------------------------------------------------------
+template <typename K>
+static cudaError_t ensure_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaSuccess;
+}
+
+#define PIRB_DISPATCH_LOGN(logn, CALL) \
+  switch (logn) {                      \
+    case 11: { CALL(11); } break;      \
+    case 12: { CALL(12); } break;      \
+    case 13: { CALL(13); } break;      \
+    case 14: { CALL(14); } break;      \
+    default: return cudaErrorInvalidValue; \
+  }
+
+cudaError_t launch_ntt_fwd(const DevParams& P, const u64* in, u64* out, int n_polys, int cycle, int off, int n_batch,
+                           u64 in_bstride, u64 out_bstride, cudaStream_t st) {
+  if (n_polys <= 0 || n_batch <= 0) return cudaSuccess;
+#define CALL(LN)                                                                                         \
+  cudaError_t e = ensure_smem(k_ntt_fwd<LN>, Cfg<LN>::SMEM);                                              \
+  if (e != cudaSuccess) return e;                                                                        \
+  k_ntt_fwd<LN><<<dim3(n_polys, n_batch), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, in, out, cycle, off, in_bstride, \
+                                                                             out_bstride);
+  PIRB_DISPATCH_LOGN(P.logn, CALL)
+#undef CALL
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ntt_inv(const DevParams& P, const u64* in, u64* out, int n_polys, int cycle, int off, int n_parts,
+                           u64 part_stride, int n_batch, u64 in_bstride, u64 out_bstride, cudaStream_t st) {
+  if (n_polys <= 0 || n_batch <= 0) return cudaSuccess;
+#define CALL(LN)                                                                                         \
+  cudaError_t e = ensure_smem(k_ntt_inv<LN>, Cfg<LN>::SMEM);                                              \
+  if (e != cudaSuccess) return e;                                                                        \
+  k_ntt_inv<LN><<<dim3(n_polys, n_batch), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, in, out, cycle, off, n_parts,    \
+                                                                             part_stride, in_bstride, out_bstride);
+  PIRB_DISPATCH_LOGN(P.logn, CALL)
+#undef CALL
+  return cudaGetLastError();
+}
+
+cudaError_t launch_db_preprocess(const DevParams& P, const u64* coeffs, u64* out, u64 n_pt, cudaStream_t st) {
+  if (!n_pt) return cudaSuccess;
+#define CALL(LN)                                                                                   \
+  cudaError_t e = ensure_smem(k_db_preprocess<LN>, Cfg<LN>::SMEM);                                  \
+  if (e != cudaSuccess) return e;                                                                  \
+  k_db_preprocess<LN><<<dim3((unsigned)n_pt, P.k), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, coeffs, out);
+  PIRB_DISPATCH_LOGN(P.logn, CALL)
+#undef CALL
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ks_digits(const DevParams& P, const u64* work, const LevelArgs& L, u64* dig, cudaStream_t st) {
+  const unsigned nodes = (unsigned)L.n_queries * L.n_trees << L.j;
+  if (!nodes) return cudaSuccess;
+#define CALL(LN)                                                                                   \
+  cudaError_t e = ensure_smem(k_ks_digits<LN>, Cfg<LN>::SMEM);                                      \
+  if (e != cudaSuccess) return e;                                                                  \
+  k_ks_digits<LN><<<dim3(nodes, P.k + 1, P.k), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, work, L, dig);
+  PIRB_DISPATCH_LOGN(P.logn, CALL)
+#undef CALL
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ks_mac_intt(const DevParams& P, const u64* dig, const u64* key, u64* acc, int n_nodes,
+                               cudaStream_t st) {
+  if (n_nodes <= 0) return cudaSuccess;
+#define CALL(LN)                                                                                   \
+  cudaError_t e = ensure_smem(k_ks_mac_intt<LN>, Cfg<LN>::SMEM);                                    \
+  if (e != cudaSuccess) return e;                                                                  \
+  k_ks_mac_intt<LN><<<dim3(n_nodes, P.k + 1, 2), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, dig, key, acc);
+  PIRB_DISPATCH_LOGN(P.logn, CALL)
+#undef CALL
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reencode_ntt(const DevParams& P, const u64* cts, u64* pts, int n_cts, cudaStream_t st) {
+  if (n_cts <= 0) return cudaSuccess;
+#define CALL(LN)                                                                                   \
+  cudaError_t e = ensure_smem(k_reencode_ntt<LN>, Cfg<LN>::SMEM);                                   \
+  if (e != cudaSuccess) return e;                                                                  \
+  k_reencode_ntt<LN><<<dim3(n_cts, P.two_er, P.k), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, cts, pts);
+  PIRB_DISPATCH_LOGN(P.logn, CALL)
+#undef CALL
+  return cudaGetLastError();
+}
+
+}  // namespace pirb

@@ -1,0 +1,331 @@
+// kernels_stream.cu — the streaming (bandwidth-bound) kernels of the answer path:
+//   k_scan            last-dimension selection-vector x database inner product (database.cpp:185-194, 238-247)
+//   k_dim_mac         upper-dimension multiply_plain + add_inplace (database.cpp:229, 243-245)
+//   k_ks_combine      mod-down of the key switch + SealPIR expansion butterfly (server.cpp:123-141)
+//   k_mul_inv_pow_x   negacyclic shift (server.cpp:78-103)
+//   k_modadd_reduce   mod-q sum of per-GPU partial replies
+#include "kernels.cuh"
+#include "pirb_device.cuh"
+
+namespace pirb {
+
+__device__ __forceinline__ ulonglong2 ldg128(const u64* p) { return __ldg(reinterpret_cast<const ulonglong2*>(p)); }
+// streaming 128-bit load that does not allocate in L1 (database limbs are read exactly once)
+__device__ __forceinline__ ulonglong2 ldg128_stream(const u64* p) {
+  ulonglong2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan: grid (slice, row tile, qi*n_split + split); 128 threads x 2 limbs = 256 limbs per slice.
+// Each CTA keeps 2 (polys) x R (rows) x 2 (limbs) 128-bit accumulators per thread in registers, streams
+// R database tiles and the two selection-vector tiles per i1, and reduces once at the end.
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_NT = 128;
+constexpr int SCAN_LIMBS = 2 * SCAN_NT;
+
+template <int R>
+__global__ void __launch_bounds__(SCAN_NT)
+k_scan(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
+       const u64* __restrict__ sv, u64 sv_qstride, int n_split, u64* __restrict__ part) {
+  const u32 kN = (u32)P.k * P.N;
+  const u32 limb = blockIdx.x * SCAN_LIMBS + threadIdx.x * 2;
+  const u32 row0 = blockIdx.y * R;
+  const u32 split = blockIdx.z % n_split, qi = blockIdx.z / n_split;
+  const ModC& m = P.m[limb / P.N];
+  const u32 per = (dimL + n_split - 1) / n_split;
+  const u32 i_lo = split * per;
+  const u32 i_hi = min(dimL, i_lo + per);
+
+  u64 alo[R][2][2], ahi[R][2][2];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) alo[r][c][0] = alo[r][c][1] = ahi[r][c][0] = ahi[r][c][1] = 0;
+
+  const u64* svq = sv + qi * sv_qstride + limb;
+  const u64 ctL = 2ull * kN;
+#pragma unroll 2
+  for (u32 i1 = i_lo; i1 < i_hi; ++i1) {
+    const ulonglong2 s0 = ldg128(svq + i1 * ctL);
+    const ulonglong2 s1 = ldg128(svq + i1 * ctL + kN);
+    ulonglong2 d[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u64 p = (u64)(row0 + r) * dimL + i1;
+      d[r] = (row0 + r < n_rows && p < num_pt) ? ldg128_stream(db + p * kN + limb) : make_ulonglong2(0, 0);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mac128(alo[r][0][0], ahi[r][0][0], s0.x, d[r].x);
+      mac128(alo[r][0][1], ahi[r][0][1], s0.y, d[r].y);
+      mac128(alo[r][1][0], ahi[r][1][0], s1.x, d[r].x);
+      mac128(alo[r][1][1], ahi[r][1][1], s1.y, d[r].y);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= n_rows) break;
+    u64* o = part + (((u64)qi * n_split + split) * n_rows + row0 + r) * ctL + limb;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      ulonglong2 v;
+      v.x = barrett128(alo[r][c][0], ahi[r][c][0], m.q, m.ratio_hi, m.ratio_lo);
+      v.y = barrett128(alo[r][c][1], ahi[r][c][1], m.q, m.ratio_hi, m.ratio_lo);
+      *reinterpret_cast<ulonglong2*>(o + (u64)c * kN) = v;
+    }
+  }
+}
+
+static int scan_rows_per_cta(u32 n_rows) { return n_rows >= 4 * 148 ? 4 : (n_rows >= 2 ? 2 : 1); }
+
+void scan_config(const DevParams& P, u32 dimL, u32 n_rows, int n_queries, int sm_count, int* n_split) {
+  // enough CTAs for ~8 resident per SM; split the i1 loop when the row count alone cannot provide them
+  const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
+  const int R = scan_rows_per_cta(n_rows);
+  const u64 base = (u64)slices * ((n_rows + R - 1) / R) * n_queries;
+  const u64 want = (u64)sm_count * 8;
+  int s = 1;
+  if (base < want) s = (int)((want + base - 1) / base);
+  const int max_split = (int)((dimL + 7) / 8);  // keep at least 8 database tiles per CTA
+  if (s > max_split) s = max_split;
+  if (s < 1) s = 1;
+  *n_split = s;
+}
+
+cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL, u32 n_rows, const u64* sv,
+                        u64 sv_qstride, int n_queries, int n_split, u64* part, cudaStream_t st) {
+  if (!n_rows || !n_queries) return cudaSuccess;
+  const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
+  const int R = scan_rows_per_cta(n_rows);
+  dim3 grid(slices, (n_rows + R - 1) / R, n_queries * n_split);
+  if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidConfiguration;
+  switch (R) {
+    case 4: k_scan<4><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); break;
+    case 2: k_scan<2><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); break;
+    default: k_scan<1><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); break;
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// upper-dimension MAC: grid (slice, x = output ct of the group, (qi*n_groups + g)*n_split + split)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_NT)
+k_dim_mac(const __grid_constant__ DevParams P, const u64* __restrict__ pts, u64 pts_qstride,
+          const u64* __restrict__ sv, u64 sv_qstride, u32 dim, u32 n_entries_in, u32 n_groups, u32 w_out, int n_split,
+          u64* __restrict__ part) {
+  const u32 kN = (u32)P.k * P.N;
+  const u64 ctL = 2ull * kN;
+  const u32 limb = blockIdx.x * SCAN_LIMBS + threadIdx.x * 2;
+  const u32 x = blockIdx.y;
+  const u32 split = blockIdx.z % n_split;
+  const u32 gq = blockIdx.z / n_split;
+  const u32 g = gq % n_groups, qi = gq / n_groups;
+  const ModC& m = P.m[limb / P.N];
+  const u32 cnt = min(dim, n_entries_in - g * dim);
+  const u32 per = (dim + n_split - 1) / n_split;
+  const u32 i_lo = split * per, i_hi = min(cnt, i_lo + per);
+  u64 alo[2][2] = {{0, 0}, {0, 0}}, ahi[2][2] = {{0, 0}, {0, 0}};
+  const u64* svq = sv + qi * sv_qstride + limb;
+  const u64* pq = pts + qi * pts_qstride + ((u64)g * dim * w_out + x) * kN + limb;
+#pragma unroll 4
+  for (u32 i = i_lo; i < i_hi; ++i) {
+    const ulonglong2 s0 = ldg128(svq + i * ctL);
+    const ulonglong2 s1 = ldg128(svq + i * ctL + kN);
+    const ulonglong2 d = ldg128_stream(pq + (u64)i * w_out * kN);
+    mac128(alo[0][0], ahi[0][0], s0.x, d.x);
+    mac128(alo[0][1], ahi[0][1], s0.y, d.y);
+    mac128(alo[1][0], ahi[1][0], s1.x, d.x);
+    mac128(alo[1][1], ahi[1][1], s1.y, d.y);
+  }
+  u64* o = part + ((((u64)qi * n_split + split) * n_groups + g) * w_out + x) * ctL + limb;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    ulonglong2 v;
+    v.x = barrett128(alo[c][0], ahi[c][0], m.q, m.ratio_hi, m.ratio_lo);
+    v.y = barrett128(alo[c][1], ahi[c][1], m.q, m.ratio_hi, m.ratio_lo);
+    *reinterpret_cast<ulonglong2*>(o + (u64)c * kN) = v;
+  }
+}
+
+cudaError_t launch_dim_mac(const DevParams& P, const u64* pts, u64 pts_qstride, const u64* sv, u64 sv_qstride,
+                           int n_queries, u32 dim, u32 n_entries_in, u32 n_groups, u32 w_out, int n_split, u64* part,
+                           cudaStream_t st) {
+  if (!n_groups || !n_queries) return cudaSuccess;
+  const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
+  dim3 grid(slices, w_out, (unsigned)n_queries * n_groups * n_split);
+  if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidConfiguration;
+  k_dim_mac<<<grid, SCAN_NT, 0, st>>>(P, pts, pts_qstride, sv, sv_qstride, dim, n_entries_in, n_groups, w_out,
+                                      n_split, part);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// key-switch mod-down + expansion combine.  grid (node z, N/256, j); one thread per coefficient.
+//   md_c = (acc_c[j] - ((acc_c[P] + P/2 mod P) mod q_j - (P/2 mod q_j))) * P^{-1}  mod q_j
+//   c0 = (sigma_g(p0) + md_0, md_1)
+//   mode 0: dst[kk] = src + c0 ; dst[kk + 2^j] = (src - c0) * x^{-2^j}           (server.cpp:123-141)
+//   mode 1: dst[kk] = c0                                                          (substitute_power_x_inplace)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 mod_down(u64 a, u64 last, const DevParams& P, int j, u64 Pq) {
+  const ModC& m = P.m[j];
+  u64 l = last + P.half_P;
+  l = l >= Pq ? l - Pq : l;
+  u64 r = submod(barrett64(l, m.q, m.ratio_hi), P.half_P_mod[j], m.q);
+  return shoup(submod(a, r, m.q), P.inv_P[j], P.inv_P_s[j], m.q);
+}
+
+__global__ void __launch_bounds__(256)
+k_ks_combine(const __grid_constant__ DevParams P, u64* __restrict__ work, const LevelArgs L,
+             const u64* __restrict__ acc, int mode) {
+  const u32 N = P.N;
+  const int k = P.k;
+  const u32 z = blockIdx.x;
+  const u32 n = blockIdx.y * 256 + threadIdx.x;
+  const int j = blockIdx.z;
+  const u32 kk = z & ((1u << L.j) - 1);
+  const u32 tq = z >> L.j;
+  const u32 ti = tq % L.n_trees, qi = tq / L.n_trees;
+  const u64 ctL = 2ull * k * N;
+  const u64 q = P.m[j].q, Pq = P.m[k].q;
+  const u64* src = work + qi * L.q_stride + L.src_off[ti] + kk * ctL;
+  u64* dstE = work + qi * L.q_stride + L.dst_off[ti] + kk * ctL;
+  const u64* a = acc + (u64)z * 2 * (k + 1) * N;
+  const u64 md0 = mod_down(a[(u64)j * N + n], a[(u64)k * N + n], P, j, Pq);
+  const u64 md1 = mod_down(a[(u64)(k + 1 + j) * N + n], a[(u64)(k + 1 + k) * N + n], P, j, Pq);
+  const u64 c00 = addmod(galois_gather(src + (u64)j * N, n, L.ginv, N, q), md0, q);
+  const u64 c01 = md1;
+  if (mode == 1) {
+    dstE[(u64)j * N + n] = c00;
+    dstE[(u64)(k + j) * N + n] = c01;
+    return;
+  }
+  const u64 p0 = src[(u64)j * N + n], p1 = src[(u64)(k + j) * N + n];
+  dstE[(u64)j * N + n] = addmod(p0, c00, q);
+  dstE[(u64)(k + j) * N + n] = addmod(p1, c01, q);
+  u64* dstO = dstE + ((u64)ctL << L.j);
+  const u32 r = n + ((2 * N - (1u << L.j)) & (2 * N - 1));
+  const u32 idx = r & (N - 1);
+  u64 d0 = submod(p0, c00, q), d1 = submod(p1, c01, q);
+  if (r & N) { d0 = negmod(d0, q); d1 = negmod(d1, q); }
+  dstO[(u64)j * N + idx] = d0;
+  dstO[(u64)(k + j) * N + idx] = d1;
+}
+
+cudaError_t launch_ks_combine(const DevParams& P, u64* work, const LevelArgs& L, const u64* acc, int mode,
+                              cudaStream_t st) {
+  const unsigned nodes = (unsigned)L.n_queries * L.n_trees << L.j;
+  if (!nodes) return cudaSuccess;
+  k_ks_combine<<<dim3(nodes, P.N / 256, P.k), 256, 0, st>>>(P, work, L, acc, mode);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mul_inv_pow_x(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* __restrict__ out, u32 shift) {
+  const u32 N = P.N;
+  const u32 n = blockIdx.y * 256 + threadIdx.x;
+  const u32 poly = blockIdx.x;  // ct*2k + i*k + j
+  const u64 q = P.m[poly % P.k].q;
+  const u32 r = n + shift;
+  u64 v = in[(u64)poly * N + n];
+  if (r & N) v = negmod(v, q);
+  out[(u64)poly * N + (r & (N - 1))] = v;
+}
+cudaError_t launch_mul_inv_pow_x(const DevParams& P, const u64* in, u64* out, u32 kpow, int n_cts, cudaStream_t st) {
+  if (n_cts <= 0) return cudaSuccess;
+  const u32 twoN = 2 * P.N;
+  const u32 shift = (twoN - kpow) % twoN;  // server.cpp:87-88 (uint32 arithmetic, wraps like the reference)
+  k_mul_inv_pow_x<<<dim3(n_cts * 2 * P.k, P.N / 256), 256, 0, st>>>(P, in, out, shift);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_modadd_reduce(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64 stride, int n_parts,
+                u64* __restrict__ out, u64 total_limbs) {
+  const u64 i = ((u64)blockIdx.x * 256 + threadIdx.x) * 2;
+  if (i >= total_limbs) return;
+  const u64 q = P.m[(i / P.N) % P.k].q;
+  ulonglong2 v = ldg128(in + i);
+  for (int g = 1; g < n_parts; ++g) {
+    const ulonglong2 w = ldg128(in + g * stride + i);
+    v.x = addmod(v.x, w.x, q);
+    v.y = addmod(v.y, w.y, q);
+  }
+  *reinterpret_cast<ulonglong2*>(out + i) = v;
+}
+cudaError_t launch_modadd_reduce(const DevParams& P, const u64* in, u64 stride, int n_parts, u64* out, u64 n_cts,
+                                 cudaStream_t st) {
+  const u64 total = n_cts * 2 * P.k * P.N;
+  if (!total) return cudaSuccess;
+  k_modadd_reduce<<<(unsigned)((total / 2 + 255) / 256), 256, 0, st>>>(P, in, stride, n_parts, out, total);
+  return cudaGetLastError();
+}
+
+// Same reduction, but every partial is read through its own pointer: with CUDA IPC / peer access those are
+// other GPUs' buffers, so the loads travel over NVLink inside the reducing kernel (no staging copy).
+__global__ void __launch_bounds__(256)
+k_modadd_reduce_ptrs(const __grid_constant__ DevParams P, const u64* const* __restrict__ peers, int n_parts,
+                     u64* __restrict__ out, u64 total_limbs) {
+  const u64 i = ((u64)blockIdx.x * 256 + threadIdx.x) * 2;
+  if (i >= total_limbs) return;
+  const u64 q = P.m[(i / P.N) % P.k].q;
+  ulonglong2 v = *reinterpret_cast<const ulonglong2*>(peers[0] + i);
+  for (int g = 1; g < n_parts; ++g) {
+    const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(peers[g] + i);
+    v.x = addmod(v.x, w.x, q);
+    v.y = addmod(v.y, w.y, q);
+  }
+  *reinterpret_cast<ulonglong2*>(out + i) = v;
+}
+cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peers_dev, int n_parts, u64* out,
+                                      u64 n_cts, cudaStream_t st) {
+  const u64 total = n_cts * 2 * P.k * P.N;
+  if (!total) return cudaSuccess;
+  k_modadd_reduce_ptrs<<<(unsigned)((total / 2 + 255) / 256), 256, 0, st>>>(P, peers_dev, n_parts, out, total);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_place_roots(const u64* __restrict__ query, u64* __restrict__ work, const u64* __restrict__ root_off, int n_trees,
+              u64 q_stride, u64 ctL) {
+  const u32 tq = blockIdx.y;
+  const u32 ti = tq % n_trees, qi = tq / n_trees;
+  const u64 i = ((u64)blockIdx.x * 256 + threadIdx.x) * 2;
+  if (i >= ctL) return;
+  const ulonglong2 v = ldg128(query + (u64)tq * ctL + i);
+  *reinterpret_cast<ulonglong2*>(work + qi * q_stride + root_off[ti] + i) = v;
+}
+cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64* work, const u64* root_off, int n_trees,
+                               int n_queries, u64 q_stride, cudaStream_t st) {
+  if (!n_trees || !n_queries) return cudaSuccess;
+  const u64 ctL = 2ull * P.k * P.N;
+  k_place_roots<<<dim3((unsigned)((ctL / 2 + 255) / 256), n_trees * n_queries), 256, 0, st>>>(query, work, root_off,
+                                                                                            n_trees, q_stride, ctL);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fill_random(const __grid_constant__ DevParams P, u64* __restrict__ out, int cycle, int off, u64 seed) {
+  const u64 poly = blockIdx.x;
+  const u64 q = P.m[(poly % cycle) + off].q;
+  for (u32 n = threadIdx.x; n < P.N; n += 256) {
+    u64 x = seed + (poly * P.N + n) * 0x9e3779b97f4a7c15ULL;  // splitmix64 finaliser as a counter-based hash
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+    x ^= x >> 31;
+    out[poly * P.N + n] = x % q;
+  }
+}
+cudaError_t launch_fill_random(const DevParams& P, u64* out, u64 n_polys, int cycle, int off, u64 seed, cudaStream_t st) {
+  if (!n_polys) return cudaSuccess;
+  k_fill_random<<<(unsigned)n_polys, 256, 0, st>>>(P, out, cycle, off, seed);
+  return cudaGetLastError();
+}
+
+}  // namespace pirb

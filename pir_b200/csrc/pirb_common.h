@@ -1,0 +1,42 @@
+// pirb_common.h — types shared by host and device code of the B200 PIR answer path.
+#pragma once
+#include <cstdint>
+
+typedef unsigned long long u64;  // == uint64_t on LP64; matches CUDA's 64-bit intrinsics
+typedef uint32_t u32;
+typedef uint8_t u8;
+
+#define PIRB_MAX_MODULI 9    // key-level moduli (k data + 1 special); BFVDefault(16384) has 9
+#define PIRB_MAX_REENC 64    // 2 * ExpansionRatio upper bound
+#define PIRB_MAX_DIMS 8
+
+// Per-modulus constants.  Tables live in device memory.
+struct ModC {
+  u64 q;
+  u64 ratio_hi, ratio_lo;  // floor(2^128 / q)
+  u64 inv_n, inv_n_s;      // N^{-1} mod q and its Shoup companion floor(inv_n * 2^64 / q)
+  const u64* rp;           // rp[bitrev(i)] = psi^i  (psi = minimal primitive 2N-th root; SEAL ordering)
+  const u64* rps;          // Shoup companions
+  const u64* irp;          // irp[i] = rp[i]^{-1}
+  const u64* irps;
+};
+
+// Passed by value (__grid_constant__) to every kernel: lives in the constant bank.
+struct DevParams {
+  int logn;
+  int k;        // data-level moduli; m[k] is the special prime P
+  u32 N;
+  u32 ptb;      // trunc(log2 t)
+  u64 t;
+  u64 thr;      // (t+1)/2  plain_upper_half_threshold
+  u64 half_P;   // P >> 1
+  ModC m[PIRB_MAX_MODULI];
+  u64 inv_P[PIRB_MAX_MODULI];       // P^{-1} mod q_j
+  u64 inv_P_s[PIRB_MAX_MODULI];     // Shoup companion
+  u64 half_P_mod[PIRB_MAX_MODULI];  // (P>>1) mod q_j
+  int two_er;                       // 2 * ExpansionRatio
+  u8 re_poly[PIRB_MAX_REENC];       // re-encode chunk e -> source poly (0/1)
+  u8 re_mod[PIRB_MAX_REENC];        //                  -> source modulus j
+  u8 re_shift[PIRB_MAX_REENC];      //                  -> right shift
+};
+

@@ -1,0 +1,220 @@
+// pirb_device.cuh — 64-bit modular arithmetic and the shared-memory NTT core for sm_100a.
+//
+// Arithmetic contract (what the reference gets from SEAL 3.5.6):
+// every public result is the canonical representative in [0,q).  Internally we use
+// Harvey lazy butterflies ([0,4q) forward, [0,2q) inverse), Shoup multiplication for
+// fixed twiddles and 128-bit lazy accumulation + one Barrett reduction for MACs.
+// All of it is exact integer arithmetic, so results are bit-identical to any other
+// correct implementation (the CPU oracle in particular).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pirb_common.h"
+
+namespace pirb {
+
+// ------------------------------------------------------------------------------------------
+// scalar helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 csub(u64 x, u64 q) { return x >= q ? x - q : x; }
+__device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
+__device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+__device__ __forceinline__ u64 negmod(u64 a, u64 q) { return a ? q - a : 0; }
+
+// x*w mod q in [0,2q) given ws = floor(w*2^64/q); valid for any 64-bit x, q < 2^63
+__device__ __forceinline__ u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {
+  u64 h = __umul64hi(x, ws);
+  return x * w - h * q;
+}
+__device__ __forceinline__ u64 shoup(u64 x, u64 w, u64 ws, u64 q) { return csub(shoup_lazy(x, w, ws, q), q); }
+
+// (hi:lo) += a*b
+__device__ __forceinline__ void mac128(u64& lo, u64& hi, u64 a, u64 b) {
+  u64 pl = a * b, ph = __umul64hi(a, b);
+  asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(lo), "+l"(hi) : "l"(pl), "l"(ph));
+}
+
+// 128-bit -> [0,q) with ratio = floor(2^128/q)
+__device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, u64 q, u64 r_hi, u64 r_lo) {
+  u64 carry = __umul64hi(lo, r_lo);
+  u64 t_lo = lo * r_hi, t_hi = __umul64hi(lo, r_hi);
+  u64 tmp1 = t_lo + carry;
+  u64 tmp3 = t_hi + (tmp1 < carry);
+  u64 u_lo = hi * r_lo, u_hi = __umul64hi(hi, r_lo);
+  u64 tmp1b = tmp1 + u_lo;
+  carry = u_hi + (tmp1b < tmp1);
+  u64 quot = hi * r_hi + tmp3 + carry;
+  return csub(lo - quot * q, q);
+}
+// 64-bit -> [0,q)
+__device__ __forceinline__ u64 barrett64(u64 a, u64 q, u64 r_hi) {
+  u64 quot = __umul64hi(a, r_hi);
+  return csub(a - quot * q, q);
+}
+__device__ __forceinline__ u64 mulmod(u64 a, u64 b, const ModC& m) {
+  return barrett128(a * b, __umul64hi(a, b), m.q, m.ratio_hi, m.ratio_lo);
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory layout: XOR swizzle so that every pass of the NTT (element strides
+// >=16, 8 and 1) is bank-conflict free for 64-bit words (a half-warp must hit 16
+// distinct 8-byte bank pairs).  No padding: a size-N transform uses exactly 8N bytes.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int swz(int i) { return i ^ (((i >> 4) & 7) | (((i >> 6) & 1) << 3)); }
+
+// One pass = R consecutive radix-2 stages done in registers on units of 2^R elements.
+// Forward (Cooley-Tukey, SEAL ordering): stage s has m=2^s blocks, gap N>>(s+1), twiddle rp[m+block].
+template <int LOGN, int NT, int S0, int R>
+__device__ __forceinline__ void ntt_fwd_pass(u64* __restrict__ s, const u64* __restrict__ rp,
+                                             const u64* __restrict__ rps, u64 q, int tid) {
+  constexpr int N = 1 << LOGN;
+  constexpr int E = 1 << R;
+  constexpr int TL = N >> (S0 + R);  // gap of the last stage of this pass
+  constexpr int UNITS = N >> R;
+  const u64 two_q = 2 * q;
+#pragma unroll 1
+  for (int u = tid; u < UNITS; u += NT) {
+    const int lo = u & (TL - 1);
+    const int hi = u / TL;
+    const int base = hi * (TL << R) + lo;
+    u64 x[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) x[e] = s[swz(base + e * TL)];
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int half = E >> (a + 1);
+      const int mbase = (1 << (S0 + a)) + (hi << a);
+#pragma unroll
+      for (int b = 0; b < (1 << a); ++b) {
+        const u64 w = __ldg(rp + mbase + b);
+        const u64 ws = __ldg(rps + mbase + b);
+#pragma unroll
+        for (int c = 0; c < half; ++c) {
+          const int e0 = b * 2 * half + c, e1 = e0 + half;
+          u64 X = x[e0];
+          X = X >= two_q ? X - two_q : X;
+          const u64 T = shoup_lazy(x[e1], w, ws, q);
+          x[e0] = X + T;
+          x[e1] = X + two_q - T;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) s[swz(base + e * TL)] = x[e];
+  }
+}
+
+// Inverse (Gentleman-Sande): same unit geometry, stages visited from the smallest gap up.
+template <int LOGN, int NT, int S0, int R>
+__device__ __forceinline__ void ntt_inv_pass(u64* __restrict__ s, const u64* __restrict__ irp,
+                                             const u64* __restrict__ irps, u64 q, int tid) {
+  constexpr int N = 1 << LOGN;
+  constexpr int E = 1 << R;
+  constexpr int TL = N >> (S0 + R);
+  constexpr int UNITS = N >> R;
+  const u64 two_q = 2 * q;
+#pragma unroll 1
+  for (int u = tid; u < UNITS; u += NT) {
+    const int lo = u & (TL - 1);
+    const int hi = u / TL;
+    const int base = hi * (TL << R) + lo;
+    u64 x[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) x[e] = s[swz(base + e * TL)];
+#pragma unroll
+    for (int a = R - 1; a >= 0; --a) {
+      const int half = E >> (a + 1);
+      const int mbase = (1 << (S0 + a)) + (hi << a);
+#pragma unroll
+      for (int b = 0; b < (1 << a); ++b) {
+        const u64 w = __ldg(irp + mbase + b);
+        const u64 ws = __ldg(irps + mbase + b);
+#pragma unroll
+        for (int c = 0; c < half; ++c) {
+          const int e0 = b * 2 * half + c, e1 = e0 + half;
+          const u64 X = x[e0], Y = x[e1];
+          u64 S = X + Y;
+          S = S >= two_q ? S - two_q : S;
+          const u64 D = X + two_q - Y;
+          x[e0] = S;
+          x[e1] = shoup_lazy(D, w, ws, q);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) s[swz(base + e * TL)] = x[e];
+  }
+}
+
+// Full transforms on a swizzled shared-memory buffer.  Stage split: first pass takes
+// R0 = ((LOGN-1) % 3) + 1 stages, every later pass 3 stages, so the last-stage gaps of the
+// passes are always ..., 64, 8, 1 (the cases the swizzle is designed for).
+// Input of forward: values < 4q.  Output: values < 4q (caller reduces).
+template <int LOGN, int NT>
+__device__ __forceinline__ void ntt_forward_smem(u64* s, const ModC& m, int tid) {
+  constexpr int R0 = ((LOGN - 1) % 3) + 1;
+  const u64 q = m.q;
+  ntt_fwd_pass<LOGN, NT, 0, R0>(s, m.rp, m.rps, q, tid);
+  __syncthreads();
+  if constexpr (LOGN > R0) {
+    ntt_fwd_pass<LOGN, NT, R0, 3>(s, m.rp, m.rps, q, tid);
+    __syncthreads();
+  }
+  if constexpr (LOGN > R0 + 3) {
+    ntt_fwd_pass<LOGN, NT, R0 + 3, 3>(s, m.rp, m.rps, q, tid);
+    __syncthreads();
+  }
+  if constexpr (LOGN > R0 + 6) {
+    ntt_fwd_pass<LOGN, NT, R0 + 6, 3>(s, m.rp, m.rps, q, tid);
+    __syncthreads();
+  }
+  if constexpr (LOGN > R0 + 9) {
+    ntt_fwd_pass<LOGN, NT, R0 + 9, 3>(s, m.rp, m.rps, q, tid);
+    __syncthreads();
+  }
+  static_assert(LOGN <= R0 + 12, "unsupported transform size");
+}
+// Input of inverse: values < 2q.  Output: values < 2q, NOT yet scaled by N^{-1}.
+template <int LOGN, int NT>
+__device__ __forceinline__ void ntt_inverse_smem(u64* s, const ModC& m, int tid) {
+  constexpr int R0 = ((LOGN - 1) % 3) + 1;
+  const u64 q = m.q;
+  if constexpr (LOGN > R0 + 9) {
+    ntt_inv_pass<LOGN, NT, R0 + 9, 3>(s, m.irp, m.irps, q, tid);
+    __syncthreads();
+  }
+  if constexpr (LOGN > R0 + 6) {
+    ntt_inv_pass<LOGN, NT, R0 + 6, 3>(s, m.irp, m.irps, q, tid);
+    __syncthreads();
+  }
+  if constexpr (LOGN > R0 + 3) {
+    ntt_inv_pass<LOGN, NT, R0 + 3, 3>(s, m.irp, m.irps, q, tid);
+    __syncthreads();
+  }
+  if constexpr (LOGN > R0) {
+    ntt_inv_pass<LOGN, NT, R0, 3>(s, m.irp, m.irps, q, tid);
+    __syncthreads();
+  }
+  ntt_inv_pass<LOGN, NT, 0, R0>(s, m.irp, m.irps, q, tid);
+  __syncthreads();
+}
+
+// reduce a forward-NTT lazy value (<4q) to canonical
+__device__ __forceinline__ u64 canon4(u64 v, u64 q) {
+  v = v >= 2 * q ? v - 2 * q : v;
+  return csub(v, q);
+}
+// scale an inverse-NTT lazy value (<2q) by N^{-1} and make canonical
+__device__ __forceinline__ u64 inv_finish(u64 v, const ModC& m) { return shoup(v, m.inv_n, m.inv_n_s, m.q); }
+
+// Galois automorphism x -> x^g in coefficient form, as a gather: value of sigma_g(a) at index n.
+// ginv = g^{-1} mod 2N.  (out[i*g mod N] = +-in[i], sign from (i*g div N) parity.)
+__device__ __forceinline__ u64 galois_gather(const u64* __restrict__ in, u32 n, u32 ginv, u32 N, u64 q) {
+  u32 i1 = (n * ginv) & (2 * N - 1);
+  if (i1 < N) return in[i1];
+  return negmod(in[i1 - N], q);
+}
+
+}  // namespace pirb

@@ -1,0 +1,149 @@
+"""Device-resident, row-sharded serving on top of the C ABI's *_dev entry points.
+
+One process per GPU.  The database is split by rows of the first dimension; every rank expands the query
+(replicated, no communication), scans its rows, re-encodes and multiplies its share of the upper dimensions and
+produces a partial reply in NTT form.  The partials are combined with a mod-q add (never a plain integer sum):
+either NCCL all-gather + the fused add-and-inverse-NTT kernel, or peer pointers read directly over NVLink.
+
+torch is used only for device memory, streams and torch.distributed — uint64 limbs are carried in int64 tensors.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .api import GaloisKeys, PIRDatabase, PIRParameters, _check, _KeyHandle
+
+
+def _dp(t: torch.Tensor):
+    assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+class ShardServer:
+    def __init__(self, params: PIRParameters, device=0, shard_index=0, shard_count=1):
+        self.params = params
+        self.device = torch.device("cuda", device)
+        self.db = PIRDatabase(params, device, shard_index, shard_count)
+        self.ctx = self.db.ctx
+        self.shard_index, self.shard_count = shard_index, shard_count
+        self.keys = None
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.Stream()
+        self.k, self.N = self.ctx.k, self.ctx.N
+        L = _lib.lib()
+        self.pt_begin = int(L.pirb_shard_pt_begin(self.ctx.h))
+        self.pt_count = int(L.pirb_shard_pt_count(self.ctx.h))
+
+    # -- setup -----------------------------------------------------------------------------------
+    def load_coeff(self, coeffs, first_pt=0):
+        """coeffs [count][N] with GLOBAL plaintext indices starting at first_pt; the shard keeps what it owns."""
+        self.db.load_coeff(coeffs, first_pt)
+
+    def set_keys(self, gk: GaloisKeys):
+        if self.keys is not None:
+            self.keys.close()
+        self.keys = _KeyHandle(self.ctx, gk)
+
+    def set_profiling(self, on=True):
+        _check(_lib.lib().pirb_set_profiling(self.ctx.h, 1 if on else 0))
+
+    def stage_ms(self):
+        out = (C.c_float * _lib.PIRB_N_STAGES)()
+        _check(_lib.lib().pirb_get_stage_ms(self.ctx.h, out))
+        return dict(zip(_lib.STAGE_NAMES, [float(x) for x in out]))
+
+    def launch_count(self):
+        return int(_lib.lib().pirb_last_launch_count(self.ctx.h))
+
+    def scan_bytes(self, n_queries=1):
+        return int(_lib.lib().pirb_scan_bytes(self.ctx.h, n_queries))
+
+    # -- stream plumbing ---------------------------------------------------------------------------
+    def _enter(self):
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def _exit(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def _empty(self, *shape):
+        return torch.empty(shape, dtype=torch.int64, device=self.device)
+
+    # -- hot path ----------------------------------------------------------------------------------
+    def answer(self, d_queries: torch.Tensor) -> torch.Tensor:
+        """[Q][n_ct][2][k][N] -> [Q][reply_cts][2][k][N] (unsharded context)."""
+        Q, n_ct = d_queries.shape[0], d_queries.shape[1]
+        out = self._empty(Q, self.ctx.reply_cts, 2, self.k, self.N)
+        st = self._enter()
+        _check(_lib.lib().pirb_answer_dev(self.ctx.h, self.keys.h if self.keys else None, _dp(d_queries), Q, n_ct,
+                                          _dp(out), st))
+        self._exit()
+        return out
+
+    def answer_partial(self, d_queries: torch.Tensor) -> torch.Tensor:
+        """This shard's NTT-form partial replies [Q][reply_cts][2][k][N]."""
+        Q, n_ct = d_queries.shape[0], d_queries.shape[1]
+        out = self._empty(Q, self.ctx.reply_cts, 2, self.k, self.N)
+        st = self._enter()
+        _check(_lib.lib().pirb_answer_partial_dev(self.ctx.h, self.keys.h if self.keys else None, _dp(d_queries), Q,
+                                                  n_ct, _dp(out), st))
+        self._exit()
+        return out
+
+    def reduce_finish(self, gathered: torch.Tensor, n_queries: int) -> torch.Tensor:
+        """gathered [G][Q][reply_cts][2][k][N] partials -> mod-q add + inverse NTT -> final replies."""
+        G = gathered.shape[0]
+        out = self._empty(n_queries, self.ctx.reply_cts, 2, self.k, self.N)
+        st = self._enter()
+        _check(_lib.lib().pirb_reduce_finish_dev(self.ctx.h, _dp(gathered), G, gathered[0].numel(), n_queries,
+                                                 _dp(out), st))
+        self._exit()
+        return out
+
+    def reduce_finish_peers(self, peer_ptrs: torch.Tensor, n_queries: int) -> torch.Tensor:
+        """peer_ptrs: int64 cuda tensor of G device pointers (own + IPC-mapped peers) to partial buffers."""
+        out = self._empty(n_queries, self.ctx.reply_cts, 2, self.k, self.N)
+        st = self._enter()
+        _check(_lib.lib().pirb_reduce_finish_peers_dev(self.ctx.h, _dp(peer_ptrs), peer_ptrs.numel(), n_queries,
+                                                       _dp(out), st))
+        self._exit()
+        return out
+
+    def answer_distributed(self, d_queries: torch.Tensor) -> torch.Tensor:
+        """Row-sharded answer across the ranks of the default process group: partial -> all-gather -> mod-q add."""
+        import torch.distributed as dist
+        part = self.answer_partial(d_queries)
+        world = dist.get_world_size()
+        if world == 1:
+            return self.reduce_finish(part[None], d_queries.shape[0])
+        gathered = self._empty(world, *part.shape)
+        dist.all_gather_into_tensor(gathered, part)
+        return self.reduce_finish(gathered, d_queries.shape[0])
+
+    def scan(self, d_sv_ntt: torch.Tensor, want_rows=True):
+        """[Q][dimL][2][k][N] NTT-form last-dimension selection cts -> rows [Q][n_rows][2][k][N] NTT form."""
+        Q = d_sv_ntt.shape[0]
+        d = len(self.params.dimensions)
+        dimL = d_sv_ntt.shape[1]
+        n_rows = 1 if d == 1 else -(-self.pt_count // dimL)
+        out = self._empty(Q, n_rows, 2, self.k, self.N) if want_rows else None
+        st = self._enter()
+        _check(_lib.lib().pirb_scan_dev(self.ctx.h, _dp(d_sv_ntt), Q, _dp(out) if want_rows else None, st))
+        self._exit()
+        return out
+
+
+def shard_rows(dim0: int, shard_count: int):
+    """Row ranges [lo, hi) of dims[0] per shard — the same split the C library makes (context.cu)."""
+    per = -(-dim0 // shard_count)
+    return [(min(dim0, per * s), min(dim0, per * s + per)) for s in range(shard_count)]
+
+
+def to_device(a: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to(device)
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy().view(np.uint64)

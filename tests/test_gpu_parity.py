@@ -1,0 +1,422 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every C-ABI entry point of the answer path against the CPU
+oracle on the same seeded inputs — bit-exact on all limbs — plus decrypt-level checks against the reference's
+known-answer vectors and size-independent properties at BASELINE.json's sizes.
+"""
+import numpy as np
+import pytest
+
+import pir_b200 as pb
+from oracle import binding as ob
+from oracle import client as oc
+
+pytestmark = pytest.mark.gpu
+N = 4096
+
+
+def _params(dbsize, elem=0, d=1, n=4096, bits=20, bpc=0):
+    ep = pb.GenerateEncryptionParams(n, bits)
+    return pb.CreatePIRParameters(dbsize, elem, d, ep, False, bpc)
+
+
+def _harness(p, seed=1):
+    ep = p.encryption_parameters
+    hp = oc.PIRParameters(p.num_items, p.num_pt, list(p.dimensions), p.bytes_per_item, p.items_per_plaintext,
+                          p.bits_per_coeff, ep.poly_modulus_degree, ep.plain_modulus, list(ep.coeff_modulus))
+    return oc.HarnessClient(hp, seed=seed)
+
+
+def _gk(cl, elts=None, seed=77):
+    elts = cl.elts if elts is None else elts
+    data = cl.galois if elts is cl.elts else cl.orc.galois_keys(cl.keys, elts, seed)
+    return pb.GaloisKeys(elts, data), data
+
+
+def _random_items(p, seed=42):
+    rng = np.random.default_rng(seed)
+    return [rng.integers(0, 256, p.bytes_per_item, dtype=np.uint8).tobytes() for _ in range(p.num_items)]
+
+
+def _random_ct(orc, rng):
+    return np.stack([rng.integers(0, orc.moduli[j], orc.N, dtype=np.uint64) for _ in range(2) for j in range(orc.k)]
+                    ).reshape(2, orc.k, orc.N)
+
+
+@pytest.fixture(scope="module")
+def srv10():
+    """server_test.cpp fixture: 10 items x 7680 B, N=4096, t 20 bit; integer database."""
+    p = _params(10, 7680, 1)
+    cl = _harness(p, seed=42)
+    rng = np.random.default_rng(42)
+    vals = [int(v) for v in rng.integers(0, 1 << 48, 10, dtype=np.int64)]
+    db = pb.PIRDatabase.Create(vals, p)
+    server = pb.PIRServer.Create(db, p)
+    return p, cl, vals, db, server
+
+
+# ------------------------------------------------------------------------------------------------
+def test_db_preprocess_matches_oracle(srv10):
+    p, cl, vals, db, server = srv10
+    want = oc.db_to_ntt(cl.orc, oc.encode_int_db(cl.params, vals))
+    assert np.array_equal(db.read_ntt(0, 10), want)
+
+
+@pytest.mark.parametrize("n,bits", [(4096, 16), (8192, 20)])
+def test_populate_strings_matches_oracle(n, bits):
+    p = _params(23, 0, 1, n, bits)
+    cl = _harness(p)
+    items = _random_items(p)
+    db = pb.PIRDatabase.Create(items, p)
+    assert db.size() == p.num_pt
+    want = oc.db_to_ntt(cl.orc, oc.encode_string_db(cl.params, items))
+    assert np.array_equal(db.read_ntt(0, p.num_pt), want)
+    with pytest.raises(pb.PIRStatusError) as e:  # database_test.cpp:326-339 / database.cpp:85-90
+        pb.PIRDatabase.Create(items[:-1], p)
+    assert e.value.code == pb.INVALID_ARGUMENT
+
+
+# ------------------------------------------------------------------------------------------------ substitution
+SUBST = [("42", 3, "42"), ("1x^1", 5, "1x^5"), ("6x^2", 3, "6x^6"), ("1x^1", N + 1, "FC000x^1"),
+         ("1x^4", N + 1, "1x^4"), ("1x^8", N // 2 + 1, "1x^8"), ("1x^8", N // 4 + 1, "1x^8"),
+         ("1x^8", N // 8 + 1, "FC000x^8"), ("77x^4095", 3, "77x^4093"), ("1x^4095", N + 1, "FC000x^4095"),
+         ("4x^4 + 33x^3 + 222x^2 + 19x^1 + 42", N + 1, "4x^4 + FBFCEx^3 + 222x^2 + FBFE8x^1 + 42")]
+
+
+@pytest.mark.parametrize("inp,power,expected", SUBST)
+def test_substitute_kat_and_bit_exact(srv10, inp, power, expected):
+    # server_test.cpp:271-305
+    p, cl, vals, db, server = srv10
+    ct = cl.encrypt(oc.parse_hex_poly(inp, N))
+    gk, raw = _gk(cl, [power])
+    want = cl.orc.substitute(ct, power, [power], raw)
+    got = ct.copy()
+    server.substitute_power_x_inplace(got, power, gk)
+    assert np.array_equal(got, want)
+    assert oc.format_hex_poly(cl.decrypt(got)) == oc.format_hex_poly(oc.parse_hex_poly(expected, N))
+
+
+def test_substitute_missing_key(srv10):
+    p, cl, vals, db, server = srv10
+    gk, _ = _gk(cl, [5])
+    ct = cl.encrypt(oc.parse_hex_poly("1x^1", N))
+    with pytest.raises(pb.PIRStatusError) as e:
+        server.substitute_power_x_inplace(ct, 3, gk)
+    assert e.value.code == pb.INTERNAL  # server.cpp:72-74
+
+
+def test_substitute_random_ciphertexts_all_levels(srv10):
+    p, cl, vals, db, server = srv10
+    rng = np.random.default_rng(3)
+    gk, raw = _gk(cl)
+    for g in cl.elts:
+        ct = _random_ct(cl.orc, rng)
+        want = cl.orc.substitute(ct, g, cl.elts, raw)
+        got = ct.copy()
+        server.substitute_power_x_inplace(got, g, gk)
+        assert np.array_equal(got, want), g
+
+
+# ------------------------------------------------------------------------------------------------ shifts
+@pytest.mark.parametrize("inp,k,expected", [("42x^1", 1, "42"), ("42x^42", 41, "42x^1"),
+                                            ("1x^4 + 1x^3 + 1x^1", 1, "1x^3 + 1x^2 + 1"),
+                                            ("1x^16 + 1x^12 + 1x^8", 4, "1x^12 + 1x^8 + 1x^4")])
+def test_multiply_inverse_power_x(srv10, inp, k, expected):
+    # server_test.cpp:307-339
+    p, cl, vals, db, server = srv10
+    ct = cl.encrypt(oc.parse_hex_poly(inp, N))
+    got = server.multiply_inverse_power_of_x(ct, k)
+    assert np.array_equal(got, cl.orc.mul_inv_pow_x(ct, k))
+    assert oc.format_hex_poly(cl.decrypt(got)) == oc.format_hex_poly(oc.parse_hex_poly(expected, N))
+
+
+def test_multiply_inverse_power_x_all_ranges(srv10):
+    p, cl, vals, db, server = srv10
+    rng = np.random.default_rng(4)
+    ct = _random_ct(cl.orc, rng)
+    ct[0, 0, :7] = 0  # zeros stay zeros under negation
+    for k in (0, 1, 2, 4095, 4096, 4097, N + 64, 2 * N - 1, 2 * N, 2 * N + 5):
+        assert np.array_equal(server.multiply_inverse_power_of_x(ct, k), cl.orc.mul_inv_pow_x(ct, k)), k
+
+
+# ------------------------------------------------------------------------------------------------ expansion
+@pytest.mark.parametrize("inp,expected", [("1", ["2", "0"]), ("1x^1", ["0", "2"]),
+                                          ("3x^3 + 2x^2 + 1x^1 + 42", ["108", "4", "8", "C"]),
+                                          ("1x^5", ["0", "0", "0", "0", "0", "8"])])
+def test_oblivious_expansion_kat(srv10, inp, expected):
+    # server_test.cpp:341-383
+    p, cl, vals, db, server = srv10
+    ct = cl.encrypt(oc.parse_hex_poly(inp, N))
+    gk, raw = _gk(cl)
+    got = server.oblivious_expansion(ct, len(expected), gk)
+    want = cl.orc.expand(ct, len(expected), cl.elts, raw, single=True)
+    assert np.array_equal(got, want)
+    for o, e in zip(got, expected):
+        assert oc.format_hex_poly(cl.decrypt(o)) == oc.format_hex_poly(oc.parse_hex_poly(e, N))
+
+
+@pytest.mark.parametrize("num_items", [1, 2, 3, 17, 100, 1000])
+def test_oblivious_expansion_single_sizes(srv10, num_items):
+    p, cl, vals, db, server = srv10
+    rng = np.random.default_rng(num_items)
+    ct = _random_ct(cl.orc, rng)
+    gk, raw = _gk(cl)
+    assert np.array_equal(server.oblivious_expansion(ct, num_items, gk),
+                          cl.orc.expand(ct, num_items, cl.elts, raw, single=True))
+
+
+@pytest.mark.parametrize("num_items,index,expected_value", [(100, 42, 128), (4096, 3007, 4096), (5000, 4095, 4096),
+                                                            (5000, 4200, 1024)])
+def test_oblivious_expansion_multi_ct(srv10, num_items, index, expected_value):
+    # server_test.cpp:385-428
+    p, cl, vals, db, server = srv10
+    n_ct = num_items // N + 1
+    cts = []
+    for i in range(n_ct):
+        pt = np.zeros(N, dtype=np.uint64)
+        if index // N == i:
+            pt[index % N] = 1
+        cts.append(cl.encrypt(pt))
+    cts = np.stack(cts)
+    gk, raw = _gk(cl)
+    got = server.oblivious_expansion(cts, num_items, gk)
+    assert got.shape[0] == num_items
+    want = cl.orc.expand(cts, num_items, cl.elts, raw)
+    assert np.array_equal(got, want)
+    for i in sorted({index, 0, num_items - 1}):
+        pt = cl.decrypt(got[i])
+        assert int(pt[0]) == (expected_value if i == index else 0) and not pt[1:].any()
+
+
+def test_expansion_argument_errors(srv10):
+    p, cl, vals, db, server = srv10
+    gk, _ = _gk(cl)
+    ct = cl.encrypt(np.zeros(N, dtype=np.uint64))
+    with pytest.raises(pb.PIRStatusError) as e:  # server.cpp:111-114
+        server.oblivious_expansion(ct, N + 1, gk)
+    assert e.value.code == pb.INVALID_ARGUMENT
+    with pytest.raises(pb.PIRStatusError) as e:  # server.cpp:154-158
+        server.oblivious_expansion(np.stack([ct, ct]), 100, gk)
+    assert e.value.code == pb.INVALID_ARGUMENT
+    gk5, _ = _gk(cl, [5])
+    with pytest.raises(pb.PIRStatusError) as e:  # missing key -> Internal
+        server.oblivious_expansion(ct, 4, gk5)
+    assert e.value.code == pb.INTERNAL
+
+
+# ------------------------------------------------------------------------------------------------ PIRDatabase::multiply
+def _selection_vector(cl, dims, indices):
+    cts = []
+    for d, dim in enumerate(dims):
+        for i in range(dim):
+            pt = np.zeros(cl.orc.N, dtype=np.uint64)
+            if i == indices[d]:
+                pt[0] = 1
+            cts.append(cl.encrypt(pt))
+    return np.stack(cts)
+
+
+@pytest.mark.parametrize("n,bits,dbsize,d,idx", [(4096, 16, 10, 1, 7), (4096, 16, 16, 2, 11), (4096, 16, 16, 2, 0),
+                                                  (4096, 16, 16, 2, 15), (4096, 16, 82, 2, 42), (8192, 20, 27, 3, 2),
+                                                  (8192, 20, 117, 3, 17), (4096, 20, 200, 1, 199), (4096, 20, 50, 3, 49),
+                                                  (4096, 24, 77, 4, 5)])
+def test_multiply_multi_dim(n, bits, dbsize, d, idx):
+    # database_test.cpp:343-388 (CTDecomp arm) + extra shapes; bit-exact vs the oracle and decrypt-correct
+    p = _params(dbsize, 0, d, n, bits)
+    cl = _harness(p, seed=11)
+    items = _random_items(p)
+    db = pb.PIRDatabase.Create(items, p)
+    sv = _selection_vector(cl, p.dimensions, db.calculate_indices(idx))
+    want, sv_after = cl.orc.db_multiply(oc.db_to_ntt(cl.orc, oc.encode_string_db(cl.params, items)), p.dimensions, sv)
+    got_sv = sv.copy()
+    got = db.multiply(got_sv)
+    assert got.shape[0] == (2 * cl.orc.ER) ** (d - 1)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got_sv, sv_after)  # in-place NTT of the selection vector (database.cpp:190,222)
+    if d <= 3:
+        res = cl.process_reply(got)
+        assert ob.string_decode(res, cl.orc.ptb, p.bytes_per_item) == items[idx]
+
+
+def test_multiply_integer_dot_product():
+    # database_test.cpp:155-178
+    p = _params(10, 0, 1)
+    cl = _harness(p, seed=3)
+    rng = np.random.default_rng(8)
+    vals = [int(v) for v in rng.integers(0, 1 << 20, 10)]
+    db = pb.PIRDatabase.Create(vals, p)
+    v = list(range(-5, 5))
+    sv = np.stack([cl.encrypt(oc.integer_encode(x, N, cl.orc.t)) for x in v])
+    out = db.multiply(sv)
+    assert oc.integer_decode(cl.decrypt(out[0]), cl.orc.t) == sum(a * b for a, b in zip(v, vals))
+
+
+def test_multiply_selection_vector_size_errors():
+    # database_test.cpp:180-219
+    p = _params(100, 0, 2)
+    db = pb.PIRDatabase.Create(p)
+    k = len(p.encryption_parameters.coeff_modulus) - 1
+    for n_sv in (19, 21):
+        with pytest.raises(pb.PIRStatusError) as e:
+            db.multiply(np.zeros((n_sv, 2, k, N), dtype=np.uint64))
+        assert e.value.code == pb.INVALID_ARGUMENT
+
+
+# ------------------------------------------------------------------------------------------------ ProcessRequest
+def test_process_request_single_ct(srv10):
+    # server_test.cpp:98-121
+    p, cl, vals, db, server = srv10
+    gk, raw = _gk(cl)
+    pt = np.zeros(N, dtype=np.uint64); pt[7] = 1
+    q = cl.encrypt(pt)[None]
+    resp = server.ProcessRequest(pb.Request([q], gk))
+    assert len(resp.reply) == 1 and resp.reply[0].shape[0] == 1
+    want = cl.orc.process_query(db.read_ntt(0, 10), p.dimensions, cl.elts, raw, q)
+    assert np.array_equal(resp.reply[0], want)
+    assert oc.integer_decode(cl.decrypt(resp.reply[0][0]), cl.orc.t) == vals[7] * pb.next_power_two(10)
+
+
+def test_process_request_multi_ct():
+    # server_test.cpp:123-151
+    p = _params(5000, 7680, 1)
+    cl = _harness(p, seed=9)
+    rng = np.random.default_rng(42)
+    vals = [int(v) for v in rng.integers(0, 1 << 48, 5000, dtype=np.int64)]
+    db = pb.PIRDatabase.Create(vals, p)
+    server = pb.PIRServer.Create(db, p)
+    gk, raw = _gk(cl)
+    idx = 4200
+    pt = np.zeros(N, dtype=np.uint64); pt[idx - N] = 1
+    q = np.stack([cl.encrypt(np.zeros(N, dtype=np.uint64)), cl.encrypt(pt)])
+    resp = server.ProcessRequest(pb.Request([q], gk))
+    want = cl.orc.process_query(db.read_ntt(0, 5000), p.dimensions, cl.elts, raw, q)
+    assert np.array_equal(resp.reply[0], want)
+    assert oc.integer_decode(cl.decrypt(resp.reply[0][0]), cl.orc.t) == vals[idx] * pb.next_power_two(5000 - N)
+    with pytest.raises(pb.PIRStatusError) as e:  # one ct short (server.cpp:154-158)
+        server.ProcessRequest(pb.Request([q[:1]], gk))
+    assert e.value.code == pb.INVALID_ARGUMENT
+
+
+def test_process_request_batch_and_zero(srv10):
+    # server_test.cpp:153-207
+    p, cl, vals, db, server = srv10
+    gk, raw = _gk(cl)
+    qs = []
+    for idx in (3, 4, 5):
+        pt = np.zeros(N, dtype=np.uint64); pt[idx] = 1
+        qs.append(cl.encrypt(pt)[None])
+    qs.append(cl.encrypt(np.zeros(N, dtype=np.uint64))[None])
+    resp = server.ProcessRequest(pb.Request(qs, gk))
+    assert len(resp.reply) == 4
+    dbn = db.read_ntt(0, 10)
+    for q, r, exp in zip(qs, resp.reply, [vals[3] * 16, vals[4] * 16, vals[5] * 16, 0]):
+        assert np.array_equal(r, cl.orc.process_query(dbn, p.dimensions, cl.elts, raw, q))
+        assert oc.integer_decode(cl.decrypt(r[0]), cl.orc.t) == exp
+
+
+def test_process_request_2dim():
+    # server_test.cpp:209-260
+    p = _params(82, 7680, 2)
+    cl = _harness(p, seed=89)
+    rng = np.random.default_rng(42)
+    vals = [int(v) for v in rng.integers(0, 1 << 48, 82, dtype=np.int64)]
+    db = pb.PIRDatabase.Create(vals, p)
+    server = pb.PIRServer.Create(db, p)
+    gk, raw = _gk(cl)
+    assert p.dimensions == [10, 9] and db.calculate_indices(42) == [4, 6]
+    m_inv = pow(pb.next_power_two(19), -1, cl.orc.t)
+    pt = np.zeros(N, dtype=np.uint64); pt[4] = m_inv; pt[16] = m_inv
+    q = cl.encrypt(pt)[None]
+    resp = server.ProcessRequest(pb.Request([q], gk))
+    assert resp.reply[0].shape[0] == cl.orc.ER * 2
+    assert np.array_equal(resp.reply[0], cl.orc.process_query(db.read_ntt(0, 82), p.dimensions, cl.elts, raw, q))
+    assert oc.integer_decode(cl.process_reply(resp.reply[0]), cl.orc.t) == vals[42]
+
+
+def test_server_create_size_mismatch():
+    p = _params(10, 0, 1)
+    db = pb.PIRDatabase.Create(p)  # empty
+    with pytest.raises(pb.PIRStatusError) as e:  # server.cpp:37-39
+        pb.PIRServer.Create(db, p)
+    assert e.value.code == pb.INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("n,bits,elem,bpc,dbsize,d,indices",
+                         [(4096, 24, 0, 0, 10, 1, [0]), (4096, 24, 0, 10, 9, 2, [1, 5]),
+                          (4096, 24, 0, 6, 500, 2, [9, 125]), (4096, 24, 64, 10, 1200, 1, [0, 80, 81, 123, 777, 1199]),
+                          (4096, 24, 289, 10, 1200, 1, [0, 47, 777, 1199]), (8192, 20, 1024, 0, 300, 2, [0, 299])])
+def test_end_to_end_correctness(n, bits, elem, bpc, dbsize, d, indices):
+    # correctness_test.cpp:82-113 (decomposition arm) + one N=8192 shape: client -> ProcessRequest -> client
+    p = _params(dbsize, elem, d, n, bits, bpc)
+    cl = _harness(p, seed=5)
+    items = _random_items(p)
+    db = pb.PIRDatabase.Create(items, p)
+    server = pb.PIRServer.Create(db, p)
+    gk, raw = _gk(cl)
+    queries = [cl.create_query(i) for i in indices]
+    resp = server.ProcessRequest(pb.Request(queries, gk))
+    assert cl.process_response_strings(indices, resp.reply) == [items[i] for i in indices]
+    dbn = db.read_ntt(0, p.num_pt)
+    want0 = cl.orc.process_query(dbn, p.dimensions, cl.elts, raw, queries[0])
+    assert np.array_equal(resp.reply[0], want0)
+
+
+# ------------------------------------------------------------------------------------------------ sharding on one GPU
+@pytest.mark.parametrize("dbsize,d,shards", [(82, 2, 2), (82, 2, 3), (200, 1, 4), (50, 3, 2), (9, 2, 4)])
+def test_row_sharded_partials_reduce_to_unsharded_answer(dbsize, d, shards):
+    import torch
+    from pir_b200 import sharded
+    p = _params(dbsize, 0, d, 4096, 20)
+    cl = _harness(p, seed=21)
+    items = _random_items(p)
+    db = pb.PIRDatabase.Create(items, p)
+    server = pb.PIRServer.Create(db, p)
+    gk, raw = _gk(cl)
+    q = cl.create_query(dbsize // 2)
+    want = server.ProcessRequest(pb.Request([q], gk)).reply[0]
+    coeffs = oc.encode_string_db(cl.params, items)
+    partials = []
+    for s in range(shards):
+        sh = sharded.ShardServer(p, device=0, shard_index=s, shard_count=shards)
+        sh.load_coeff(coeffs)
+        sh.set_keys(gk)
+        partials.append(sh.answer_partial(torch.from_numpy(q.view(np.int64)).cuda()[None]))
+    stacked = torch.stack(partials)
+    out = sh.reduce_finish(stacked, n_queries=1)
+    got = out.cpu().numpy().view(np.uint64).reshape(want.shape)
+    assert np.array_equal(got, want)
+    assert ob.string_decode(cl.process_reply(got), cl.orc.ptb, p.bytes_per_item) == items[dbsize // 2]
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_scan_selects_database_rows_at_baseline_size():
+    """BASELINE config 2 shape (2^16 x 288 B, d=2, t 24 bit: 1639 plaintexts, dims [41,40]); size-independent
+    property: a selection vector whose NTT form is (1,0) at column j and 0 elsewhere makes the scan return
+    row r = DB[r*40 + j] exactly (c0) and 0 (c1)."""
+    import torch
+    from pir_b200 import sharded
+    ep = pb.GenerateEncryptionParams(4096, 24)
+    p = pb.CreatePIRParameters(1 << 16, 288, 2, ep)
+    assert (p.num_pt, p.dimensions) == (1639, [41, 40])
+    sh = sharded.ShardServer(p, device=0)
+    sh.db.fill_random(7)
+    k = 2
+    j = 13
+    sv = torch.zeros((40, 2, k, N), dtype=torch.int64, device="cuda")
+    sv[j, 0] = 1  # NTT of the constant polynomial 1 is all-ones
+    rows = sh.scan(sv[None])  # [1][41][2][k][N] NTT form
+    rows = rows.cpu().numpy().view(np.uint64)[0]
+    for r in (0, 1, 20, 40):
+        idx = r * 40 + j
+        if idx < p.num_pt:
+            assert np.array_equal(rows[r, 0], sh.db.read_ntt(idx, 1)[0]), r
+        else:
+            assert not rows[r, 0].any()
+        assert not rows[r, 1].any()
+    # linearity: scan(a + b) == scan(a) + scan(b) mod q
+    rng = np.random.default_rng(0)
+    q = np.array(ep.coeff_modulus[:k], dtype=np.uint64)
+    a = np.stack([rng.integers(0, int(q[jj]), (40, 2, N), dtype=np.uint64) for jj in range(k)], axis=2)
+    b = np.stack([rng.integers(0, int(q[jj]), (40, 2, N), dtype=np.uint64) for jj in range(k)], axis=2)
+    s = (a + b) % q[None, None, :, None]
+    f = lambda x: sh.scan(torch.from_numpy(np.ascontiguousarray(x).view(np.int64)).cuda()[None]).cpu().numpy().view(np.uint64)[0]
+    ra, rb, rs = f(a), f(b), f(s)
+    assert np.array_equal((ra + rb) % q[None, None, :, None], rs)
