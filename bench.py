@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — PIR server answer path on B200 (BASELINE.json metric: queries/sec + p50 latency + DB-scan GB/s).
+
+Workload (config.workload): BASELINE.json configs[1] — d=2, 2^16 elements x 288 B, BFV N=4096, 24-bit plain modulus
+(pir/cpp/benchmark.cpp:17-23 shape: 1639 plaintexts, dims [41,40], 127 key switches and 8 reply ciphertexts per
+query).  A step = one pass of the hot path (oblivious expansion + database multiply) over one batch of queries:
+  N=1  : one query on one GPU (the configuration the metric is quoted on);
+  N>1  : one query per GPU per step (weak scaling).  The database is row-sharded across the N GPUs; each rank
+         expands its own query, NTT-form selection vectors are all-gathered (NCCL), every rank multiplies all N
+         queries against its rows, partial replies are all-gathered and added mod q (fused into the final inverse NTT).
+Synthetic data: uniform limbs in [0,q_j) for the NTT-form database, query ciphertexts and Galois keys (every kernel
+on the path is data-independent).  `value` is device-resident throughput (inputs already in HBM); `e2e` goes through
+the reference-facing call (PIRServer.ProcessRequest -> C ABI pirb_answer) with pinned HOST buffers, H2D/D2H inside.
+
+--impl reference times the CPU restatement of the reference path (oracle/, SEAL-3.5.6-equivalent algorithms; SEAL itself
+cannot be built here) on all host threads for the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (num_items, bytes_per_item, dims, N, plain_bits, description)
+    "cfg2": (1 << 16, 288, 2, 4096, 24, "d=2, 2^16 x 288 B, N=4096, t 24-bit (BASELINE configs[1])"),
+    "cfg1": (4096, 64, 1, 4096, 20, "d=1, 4096 x 64 B, N=4096 (BASELINE configs[0])"),
+    "cfg4": (1 << 22, 256, 2, 4096, 20, "d=2, 2^22 x 256 B, N=4096 (BASELINE configs[3] database)"),
+    "cfg3": (1 << 20, 1024, 2, 8192, 20, "d=2, 2^20 x 1 KiB, N=8192 (BASELINE configs[2] database)"),
+}
+
+
+def make_params(name):
+    import pir_b200 as pb
+    items, size, d, n, bits, _ = WORKLOADS[name]
+    return pb.CreatePIRParameters(items, size, d, pb.GenerateEncryptionParams(n, bits))
+
+
+def random_limbs(rng, moduli, shape_prefix, N):
+    """uniform [*shape_prefix][len(moduli)][N] with limb j < moduli[j]"""
+    cols = [rng.integers(0, int(q), size=tuple(shape_prefix) + (N,), dtype=np.uint64) for q in moduli]
+    return np.ascontiguousarray(np.stack(cols, axis=len(shape_prefix)))
+
+
+def synth_inputs(params, n_queries, seed):
+    ep = params.encryption_parameters
+    N, mods = ep.poly_modulus_degree, ep.coeff_modulus
+    k = len(mods) - 1
+    rng = np.random.default_rng(seed)
+    n_ct = sum(params.dimensions) // N + 1
+    queries = random_limbs(rng, mods[:k], (n_queries, n_ct, 2), N)                 # [Q][n_ct][2][k][N]
+    elts = [(N >> i) + 1 for i in range(N.bit_length() - 1)]
+    keys = random_limbs(rng, mods, (len(elts), k, 2), N)                           # [n][k][2][k+1][N]
+    return queries, elts, keys
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# =====================================================================================================
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference's path on all host threads (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import binding as ob
+    params = make_params(args.workload)
+    ep = params.encryption_parameters
+    N, mods = ep.poly_modulus_degree, ep.coeff_modulus
+    k = len(mods) - 1
+    cores = os.cpu_count() or 1
+    orc = ob.Oracle(N, mods, ep.plain_modulus)
+    rng = np.random.default_rng(1234)
+    # bounded sample of the workload when the database is large: keep the first rows (whole rows of the hypercube)
+    max_pt = min(params.num_pt, max(params.dimensions[-1], (2 << 30) // (k * N * 8)))
+    dims = list(params.dimensions)
+    sample = "full workload"
+    if max_pt < params.num_pt:
+        rows = max(1, max_pt // dims[-1])
+        max_pt = rows * dims[-1]
+        sample = "first %d of %d rows of the database (expansion in full); scaled to the full scan by rows" % (
+            rows, -(-params.num_pt // dims[-1]))
+    db = random_limbs(rng, mods[:k], (max_pt,), N)
+    queries, elts, keys = synth_inputs(params, cores, 99)
+    keys = keys.reshape(-1)
+
+    def one(i):
+        return orc.process_query(db, dims, elts, keys, queries[i % len(queries)])
+
+    pool = ThreadPoolExecutor(cores)
+    t_one0 = time.perf_counter(); one(0); t_one = time.perf_counter() - t_one0
+    steps = args.steps
+    # bound the whole run to a few minutes
+    while steps > 1 and (steps + args.warmup) * t_one * 1.3 > 240:
+        steps -= 1
+    for _ in range(max(1, min(args.warmup, 2))):
+        list(pool.map(one, range(cores)))
+    lat = []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s0 = time.perf_counter()
+        list(pool.map(one, range(cores)))
+        lat.append(time.perf_counter() - s0)
+    total = time.perf_counter() - t0
+    qps = cores * steps / total
+    line = {
+        "impl": "reference", "metric": "pir_queries_per_sec", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][5], "queries_per_step": cores, "num_pt": params.num_pt,
+                   "dims": dims},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": sample + "; %d concurrent queries per step, one per thread" % cores,
+                         "single_query_latency_ms": 1e3 * t_one},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference path (SEAL 3.5.6 algorithms; SEAL itself is not buildable offline)",
+    }
+    print(json.dumps(line))
+
+
+# =====================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import pir_b200 as pb
+    from pir_b200 import _lib, sharded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus must equal WORLD_SIZE")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    params = make_params(args.workload)
+    ep = params.encryption_parameters
+    N, mods = ep.poly_modulus_degree, ep.coeff_modulus
+    k = len(mods) - 1
+    ctL = 2 * k * N
+    srv = sharded.ShardServer(params, device=local_rank, shard_index=rank, shard_count=world)
+    srv.db.fill_random(2024)
+    ql = args.queries_per_gpu
+    queries, elts, keys = synth_inputs(params, world * ql, 99)
+    gk = pb.GaloisKeys(elts, keys.reshape(-1))
+    srv.set_keys(gk)
+    n_ct = queries.shape[1]
+    q_local = queries[rank * ql:(rank + 1) * ql]
+    d_q = sharded.to_device(q_local, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_dev():
+        if world == 1:
+            return srv.answer(d_q)
+        return srv.answer_batch_distributed(d_q)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ----------------
+    for _ in range(max(3, args.warmup)):
+        flush.zero_()
+        step_dev()
+    srv.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_acc = {}
+    launches = 0
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations, outside the per-step events
+        ev[i][0].record()
+        out = step_dev()
+        ev[i][1].record()
+        ev[i][1].synchronize()
+        launches += srv.launch_count()
+        for nm, v in srv.stage_ms().items():
+            stage_acc.setdefault(nm, []).append(v)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    srv.set_profiling(False)
+    qps = world * ql * args.steps / (total_ms / 1e3)
+
+    # ---------------- end to end through the reference-facing call, host buffers ----------------
+    q_pin = torch.empty(q_local.shape, dtype=torch.int64).pin_memory()
+    q_pin.copy_(torch.from_numpy(q_local.view(np.int64)))
+    out_pin = torch.empty((ql, srv.ctx.reply_cts, 2, k, N), dtype=torch.int64).pin_memory()
+    q_np = q_pin.numpy().view(np.uint64)
+    out_np = out_pin.numpy().view(np.uint64)
+    if world == 1:
+        server = pb.PIRServer(srv.db, params)
+        req = pb.Request([q_np[i] for i in range(ql)], gk)
+
+        def step_e2e():
+            server.ProcessRequest(req, out=out_np)  # H2D + kernels + D2H + sync inside pirb_answer
+    else:
+        def step_e2e():
+            d = q_pin.to(dev, non_blocking=True)
+            r = srv.answer_batch_distributed(d)
+            out_pin.copy_(r, non_blocking=True)
+            torch.cuda.synchronize()
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    lat = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s0 = time.perf_counter()
+        step_e2e()
+        lat.append(time.perf_counter() - s0)
+    barrier()
+    e2e_total = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_qps = world * ql * args.steps / float(e2e_total.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the scan kernel (HBM-bound) ----------------
+    peak, peak_src = measured_peak()
+    scan_ms = statistics.mean(stage_acc["scan"])
+    nq_scan = ql if world == 1 else world * ql
+    scan_bytes = srv.scan_bytes(nq_scan)
+    achieved = scan_bytes / (scan_ms * 1e-3) / 1e9
+    stage_mean = {nm: statistics.mean(v) for nm, v in stage_acc.items()}
+
+    # ---------------- CPU baseline: the oracle port on one host core, bounded sample ----------------
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as ob
+        orc = ob.Oracle(N, mods, ep.plain_modulus)
+        db_host = srv.db.read_ntt(0, params.num_pt) if params.num_pt * k * N * 8 <= (4 << 30) else None
+        if db_host is not None:
+            t0 = time.perf_counter()
+            want = orc.process_query(db_host, params.dimensions, elts, keys.reshape(-1), q_local[0])
+            t_one = time.perf_counter() - t0
+            n_more = int(max(0, min(8, 15.0 / max(t_one, 1e-3) - 1)))
+            ts = [t_one]
+            for _ in range(n_more):
+                t0 = time.perf_counter()
+                orc.process_query(db_host, params.dimensions, elts, keys.reshape(-1), q_local[0])
+                ts.append(time.perf_counter() - t0)
+            med = statistics.median(ts)
+            got = sharded.to_host(step_dev())[0]
+            parity = bool(np.array_equal(got, want))
+            cpu = {"value": 1.0 / med, "unit": "queries/s", "cores": 1, "kind": "port",
+                   "sample": "%d full queries of this workload on one host thread (median); reply compared limb-for-limb "
+                             "with the GPU reply: %s" % (len(ts), "identical" if parity else "MISMATCH"),
+                   "p50_latency_ms": 1e3 * med, "host_cpus": os.cpu_count()}
+
+    line = {
+        "metric": "pir_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][5], "queries_per_step": world * ql, "num_pt": params.num_pt,
+                   "dims": list(params.dimensions), "key_switches_per_query": sum(
+                       int(pb.next_power_two(min(N, max(0, sum(params.dimensions) - t * N)))) - 1 for t in range(n_ct)),
+                   "reply_cts": srv.ctx.reply_cts, "parallelism": "rows sharded x%d, expansion split by query" % world,
+                   "l2": "256 MiB buffer written between timed iterations (outside the per-step CUDA events)",
+                   "galois_keys": "resident in HBM, uploaded once per client"},
+        "p50_latency_ms": statistics.median(step_ms),
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(world * ql * n_ct * ctL * 8),
+                "d2h_bytes_per_step": int(world * ql * srv.ctx.reply_cts * ctL * 8),
+                "p50_latency_ms": 1e3 * statistics.median(lat)},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": args.scan_traffic, "peak_source": peak_src,
+                     "bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms,
+                     "share_of_step": scan_ms / stage_mean["total"]},
+        "stages_ms": stage_mean,
+        "cpu_baseline": cpu,
+        "parity_vs_oracle": parity,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--queries-per-gpu", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scan-traffic", type=float, default=None,
+                    help="dram bytes per scan launch from the committed ncu capture (profiles/), if known")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

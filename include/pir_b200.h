@@ -114,6 +114,15 @@ int pirb_answer_dev(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* d_quer
                     uint64_t n_ct, uint64_t* d_replies, void* stream);
 int pirb_answer_partial_dev(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries,
                             uint64_t n_ct, uint64_t* d_partial, void* stream);
+/* The two halves of pirb_answer_partial_dev, for batches whose expansion is split by query across ranks:
+ * pirb_expand_ntt_dev: oblivious expansion (server.cpp:148-171) + the selection-vector NTT (database.cpp:190,222)
+ *   -> d_sv_ntt[n_queries][dim_sum][2][k][N];
+ * pirb_multiply_partial_dev: scan + re-encode + upper dimensions of this shard's rows for NTT-form selection
+ *   vectors (own and all-gathered ones) -> d_partial[n_queries][reply_cts][2][k][N], NTT form. */
+int pirb_expand_ntt_dev(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries,
+                        uint64_t n_ct, uint64_t* d_sv_ntt, void* stream);
+int pirb_multiply_partial_dev(pirb_ctx* ctx, const uint64_t* d_sv_ntt, uint32_t n_queries, uint64_t* d_partial,
+                              void* stream);
 int pirb_reduce_finish_dev(pirb_ctx* ctx, const uint64_t* d_partials, uint32_t n_parts, uint64_t part_stride_limbs,
                            uint32_t n_queries, uint64_t* d_replies, void* stream);
 int pirb_reduce_finish_peers_dev(pirb_ctx* ctx, const uint64_t* const* d_peer_ptrs, uint32_t n_parts,

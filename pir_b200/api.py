@@ -413,21 +413,31 @@ class PIRServer:
                 old.close()
         return self._key_cache[1]
 
-    def ProcessRequest(self, request: Request) -> Response:
-        """server.cpp:44-65: every query of the request, in order, with the request's Galois keys."""
+    def ProcessRequest(self, request: Request, out: np.ndarray = None) -> Response:
+        """server.cpp:44-65: every query of the request, in order, with the request's Galois keys.
+        `out` (optional, extension): caller-provided [n_queries][reply_cts][2][k][N] uint64 buffer (e.g. pinned)."""
         keys = self._keys(request.galois_keys)
         resp = Response()
         if not request.query:
             return resp
+        n_q = len(request.query)
         n_ct = request.query[0].size // self.ctx.ct_limbs
         same = all(q.size // self.ctx.ct_limbs == n_ct for q in request.query)
         if not same or n_ct != self.ctx.query_cts:
             raise PIRStatusError(INVALID_ARGUMENT,
                                  "Number of ciphertexts doesn't match number of items for oblivious expansion.")
-        q = _u64(np.stack([np.asarray(x).reshape(n_ct, 2, self.ctx.k, self.ctx.N) for x in request.query]))
-        out = np.zeros((len(request.query), self.ctx.reply_cts, 2, self.ctx.k, self.ctx.N), dtype=np.uint64)
-        _check(_lib.lib().pirb_answer(self.ctx.h, keys.h, _ptr(q), len(request.query), n_ct, _ptr(out)))
-        resp.reply = [out[i] for i in range(out.shape[0])]
+        if n_q == 1:
+            q = _u64(request.query[0])  # no copy when already contiguous uint64
+        else:
+            q = _u64(np.stack([np.asarray(x).reshape(n_ct, 2, self.ctx.k, self.ctx.N) for x in request.query]))
+        shape = (n_q, self.ctx.reply_cts, 2, self.ctx.k, self.ctx.N)
+        if out is None:
+            out = np.empty(shape, dtype=np.uint64)
+        elif out.dtype != np.uint64 or out.size != int(np.prod(shape)) or not out.flags["C_CONTIGUOUS"]:
+            raise PIRStatusError(INVALID_ARGUMENT, "bad output buffer")
+        _check(_lib.lib().pirb_answer(self.ctx.h, keys.h, _ptr(q), n_q, n_ct, _ptr(out)))
+        out = out.reshape(shape)
+        resp.reply = [out[i] for i in range(n_q)]
         return resp
 
     def substitute_power_x_inplace(self, ct: np.ndarray, power: int, gal_keys: GaloisKeys):

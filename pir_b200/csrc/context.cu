@@ -217,12 +217,14 @@ int choose_split(u64 base_ctas, u32 len, int sm_count) {
 // DatabaseMultiplier::multiply on the device.  d_sv: [n_queries] x (sv_qstride limbs apart) x [dim_sum][2][k][N]
 // coefficient form; transformed to NTT form in place.  d_out: [n_queries][reply_cts][2][k][N]; coefficient form,
 // or (partial != 0) the NTT-form sum over this shard's rows, to be reduced across shards.
-int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_out, int partial, cudaStream_t st) {
+int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_out, int partial, cudaStream_t st,
+                 bool sv_is_ntt = false) {
   const int d = c->d, k = c->k;
   const u64 ctL = c->ctL;
   const DevParams& P = c->P;
   if (c->profiling) cudaEventRecord(c->ev[1], st);
-  LAUNCH(c, launch_ntt_fwd(P, d_sv, d_sv, (int)(c->dim_sum * 2 * k), k, 0, n_queries, sv_qstride, sv_qstride, st));
+  if (!sv_is_ntt)
+    LAUNCH(c, launch_ntt_fwd(P, d_sv, d_sv, (int)(c->dim_sum * 2 * k), k, 0, n_queries, sv_qstride, sv_qstride, st));
   if (c->profiling) cudaEventRecord(c->ev[2], st);
 
   const u64 out_cts = c->reply_cts;
@@ -688,6 +690,37 @@ int pirb_answer_partial_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* 
   if (!c || !d_queries || !d_partial) return fail(PIRB_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(c->device));
   return run_answer(c, keys, U(d_queries), n_queries, n_ct, U(d_partial), 1, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int pirb_expand_ntt_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries,
+                        uint64_t n_ct, uint64_t* d_sv_ntt, void* stream) {
+  if (!c || !d_queries || !d_sv_ntt) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (!n_queries) return 0;
+  if (n_ct != c->dim_sum / c->N + 1)
+    return fail(PIRB_INVALID_ARGUMENT, "Number of ciphertexts doesn't match number of items for oblivious expansion.");
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  int rc;
+  ExpandPlan* pl = get_plan(c, c->dim_sum, 0, &rc);
+  if (!pl) return rc;
+  c->launches = 0;
+  if (c->profiling) cudaEventRecord(c->ev[0], st);
+  RC(run_expand(c, keys, pl, U(d_queries), (int)n_queries, st));
+  LAUNCH(c, launch_ntt_fwd(c->P, c->work.p, U(d_sv_ntt), (int)(c->dim_sum * 2 * c->k), c->k, 0, (int)n_queries,
+                           2 * pl->cap * c->ctL, c->dim_sum * c->ctL, st));
+  return 0;
+}
+
+int pirb_multiply_partial_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_queries, uint64_t* d_partial,
+                              void* stream) {
+  if (!c || !d_sv_ntt || !d_partial) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (!n_queries) return 0;
+  if (c->loaded != c->pt_count) return fail(PIRB_INVALID_ARGUMENT, "database size mismatch");
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const int rc = run_multiply(c, const_cast<u64*>(U(d_sv_ntt)), c->dim_sum * c->ctL, (int)n_queries, U(d_partial), 1, st, true);
+  c->ev_valid = c->profiling && rc == 0;
+  return rc;
 }
 
 int pirb_reduce_finish_dev(pirb_ctx* c, const uint64_t* d_partials, uint32_t n_parts, uint64_t part_stride,

@@ -92,6 +92,25 @@ class ShardServer:
         self._exit()
         return out
 
+    def expand_ntt(self, d_queries: torch.Tensor) -> torch.Tensor:
+        """Expansion + selection-vector NTT: [Q][n_ct][2][k][N] -> [Q][dim_sum][2][k][N] (NTT form)."""
+        Q, n_ct = d_queries.shape[0], d_queries.shape[1]
+        out = self._empty(Q, self.ctx.dim_sum, 2, self.k, self.N)
+        st = self._enter()
+        _check(_lib.lib().pirb_expand_ntt_dev(self.ctx.h, self.keys.h if self.keys else None, _dp(d_queries), Q, n_ct,
+                                              _dp(out), st))
+        self._exit()
+        return out
+
+    def multiply_partial(self, d_sv_ntt: torch.Tensor) -> torch.Tensor:
+        """NTT-form selection vectors [Q][dim_sum][2][k][N] -> this shard's NTT-form partial replies."""
+        Q = d_sv_ntt.shape[0]
+        out = self._empty(Q, self.ctx.reply_cts, 2, self.k, self.N)
+        st = self._enter()
+        _check(_lib.lib().pirb_multiply_partial_dev(self.ctx.h, _dp(d_sv_ntt), Q, _dp(out), st))
+        self._exit()
+        return out
+
     def reduce_finish(self, gathered: torch.Tensor, n_queries: int) -> torch.Tensor:
         """gathered [G][Q][reply_cts][2][k][N] partials -> mod-q add + inverse NTT -> final replies."""
         G = gathered.shape[0]
@@ -121,6 +140,30 @@ class ShardServer:
         gathered = self._empty(world, *part.shape)
         dist.all_gather_into_tensor(gathered, part)
         return self.reduce_finish(gathered, d_queries.shape[0])
+
+    def answer_batch_distributed(self, d_queries_local: torch.Tensor) -> torch.Tensor:
+        """Batch path: every rank expands only ITS queries, the NTT-form selection vectors are
+        all-gathered, every rank multiplies ALL queries against its row shard, the partial replies are all-gathered
+        and each rank finishes (mod-q add + inverse NTT) its own queries.  Returns this rank's replies."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ql = d_queries_local.shape[0]
+        sv_local = self.expand_ntt(d_queries_local)
+        if world == 1:
+            part = self.multiply_partial(sv_local)
+            return self.reduce_finish(part[None], ql)
+        sv_all = self._empty(world * ql, *sv_local.shape[1:])
+        dist.all_gather_into_tensor(sv_all, sv_local)
+        part = self.multiply_partial(sv_all)                     # [world*ql][reply_cts]...
+        gathered = self._empty(world, *part.shape)
+        dist.all_gather_into_tensor(gathered, part)
+        own = gathered[:, rank * ql:(rank + 1) * ql]             # view: [world][ql][reply_cts]...
+        out = self._empty(ql, self.ctx.reply_cts, 2, self.k, self.N)
+        st = self._enter()
+        _check(_lib.lib().pirb_reduce_finish_dev(self.ctx.h, C.c_void_p(own.data_ptr()), world, gathered[0].numel(),
+                                                 ql, _dp(out), st))
+        self._exit()
+        return out
 
     def scan(self, d_sv_ntt: torch.Tensor, want_rows=True):
         """[Q][dimL][2][k][N] NTT-form last-dimension selection cts -> rows [Q][n_rows][2][k][N] NTT form."""
