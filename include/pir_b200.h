@@ -137,6 +137,8 @@ int pirb_sync(pirb_ctx* ctx);
 #define PIRB_N_STAGES 6
 int pirb_set_profiling(pirb_ctx* ctx, int enabled);
 int pirb_get_stage_ms(pirb_ctx* ctx, float* out_ms /*[PIRB_N_STAGES]*/);
+/* device time of the scan kernel of the last profiled pirb_scan_dev / pirb_answer* call */
+int pirb_last_scan_ms(pirb_ctx* ctx, float* out_ms);
 /* kernels launched by the last pirb_answer* call, and algorithmic scan bytes of one scan launch. */
 uint64_t pirb_last_launch_count(const pirb_ctx* ctx);
 uint64_t pirb_scan_bytes(const pirb_ctx* ctx, uint32_t n_queries);

@@ -72,6 +72,7 @@ SYMBOLS = {
     "pirb_sync": (C.c_int, [C.c_void_p]),
     "pirb_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "pirb_get_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "pirb_last_scan_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pirb_last_launch_count": (C.c_uint64, [C.c_void_p]),
     "pirb_scan_bytes": (C.c_uint64, [C.c_void_p, C.c_uint32]),
     "pirb_calculate_dimensions": (None, [C.c_uint32, C.c_uint32, u32p]),

@@ -432,6 +432,20 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
       }
     }
   P.two_er = (int)e;
+  int max_bits = 0;
+  for (u32 i = 0; i < prm->n_moduli; ++i) max_bits = std::max(max_bits, 64 - __builtin_clzll(prm->coeff_modulus[i]));
+  P.half_bits = (max_bits + 1) / 2;
+  if (max_bits <= 44) {
+    P.mac_mode = 2;  // Karatsuba middle term < 2^(2h+2): chains of 2^(53-2h-2) terms stay below 2^53
+    P.mac_max_terms = 1u << std::min(14, 51 - 2 * P.half_bits);
+  } else if (max_bits <= 48) {
+    P.mac_mode = 1;
+    P.half_bits = 24;
+    P.mac_max_terms = 1u << 14;
+  } else {
+    P.mac_mode = 0;
+    P.mac_max_terms = 1u << 30;
+  }
   c->two_er = e;
   for (int i = 1; i < c->d; ++i) c->reply_cts *= e;
 
@@ -762,8 +776,10 @@ int pirb_scan_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_queries, uin
     RC(c->part.ensure((size_t)n_queries * n_split * n_rows * c->ctL * sizeof(u64)));
     dst = c->part.p;
   }
+  if (c->profiling) cudaEventRecord(c->ev[2], st);
   LAUNCH(c, launch_scan(c->P, c->db.p, c->pt_count, dimL, n_rows, U(d_sv_ntt), (u64)dimL * c->ctL, (int)n_queries, n_split,
                         dst, st));
+  if (c->profiling) cudaEventRecord(c->ev[3], st);
   if (d_rows && n_split != 1) {
     for (u32 qi = 0; qi < n_queries; ++qi)
       LAUNCH(c, launch_modadd_reduce(c->P, c->part.p + (u64)qi * n_split * n_rows * c->ctL, (u64)n_rows * c->ctL,
@@ -792,6 +808,14 @@ int pirb_get_stage_ms(pirb_ctx* c, float* out) {
   CU(cudaEventSynchronize(c->ev[5]));
   for (int i = 0; i < 5; ++i) CU(cudaEventElapsedTime(out + i, c->ev[i], c->ev[i + 1]));
   CU(cudaEventElapsedTime(out + 5, c->ev[0], c->ev[5]));
+  return 0;
+}
+int pirb_last_scan_ms(pirb_ctx* c, float* out) {
+  if (!c || !out) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  if (!c->profiling) return fail(PIRB_INVALID_ARGUMENT, "profiling is off");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->ev[3]));
+  CU(cudaEventElapsedTime(out, c->ev[2], c->ev[3]));
   return 0;
 }
 uint64_t pirb_last_launch_count(const pirb_ctx* c) { return c ? c->launches : 0; }

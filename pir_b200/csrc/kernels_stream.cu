@@ -4,6 +4,9 @@
 //   k_ks_combine      mod-down of the key switch + SealPIR expansion butterfly (server.cpp:123-141)
 //   k_mul_inv_pow_x   negacyclic shift (server.cpp:78-103)
 //   k_modadd_reduce   mod-q sum of per-GPU partial replies
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "pirb_device.cuh"
 
@@ -25,7 +28,7 @@ __device__ __forceinline__ ulonglong2 ldg128_stream(const u64* p) {
 constexpr int SCAN_NT = 128;
 constexpr int SCAN_LIMBS = 2 * SCAN_NT;
 
-template <int R>
+template <int R, int U, int MODE>
 __global__ void __launch_bounds__(SCAN_NT)
 k_scan(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
        const u64* __restrict__ sv, u64 sv_qstride, int n_split, u64* __restrict__ part) {
@@ -38,30 +41,43 @@ k_scan(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_
   const u32 i_lo = split * per;
   const u32 i_hi = min(dimL, i_lo + per);
 
-  u64 alo[R][2][2], ahi[R][2][2];
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int c = 0; c < 2; ++c) alo[r][c][0] = alo[r][c][1] = ahi[r][c][0] = ahi[r][c][1] = 0;
-
-  const u64* svq = sv + qi * sv_qstride + limb;
+  Acc<MODE> acc[R][2][2];
+  const int hb = P.half_bits;
   const u64 ctL = 2ull * kN;
-#pragma unroll 2
-  for (u32 i1 = i_lo; i1 < i_hi; ++i1) {
-    const ulonglong2 s0 = ldg128(svq + i1 * ctL);
-    const ulonglong2 s1 = ldg128(svq + i1 * ctL + kN);
-    ulonglong2 d[R];
+  const u64* svq = sv + qi * sv_qstride + limb;
+  // per-row database pointers and the number of valid plaintexts in each row (short last row, database.cpp:183)
+  const u64* dbr[R];
+  u32 cnt[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const u64 p = (u64)(row0 + r) * dimL + i1;
-      d[r] = (row0 + r < n_rows && p < num_pt) ? ldg128_stream(db + p * kN + limb) : make_ulonglong2(0, 0);
+  for (int r = 0; r < R; ++r) {
+    const u64 first = (u64)(row0 + r) * dimL;
+    dbr[r] = db + first * kN + limb;
+    cnt[r] = (row0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
+  }
+#pragma unroll 1
+  for (u32 i1 = i_lo; i1 < i_hi; i1 += U) {
+    ulonglong2 s0[U], s1[U], d[U][R];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const u32 i = i1 + u;
+      const bool in = i < i_hi;
+      s0[u] = in ? ldg128(svq + i * ctL) : make_ulonglong2(0, 0);
+      s1[u] = in ? ldg128(svq + i * ctL + kN) : make_ulonglong2(0, 0);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        d[u][r] = (in && i < cnt[r]) ? ldg128_stream(dbr[r] + (u64)i * kN) : make_ulonglong2(0, 0);
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      mac128(alo[r][0][0], ahi[r][0][0], s0.x, d[r].x);
-      mac128(alo[r][0][1], ahi[r][0][1], s0.y, d[r].y);
-      mac128(alo[r][1][0], ahi[r][1][0], s1.x, d[r].x);
-      mac128(alo[r][1][1], ahi[r][1][1], s1.y, d[r].y);
+    for (int u = 0; u < U; ++u) {
+      const Opnd<MODE> a0x(s0[u].x, hb), a0y(s0[u].y, hb), a1x(s1[u].x, hb), a1y(s1[u].y, hb);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const Opnd<MODE> bx(d[u][r].x, hb), by(d[u][r].y, hb);
+        acc[r][0][0].mac(a0x, bx);
+        acc[r][0][1].mac(a0y, by);
+        acc[r][1][0].mac(a1x, bx);
+        acc[r][1][1].mac(a1y, by);
+      }
     }
   }
 #pragma unroll
@@ -71,25 +87,207 @@ k_scan(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       ulonglong2 v;
-      v.x = barrett128(alo[r][c][0], ahi[r][c][0], m.q, m.ratio_hi, m.ratio_lo);
-      v.y = barrett128(alo[r][c][1], ahi[r][c][1], m.q, m.ratio_hi, m.ratio_lo);
+      v.x = acc[r][c][0].reduce(m, hb);
+      v.y = acc[r][c][1].reduce(m, hb);
       *reinterpret_cast<ulonglong2*>(o + (u64)c * kN) = v;
     }
   }
 }
 
-static int scan_rows_per_cta(u32 n_rows) { return n_rows >= 4 * 148 ? 4 : (n_rows >= 2 ? 2 : 1); }
+// ---------------------------------------------------------------------------------------------
+// scan, TMA variant: the same arithmetic, but database and selection-vector tiles are moved global->shared by the
+// bulk-copy engine (cp.async.bulk, completion on an mbarrier) through a STAGES-deep ring, issued by one producer
+// lane; four consumer warps read the tiles from shared memory and keep the accumulators in registers.  Bytes in
+// flight per SM are set by the ring depth instead of by registers.
+//   grid (slice of 256 limbs, row tile of R rows, qi*n_split + split); 160 threads = 1 producer warp + 128 consumers
+// ---------------------------------------------------------------------------------------------
+constexpr int TMA_L = 256;              // limbs per tile (2 KiB)
+constexpr int TMA_CONSUMERS = 128;
+constexpr int TMA_NT = TMA_CONSUMERS + 32;
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar, u64 policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+// G consumer groups of 128 threads share the selection-vector tiles of a stage; group g owns rows g*RG .. g*RG+RG-1
+// of the CTA's R = G*RG rows, so L2->SM traffic per database byte is (R + 2) / R.
+template <int RG, int G, int STAGES, int MODE>
+__global__ void __launch_bounds__(32 + TMA_CONSUMERS * G)
+k_scan_tma(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
+           const u64* __restrict__ sv, u64 sv_qstride, int n_split, u64* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int R = RG * G;
+  constexpr u32 TILE_BYTES = TMA_L * sizeof(u64);
+  constexpr u32 STAGE_BYTES = (R + 2) * TILE_BYTES;
+  u64* tiles = reinterpret_cast<u64*>(smem_raw);
+  u64* full = reinterpret_cast<u64*>(smem_raw + (size_t)STAGES * STAGE_BYTES);
+  u64* empty = full + STAGES;
+
+  const u32 kN = (u32)P.k * P.N;
+  const u64 ctL = 2ull * kN;
+  const u32 limb0 = blockIdx.x * TMA_L;
+  const u32 row0 = blockIdx.y * R;
+  const u32 split = blockIdx.z % n_split, qi = blockIdx.z / n_split;
+  const u32 per = (dimL + n_split - 1) / n_split;
+  const u32 i_lo = split * per;
+  const u32 i_hi = min(dimL, i_lo + per);
+  const int warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, G * TMA_CONSUMERS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    if (threadIdx.x == 0) {
+      u32 cnt[R];  // valid plaintexts per row (short last row; rows past the end)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const u64 first = (u64)(row0 + r) * dimL;
+        cnt[r] = (row0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
+      }
+      u64 pol_stream, pol_keep;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      const u64* svq = sv + qi * sv_qstride + limb0;
+      u32 stage = 0, phase = 0;
+      for (u32 i = i_lo; i < i_hi; ++i) {
+        mbar_wait(empty + stage, phase ^ 1);
+        u64* dst = tiles + (size_t)stage * (R + 2) * TMA_L;
+        u32 nvalid = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) nvalid += (i < cnt[r]);
+        mbar_expect_tx(full + stage, (2 + nvalid) * TILE_BYTES);
+        bulk_g2s(dst, svq + i * ctL, TILE_BYTES, full + stage, pol_keep);
+        bulk_g2s(dst + TMA_L, svq + i * ctL + kN, TILE_BYTES, full + stage, pol_keep);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (i < cnt[r])
+            bulk_g2s(dst + (2 + r) * TMA_L, db + ((u64)(row0 + r) * dimL + i) * kN + limb0, TILE_BYTES, full + stage,
+                     pol_stream);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+  // ---------------- consumers ----------------
+  const int ct = threadIdx.x - 32;
+  const int g = ct / TMA_CONSUMERS, t = ct % TMA_CONSUMERS;
+  const u32 grow0 = row0 + g * RG;
+  u32 cnt[RG];
+#pragma unroll
+  for (int r = 0; r < RG; ++r) {
+    const u64 first = (u64)(grow0 + r) * dimL;
+    cnt[r] = (grow0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
+  }
+  const ModC& m = P.m[limb0 / P.N];
+  Acc<MODE> acc[RG][2][2];
+  const int hb = P.half_bits;
+  u32 stage = 0, phase = 0;
+#pragma unroll 1
+  for (u32 i = i_lo; i < i_hi; ++i) {
+    mbar_wait(full + stage, phase);
+    const u64* src = tiles + (size_t)stage * (R + 2) * TMA_L + 2 * t;
+    const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(src);
+    const ulonglong2 s1 = *reinterpret_cast<const ulonglong2*>(src + TMA_L);
+    ulonglong2 d[RG];
+#pragma unroll
+    for (int r = 0; r < RG; ++r)
+      d[r] = (i < cnt[r]) ? *reinterpret_cast<const ulonglong2*>(src + (2 + g * RG + r) * TMA_L) : make_ulonglong2(0, 0);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty + stage);  // tile values are in registers: free the slot
+    const Opnd<MODE> a0x(s0.x, hb), a0y(s0.y, hb), a1x(s1.x, hb), a1y(s1.y, hb);
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+      const Opnd<MODE> bx(d[r].x, hb), by(d[r].y, hb);
+      acc[r][0][0].mac(a0x, bx);
+      acc[r][0][1].mac(a0y, by);
+      acc[r][1][0].mac(a1x, bx);
+      acc[r][1][1].mac(a1y, by);
+    }
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  }
+#pragma unroll
+  for (int r = 0; r < RG; ++r) {
+    if (grow0 + r >= n_rows) break;
+    u64* o = part + (((u64)qi * n_split + split) * n_rows + grow0 + r) * ctL + limb0 + 2 * t;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      ulonglong2 v;
+      v.x = acc[r][c][0].reduce(m, hb);
+      v.y = acc[r][c][1].reduce(m, hb);
+      *reinterpret_cast<ulonglong2*>(o + (u64)c * kN) = v;
+    }
+  }
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// tuning knobs (overridable through the environment for sweeps): rows per CTA, unroll, generic MAC
+static int scan_mode() { return env_int("PIRB_SCAN_MODE", 0); }  // 0 = LDG kernel (default), 1 = TMA bulk-copy ring
+static int scan_groups(int R) {  // consumer groups per CTA of the TMA kernel
+  int g = R >= 8 ? 4 : (R >= 4 ? 2 : 1);
+  g = env_int("PIRB_SCAN_G", g);
+  return (g >= 1 && R % g == 0) ? g : 1;
+}
+static void scan_pick(const DevParams& P, u32 n_rows, int* R, int* U, int* mode) {
+  // measured on B200 (tools/bench_scan.py, profiles/): 2 rows x unroll 2 with the FP64 MAC is the fastest LDG shape
+  int r = n_rows >= 2 ? 2 : 1;
+  int u = r == 2 ? 2 : 4;
+  if (scan_mode() == 1) u = 8;  // U = ring depth for the TMA kernel
+  r = env_int("PIRB_SCAN_R", r);
+  u = env_int("PIRB_SCAN_U", u);
+  *R = r; *U = u;
+  *mode = std::min(P.mac_mode, env_int("PIRB_MAC_MODE", 2));
+}
 
 void scan_config(const DevParams& P, u32 dimL, u32 n_rows, int n_queries, int sm_count, int* n_split) {
-  // enough CTAs for ~8 resident per SM; split the i1 loop when the row count alone cannot provide them
+  // enough CTAs for several resident per SM; split the i1 loop when the row count alone cannot provide them
+  int R, U, mode;
+  scan_pick(P, n_rows, &R, &U, &mode);
   const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
-  const int R = scan_rows_per_cta(n_rows);
   const u64 base = (u64)slices * ((n_rows + R - 1) / R) * n_queries;
-  const u64 want = (u64)sm_count * 8;
+  const u64 want = (u64)sm_count * env_int("PIRB_SCAN_CTAS_PER_SM", 8);
   int s = 1;
   if (base < want) s = (int)((want + base - 1) / base);
   const int max_split = (int)((dimL + 7) / 8);  // keep at least 8 database tiles per CTA
   if (s > max_split) s = max_split;
+  // exact lazy accumulation chains have a maximum length (pirb_device.cuh)
+  const u32 max_terms = mode >= MAC_FP64 ? P.mac_max_terms : (mode == MAC_INT24 ? PIRB_SMALL_MAX_TERMS : (1u << 30));
+  const int min_split = (int)((dimL + max_terms - 1) / max_terms);
+  if (s < min_split) s = min_split;
+  s = env_int("PIRB_SCAN_SPLIT", s);
   if (s < 1) s = 1;
   *n_split = s;
 }
@@ -97,16 +295,55 @@ void scan_config(const DevParams& P, u32 dimL, u32 n_rows, int n_queries, int sm
 cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL, u32 n_rows, const u64* sv,
                         u64 sv_qstride, int n_queries, int n_split, u64* part, cudaStream_t st) {
   if (!n_rows || !n_queries) return cudaSuccess;
+  int R, U, mode;
+  scan_pick(P, n_rows, &R, &U, &mode);
+  {
+    const u32 chain = (dimL + n_split - 1) / n_split;
+    if (mode >= MAC_FP64 && chain > P.mac_max_terms) mode = P.mac_mode >= 1 && P.half_bits <= 24 ? MAC_INT24 : MAC_WIDE;
+    if (mode == MAC_INT24 && chain > PIRB_SMALL_MAX_TERMS) mode = MAC_WIDE;
+  }
   const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
-  const int R = scan_rows_per_cta(n_rows);
   dim3 grid(slices, (n_rows + R - 1) / R, n_queries * n_split);
   if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidConfiguration;
-  switch (R) {
-    case 4: k_scan<4><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); break;
-    case 2: k_scan<2><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); break;
-    default: k_scan<1><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); break;
+  if (scan_mode() == 1) {
+    const int G = scan_groups(R);
+    const int RG = R / G;
+#define TMA_LAUNCH(RGG, GG, SS, MM)                                                                                \
+  if (mode == MM) {                                                                                                \
+    cudaError_t e = cudaFuncSetAttribute(k_scan_tma<RGG, GG, SS, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                \
+    k_scan_tma<RGG, GG, SS, MM><<<grid, 32 + TMA_CONSUMERS * GG, smem, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
+    return cudaGetLastError();                                                                                     \
   }
-  return cudaGetLastError();
+#define TMA_CASE(RGG, GG, SS)                                                                                      \
+  if (RG == RGG && G == GG && U == SS) {                                                                           \
+    const size_t smem = (size_t)SS * (RGG * GG + 2) * TMA_L * sizeof(u64) + 2 * SS * sizeof(u64);                    \
+    TMA_LAUNCH(RGG, GG, SS, MAC_WIDE) TMA_LAUNCH(RGG, GG, SS, MAC_INT24) TMA_LAUNCH(RGG, GG, SS, MAC_FP64)          \
+    return cudaErrorInvalidValue;                                                                                  \
+  }
+    TMA_CASE(1, 1, 8)
+    TMA_CASE(2, 1, 8)
+    TMA_CASE(4, 1, 8)
+    TMA_CASE(1, 2, 8) TMA_CASE(2, 2, 6) TMA_CASE(2, 2, 8)
+    TMA_CASE(1, 4, 8) TMA_CASE(2, 4, 4) TMA_CASE(2, 4, 6) TMA_CASE(2, 4, 8)
+    TMA_CASE(4, 2, 6)
+#undef TMA_CASE
+#undef TMA_LAUNCH
+    return cudaErrorInvalidValue;
+  }
+#define SCAN_CASE(RR, UU)                                                                                          \
+  if (R == RR && U == UU) {                                                                                        \
+    if (mode == MAC_FP64) k_scan<RR, UU, MAC_FP64><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
+    else if (mode == MAC_INT24) k_scan<RR, UU, MAC_INT24><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
+    else k_scan<RR, UU, MAC_WIDE><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part);      \
+    return cudaGetLastError();                                                                                     \
+  }
+  SCAN_CASE(1, 1) SCAN_CASE(1, 2) SCAN_CASE(1, 4)
+  SCAN_CASE(2, 1) SCAN_CASE(2, 2) SCAN_CASE(2, 4)
+  SCAN_CASE(4, 1) SCAN_CASE(4, 2)
+  SCAN_CASE(8, 1)
+#undef SCAN_CASE
+  return cudaErrorInvalidValue;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -35,6 +35,9 @@ struct DevParams {
   u64 inv_P_s[PIRB_MAX_MODULI];     // Shoup companion
   u64 half_P_mod[PIRB_MAX_MODULI];  // (P>>1) mod q_j
   int two_er;                       // 2 * ExpansionRatio
+  int mac_mode;                     // lazy MAC flavour the moduli allow: 0 wide (any), 1 int24 (< 2^48), 2 fp64 (<= 44 bit)
+  int half_bits;                    // h: operand split position for the fp64 MAC (ceil(max modulus bits / 2))
+  u32 mac_max_terms;                // longest exact accumulation chain for mac_mode
   u8 re_poly[PIRB_MAX_REENC];       // re-encode chunk e -> source poly (0/1)
   u8 re_mod[PIRB_MAX_REENC];        //                  -> source modulus j
   u8 re_shift[PIRB_MAX_REENC];      //                  -> right shift

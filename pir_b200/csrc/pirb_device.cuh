@@ -34,6 +34,96 @@ __device__ __forceinline__ void mac128(u64& lo, u64& hi, u64 a, u64 b) {
   asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(lo), "+l"(hi) : "l"(pl), "l"(ph));
 }
 
+__device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, u64 q, u64 r_hi, u64 r_lo);
+
+// ------------------------------------------------------------------------------------------
+// Lazy multiply-accumulate chains  sum_i a_i*b_i  (mod q taken once at the end).
+//   MAC_WIDE : any 64-bit operands, one 128-bit accumulator (64x64->128 products with carries).
+//   MAC_INT24: operands below 2^48 split into 24-bit halves, Karatsuba: three carry-free 64-bit partial sums,
+//              3 IMAD.WIDE.U32 per product, <= 2^14 terms per chain.
+//   MAC_FP64 : operands below 2^44 (all BFVDefault primes up to N=8192) split into h<=22-bit halves held as
+//              doubles; 3 DFMA per product on the FP64 pipe, <= 2^(51-2h) terms per chain.
+// All three are exact, so the reduced result is identical.
+// ------------------------------------------------------------------------------------------
+constexpr u32 PIRB_SMALL_MAX_TERMS = 1u << 14;
+enum { MAC_WIDE = 0, MAC_INT24 = 1, MAC_FP64 = 2 };
+
+template <int MODE>
+struct Opnd;
+template <int MODE>
+struct Acc;
+
+// ---- MAC_WIDE: any 64-bit operands, 128-bit accumulator ----
+template <>
+struct Opnd<MAC_WIDE> {
+  u64 v;
+  __device__ __forceinline__ Opnd(u64 x, int) : v(x) {}
+};
+template <>
+struct Acc<MAC_WIDE> {
+  u64 lo = 0, hi = 0;
+  __device__ __forceinline__ void mac(const Opnd<MAC_WIDE>& a, const Opnd<MAC_WIDE>& b) { mac128(lo, hi, a.v, b.v); }
+  __device__ __forceinline__ u64 reduce(const ModC& m, int) const {
+    return barrett128(lo, hi, m.q, m.ratio_hi, m.ratio_lo);
+  }
+};
+
+// value = s0 + s1*2^h + s2*2^(2h) (s1 = sk - s0 - s2: Karatsuba cross terms) reduced mod q
+__device__ __forceinline__ u64 karatsuba_reduce(u64 s0, u64 sk, u64 s2, int h, const ModC& m) {
+  const u64 s1 = sk - s0 - s2;
+  u64 lo = s0, hi = 0;
+  u64 t = s1 << h;
+  lo += t;
+  hi += (s1 >> (64 - h)) + (lo < t);
+  t = s2 << (2 * h);
+  lo += t;
+  hi += (s2 >> (64 - 2 * h)) + (lo < t);
+  return barrett128(lo, hi, m.q, m.ratio_hi, m.ratio_lo);
+}
+
+// ---- MAC_INT24: operands < 2^48 split at bit 24; three 64-bit partial sums on the integer pipe ----
+template <>
+struct Opnd<MAC_INT24> {
+  u32 lo, hi, sum;
+  __device__ __forceinline__ Opnd(u64 x, int) : lo((u32)x & 0xFFFFFFu), hi((u32)(x >> 24)) { sum = lo + hi; }
+};
+template <>
+struct Acc<MAC_INT24> {
+  u64 s0 = 0, sk = 0, s2 = 0;
+  __device__ __forceinline__ void mac(const Opnd<MAC_INT24>& a, const Opnd<MAC_INT24>& b) {
+    s0 += (u64)a.lo * b.lo;
+    sk += (u64)a.sum * b.sum;
+    s2 += (u64)a.hi * b.hi;
+  }
+  __device__ __forceinline__ u64 reduce(const ModC& m, int) const { return karatsuba_reduce(s0, sk, s2, 24, m); }
+};
+
+// ---- MAC_FP64: operands < 2^(2h) with h <= 22 split at bit h; the three partial sums live in doubles and every
+// product-accumulate is one DFMA on the FP64 pipe.  All values are integers below 2^53, so the arithmetic is exact.
+__device__ __forceinline__ double u32_to_double_exact(u32 v) {
+  return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;  // (2^52 + v) - 2^52
+}
+template <>
+struct Opnd<MAC_FP64> {
+  double lo, hi, sum;
+  __device__ __forceinline__ Opnd(u64 x, int h)
+      : lo(u32_to_double_exact((u32)x & ((1u << h) - 1))), hi(u32_to_double_exact((u32)(x >> h))) {
+    sum = lo + hi;
+  }
+};
+template <>
+struct Acc<MAC_FP64> {
+  double s0 = 0.0, sk = 0.0, s2 = 0.0;
+  __device__ __forceinline__ void mac(const Opnd<MAC_FP64>& a, const Opnd<MAC_FP64>& b) {
+    s0 = fma(a.lo, b.lo, s0);
+    sk = fma(a.sum, b.sum, sk);
+    s2 = fma(a.hi, b.hi, s2);
+  }
+  __device__ __forceinline__ u64 reduce(const ModC& m, int h) const {
+    return karatsuba_reduce(__double2ull_rz(s0), __double2ull_rz(sk), __double2ull_rz(s2), h, m);
+  }
+};
+
 // 128-bit -> [0,q) with ratio = floor(2^128/q)
 __device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, u64 q, u64 r_hi, u64 r_lo) {
   u64 carry = __umul64hi(lo, r_lo);

@@ -54,6 +54,11 @@ class ShardServer:
         _check(_lib.lib().pirb_get_stage_ms(self.ctx.h, out))
         return dict(zip(_lib.STAGE_NAMES, [float(x) for x in out]))
 
+    def last_scan_ms(self):
+        out = C.c_float(0)
+        _check(_lib.lib().pirb_last_scan_ms(self.ctx.h, C.byref(out)))
+        return float(out.value)
+
     def launch_count(self):
         return int(_lib.lib().pirb_last_launch_count(self.ctx.h))
 
