@@ -7,6 +7,7 @@
 //   -> CiphertextReencoder::Encode (ct_reencoder.cpp:40-71)
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -104,6 +105,7 @@ struct pirb_ctx {
   bool ev_valid = false;
   u64 launches = 0;
   int scan_split = 1;
+  bool use_cluster = false;  // one-launch-per-level key switch on thread-block clusters
 };
 
 namespace {
@@ -198,9 +200,13 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
     L.q_stride = q_stride;
     L.n_queries = n_queries;
     const int n_nodes = (n_queries * L.n_trees) << j;
-    LAUNCH(c, launch_ks_digits(c->P, c->work.p, L, c->dig.p, st));
-    LAUNCH(c, launch_ks_mac_intt(c->P, c->dig.p, key, c->acc.p, n_nodes, st));
-    LAUNCH(c, launch_ks_combine(c->P, c->work.p, L, c->acc.p, 0, st));
+    if (c->use_cluster) {
+      LAUNCH(c, launch_ks_level_cluster(c->P, c->work.p, L, key, 0, st));
+    } else {
+      LAUNCH(c, launch_ks_digits(c->P, c->work.p, L, c->dig.p, st));
+      LAUNCH(c, launch_ks_mac_intt(c->P, c->dig.p, key, c->acc.p, n_nodes, st));
+      LAUNCH(c, launch_ks_combine(c->P, c->work.p, L, c->acc.p, 0, st));
+    }
   }
   return 0;
 }
@@ -434,6 +440,7 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   P.two_er = (int)e;
   int max_bits = 0;
   for (u32 i = 0; i < prm->n_moduli; ++i) max_bits = std::max(max_bits, 64 - __builtin_clzll(prm->coeff_modulus[i]));
+  P.lazy_ntt = (max_bits <= 62 - logn - 1) ? 1 : 0;
   P.half_bits = (max_bits + 1) / 2;
   if (max_bits <= 44) {
     P.mac_mode = 2;  // Karatsuba middle term < 2^(2h+2): chains of 2^(53-2h-2) terms stay below 2^53
@@ -460,6 +467,10 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   c->pt_count = hi - lo;
   RC(c->db.ensure(std::max<size_t>(c->pt_count * c->ptL * sizeof(u64), 256)));
 
+  {
+    const char* e = getenv("PIRB_KS_CLUSTER");
+    c->use_cluster = ks_cluster_supported(c->P) && !(e && *e == '0');
+  }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
   *out = c.release();
@@ -585,9 +596,13 @@ int pirb_substitute(pirb_ctx* c, const pirb_keys* keys, uint64_t* ct, uint32_t p
   L.ginv = inv_mod_2n(power, c->N);
   L.q_stride = 0;
   L.n_queries = 1;
-  LAUNCH(c, launch_ks_digits(c->P, c->work.p, L, c->dig.p, st));
-  LAUNCH(c, launch_ks_mac_intt(c->P, c->dig.p, key, c->acc.p, 1, st));
-  LAUNCH(c, launch_ks_combine(c->P, c->work.p, L, c->acc.p, 1, st));
+  if (c->use_cluster) {
+    LAUNCH(c, launch_ks_level_cluster(c->P, c->work.p, L, key, 1, st));
+  } else {
+    LAUNCH(c, launch_ks_digits(c->P, c->work.p, L, c->dig.p, st));
+    LAUNCH(c, launch_ks_mac_intt(c->P, c->dig.p, key, c->acc.p, 1, st));
+    LAUNCH(c, launch_ks_combine(c->P, c->work.p, L, c->acc.p, 1, st));
+  }
   CU(cudaMemcpyAsync(ct, c->work.p + c->ctL, c->ctL * sizeof(u64), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return 0;

@@ -38,6 +38,12 @@ cudaError_t launch_ks_mac_intt(const DevParams& P, const u64* dig, const u64* ke
 cudaError_t launch_ks_combine(const DevParams& P, u64* work, const LevelArgs& L, const u64* acc, int mode,
                               cudaStream_t st);
 
+// all three steps in one launch: a thread-block cluster of 2(k+1) CTAs per node, digits and accumulators stay in
+// (distributed) shared memory (kernels_cluster.cu)
+bool ks_cluster_supported(const DevParams& P);
+cudaError_t launch_ks_level_cluster(const DevParams& P, u64* work, const LevelArgs& L, const u64* key, int mode,
+                                    cudaStream_t st);
+
 // ct * x^{-kpow}  (server.cpp:78-103)
 cudaError_t launch_mul_inv_pow_x(const DevParams& P, const u64* in, u64* out, u32 kpow, int n_cts, cudaStream_t st);
 

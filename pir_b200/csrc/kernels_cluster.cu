@@ -1,0 +1,190 @@
+// kernels_cluster.cu — one expansion level (Galois automorphism + key switch + SealPIR butterfly) in ONE launch.
+//
+// Reference: server.cpp:123-141 per tree node; Evaluator::apply_galois_inplace -> switch_key_inplace.
+// A thread-block cluster of 2(k+1) CTAs owns one node.  CTA rank r works on key-level modulus I = r/2 and key
+// component c = r%2:
+//   phase 1  the pair (I,0),(I,1) splits the k RNS digits: sigma_g(c1) digit J (J%2 == c) is re-reduced mod m_I and
+//            forward-transformed in shared memory;
+//   phase 2  acc[c][I] = sum_J dig[I][J] (.) key[J][c][I]  — own digits from local shared memory, the partner's through
+//            distributed shared memory — then the inverse transform, all without leaving the SM;
+//   phase 3  CTAs with I < k mod-down their polynomial by P (reading acc[c][P] from the (k,c) CTA's shared memory), add
+//            sigma_g(c0) and write the even/odd children of the node.
+// Compared with the three-kernel path (k_ks_digits, k_ks_mac_intt, k_ks_combine) the digit and accumulator
+// polynomials never touch global memory and a tree level costs one launch instead of three.
+#include <cooperative_groups.h>
+
+#include <type_traits>
+
+#include "kernels.cuh"
+#include "pirb_device.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace pirb {
+
+template <int LOGN>
+struct CCfg {
+  static constexpr int N = 1 << LOGN;
+  static constexpr int NT = (N / 8 < 512) ? N / 8 : 512;
+};
+
+__device__ __forceinline__ u64 mod_down_c(u64 a, u64 last, const DevParams& P, int j, u64 Pq) {
+  const ModC& m = P.m[j];
+  u64 l = last + P.half_P;
+  l = l >= Pq ? l - Pq : l;
+  u64 r = submod(barrett64(l, m.q, m.ratio_hi), P.half_P_mod[j], m.q);
+  return shoup(submod(a, r, m.q), P.inv_P[j], P.inv_P_s[j], m.q);
+}
+
+template <int LOGN, bool LAZY, int MODE>
+__global__ void __launch_bounds__(CCfg<LOGN>::NT, 1)
+k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, const LevelArgs L,
+                   const u64* __restrict__ key, int mode) {
+  constexpr int N = CCfg<LOGN>::N, NT = CCfg<LOGN>::NT;
+  extern __shared__ u64 smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const int k = P.k;
+  const int csize = 2 * (k + 1);
+  const unsigned rank = cluster.block_rank();
+  const int I = rank >> 1, c = rank & 1;
+  const u32 z = blockIdx.x / csize;  // node
+  const u32 kk = z & ((1u << L.j) - 1);
+  const u32 tq = z >> L.j;
+  const u32 ti = tq % L.n_trees, qi = tq / L.n_trees;
+  const u64 ctL = (u64)2 * k * N;
+  const u64* src = work + qi * L.q_stride + L.src_off[ti] + kk * ctL;
+  const ModC& mI = P.m[I];
+  const int nd = (k + 1) / 2;  // digit buffers per CTA
+  u64* A = smem + (size_t)nd * N;
+
+  // ---- phase 1: my digits ----
+  for (int J = c; J < k; J += 2) {
+    u64* D = smem + (size_t)(J >> 1) * N;
+    const u64* c1 = src + (u64)(k + J) * N;
+    const u64 qJ = P.m[J].q;
+    const bool need_reduce = qJ > mI.q;
+#pragma unroll
+    for (int i = tid; i < N; i += NT) {
+      u64 v = galois_gather(c1, i, L.ginv, N, qJ);
+      if (need_reduce) v = barrett64(v, mI.q, mI.ratio_hi);
+      D[swz(i)] = v;
+    }
+    __syncthreads();
+    ntt_forward_smem_t<LOGN, NT, LAZY>(D, mI, tid);
+#pragma unroll
+    for (int i = tid; i < N; i += NT) D[swz(i)] = canon_fwd(D[swz(i)], mI, LAZY);
+  }
+  cluster.sync();
+
+  // ---- phase 2: MAC with the key, inverse transform ----
+  {
+    const u64* peer = cluster.map_shared_rank(smem, rank ^ 1);
+    const int hb = P.half_bits;
+#pragma unroll
+    for (int i = tid; i < N; i += NT) {
+      Acc<MODE> acc;
+      const int si = swz(i);
+      for (int J = 0; J < k; ++J) {
+        const u64* buf = ((J & 1) == c) ? smem : peer;
+        const u64 dv = buf[(size_t)(J >> 1) * N + si];
+        const u64 kv = __ldg(key + ((u64)(J * 2 + c) * (k + 1) + I) * N + i);
+        acc.mac(Opnd<MODE>(dv, hb), Opnd<MODE>(kv, hb));
+      }
+      A[si] = acc.reduce(mI, hb);
+    }
+    __syncthreads();
+    ntt_inverse_smem_t<LOGN, NT, LAZY>(A, mI, tid);
+#pragma unroll
+    for (int i = tid; i < N; i += NT) A[swz(i)] = inv_finish(A[swz(i)], mI);
+  }
+  cluster.sync();
+
+  // ---- phase 3: mod-down by P, add sigma_g(c0), expansion butterfly ----
+  if (I < k) {
+    const int j = I;
+    const u64 q = mI.q, Pq = P.m[k].q;
+    const u64* lastA = cluster.map_shared_rank(A, 2 * k + c);
+    u64* dstE = work + qi * L.q_stride + L.dst_off[ti] + kk * ctL;
+    const u64* sp = src + (u64)(c * k + j) * N;
+    const u32 s1 = (2 * N - (1u << L.j)) & (2 * N - 1);
+#pragma unroll
+    for (int i = tid; i < N; i += NT) {
+      const int si = swz(i);
+      u64 c0 = mod_down_c(A[si], lastA[si], P, j, Pq);
+      if (c == 0) c0 = addmod(galois_gather(sp, i, L.ginv, N, q), c0, q);
+      if (mode == 1) {
+        dstE[(u64)(c * k + j) * N + i] = c0;
+      } else {
+        const u64 p = sp[i];
+        dstE[(u64)(c * k + j) * N + i] = addmod(p, c0, q);
+        const u32 r = i + s1;
+        u64 d = submod(p, c0, q);
+        if (r & N) d = negmod(d, q);
+        (dstE + ((u64)ctL << L.j))[(u64)(c * k + j) * N + (r & (N - 1))] = d;
+      }
+    }
+  }
+  cluster.sync();  // keep shared memory alive until every peer has finished reading it
+}
+
+bool ks_cluster_supported(const DevParams& P) {
+  const int k = P.k;
+  const size_t smem = (size_t)((k + 1) / 2 + 1) * P.N * sizeof(u64);
+  return 2 * (k + 1) <= 16 && smem <= 227 * 1024 && P.logn >= 11 && P.logn <= 14;
+}
+
+cudaError_t launch_ks_level_cluster(const DevParams& P, u64* work, const LevelArgs& L, const u64* key, int mode,
+                                    cudaStream_t st) {
+  const unsigned nodes = (unsigned)L.n_queries * L.n_trees << L.j;
+  if (!nodes) return cudaSuccess;
+  const int k = P.k;
+  const unsigned csize = 2 * (k + 1);
+  const size_t smem = (size_t)((k + 1) / 2 + 1) * P.N * sizeof(u64);
+  auto go = [&](auto ln, auto lz, auto mm) -> cudaError_t {
+    constexpr int LN = decltype(ln)::value;
+    constexpr bool LZ = decltype(lz)::value;
+    constexpr int MM = decltype(mm)::value;
+    auto kern = k_ks_level_cluster<LN, LZ, MM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (csize > 8) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nodes * csize);
+    cfg.blockDim = dim3(CCfg<LN>::NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, P, work, L, key, mode);
+  };
+  auto by_mode = [&](auto ln, auto lz) -> cudaError_t {
+    switch (P.mac_mode) {
+      case MAC_FP64: return go(ln, lz, std::integral_constant<int, MAC_FP64>{});
+      case MAC_INT24: return go(ln, lz, std::integral_constant<int, MAC_INT24>{});
+      default: return go(ln, lz, std::integral_constant<int, MAC_WIDE>{});
+    }
+  };
+#define PIRB_CASE(LN)                                                                             \
+  case LN:                                                                                        \
+    return P.lazy_ntt ? by_mode(std::integral_constant<int, LN>{}, std::true_type{})              \
+                      : by_mode(std::integral_constant<int, LN>{}, std::false_type{});
+  switch (P.logn) {
+    PIRB_CASE(11)
+    PIRB_CASE(12)
+    PIRB_CASE(13)
+    PIRB_CASE(14)
+    default: return cudaErrorInvalidValue;
+  }
+#undef PIRB_CASE
+}
+
+}  // namespace pirb

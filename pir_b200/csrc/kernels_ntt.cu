@@ -5,6 +5,8 @@
 //   k_reencode_ntt            CiphertextReencoder::Encode + plaintext NTT (ct_reencoder.cpp:40-71, database.cpp:217-228)
 // One CTA owns one size-N transform; the polynomial lives in (swizzled) shared memory between
 // a fused load-side transform and a fused store-side transform.
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "pirb_device.cuh"
 
@@ -15,11 +17,12 @@ struct Cfg {
   static constexpr int N = 1 << LOGN;
   static constexpr int NT = (N / 8 < 512) ? N / 8 : 512;
   static constexpr size_t SMEM = sizeof(u64) * N;
+  static constexpr int MINB = LOGN <= 13 ? 2 : 1;  // resident CTAs per SM the register budget must allow
 };
 
 // ---------------------------------------------------------------------------------------------
-template <int LOGN>
-__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+template <int LOGN, bool LAZY>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_ntt_fwd(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* __restrict__ out, int cycle, int off,
           u64 in_bstride, u64 out_bstride) {
   constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
@@ -32,13 +35,13 @@ k_ntt_fwd(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* 
 #pragma unroll
   for (int i = tid; i < N; i += NT) s[swz(i)] = src[i];
   __syncthreads();
-  ntt_forward_smem<LOGN, NT>(s, m, tid);
+  ntt_forward_smem_t<LOGN, NT, LAZY>(s, m, tid);
 #pragma unroll
-  for (int i = tid; i < N; i += NT) dst[i] = canon4(s[swz(i)], m.q);
+  for (int i = tid; i < N; i += NT) dst[i] = canon_fwd(s[swz(i)], m, LAZY);
 }
 
-template <int LOGN>
-__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+template <int LOGN, bool LAZY>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_ntt_inv(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* __restrict__ out, int cycle, int off,
           int n_parts, u64 part_stride, u64 in_bstride, u64 out_bstride) {
   constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
@@ -55,14 +58,14 @@ k_ntt_inv(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* 
     s[swz(i)] = v;
   }
   __syncthreads();
-  ntt_inverse_smem<LOGN, NT>(s, m, tid);
+  ntt_inverse_smem_t<LOGN, NT, LAZY>(s, m, tid);
 #pragma unroll
   for (int i = tid; i < N; i += NT) dst[i] = inv_finish(s[swz(i)], m);
 }
 
 // plaintext coefficient c (< t) -> c >= (t+1)/2 ? c + (q_j - t) : c   (SURVEY A.7), then NTT mod q_j
-template <int LOGN>
-__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+template <int LOGN, bool LAZY>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_db_preprocess(const __grid_constant__ DevParams P, const u64* __restrict__ coeffs, u64* __restrict__ out) {
   constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
   extern __shared__ u64 s[];
@@ -79,14 +82,14 @@ k_db_preprocess(const __grid_constant__ DevParams P, const u64* __restrict__ coe
     s[swz(i)] = c >= P.thr ? c + inc : c;
   }
   __syncthreads();
-  ntt_forward_smem<LOGN, NT>(s, m, tid);
+  ntt_forward_smem_t<LOGN, NT, LAZY>(s, m, tid);
 #pragma unroll
-  for (int i = tid; i < N; i += NT) dst[i] = canon4(s[swz(i)], m.q);
+  for (int i = tid; i < N; i += NT) dst[i] = canon_fwd(s[swz(i)], m, LAZY);
 }
 
 // grid (z = node, I = key-level modulus, J = RNS digit)
-template <int LOGN>
-__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+template <int LOGN, bool LAZY>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_ks_digits(const __grid_constant__ DevParams P, const u64* __restrict__ work, const LevelArgs L,
             u64* __restrict__ dig) {
   constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
@@ -110,15 +113,15 @@ k_ks_digits(const __grid_constant__ DevParams P, const u64* __restrict__ work, c
     s[swz(i)] = v;
   }
   __syncthreads();
-  ntt_forward_smem<LOGN, NT>(s, mI, tid);
+  ntt_forward_smem_t<LOGN, NT, LAZY>(s, mI, tid);
   u64* dst = dig + (((u64)z * (k + 1) + I) * k + J) * N;
 #pragma unroll
-  for (int i = tid; i < N; i += NT) dst[i] = canon4(s[swz(i)], mI.q);
+  for (int i = tid; i < N; i += NT) dst[i] = canon_fwd(s[swz(i)], mI, LAZY);
 }
 
 // grid (z = node, I, c = key component)
-template <int LOGN>
-__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+template <int LOGN, bool LAZY>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_ks_mac_intt(const __grid_constant__ DevParams P, const u64* __restrict__ dig, const u64* __restrict__ key,
               u64* __restrict__ acc) {
   constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
@@ -139,15 +142,15 @@ k_ks_mac_intt(const __grid_constant__ DevParams P, const u64* __restrict__ dig, 
     s[swz(i)] = barrett128(lo, hi, mI.q, mI.ratio_hi, mI.ratio_lo);
   }
   __syncthreads();
-  ntt_inverse_smem<LOGN, NT>(s, mI, tid);
+  ntt_inverse_smem_t<LOGN, NT, LAZY>(s, mI, tid);
   u64* dst = acc + (((u64)z * 2 + c) * (k + 1) + I) * N;
 #pragma unroll
   for (int i = tid; i < N; i += NT) dst[i] = inv_finish(s[swz(i)], mI);
 }
 
 // grid (x = ciphertext, e = chunk, j' = target data modulus)
-template <int LOGN>
-__global__ void __launch_bounds__(Cfg<LOGN>::NT)
+template <int LOGN, bool LAZY>
+__global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_reencode_ntt(const __grid_constant__ DevParams P, const u64* __restrict__ cts, u64* __restrict__ pts) {
   constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
   extern __shared__ u64 s[];
@@ -166,14 +169,14 @@ k_reencode_ntt(const __grid_constant__ DevParams P, const u64* __restrict__ cts,
     s[swz(i)] = c >= P.thr ? c + inc : c;
   }
   __syncthreads();
-  ntt_forward_smem<LOGN, NT>(s, m, tid);
+  ntt_forward_smem_t<LOGN, NT, LAZY>(s, m, tid);
   u64* dst = pts + ((x * P.two_er + e) * k + jp) * N;
 #pragma unroll
-  for (int i = tid; i < N; i += NT) dst[i] = canon4(s[swz(i)], m.q);
+  for (int i = tid; i < N; i += NT) dst[i] = canon_fwd(s[swz(i)], m, LAZY);
 }
 
 // ---------------------------------------------------------------------------------------------
-// host-side dispatch on log2(N)
+// host-side dispatch on log2(N) and on the lazy-butterfly flag
 // ---------------------------------------------------------------------------------------------
 template <typename K>
 static cudaError_t ensure_smem(K kernel, size_t bytes) {
@@ -181,85 +184,104 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
   return cudaSuccess;
 }
 
-#define PIRB_DISPATCH_LOGN(logn, CALL) \
-  switch (logn) {                      \
-    case 11: { CALL(11); } break;      \
-    case 12: { CALL(12); } break;      \
-    case 13: { CALL(13); } break;      \
-    case 14: { CALL(14); } break;      \
-    default: return cudaErrorInvalidValue; \
+template <int V>
+using IntC = std::integral_constant<int, V>;
+
+template <typename F>
+static cudaError_t dispatch(const DevParams& P, F&& f) {
+#define PIRB_CASE(LN) \
+  case LN: return P.lazy_ntt ? f(IntC<LN>{}, std::true_type{}) : f(IntC<LN>{}, std::false_type{});
+  switch (P.logn) {
+    PIRB_CASE(11)
+    PIRB_CASE(12)
+    PIRB_CASE(13)
+    PIRB_CASE(14)
+    default: return cudaErrorInvalidValue;
   }
+#undef PIRB_CASE
+}
 
 cudaError_t launch_ntt_fwd(const DevParams& P, const u64* in, u64* out, int n_polys, int cycle, int off, int n_batch,
                            u64 in_bstride, u64 out_bstride, cudaStream_t st) {
   if (n_polys <= 0 || n_batch <= 0) return cudaSuccess;
-#define CALL(LN)                                                                                         \
-  cudaError_t e = ensure_smem(k_ntt_fwd<LN>, Cfg<LN>::SMEM);                                              \
-  if (e != cudaSuccess) return e;                                                                        \
-  k_ntt_fwd<LN><<<dim3(n_polys, n_batch), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, in, out, cycle, off, in_bstride, \
-                                                                             out_bstride);
-  PIRB_DISPATCH_LOGN(P.logn, CALL)
-#undef CALL
-  return cudaGetLastError();
+  return dispatch(P, [&](auto ln, auto lz) {
+    constexpr int LN = decltype(ln)::value;
+    constexpr bool LZ = decltype(lz)::value;
+    auto kern = k_ntt_fwd<LN, LZ>;
+    cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3(n_polys, n_batch), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, in, out, cycle, off, in_bstride, out_bstride);
+    return cudaGetLastError();
+  });
 }
 
 cudaError_t launch_ntt_inv(const DevParams& P, const u64* in, u64* out, int n_polys, int cycle, int off, int n_parts,
                            u64 part_stride, int n_batch, u64 in_bstride, u64 out_bstride, cudaStream_t st) {
   if (n_polys <= 0 || n_batch <= 0) return cudaSuccess;
-#define CALL(LN)                                                                                         \
-  cudaError_t e = ensure_smem(k_ntt_inv<LN>, Cfg<LN>::SMEM);                                              \
-  if (e != cudaSuccess) return e;                                                                        \
-  k_ntt_inv<LN><<<dim3(n_polys, n_batch), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, in, out, cycle, off, n_parts,    \
-                                                                             part_stride, in_bstride, out_bstride);
-  PIRB_DISPATCH_LOGN(P.logn, CALL)
-#undef CALL
-  return cudaGetLastError();
+  return dispatch(P, [&](auto ln, auto lz) {
+    constexpr int LN = decltype(ln)::value;
+    constexpr bool LZ = decltype(lz)::value;
+    auto kern = k_ntt_inv<LN, LZ>;
+    cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3(n_polys, n_batch), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, in, out, cycle, off, n_parts, part_stride,
+                                                                     in_bstride, out_bstride);
+    return cudaGetLastError();
+  });
 }
 
 cudaError_t launch_db_preprocess(const DevParams& P, const u64* coeffs, u64* out, u64 n_pt, cudaStream_t st) {
   if (!n_pt) return cudaSuccess;
-#define CALL(LN)                                                                                   \
-  cudaError_t e = ensure_smem(k_db_preprocess<LN>, Cfg<LN>::SMEM);                                  \
-  if (e != cudaSuccess) return e;                                                                  \
-  k_db_preprocess<LN><<<dim3((unsigned)n_pt, P.k), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, coeffs, out);
-  PIRB_DISPATCH_LOGN(P.logn, CALL)
-#undef CALL
-  return cudaGetLastError();
+  return dispatch(P, [&](auto ln, auto lz) {
+    constexpr int LN = decltype(ln)::value;
+    constexpr bool LZ = decltype(lz)::value;
+    auto kern = k_db_preprocess<LN, LZ>;
+    cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3((unsigned)n_pt, P.k), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, coeffs, out);
+    return cudaGetLastError();
+  });
 }
 
 cudaError_t launch_ks_digits(const DevParams& P, const u64* work, const LevelArgs& L, u64* dig, cudaStream_t st) {
   const unsigned nodes = (unsigned)L.n_queries * L.n_trees << L.j;
   if (!nodes) return cudaSuccess;
-#define CALL(LN)                                                                                   \
-  cudaError_t e = ensure_smem(k_ks_digits<LN>, Cfg<LN>::SMEM);                                      \
-  if (e != cudaSuccess) return e;                                                                  \
-  k_ks_digits<LN><<<dim3(nodes, P.k + 1, P.k), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, work, L, dig);
-  PIRB_DISPATCH_LOGN(P.logn, CALL)
-#undef CALL
-  return cudaGetLastError();
+  return dispatch(P, [&](auto ln, auto lz) {
+    constexpr int LN = decltype(ln)::value;
+    constexpr bool LZ = decltype(lz)::value;
+    auto kern = k_ks_digits<LN, LZ>;
+    cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3(nodes, P.k + 1, P.k), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, work, L, dig);
+    return cudaGetLastError();
+  });
 }
 
 cudaError_t launch_ks_mac_intt(const DevParams& P, const u64* dig, const u64* key, u64* acc, int n_nodes,
                                cudaStream_t st) {
   if (n_nodes <= 0) return cudaSuccess;
-#define CALL(LN)                                                                                   \
-  cudaError_t e = ensure_smem(k_ks_mac_intt<LN>, Cfg<LN>::SMEM);                                    \
-  if (e != cudaSuccess) return e;                                                                  \
-  k_ks_mac_intt<LN><<<dim3(n_nodes, P.k + 1, 2), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, dig, key, acc);
-  PIRB_DISPATCH_LOGN(P.logn, CALL)
-#undef CALL
-  return cudaGetLastError();
+  return dispatch(P, [&](auto ln, auto lz) {
+    constexpr int LN = decltype(ln)::value;
+    constexpr bool LZ = decltype(lz)::value;
+    auto kern = k_ks_mac_intt<LN, LZ>;
+    cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3(n_nodes, P.k + 1, 2), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, dig, key, acc);
+    return cudaGetLastError();
+  });
 }
 
 cudaError_t launch_reencode_ntt(const DevParams& P, const u64* cts, u64* pts, int n_cts, cudaStream_t st) {
   if (n_cts <= 0) return cudaSuccess;
-#define CALL(LN)                                                                                   \
-  cudaError_t e = ensure_smem(k_reencode_ntt<LN>, Cfg<LN>::SMEM);                                   \
-  if (e != cudaSuccess) return e;                                                                  \
-  k_reencode_ntt<LN><<<dim3(n_cts, P.two_er, P.k), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, cts, pts);
-  PIRB_DISPATCH_LOGN(P.logn, CALL)
-#undef CALL
-  return cudaGetLastError();
+  return dispatch(P, [&](auto ln, auto lz) {
+    constexpr int LN = decltype(ln)::value;
+    constexpr bool LZ = decltype(lz)::value;
+    auto kern = k_reencode_ntt<LN, LZ>;
+    cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3(n_cts, P.two_er, P.k), Cfg<LN>::NT, Cfg<LN>::SMEM, st>>>(P, cts, pts);
+    return cudaGetLastError();
+  });
 }
 
 }  // namespace pirb

@@ -35,6 +35,7 @@ struct DevParams {
   u64 inv_P_s[PIRB_MAX_MODULI];     // Shoup companion
   u64 half_P_mod[PIRB_MAX_MODULI];  // (P>>1) mod q_j
   int two_er;                       // 2 * ExpansionRatio
+  int lazy_ntt;                     // 1 if every modulus is below 2^(62 - log2 N): fully lazy butterflies
   int mac_mode;                     // lazy MAC flavour the moduli allow: 0 wide (any), 1 int24 (< 2^48), 2 fp64 (<= 44 bit)
   int half_bits;                    // h: operand split position for the fp64 MAC (ceil(max modulus bits / 2))
   u32 mac_max_terms;                // longest exact accumulation chain for mac_mode

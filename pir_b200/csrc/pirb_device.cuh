@@ -154,7 +154,9 @@ __device__ __forceinline__ int swz(int i) { return i ^ (((i >> 4) & 7) | (((i >>
 
 // One pass = R consecutive radix-2 stages done in registers on units of 2^R elements.
 // Forward (Cooley-Tukey, SEAL ordering): stage s has m=2^s blocks, gap N>>(s+1), twiddle rp[m+block].
-template <int LOGN, int NT, int S0, int R>
+// LAZY (all moduli < 2^58): no per-stage correction at all.  Shoup's lazy product is < 2q for ANY 64-bit input, so
+// only the additive path grows, by 2q per stage: after log2(N) stages values are < (4 + 2 log2 N) q <= 32 q < 2^64.
+template <int LOGN, int NT, int S0, int R, bool LAZY>
 __device__ __forceinline__ void ntt_fwd_pass(u64* __restrict__ s, const u64* __restrict__ rp,
                                              const u64* __restrict__ rps, u64 q, int tid) {
   constexpr int N = 1 << LOGN;
@@ -172,8 +174,6 @@ __device__ __forceinline__ void ntt_fwd_pass(u64* __restrict__ s, const u64* __r
     for (int e = 0; e < E; ++e) x[e] = s[swz(base + e * TL)];
 #pragma unroll
     for (int a = 0; a < R; ++a) {
-      constexpr int dummy = 0;
-      (void)dummy;
       const int half = E >> (a + 1);
       const int mbase = (1 << (S0 + a)) + (hi << a);
 #pragma unroll
@@ -184,7 +184,7 @@ __device__ __forceinline__ void ntt_fwd_pass(u64* __restrict__ s, const u64* __r
         for (int c = 0; c < half; ++c) {
           const int e0 = b * 2 * half + c, e1 = e0 + half;
           u64 X = x[e0];
-          X = X >= two_q ? X - two_q : X;
+          if (!LAZY) X = X >= two_q ? X - two_q : X;
           const u64 T = shoup_lazy(x[e1], w, ws, q);
           x[e0] = X + T;
           x[e1] = X + two_q - T;
@@ -197,7 +197,9 @@ __device__ __forceinline__ void ntt_fwd_pass(u64* __restrict__ s, const u64* __r
 }
 
 // Inverse (Gentleman-Sande): same unit geometry, stages visited from the smallest gap up.
-template <int LOGN, int NT, int S0, int R>
+// LAZY (all moduli < 2^(62 - log2 N)): sums are never corrected; the bound doubles per stage (B_p = 2^p * 2q for the
+// p-th processed stage) and the difference uses X + B_p - Y.  The final N^{-1} Shoup product accepts any 64-bit value.
+template <int LOGN, int NT, int S0, int R, bool LAZY>
 __device__ __forceinline__ void ntt_inv_pass(u64* __restrict__ s, const u64* __restrict__ irp,
                                              const u64* __restrict__ irps, u64 q, int tid) {
   constexpr int N = 1 << LOGN;
@@ -226,8 +228,8 @@ __device__ __forceinline__ void ntt_inv_pass(u64* __restrict__ s, const u64* __r
           const int e0 = b * 2 * half + c, e1 = e0 + half;
           const u64 X = x[e0], Y = x[e1];
           u64 S = X + Y;
-          S = S >= two_q ? S - two_q : S;
-          const u64 D = X + two_q - Y;
+          if (!LAZY) S = S >= two_q ? S - two_q : S;
+          const u64 D = LAZY ? X + (two_q << (LOGN - 1 - (S0 + a))) - Y : X + two_q - Y;
           x[e0] = S;
           x[e1] = shoup_lazy(D, w, ws, q);
         }
@@ -242,59 +244,71 @@ __device__ __forceinline__ void ntt_inv_pass(u64* __restrict__ s, const u64* __r
 // R0 = ((LOGN-1) % 3) + 1 stages, every later pass 3 stages, so the last-stage gaps of the
 // passes are always ..., 64, 8, 1 (the cases the swizzle is designed for).
 // Input of forward: values < 4q.  Output: values < 4q (caller reduces).
-template <int LOGN, int NT>
-__device__ __forceinline__ void ntt_forward_smem(u64* s, const ModC& m, int tid) {
+template <int LOGN, int NT, bool LAZY>
+__device__ __forceinline__ void ntt_forward_smem_t(u64* s, const ModC& m, int tid) {
   constexpr int R0 = ((LOGN - 1) % 3) + 1;
   const u64 q = m.q;
-  ntt_fwd_pass<LOGN, NT, 0, R0>(s, m.rp, m.rps, q, tid);
+  ntt_fwd_pass<LOGN, NT, 0, R0, LAZY>(s, m.rp, m.rps, q, tid);
   __syncthreads();
   if constexpr (LOGN > R0) {
-    ntt_fwd_pass<LOGN, NT, R0, 3>(s, m.rp, m.rps, q, tid);
+    ntt_fwd_pass<LOGN, NT, R0, 3, LAZY>(s, m.rp, m.rps, q, tid);
     __syncthreads();
   }
   if constexpr (LOGN > R0 + 3) {
-    ntt_fwd_pass<LOGN, NT, R0 + 3, 3>(s, m.rp, m.rps, q, tid);
+    ntt_fwd_pass<LOGN, NT, R0 + 3, 3, LAZY>(s, m.rp, m.rps, q, tid);
     __syncthreads();
   }
   if constexpr (LOGN > R0 + 6) {
-    ntt_fwd_pass<LOGN, NT, R0 + 6, 3>(s, m.rp, m.rps, q, tid);
+    ntt_fwd_pass<LOGN, NT, R0 + 6, 3, LAZY>(s, m.rp, m.rps, q, tid);
     __syncthreads();
   }
   if constexpr (LOGN > R0 + 9) {
-    ntt_fwd_pass<LOGN, NT, R0 + 9, 3>(s, m.rp, m.rps, q, tid);
+    ntt_fwd_pass<LOGN, NT, R0 + 9, 3, LAZY>(s, m.rp, m.rps, q, tid);
     __syncthreads();
   }
   static_assert(LOGN <= R0 + 12, "unsupported transform size");
 }
 // Input of inverse: values < 2q.  Output: values < 2q, NOT yet scaled by N^{-1}.
-template <int LOGN, int NT>
-__device__ __forceinline__ void ntt_inverse_smem(u64* s, const ModC& m, int tid) {
+template <int LOGN, int NT, bool LAZY>
+__device__ __forceinline__ void ntt_inverse_smem_t(u64* s, const ModC& m, int tid) {
   constexpr int R0 = ((LOGN - 1) % 3) + 1;
   const u64 q = m.q;
   if constexpr (LOGN > R0 + 9) {
-    ntt_inv_pass<LOGN, NT, R0 + 9, 3>(s, m.irp, m.irps, q, tid);
+    ntt_inv_pass<LOGN, NT, R0 + 9, 3, LAZY>(s, m.irp, m.irps, q, tid);
     __syncthreads();
   }
   if constexpr (LOGN > R0 + 6) {
-    ntt_inv_pass<LOGN, NT, R0 + 6, 3>(s, m.irp, m.irps, q, tid);
+    ntt_inv_pass<LOGN, NT, R0 + 6, 3, LAZY>(s, m.irp, m.irps, q, tid);
     __syncthreads();
   }
   if constexpr (LOGN > R0 + 3) {
-    ntt_inv_pass<LOGN, NT, R0 + 3, 3>(s, m.irp, m.irps, q, tid);
+    ntt_inv_pass<LOGN, NT, R0 + 3, 3, LAZY>(s, m.irp, m.irps, q, tid);
     __syncthreads();
   }
   if constexpr (LOGN > R0) {
-    ntt_inv_pass<LOGN, NT, R0, 3>(s, m.irp, m.irps, q, tid);
+    ntt_inv_pass<LOGN, NT, R0, 3, LAZY>(s, m.irp, m.irps, q, tid);
     __syncthreads();
   }
-  ntt_inv_pass<LOGN, NT, 0, R0>(s, m.irp, m.irps, q, tid);
+  ntt_inv_pass<LOGN, NT, 0, R0, LAZY>(s, m.irp, m.irps, q, tid);
   __syncthreads();
 }
 
-// reduce a forward-NTT lazy value (<4q) to canonical
-__device__ __forceinline__ u64 canon4(u64 v, u64 q) {
-  v = v >= 2 * q ? v - 2 * q : v;
-  return csub(v, q);
+// `lazy` is uniform per launch (DevParams::lazy_ntt): both variants give identical canonical results.
+template <int LOGN, int NT>
+__device__ __forceinline__ void ntt_forward_smem(u64* s, const ModC& m, int tid, bool lazy) {
+  if (lazy) ntt_forward_smem_t<LOGN, NT, true>(s, m, tid);
+  else ntt_forward_smem_t<LOGN, NT, false>(s, m, tid);
+}
+template <int LOGN, int NT>
+__device__ __forceinline__ void ntt_inverse_smem(u64* s, const ModC& m, int tid, bool lazy) {
+  if (lazy) ntt_inverse_smem_t<LOGN, NT, true>(s, m, tid);
+  else ntt_inverse_smem_t<LOGN, NT, false>(s, m, tid);
+}
+// reduce a forward-NTT output to canonical: < 4q (corrected butterflies) or < 32q (lazy)
+__device__ __forceinline__ u64 canon_fwd(u64 v, const ModC& m, bool lazy) {
+  if (lazy) return barrett64(v, m.q, m.ratio_hi);
+  v = v >= 2 * m.q ? v - 2 * m.q : v;
+  return csub(v, m.q);
 }
 // scale an inverse-NTT lazy value (<2q) by N^{-1} and make canonical
 __device__ __forceinline__ u64 inv_finish(u64 v, const ModC& m) { return shoup(v, m.inv_n, m.inv_n_s, m.q); }
