@@ -404,7 +404,7 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   for (u32 i = 0; i < prm->n_moduli; ++i) {
     const u64 q = prm->coeff_modulus[i];
     hm::Tables T = hm::build_tables(q, logn);
-    RC(c->tables[i].ensure(4ull * N * sizeof(u64)));
+    RC(c->tables[i].ensure(10ull * N * sizeof(u64)));
     u64* base = c->tables[i].p;
     CU(cudaMemcpy(base, T.rp.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(base + N, T.rps.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
@@ -419,6 +419,16 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
     m.rps = base + N;
     m.irp = base + 2ull * N;
     m.irps = base + 3ull * N;
+    m.qd = (double)q;
+    m.qinv = 1.0 / (double)q;
+    if (!T.fw.empty()) {
+      double* dbase = reinterpret_cast<double*>(base + 4ull * N);
+      const std::vector<double>* src[6] = {&T.fw, &T.fwi, &T.iw, &T.iwi, &T.fin, &T.fini};
+      for (int t6 = 0; t6 < 6; ++t6)
+        CU(cudaMemcpy(dbase + (size_t)t6 * N, src[t6]->data(), N * sizeof(double), cudaMemcpyHostToDevice));
+      m.fw = dbase; m.fwi = dbase + N; m.iw = dbase + 2ull * N; m.iwi = dbase + 3ull * N;
+      m.fin = dbase + 4ull * N; m.fini = dbase + 5ull * N;
+    }
     if ((int)i < c->k) {
       P.inv_P[i] = hm::invmod_prime(Pq % q, q);
       P.inv_P_s[i] = hm::shoup(P.inv_P[i], q);
@@ -441,6 +451,12 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   int max_bits = 0;
   for (u32 i = 0; i < prm->n_moduli; ++i) max_bits = std::max(max_bits, 64 - __builtin_clzll(prm->coeff_modulus[i]));
   P.lazy_ntt = (max_bits <= 62 - logn - 1) ? 1 : 0;
+  P.ntt_engine = max_bits <= 44 ? 2 : (P.lazy_ntt ? 1 : 0);
+  if (const char* e = getenv("PIRB_NTT_ENGINE")) {  // testing: force a slower-but-more-general engine
+    const int want = atoi(e);
+    if (want == 0) P.ntt_engine = 0;
+    if (want == 1 && P.lazy_ntt) P.ntt_engine = 1;
+  }
   P.half_bits = (max_bits + 1) / 2;
   if (max_bits <= 44) {
     P.mac_mode = 2;  // Karatsuba middle term < 2^(2h+2): chains of 2^(53-2h-2) terms stay below 2^53

@@ -83,6 +83,8 @@ inline u64 minimal_primitive_root(u64 q, u64 N) {
 struct Tables {
   std::vector<u64> rp, rps, irp, irps;
   u64 inv_n, inv_n_s, psi;
+  // FP64 engine tables (exact integers as doubles and their x/q companions)
+  std::vector<double> fw, fwi, iw, iwi, fin, fini;
 };
 inline Tables build_tables(u64 q, int logn) {
   Tables T;
@@ -104,6 +106,29 @@ inline Tables build_tables(u64 q, int logn) {
   }
   T.inv_n = invmod_prime(N % q, q);
   T.inv_n_s = shoup(T.inv_n, q);
+  if (q >> 52) return T;  // no FP64 tables for moduli that are not exactly representable
+  const double qd = (double)q;
+  T.fw.assign(N, 0); T.fwi.assign(N, 0); T.iw.assign(N, 0); T.iwi.assign(N, 0); T.fin.assign(N, 0); T.fini.assign(N, 0);
+  for (u64 i = 0; i < N; ++i) {
+    T.fw[i] = (double)T.rp[i];
+    T.fwi[i] = (double)T.rp[i] / qd;
+  }
+  // iw[g + j] = psi^(-j*N/g): cyclic inverse DFT twiddles (root psi^-2) of the stage with gap g
+  for (u64 g = 1; g < N; g <<= 1) {
+    const u64 step = powmod(psi_inv, N / g, q);
+    u64 cur = 1;
+    for (u64 j = 0; j < g; ++j) {
+      T.iw[g + j] = (double)cur;
+      T.iwi[g + j] = (double)cur / qd;
+      cur = mulmod(cur, step, q);
+    }
+  }
+  u64 cur = T.inv_n;  // fin[i] = N^-1 * psi^-i
+  for (u64 i = 0; i < N; ++i) {
+    T.fin[i] = (double)cur;
+    T.fini[i] = (double)cur / qd;
+    cur = mulmod(cur, psi_inv, q);
+  }
   return T;
 }
 

@@ -36,7 +36,7 @@ __device__ __forceinline__ u64 mod_down_c(u64 a, u64 last, const DevParams& P, i
   return shoup(submod(a, r, m.q), P.inv_P[j], P.inv_P_s[j], m.q);
 }
 
-template <int LOGN, bool LAZY, int MODE>
+template <int LOGN, int ENG, int MODE>
 __global__ void __launch_bounds__(CCfg<LOGN>::NT, 1)
 k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, const LevelArgs L,
                    const u64* __restrict__ key, int mode) {
@@ -68,12 +68,12 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
     for (int i = tid; i < N; i += NT) {
       u64 v = galois_gather(c1, i, L.ginv, N, qJ);
       if (need_reduce) v = barrett64(v, mI.q, mI.ratio_hi);
-      D[swz(i)] = v;
+      D[swz(i)] = eng_load<ENG>(v);
     }
     __syncthreads();
-    ntt_forward_smem_t<LOGN, NT, LAZY>(D, mI, tid);
+    eng_forward<LOGN, NT, ENG>(D, mI, tid);
 #pragma unroll
-    for (int i = tid; i < N; i += NT) D[swz(i)] = canon_fwd(D[swz(i)], mI, LAZY);
+    for (int i = tid; i < N; i += NT) D[swz(i)] = eng_store_fwd<ENG>(D[swz(i)], mI);
   }
   cluster.sync();
 
@@ -91,12 +91,12 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
         const u64 kv = __ldg(key + ((u64)(J * 2 + c) * (k + 1) + I) * N + i);
         acc.mac(Opnd<MODE>(dv, hb), Opnd<MODE>(kv, hb));
       }
-      A[si] = acc.reduce(mI, hb);
+      A[si] = eng_load<ENG>(acc.reduce(mI, hb));
     }
     __syncthreads();
-    ntt_inverse_smem_t<LOGN, NT, LAZY>(A, mI, tid);
+    eng_inverse<LOGN, NT, ENG>(A, mI, tid);
 #pragma unroll
-    for (int i = tid; i < N; i += NT) A[swz(i)] = inv_finish(A[swz(i)], mI);
+    for (int i = tid; i < N; i += NT) A[swz(i)] = eng_store_inv<ENG>(A[swz(i)], i, mI);
   }
   cluster.sync();
 
@@ -143,7 +143,7 @@ cudaError_t launch_ks_level_cluster(const DevParams& P, u64* work, const LevelAr
   const size_t smem = (size_t)((k + 1) / 2 + 1) * P.N * sizeof(u64);
   auto go = [&](auto ln, auto lz, auto mm) -> cudaError_t {
     constexpr int LN = decltype(ln)::value;
-    constexpr bool LZ = decltype(lz)::value;
+    constexpr int LZ = decltype(lz)::value;
     constexpr int MM = decltype(mm)::value;
     auto kern = k_ks_level_cluster<LN, LZ, MM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -175,8 +175,11 @@ cudaError_t launch_ks_level_cluster(const DevParams& P, u64* work, const LevelAr
   };
 #define PIRB_CASE(LN)                                                                             \
   case LN:                                                                                        \
-    return P.lazy_ntt ? by_mode(std::integral_constant<int, LN>{}, std::true_type{})              \
-                      : by_mode(std::integral_constant<int, LN>{}, std::false_type{});
+    switch (P.ntt_engine) {                                                                       \
+      case ENG_FP64: return by_mode(std::integral_constant<int, LN>{}, std::integral_constant<int, ENG_FP64>{});         \
+      case ENG_INT_LAZY: return by_mode(std::integral_constant<int, LN>{}, std::integral_constant<int, ENG_INT_LAZY>{}); \
+      default: return by_mode(std::integral_constant<int, LN>{}, std::integral_constant<int, ENG_INT>{});                \
+    }
   switch (P.logn) {
     PIRB_CASE(11)
     PIRB_CASE(12)

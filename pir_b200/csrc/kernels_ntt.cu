@@ -21,7 +21,7 @@ struct Cfg {
 };
 
 // ---------------------------------------------------------------------------------------------
-template <int LOGN, bool LAZY>
+template <int LOGN, int ENG>
 __global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_ntt_fwd(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* __restrict__ out, int cycle, int off,
           u64 in_bstride, u64 out_bstride) {
@@ -33,14 +33,14 @@ k_ntt_fwd(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* 
   const u64* src = in + blockIdx.y * in_bstride + (u64)p * N;
   u64* dst = out + blockIdx.y * out_bstride + (u64)p * N;
 #pragma unroll
-  for (int i = tid; i < N; i += NT) s[swz(i)] = src[i];
+  for (int i = tid; i < N; i += NT) s[swz(i)] = eng_load<ENG>(src[i]);
   __syncthreads();
-  ntt_forward_smem_t<LOGN, NT, LAZY>(s, m, tid);
+  eng_forward<LOGN, NT, ENG>(s, m, tid);
 #pragma unroll
-  for (int i = tid; i < N; i += NT) dst[i] = canon_fwd(s[swz(i)], m, LAZY);
+  for (int i = tid; i < N; i += NT) dst[i] = eng_store_fwd<ENG>(s[swz(i)], m);
 }
 
-template <int LOGN, bool LAZY>
+template <int LOGN, int ENG>
 __global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_ntt_inv(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* __restrict__ out, int cycle, int off,
           int n_parts, u64 part_stride, u64 in_bstride, u64 out_bstride) {
@@ -55,16 +55,16 @@ k_ntt_inv(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64* 
   for (int i = tid; i < N; i += NT) {
     u64 v = src[i];
     for (int g = 1; g < n_parts; ++g) v = addmod(v, src[g * part_stride + i], m.q);
-    s[swz(i)] = v;
+    s[swz(i)] = eng_load<ENG>(v);
   }
   __syncthreads();
-  ntt_inverse_smem_t<LOGN, NT, LAZY>(s, m, tid);
+  eng_inverse<LOGN, NT, ENG>(s, m, tid);
 #pragma unroll
-  for (int i = tid; i < N; i += NT) dst[i] = inv_finish(s[swz(i)], m);
+  for (int i = tid; i < N; i += NT) dst[i] = eng_store_inv<ENG>(s[swz(i)], i, m);
 }
 
 // plaintext coefficient c (< t) -> c >= (t+1)/2 ? c + (q_j - t) : c   (SURVEY A.7), then NTT mod q_j
-template <int LOGN, bool LAZY>
+template <int LOGN, int ENG>
 __global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_db_preprocess(const __grid_constant__ DevParams P, const u64* __restrict__ coeffs, u64* __restrict__ out) {
   constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
@@ -79,16 +79,16 @@ k_db_preprocess(const __grid_constant__ DevParams P, const u64* __restrict__ coe
 #pragma unroll
   for (int i = tid; i < N; i += NT) {
     u64 c = src[i];
-    s[swz(i)] = c >= P.thr ? c + inc : c;
+    s[swz(i)] = eng_load<ENG>(c >= P.thr ? c + inc : c);
   }
   __syncthreads();
-  ntt_forward_smem_t<LOGN, NT, LAZY>(s, m, tid);
+  eng_forward<LOGN, NT, ENG>(s, m, tid);
 #pragma unroll
-  for (int i = tid; i < N; i += NT) dst[i] = canon_fwd(s[swz(i)], m, LAZY);
+  for (int i = tid; i < N; i += NT) dst[i] = eng_store_fwd<ENG>(s[swz(i)], m);
 }
 
 // grid (z = node, I = key-level modulus, J = RNS digit)
-template <int LOGN, bool LAZY>
+template <int LOGN, int ENG>
 __global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_ks_digits(const __grid_constant__ DevParams P, const u64* __restrict__ work, const LevelArgs L,
             u64* __restrict__ dig) {
@@ -110,17 +110,17 @@ k_ks_digits(const __grid_constant__ DevParams P, const u64* __restrict__ work, c
   for (int i = tid; i < N; i += NT) {
     u64 v = galois_gather(c1, i, L.ginv, N, qJ);
     if (need_reduce) v = barrett64(v, mI.q, mI.ratio_hi);
-    s[swz(i)] = v;
+    s[swz(i)] = eng_load<ENG>(v);
   }
   __syncthreads();
-  ntt_forward_smem_t<LOGN, NT, LAZY>(s, mI, tid);
+  eng_forward<LOGN, NT, ENG>(s, mI, tid);
   u64* dst = dig + (((u64)z * (k + 1) + I) * k + J) * N;
 #pragma unroll
-  for (int i = tid; i < N; i += NT) dst[i] = canon_fwd(s[swz(i)], mI, LAZY);
+  for (int i = tid; i < N; i += NT) dst[i] = eng_store_fwd<ENG>(s[swz(i)], mI);
 }
 
 // grid (z = node, I, c = key component)
-template <int LOGN, bool LAZY>
+template <int LOGN, int ENG>
 __global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_ks_mac_intt(const __grid_constant__ DevParams P, const u64* __restrict__ dig, const u64* __restrict__ key,
               u64* __restrict__ acc) {
@@ -139,17 +139,17 @@ k_ks_mac_intt(const __grid_constant__ DevParams P, const u64* __restrict__ dig, 
       const u64 kv = __ldg(key + ((u64)(J * 2 + c) * (k + 1) + I) * N + i);
       mac128(lo, hi, d[(u64)J * N + i], kv);
     }
-    s[swz(i)] = barrett128(lo, hi, mI.q, mI.ratio_hi, mI.ratio_lo);
+    s[swz(i)] = eng_load<ENG>(barrett128(lo, hi, mI.q, mI.ratio_hi, mI.ratio_lo));
   }
   __syncthreads();
-  ntt_inverse_smem_t<LOGN, NT, LAZY>(s, mI, tid);
+  eng_inverse<LOGN, NT, ENG>(s, mI, tid);
   u64* dst = acc + (((u64)z * 2 + c) * (k + 1) + I) * N;
 #pragma unroll
-  for (int i = tid; i < N; i += NT) dst[i] = inv_finish(s[swz(i)], mI);
+  for (int i = tid; i < N; i += NT) dst[i] = eng_store_inv<ENG>(s[swz(i)], i, mI);
 }
 
 // grid (x = ciphertext, e = chunk, j' = target data modulus)
-template <int LOGN, bool LAZY>
+template <int LOGN, int ENG>
 __global__ void __launch_bounds__(Cfg<LOGN>::NT, Cfg<LOGN>::MINB)
 k_reencode_ntt(const __grid_constant__ DevParams P, const u64* __restrict__ cts, u64* __restrict__ pts) {
   constexpr int N = Cfg<LOGN>::N, NT = Cfg<LOGN>::NT;
@@ -166,17 +166,17 @@ k_reencode_ntt(const __grid_constant__ DevParams P, const u64* __restrict__ cts,
 #pragma unroll
   for (int i = tid; i < N; i += NT) {
     u64 c = (src[i] >> shift) & mask;
-    s[swz(i)] = c >= P.thr ? c + inc : c;
+    s[swz(i)] = eng_load<ENG>(c >= P.thr ? c + inc : c);
   }
   __syncthreads();
-  ntt_forward_smem_t<LOGN, NT, LAZY>(s, m, tid);
+  eng_forward<LOGN, NT, ENG>(s, m, tid);
   u64* dst = pts + ((x * P.two_er + e) * k + jp) * N;
 #pragma unroll
-  for (int i = tid; i < N; i += NT) dst[i] = canon_fwd(s[swz(i)], m, LAZY);
+  for (int i = tid; i < N; i += NT) dst[i] = eng_store_fwd<ENG>(s[swz(i)], m);
 }
 
 // ---------------------------------------------------------------------------------------------
-// host-side dispatch on log2(N) and on the lazy-butterfly flag
+// host-side dispatch on log2(N) and on the NTT engine
 // ---------------------------------------------------------------------------------------------
 template <typename K>
 static cudaError_t ensure_smem(K kernel, size_t bytes) {
@@ -189,8 +189,13 @@ using IntC = std::integral_constant<int, V>;
 
 template <typename F>
 static cudaError_t dispatch(const DevParams& P, F&& f) {
-#define PIRB_CASE(LN) \
-  case LN: return P.lazy_ntt ? f(IntC<LN>{}, std::true_type{}) : f(IntC<LN>{}, std::false_type{});
+#define PIRB_CASE(LN)                                                   \
+  case LN:                                                              \
+    switch (P.ntt_engine) {                                             \
+      case ENG_FP64: return f(IntC<LN>{}, IntC<ENG_FP64>{});            \
+      case ENG_INT_LAZY: return f(IntC<LN>{}, IntC<ENG_INT_LAZY>{});    \
+      default: return f(IntC<LN>{}, IntC<ENG_INT>{});                   \
+    }
   switch (P.logn) {
     PIRB_CASE(11)
     PIRB_CASE(12)
@@ -206,7 +211,7 @@ cudaError_t launch_ntt_fwd(const DevParams& P, const u64* in, u64* out, int n_po
   if (n_polys <= 0 || n_batch <= 0) return cudaSuccess;
   return dispatch(P, [&](auto ln, auto lz) {
     constexpr int LN = decltype(ln)::value;
-    constexpr bool LZ = decltype(lz)::value;
+    constexpr int LZ = decltype(lz)::value;
     auto kern = k_ntt_fwd<LN, LZ>;
     cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
     if (e != cudaSuccess) return e;
@@ -220,7 +225,7 @@ cudaError_t launch_ntt_inv(const DevParams& P, const u64* in, u64* out, int n_po
   if (n_polys <= 0 || n_batch <= 0) return cudaSuccess;
   return dispatch(P, [&](auto ln, auto lz) {
     constexpr int LN = decltype(ln)::value;
-    constexpr bool LZ = decltype(lz)::value;
+    constexpr int LZ = decltype(lz)::value;
     auto kern = k_ntt_inv<LN, LZ>;
     cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
     if (e != cudaSuccess) return e;
@@ -234,7 +239,7 @@ cudaError_t launch_db_preprocess(const DevParams& P, const u64* coeffs, u64* out
   if (!n_pt) return cudaSuccess;
   return dispatch(P, [&](auto ln, auto lz) {
     constexpr int LN = decltype(ln)::value;
-    constexpr bool LZ = decltype(lz)::value;
+    constexpr int LZ = decltype(lz)::value;
     auto kern = k_db_preprocess<LN, LZ>;
     cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
     if (e != cudaSuccess) return e;
@@ -248,7 +253,7 @@ cudaError_t launch_ks_digits(const DevParams& P, const u64* work, const LevelArg
   if (!nodes) return cudaSuccess;
   return dispatch(P, [&](auto ln, auto lz) {
     constexpr int LN = decltype(ln)::value;
-    constexpr bool LZ = decltype(lz)::value;
+    constexpr int LZ = decltype(lz)::value;
     auto kern = k_ks_digits<LN, LZ>;
     cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
     if (e != cudaSuccess) return e;
@@ -262,7 +267,7 @@ cudaError_t launch_ks_mac_intt(const DevParams& P, const u64* dig, const u64* ke
   if (n_nodes <= 0) return cudaSuccess;
   return dispatch(P, [&](auto ln, auto lz) {
     constexpr int LN = decltype(ln)::value;
-    constexpr bool LZ = decltype(lz)::value;
+    constexpr int LZ = decltype(lz)::value;
     auto kern = k_ks_mac_intt<LN, LZ>;
     cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
     if (e != cudaSuccess) return e;
@@ -275,7 +280,7 @@ cudaError_t launch_reencode_ntt(const DevParams& P, const u64* cts, u64* pts, in
   if (n_cts <= 0) return cudaSuccess;
   return dispatch(P, [&](auto ln, auto lz) {
     constexpr int LN = decltype(ln)::value;
-    constexpr bool LZ = decltype(lz)::value;
+    constexpr int LZ = decltype(lz)::value;
     auto kern = k_reencode_ntt<LN, LZ>;
     cudaError_t e = ensure_smem(kern, Cfg<LN>::SMEM);
     if (e != cudaSuccess) return e;

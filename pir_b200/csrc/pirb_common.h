@@ -19,6 +19,14 @@ struct ModC {
   const u64* rps;          // Shoup companions
   const u64* irp;          // irp[i] = rp[i]^{-1}
   const u64* irps;
+  // FP64 engine (moduli <= 44 bits): the same constants as integer-valued doubles, plus x/q companions
+  double qd, qinv;         // q and 1/q
+  const double* fw;        // fw[i]  = (double)rp[i]                      forward twiddles, SEAL ordering
+  const double* fwi;       // fwi[i] = rp[i] / q
+  const double* iw;        // iw[g + j] = psi^(-j*N/g)   for gap g = 1,2,4,...,N/2, j < g   (inverse, DIT form)
+  const double* iwi;
+  const double* fin;       // fin[i] = N^{-1} * psi^{-i}   final scaling of the inverse
+  const double* fini;
 };
 
 // Passed by value (__grid_constant__) to every kernel: lives in the constant bank.
@@ -36,6 +44,7 @@ struct DevParams {
   u64 half_P_mod[PIRB_MAX_MODULI];  // (P>>1) mod q_j
   int two_er;                       // 2 * ExpansionRatio
   int lazy_ntt;                     // 1 if every modulus is below 2^(62 - log2 N): fully lazy butterflies
+  int ntt_engine;                   // 0 integer, 1 integer lazy, 2 FP64 (moduli <= 44 bits)
   int mac_mode;                     // lazy MAC flavour the moduli allow: 0 wide (any), 1 int24 (< 2^48), 2 fp64 (<= 44 bit)
   int half_bits;                    // h: operand split position for the fp64 MAC (ceil(max modulus bits / 2))
   u32 mac_max_terms;                // longest exact accumulation chain for mac_mode

@@ -293,25 +293,180 @@ __device__ __forceinline__ void ntt_inverse_smem_t(u64* s, const ModC& m, int ti
   __syncthreads();
 }
 
-// `lazy` is uniform per launch (DevParams::lazy_ntt): both variants give identical canonical results.
-template <int LOGN, int NT>
-__device__ __forceinline__ void ntt_forward_smem(u64* s, const ModC& m, int tid, bool lazy) {
-  if (lazy) ntt_forward_smem_t<LOGN, NT, true>(s, m, tid);
-  else ntt_forward_smem_t<LOGN, NT, false>(s, m, tid);
-}
-template <int LOGN, int NT>
-__device__ __forceinline__ void ntt_inverse_smem(u64* s, const ModC& m, int tid, bool lazy) {
-  if (lazy) ntt_inverse_smem_t<LOGN, NT, true>(s, m, tid);
-  else ntt_inverse_smem_t<LOGN, NT, false>(s, m, tid);
-}
-// reduce a forward-NTT output to canonical: < 4q (corrected butterflies) or < 32q (lazy)
+// reduce a forward-NTT output of the integer engines to canonical: < 4q (corrected butterflies) or < 32q (lazy)
 __device__ __forceinline__ u64 canon_fwd(u64 v, const ModC& m, bool lazy) {
   if (lazy) return barrett64(v, m.q, m.ratio_hi);
   v = v >= 2 * m.q ? v - 2 * m.q : v;
   return csub(v, m.q);
 }
-// scale an inverse-NTT lazy value (<2q) by N^{-1} and make canonical
+// scale an inverse-NTT lazy value by N^{-1} and make canonical (accepts any 64-bit input)
 __device__ __forceinline__ u64 inv_finish(u64 v, const ModC& m) { return shoup(v, m.inv_n, m.inv_n_s, m.q); }
+
+// ------------------------------------------------------------------------------------------
+// FP64 engine (moduli <= 44 bits): the polynomial lives in shared memory as integer-valued doubles and a
+// butterfly is 8 FP64-pipe instructions.  Exact modular product of an integer-valued double y (|y| < 2^48) with a
+// table constant w in [0,q) (wi = w/q rounded):
+//     h = y*w (rounded)          l = fma(y, w, -h)      (exact low part, |l| <= ulp(h)/2)
+//     c = rint(y*wi)             via fma(y, wi, 1.5*2^52) - 1.5*2^52
+//     r = fma(-c, q, h)          (exact: an integer below 2^46)        t = r + l = y*w - c*q,  |t| <= 0.54 q
+// Every intermediate is an integer below 2^53, so results are exact; values grow by <= 0.54 q per stage
+// (< 9q after 14 stages from a canonical input).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double f64_modmul(double y, double w, double wi, double q) {
+  const double M = 6755399441055744.0;  // 1.5 * 2^52
+  const double h = __dmul_rn(y, w);
+  const double l = __fma_rn(y, w, -h);
+  const double c = __dadd_rn(__fma_rn(y, wi, M), -M);
+  const double r = __fma_rn(-c, q, h);
+  return __dadd_rn(r, l);
+}
+// integer-valued double v (|v| < 2^51) -> canonical residue as a double in [0,q)
+__device__ __forceinline__ double f64_canon(double v, double q, double qinv) {
+  const double M = 6755399441055744.0;
+  const double c = __dadd_rn(__fma_rn(v, qinv, M), -M);
+  double r = __fma_rn(-c, q, v);
+  return r < 0.0 ? __dadd_rn(r, q) : r;
+}
+__device__ __forceinline__ double u64_to_f64_exact(u64 v) {  // v < 2^52
+  return __dadd_rn(__longlong_as_double((long long)(v | 0x4330000000000000ull)), -4503599627370496.0);
+}
+__device__ __forceinline__ u64 f64_to_u64_exact(double d) {  // integer-valued, 0 <= d < 2^52
+  return (u64)__double_as_longlong(__dadd_rn(d, 4503599627370496.0)) & 0x000FFFFFFFFFFFFFull;
+}
+
+// forward pass (Cooley-Tukey, SEAL ordering) on doubles; same unit geometry as ntt_fwd_pass
+template <int LOGN, int NT, int S0, int R>
+__device__ __forceinline__ void f64_fwd_pass(double* __restrict__ s, const double* __restrict__ tw,
+                                             const double* __restrict__ twi, double q, int tid) {
+  constexpr int N = 1 << LOGN;
+  constexpr int E = 1 << R;
+  constexpr int TL = N >> (S0 + R);
+  constexpr int UNITS = N >> R;
+#pragma unroll 1
+  for (int u = tid; u < UNITS; u += NT) {
+    const int lo = u & (TL - 1);
+    const int hi = u / TL;
+    const int base = hi * (TL << R) + lo;
+    double x[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) x[e] = s[swz(base + e * TL)];
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      const int half = E >> (a + 1);
+      const int mbase = (1 << (S0 + a)) + (hi << a);
+#pragma unroll
+      for (int b = 0; b < (1 << a); ++b) {
+        const double w = __ldg(tw + mbase + b);
+        const double wi = __ldg(twi + mbase + b);
+#pragma unroll
+        for (int c = 0; c < half; ++c) {
+          const int e0 = b * 2 * half + c, e1 = e0 + half;
+          const double T = f64_modmul(x[e1], w, wi, q);
+          x[e1] = __dadd_rn(x[e0], -T);
+          x[e0] = __dadd_rn(x[e0], T);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) s[swz(base + e * TL)] = x[e];
+  }
+}
+// inverse pass: decimation-in-time butterflies (X + W*Y, X - W*Y) on the bit-reversed input, gaps increasing.
+// For the stage with gap g the twiddle of the pair at in-block offset j is iw[g + j] = psi^(-j*N/g)  (cyclic
+// inverse DFT with root psi^-2); the remaining psi^-i * N^-1 is applied per element at the end (fin table).
+template <int LOGN, int NT, int S0, int R>
+__device__ __forceinline__ void f64_inv_pass(double* __restrict__ s, const double* __restrict__ iw,
+                                             const double* __restrict__ iwi, double q, int tid) {
+  constexpr int N = 1 << LOGN;
+  constexpr int E = 1 << R;
+  constexpr int TL = N >> (S0 + R);
+  constexpr int UNITS = N >> R;
+#pragma unroll 1
+  for (int u = tid; u < UNITS; u += NT) {
+    const int lo = u & (TL - 1);
+    const int hi = u / TL;
+    const int base = hi * (TL << R) + lo;
+    double x[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) x[e] = s[swz(base + e * TL)];
+#pragma unroll
+    for (int a = R - 1; a >= 0; --a) {
+      const int dist = E >> (a + 1);   // pair distance in unit elements; gap = dist * TL
+      const int g = dist * TL;
+#pragma unroll
+      for (int c = 0; c < dist; ++c) {  // in-block offset j = c*TL + lo
+        const double w = __ldg(iw + g + c * TL + lo);
+        const double wi = __ldg(iwi + g + c * TL + lo);
+#pragma unroll
+        for (int b = 0; b < (1 << a); ++b) {
+          const int e0 = b * 2 * dist + c, e1 = e0 + dist;
+          const double T = f64_modmul(x[e1], w, wi, q);
+          x[e1] = __dadd_rn(x[e0], -T);
+          x[e0] = __dadd_rn(x[e0], T);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) s[swz(base + e * TL)] = x[e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Engine front-end used by every NTT-based kernel.  ENG: 0 integer (corrected butterflies, any modulus < 2^61),
+// 1 integer fully lazy, 2 FP64.  Shared memory holds one 64-bit word per coefficient in all engines.
+// ------------------------------------------------------------------------------------------
+enum { ENG_INT = 0, ENG_INT_LAZY = 1, ENG_FP64 = 2 };
+
+template <int ENG>
+__device__ __forceinline__ u64 eng_load(u64 v) {  // canonical (or < 4q) value -> shared-memory word
+  if constexpr (ENG == ENG_FP64) return (u64)__double_as_longlong(u64_to_f64_exact(v));
+  else return v;
+}
+template <int ENG>
+__device__ __forceinline__ u64 eng_store_fwd(u64 word, const ModC& m) {  // forward output word -> canonical
+  if constexpr (ENG == ENG_FP64) return f64_to_u64_exact(f64_canon(__longlong_as_double((long long)word), m.qd, m.qinv));
+  else return canon_fwd(word, m, ENG == ENG_INT_LAZY);
+}
+template <int ENG>
+__device__ __forceinline__ u64 eng_store_inv(u64 word, int i, const ModC& m) {  // inverse output word -> canonical
+  if constexpr (ENG == ENG_FP64) {
+    double t = f64_modmul(__longlong_as_double((long long)word), __ldg(m.fin + i), __ldg(m.fini + i), m.qd);
+    t = t < 0.0 ? __dadd_rn(t, m.qd) : t;
+    return f64_to_u64_exact(t);
+  } else {
+    return inv_finish(word, m);
+  }
+}
+template <int LOGN, int NT, int ENG>
+__device__ __forceinline__ void eng_forward(u64* s, const ModC& m, int tid) {
+  if constexpr (ENG == ENG_FP64) {
+    constexpr int R0 = ((LOGN - 1) % 3) + 1;
+    double* d = reinterpret_cast<double*>(s);
+    f64_fwd_pass<LOGN, NT, 0, R0>(d, m.fw, m.fwi, m.qd, tid);
+    __syncthreads();
+    if constexpr (LOGN > R0) { f64_fwd_pass<LOGN, NT, R0, 3>(d, m.fw, m.fwi, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0 + 3) { f64_fwd_pass<LOGN, NT, R0 + 3, 3>(d, m.fw, m.fwi, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0 + 6) { f64_fwd_pass<LOGN, NT, R0 + 6, 3>(d, m.fw, m.fwi, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0 + 9) { f64_fwd_pass<LOGN, NT, R0 + 9, 3>(d, m.fw, m.fwi, m.qd, tid); __syncthreads(); }
+  } else {
+    ntt_forward_smem_t<LOGN, NT, ENG == ENG_INT_LAZY>(s, m, tid);
+  }
+}
+template <int LOGN, int NT, int ENG>
+__device__ __forceinline__ void eng_inverse(u64* s, const ModC& m, int tid) {
+  if constexpr (ENG == ENG_FP64) {
+    constexpr int R0 = ((LOGN - 1) % 3) + 1;
+    double* d = reinterpret_cast<double*>(s);
+    if constexpr (LOGN > R0 + 9) { f64_inv_pass<LOGN, NT, R0 + 9, 3>(d, m.iw, m.iwi, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0 + 6) { f64_inv_pass<LOGN, NT, R0 + 6, 3>(d, m.iw, m.iwi, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0 + 3) { f64_inv_pass<LOGN, NT, R0 + 3, 3>(d, m.iw, m.iwi, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0) { f64_inv_pass<LOGN, NT, R0, 3>(d, m.iw, m.iwi, m.qd, tid); __syncthreads(); }
+    f64_inv_pass<LOGN, NT, 0, R0>(d, m.iw, m.iwi, m.qd, tid);
+    __syncthreads();
+  } else {
+    ntt_inverse_smem_t<LOGN, NT, ENG == ENG_INT_LAZY>(s, m, tid);
+  }
+}
 
 // Galois automorphism x -> x^g in coefficient form, as a gather: value of sigma_g(a) at index n.
 // ginv = g^{-1} mod 2N.  (out[i*g mod N] = +-in[i], sign from (i*g div N) parity.)
