@@ -64,54 +64,46 @@ def synth_inputs(params, n_queries, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML every ~1 ms; nvidia-smi -lms as fallback)."""
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+        self.sm, self.mx, self.reasons = [], None, set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = get_reasons(h)
+                for nm, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.001)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add("nvml unavailable: %s" % type(e).__name__)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def measured_peak():
@@ -235,32 +227,36 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         flush.zero_()
         step_dev()
-    srv.set_profiling(True)
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
+        time.sleep(0.005)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage_acc = {}
-    launches = 0
     barrier()
     for i in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations, outside the per-step events
         ev[i][0].record()
         out = step_dev()
         ev[i][1].record()
-        ev[i][1].synchronize()
-        launches += srv.launch_count()
-        for nm, v in srv.stage_ms().items():
-            stage_acc.setdefault(nm, []).append(v)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    launches = srv.launch_count() * args.steps
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
-    srv.set_profiling(False)
+    # per-stage device times (CUDA events recorded by the library on its launching stream), measured live on a few
+    # extra steps: profiling inserts events between kernels, so those steps run eagerly instead of as one graph
+    srv.set_profiling(True)
+    stage_acc = {}
+    for i in range(min(args.steps, 10)):
+        flush.zero_()
+        step_dev()
+        torch.cuda.synchronize()
+        for nm, v in srv.stage_ms().items():
+            stage_acc.setdefault(nm, []).append(v)
     qps = world * ql * args.steps / (total_ms / 1e3)
 
     # ---------------- end to end through the reference-facing call, host buffers ----------------

@@ -131,6 +131,8 @@ int pirb_reduce_finish_peers_dev(pirb_ctx* ctx, const uint64_t* const* d_peer_pt
  * Used by the bench to time the scan in isolation.  d_rows may be NULL (internal scratch). */
 int pirb_scan_dev(pirb_ctx* ctx, const uint64_t* d_sv_ntt, uint32_t n_queries, uint64_t* d_rows, void* stream);
 int pirb_sync(pirb_ctx* ctx);
+/* development aid: clock64 phase stamps of one expansion level (env PIRB_DEBUG_STAMPS=<level> at context creation) */
+int pirb_debug_stamps(pirb_ctx* ctx, uint64_t* out, uint64_t n);
 
 /* Per-stage device times of the last pirb_answer* call, measured with CUDA events on the launching stream
  * when profiling is enabled.  stage: 0 expand, 1 sv NTT, 2 scan, 3 row INTT, 4 upper dims, 5 total. */

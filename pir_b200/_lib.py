@@ -70,6 +70,7 @@ SYMBOLS = {
                                                C.c_void_p]),
     "pirb_scan_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "pirb_sync": (C.c_int, [C.c_void_p]),
+    "pirb_debug_stamps": (C.c_int, [C.c_void_p, u64p, C.c_uint64]),
     "pirb_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "pirb_get_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pirb_last_scan_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

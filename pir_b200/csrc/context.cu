@@ -12,6 +12,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/pir_b200.h"
@@ -38,12 +39,15 @@ int fail(int code, const std::string& msg) {
     if (rc_) return rc_;  \
   } while (0)
 
+unsigned long long g_alloc_epoch = 0;  // bumped whenever a workspace buffer moves: captured graphs become stale
+
 struct DevBuf {
   u64* p = nullptr;
   size_t bytes = 0;
   ~DevBuf() { if (p) cudaFree(p); }
   int ensure(size_t b) {
     if (b <= bytes) return 0;
+    ++g_alloc_epoch;
     if (p) { cudaFree(p); p = nullptr; bytes = 0; }
     cudaError_t e = cudaMalloc(&p, b);
     if (e != cudaSuccess) {
@@ -105,6 +109,13 @@ struct pirb_ctx {
   bool ev_valid = false;
   u64 launches = 0;
   int scan_split = 1;
+  // CUDA graphs of the whole answer path (expansion + multiply), one per (batch size, key handle, partial flag);
+  // they read c->qbuf and write c->rbuf, so they stay valid as long as no workspace buffer moves.
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; unsigned long long epoch = 0; u64 launches = 0; };
+  std::map<std::tuple<u32, const void*, int>, GraphEntry> graphs;
+  bool use_graphs = true;
+  DevBuf dbg;            // PIRB_DEBUG_STAMPS=<level>: clock64 phase stamps of that expansion level
+  int dbg_level = -1;
   bool use_cluster = false;  // one-launch-per-level key switch on thread-block clusters
 };
 
@@ -199,6 +210,7 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
     L.ginv = inv_mod_2n(g, c->N);
     L.q_stride = q_stride;
     L.n_queries = n_queries;
+    L.dbg = !c->dbg.p ? nullptr : (c->dbg_level == -2 ? c->dbg.p + (size_t)j * 65536 : (j == c->dbg_level ? c->dbg.p : nullptr));
     const int n_nodes = (n_queries * L.n_trees) << j;
     if (c->use_cluster) {
       LAUNCH(c, launch_ks_level_cluster(c->P, c->work.p, L, key, 0, st));
@@ -335,6 +347,50 @@ int run_answer(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u32 n_q
   return 0;
 }
 
+// Answer n_queries queries held in c->qbuf into c->rbuf, replaying a captured CUDA graph when one is valid.
+// The first call with a given shape runs eagerly (it sizes every workspace), the second one captures.
+int answer_buffers(pirb_ctx* c, const pirb_keys* keys, u32 n_queries, u64 n_ct, int partial, cudaStream_t st) {
+  if (!c->use_graphs || c->profiling || c->dbg.p)
+    return run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, st);
+  auto key = std::make_tuple(n_queries, (const void*)keys, partial);
+  auto it = c->graphs.find(key);
+  if (it != c->graphs.end() && it->second.exec && it->second.epoch == g_alloc_epoch) {
+    c->launches = it->second.launches;
+    CU(cudaGraphLaunch(it->second.exec, st));
+    return 0;
+  }
+  if (it == c->graphs.end()) {  // first sight of this shape: eager run, remember that we have seen it
+    c->graphs[key] = pirb_ctx::GraphEntry();
+    return run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, st);
+  }
+  if (it->second.exec) { cudaGraphExecDestroy(it->second.exec); it->second.exec = nullptr; }
+  const unsigned long long epoch_before = g_alloc_epoch;
+  CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  const int rc = run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, st);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc || e != cudaSuccess || epoch_before != g_alloc_epoch) {
+    // argument error, or a workspace had to grow during capture: fall back to an eager run (and try again next time)
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc) return rc;
+    return run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, st);
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    c->use_graphs = false;
+    return run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, st);
+  }
+  it->second.exec = exec;
+  it->second.epoch = g_alloc_epoch;
+  it->second.launches = c->launches;
+  CU(cudaGraphLaunch(exec, st));
+  return 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -433,6 +489,9 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
       P.inv_P[i] = hm::invmod_prime(Pq % q, q);
       P.inv_P_s[i] = hm::shoup(P.inv_P[i], q);
       P.half_P_mod[i] = P.half_P % q;
+      P.inv_P_d[i] = (double)P.inv_P[i];
+      P.inv_P_di[i] = (double)P.inv_P[i] / (double)q;
+      P.half_P_mod_d[i] = (double)P.half_P_mod[i];
     }
   }
   // re-encode chunk table (ct_reencoder.cpp:29-71: double log2, ceil)
@@ -458,6 +517,15 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
     if (want == 1 && P.lazy_ntt) P.ntt_engine = 1;
   }
   P.half_bits = (max_bits + 1) / 2;
+  P.half_P_d = (double)P.half_P;
+  for (u32 i = 0; i < prm->n_moduli; ++i) {
+    const u64 q = prm->coeff_modulus[i];
+    const u64 ph = hm::powmod(2, (u64)P.half_bits, q), p2h = hm::powmod(2, 2ull * P.half_bits, q);
+    P.m[i].pow_h = (double)ph;
+    P.m[i].pow_h_i = (double)ph / (double)q;
+    P.m[i].pow_2h = (double)p2h;
+    P.m[i].pow_2h_i = (double)p2h / (double)q;
+  }
   if (max_bits <= 44) {
     P.mac_mode = 2;  // Karatsuba middle term < 2^(2h+2): chains of 2^(53-2h-2) terms stay below 2^53
     P.mac_max_terms = 1u << std::min(14, 51 - 2 * P.half_bits);
@@ -487,6 +555,12 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
     const char* e = getenv("PIRB_KS_CLUSTER");
     c->use_cluster = ks_cluster_supported(c->P) && !(e && *e == '0');
   }
+  if (const char* e = getenv("PIRB_GRAPHS")) c->use_graphs = atoi(e) != 0;
+  if (const char* e = getenv("PIRB_DEBUG_STAMPS")) {
+    c->dbg_level = atoi(e);
+    RC(c->dbg.ensure(8 << 20));
+    CU(cudaMemset(c->dbg.p, 0, 8 << 20));
+  }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
   *out = c.release();
@@ -499,6 +573,8 @@ void pirb_ctx_destroy(pirb_ctx* c) {
   cudaDeviceSynchronize();
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& kv : c->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -588,6 +664,7 @@ int pirb_keys_load(pirb_ctx* c, const uint32_t* elts, uint32_t n, const uint64_t
 void pirb_keys_destroy(pirb_keys* kz) {
   if (!kz) return;
   cudaSetDevice(kz->device);
+  ++g_alloc_epoch;  // graphs that captured this handle's device pointer must not be replayed
   delete kz;
 }
 
@@ -612,6 +689,7 @@ int pirb_substitute(pirb_ctx* c, const pirb_keys* keys, uint64_t* ct, uint32_t p
   L.ginv = inv_mod_2n(power, c->N);
   L.q_stride = 0;
   L.n_queries = 1;
+  L.dbg = nullptr;
   if (c->use_cluster) {
     LAUNCH(c, launch_ks_level_cluster(c->P, c->work.p, L, key, 1, st));
   } else {
@@ -716,9 +794,25 @@ int pirb_answer(pirb_ctx* c, const pirb_keys* keys, const uint64_t* queries, uin
   RC(c->qbuf.ensure(std::max<size_t>(qbytes, 256)));
   RC(c->rbuf.ensure(std::max<size_t>(rbytes, 256)));
   CU(cudaMemcpyAsync(c->qbuf.p, queries, qbytes, cudaMemcpyHostToDevice, st));
-  RC(run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, 0, st));
+  RC(answer_buffers(c, keys, n_queries, n_ct, 0, st));
   CU(cudaMemcpyAsync(replies, c->rbuf.p, rbytes, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int answer_dev_common(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u32 n_queries, u64 n_ct,
+                             u64* d_out, int partial, cudaStream_t st) {
+  if (!n_queries) return 0;
+  if (n_ct != c->dim_sum / c->N + 1)
+    return fail(PIRB_INVALID_ARGUMENT, "Number of ciphertexts doesn't match number of items for oblivious expansion.");
+  const size_t qbytes = (size_t)n_queries * n_ct * c->ctL * sizeof(u64);
+  const size_t rbytes = (size_t)n_queries * c->reply_cts * c->ctL * sizeof(u64);
+  RC(c->qbuf.ensure(std::max<size_t>(qbytes, 256)));
+  RC(c->rbuf.ensure(std::max<size_t>(rbytes, 256)));
+  // the captured graph works on the context's own buffers; the caller's tensors are copied in and out
+  CU(cudaMemcpyAsync(c->qbuf.p, d_queries, qbytes, cudaMemcpyDeviceToDevice, st));
+  RC(answer_buffers(c, keys, n_queries, n_ct, partial, st));
+  CU(cudaMemcpyAsync(d_out, c->rbuf.p, rbytes, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -727,14 +821,14 @@ int pirb_answer_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_querie
   if (!c || !d_queries || !d_replies) return fail(PIRB_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(c->device));
   if (c->prm.shard_count != 1) return fail(PIRB_INVALID_ARGUMENT, "use pirb_answer_partial_dev on a sharded context");
-  return run_answer(c, keys, U(d_queries), n_queries, n_ct, U(d_replies), 0, stream ? (cudaStream_t)stream : c->stream);
+  return answer_dev_common(c, keys, U(d_queries), n_queries, n_ct, U(d_replies), 0, stream ? (cudaStream_t)stream : c->stream);
 }
 
 int pirb_answer_partial_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries,
                             uint64_t n_ct, uint64_t* d_partial, void* stream) {
   if (!c || !d_queries || !d_partial) return fail(PIRB_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(c->device));
-  return run_answer(c, keys, U(d_queries), n_queries, n_ct, U(d_partial), 1, stream ? (cudaStream_t)stream : c->stream);
+  return answer_dev_common(c, keys, U(d_queries), n_queries, n_ct, U(d_partial), 1, stream ? (cudaStream_t)stream : c->stream);
 }
 
 int pirb_expand_ntt_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries,
@@ -819,6 +913,13 @@ int pirb_scan_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_queries, uin
   return 0;
 }
 
+int pirb_debug_stamps(pirb_ctx* c, uint64_t* out, uint64_t n) {
+  if (!c || !out || !c->dbg.p) return fail(PIRB_INVALID_ARGUMENT, "debug stamps are off (PIRB_DEBUG_STAMPS)");
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out, c->dbg.p, std::min<size_t>(n * sizeof(u64), 8 << 20), cudaMemcpyDeviceToHost));
+  return 0;
+}
 int pirb_sync(pirb_ctx* c) {
   if (!c) return fail(PIRB_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(c->device));

@@ -17,6 +17,7 @@ struct LevelArgs {
   u32 ginv;      // inverse of the Galois element (N>>j)+1 modulo 2N
   u64 q_stride;  // limbs between consecutive queries' workspaces
   int n_queries;
+  u64* dbg;      // optional per-CTA phase timestamps (clock64), 8 slots per CTA; nullptr in production
 };
 
 // generic batched transforms on [n_polys][N] arrays; modulus of poly p is m[(p % cycle) + off].

@@ -37,7 +37,7 @@ __device__ __forceinline__ u64 mod_down_c(u64 a, u64 last, const DevParams& P, i
 }
 
 template <int LOGN, int ENG, int MODE>
-__global__ void __launch_bounds__(CCfg<LOGN>::NT, 1)
+__global__ void __launch_bounds__(CCfg<LOGN>::NT, (LOGN <= 12 ? 2 : 1))
 k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, const LevelArgs L,
                    const u64* __restrict__ key, int mode) {
   constexpr int N = CCfg<LOGN>::N, NT = CCfg<LOGN>::NT;
@@ -57,6 +57,16 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
   const ModC& mI = P.m[I];
   const int nd = (k + 1) / 2;  // digit buffers per CTA
   u64* A = smem + (size_t)nd * N;
+#define PIRB_STAMP(slot)                                                                   \
+  do {                                                                                     \
+    if (L.dbg && tid == 0) {                                                               \
+      u64 t_;                                                                              \
+      if ((slot) == 0 || (slot) == 7) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+      else t_ = clock64();                                                                 \
+      L.dbg[(u64)blockIdx.x * 8 + (slot)] = t_;                                            \
+    }                                                                                      \
+  } while (0)
+  PIRB_STAMP(0);
 
   // ---- phase 1: my digits ----
   for (int J = c; J < k; J += 2) {
@@ -71,32 +81,54 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
       D[swz(i)] = eng_load<ENG>(v);
     }
     __syncthreads();
+    PIRB_STAMP(1);
     eng_forward<LOGN, NT, ENG>(D, mI, tid);
+    PIRB_STAMP(2);
 #pragma unroll
     for (int i = tid; i < N; i += NT) D[swz(i)] = eng_store_fwd<ENG>(D[swz(i)], mI);
   }
+  PIRB_STAMP(3);
   cluster.sync();
+  PIRB_STAMP(4);
 
   // ---- phase 2: MAC with the key, inverse transform ----
   {
     const u64* peer = cluster.map_shared_rank(smem, rank ^ 1);
     const int hb = P.half_bits;
+    // four coefficients per thread at a time; for every digit all operand loads (shared / distributed shared /
+    // global) are issued before the first multiply so their latencies overlap
+    constexpr int CH = 4;
+#pragma unroll 1
+    for (int i0 = tid; i0 < N; i0 += CH * NT) {
+      Acc<MODE> acc[CH];
+      int si[CH];
 #pragma unroll
-    for (int i = tid; i < N; i += NT) {
-      Acc<MODE> acc;
-      const int si = swz(i);
+      for (int e = 0; e < CH; ++e) si[e] = swz(i0 + e * NT);
+#pragma unroll 1
       for (int J = 0; J < k; ++J) {
-        const u64* buf = ((J & 1) == c) ? smem : peer;
-        const u64 dv = buf[(size_t)(J >> 1) * N + si];
-        const u64 kv = __ldg(key + ((u64)(J * 2 + c) * (k + 1) + I) * N + i);
-        acc.mac(Opnd<MODE>(dv, hb), Opnd<MODE>(kv, hb));
+        const u64* buf = (((J & 1) == c) ? smem : peer) + (size_t)(J >> 1) * N;
+        const u64* kp = key + ((u64)(J * 2 + c) * (k + 1) + I) * N + i0;
+        u64 dv[CH], kv[CH];
+#pragma unroll
+        for (int e = 0; e < CH; ++e) {
+          dv[e] = buf[si[e]];
+          kv[e] = __ldg(kp + e * NT);
+        }
+#pragma unroll
+        for (int e = 0; e < CH; ++e) acc[e].mac(Opnd<MODE>(dv[e], hb), Opnd<MODE>(kv[e], hb));
       }
-      A[si] = eng_load<ENG>(acc.reduce(mI, hb));
+#pragma unroll
+      for (int e = 0; e < CH; ++e) {
+        if constexpr (ENG == ENG_FP64 && MODE == MAC_FP64) A[si[e]] = (u64)__double_as_longlong(acc[e].reduce_d(mI));
+        else A[si[e]] = eng_load<ENG>(acc[e].reduce(mI, hb));
+      }
     }
     __syncthreads();
+    PIRB_STAMP(5);
     eng_inverse<LOGN, NT, ENG>(A, mI, tid);
+    PIRB_STAMP(6);
 #pragma unroll
-    for (int i = tid; i < N; i += NT) A[swz(i)] = eng_store_inv<ENG>(A[swz(i)], i, mI);
+    for (int i = tid; i < N; i += NT) A[swz(i)] = eng_finish_inv_native<ENG>(A[swz(i)], i, mI);
   }
   cluster.sync();
 
@@ -111,7 +143,20 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
 #pragma unroll
     for (int i = tid; i < N; i += NT) {
       const int si = swz(i);
-      u64 c0 = mod_down_c(A[si], lastA[si], P, j, Pq);
+      u64 c0;
+      if constexpr (ENG == ENG_FP64) {
+        // mod-down by P on the FP64 pipe: ((a - ((l + P/2 mod P) mod q - P/2 mod q)) * P^-1) mod q
+        const double qd = mI.qd;
+        double l = __dadd_rn(__longlong_as_double((long long)lastA[si]), P.half_P_d);
+        l = l >= P.m[k].qd ? __dadd_rn(l, -P.m[k].qd) : l;
+        const double r = f64_submod(f64_canon(l, qd, mI.qinv), P.half_P_mod_d[j], qd);
+        const double dd = f64_submod(__longlong_as_double((long long)A[si]), r, qd);
+        double md = f64_modmul(dd, P.inv_P_d[j], P.inv_P_di[j], qd);
+        md = md < 0.0 ? __dadd_rn(md, qd) : md;
+        c0 = f64_to_u64_exact(md);
+      } else {
+        c0 = mod_down_c(A[si], lastA[si], P, j, Pq);
+      }
       if (c == 0) c0 = addmod(galois_gather(sp, i, L.ginv, N, q), c0, q);
       if (mode == 1) {
         dstE[(u64)(c * k + j) * N + i] = c0;
@@ -125,6 +170,7 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
       }
     }
   }
+  PIRB_STAMP(7);
   cluster.sync();  // keep shared memory alive until every peer has finished reading it
 }
 
@@ -146,11 +192,17 @@ cudaError_t launch_ks_level_cluster(const DevParams& P, u64* work, const LevelAr
     constexpr int LZ = decltype(lz)::value;
     constexpr int MM = decltype(mm)::value;
     auto kern = k_ks_level_cluster<LN, LZ, MM>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (csize > 8) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    static size_t configured[64] = {};  // per device: largest dynamic shared memory size already set
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured[dev & 63] < smem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
+      if (csize > 8) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+      }
+      configured[dev & 63] = smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nodes * csize);

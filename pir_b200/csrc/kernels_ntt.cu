@@ -5,7 +5,9 @@
 //   k_reencode_ntt            CiphertextReencoder::Encode + plaintext NTT (ct_reencoder.cpp:40-71, database.cpp:217-228)
 // One CTA owns one size-N transform; the polynomial lives in (swizzled) shared memory between
 // a fused load-side transform and a fused store-side transform.
+#include <set>
 #include <type_traits>
+#include <utility>
 
 #include "kernels.cuh"
 #include "pirb_device.cuh"
@@ -180,8 +182,15 @@ k_reencode_ntt(const __grid_constant__ DevParams P, const u64* __restrict__ cts,
 // ---------------------------------------------------------------------------------------------
 template <typename K>
 static cudaError_t ensure_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  return cudaSuccess;
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  static std::set<std::pair<int, const void*>> configured;  // (device, kernel) pairs already set up
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const auto key = std::make_pair(dev, reinterpret_cast<const void*>(kernel));
+  if (configured.count(key)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) configured.insert(key);
+  return e;
 }
 
 template <int V>

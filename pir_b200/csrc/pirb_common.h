@@ -27,6 +27,8 @@ struct ModC {
   const double* iwi;
   const double* fin;       // fin[i] = N^{-1} * psi^{-i}   final scaling of the inverse
   const double* fini;
+  double pow_h, pow_h_i;    // 2^h mod q and (2^h mod q)/q     (h = DevParams::half_bits; FP64 Karatsuba recombination)
+  double pow_2h, pow_2h_i;  // 2^(2h) mod q and its /q companion
 };
 
 // Passed by value (__grid_constant__) to every kernel: lives in the constant bank.
@@ -42,6 +44,10 @@ struct DevParams {
   u64 inv_P[PIRB_MAX_MODULI];       // P^{-1} mod q_j
   u64 inv_P_s[PIRB_MAX_MODULI];     // Shoup companion
   u64 half_P_mod[PIRB_MAX_MODULI];  // (P>>1) mod q_j
+  double inv_P_d[PIRB_MAX_MODULI];  // the same constants as doubles for the FP64 engine's mod-down
+  double inv_P_di[PIRB_MAX_MODULI]; // inv_P / q_j
+  double half_P_mod_d[PIRB_MAX_MODULI];
+  double half_P_d;
   int two_er;                       // 2 * ExpansionRatio
   int lazy_ntt;                     // 1 if every modulus is below 2^(62 - log2 N): fully lazy butterflies
   int ntt_engine;                   // 0 integer, 1 integer lazy, 2 FP64 (moduli <= 44 bits)

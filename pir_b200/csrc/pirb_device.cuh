@@ -35,6 +35,9 @@ __device__ __forceinline__ void mac128(u64& lo, u64& hi, u64 a, u64 b) {
 }
 
 __device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, u64 q, u64 r_hi, u64 r_lo);
+__device__ __forceinline__ double f64_modmul(double y, double w, double wi, double q);
+__device__ __forceinline__ double f64_canon(double v, double q, double qinv);
+__device__ __forceinline__ u64 f64_to_u64_exact(double d);
 
 // ------------------------------------------------------------------------------------------
 // Lazy multiply-accumulate chains  sum_i a_i*b_i  (mod q taken once at the end).
@@ -119,9 +122,18 @@ struct Acc<MAC_FP64> {
     sk = fma(a.sum, b.sum, sk);
     s2 = fma(a.hi, b.hi, s2);
   }
-  __device__ __forceinline__ u64 reduce(const ModC& m, int h) const {
-    return karatsuba_reduce(__double2ull_rz(s0), __double2ull_rz(sk), __double2ull_rz(s2), h, m);
+  // value = s0 + s1*2^h + s2*2^(2h) mod q entirely on the FP64 pipe: canonicalise the three partial sums, multiply
+  // two of them by the precomputed 2^h, 2^(2h) mod q, add, canonicalise.  Returns a canonical integer-valued double.
+  __device__ __forceinline__ double reduce_d(const ModC& m) const {
+    const double s1 = __dadd_rn(__dadd_rn(sk, -s0), -s2);
+    const double r0 = f64_canon(s0, m.qd, m.qinv);
+    const double r1 = f64_canon(s1, m.qd, m.qinv);
+    const double r2 = f64_canon(s2, m.qd, m.qinv);
+    const double t1 = f64_modmul(r1, m.pow_h, m.pow_h_i, m.qd);    // |t| <= 0.54 q
+    const double t2 = f64_modmul(r2, m.pow_2h, m.pow_2h_i, m.qd);
+    return f64_canon(__dadd_rn(__dadd_rn(r0, t1), t2), m.qd, m.qinv);
   }
+  __device__ __forceinline__ u64 reduce(const ModC& m, int) const { return f64_to_u64_exact(reduce_d(m)); }
 };
 
 // 128-bit -> [0,q) with ratio = floor(2^128/q)
@@ -437,6 +449,28 @@ __device__ __forceinline__ u64 eng_store_inv(u64 word, int i, const ModC& m) {  
     return inv_finish(word, m);
   }
 }
+// canonical doubles in [0,q)
+__device__ __forceinline__ double f64_addmod(double a, double b, double q) {
+  const double s = __dadd_rn(a, b);
+  return s >= q ? __dadd_rn(s, -q) : s;
+}
+__device__ __forceinline__ double f64_submod(double a, double b, double q) {
+  const double d = __dadd_rn(a, -b);
+  return d < 0.0 ? __dadd_rn(d, q) : d;
+}
+__device__ __forceinline__ double f64_negmod(double a, double q) { return a == 0.0 ? 0.0 : __dadd_rn(q, -a); }
+// inverse output word -> canonical value kept in the engine's own representation (double bits for ENG_FP64)
+template <int ENG>
+__device__ __forceinline__ u64 eng_finish_inv_native(u64 word, int i, const ModC& m) {
+  if constexpr (ENG == ENG_FP64) {
+    double t = f64_modmul(__longlong_as_double((long long)word), __ldg(m.fin + i), __ldg(m.fini + i), m.qd);
+    t = t < 0.0 ? __dadd_rn(t, m.qd) : t;
+    return (u64)__double_as_longlong(t);
+  } else {
+    return inv_finish(word, m);
+  }
+}
+
 template <int LOGN, int NT, int ENG>
 __device__ __forceinline__ void eng_forward(u64* s, const ModC& m, int tid) {
   if constexpr (ENG == ENG_FP64) {

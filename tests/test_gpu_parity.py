@@ -420,3 +420,24 @@ def test_scan_selects_database_rows_at_baseline_size():
     f = lambda x: sh.scan(torch.from_numpy(np.ascontiguousarray(x).view(np.int64)).cuda()[None]).cpu().numpy().view(np.uint64)[0]
     ra, rb, rs = f(a), f(b), f(s)
     assert np.array_equal((ra + rb) % q[None, None, :, None], rs)
+
+
+def test_repeated_requests_replay_the_captured_graph(srv10):
+    """The first ProcessRequest of a shape runs eagerly, the second captures a CUDA graph, later ones replay it:
+    every reply must still match the oracle, also after the client (key handle) changes."""
+    p, cl, vals, db, server = srv10
+    gk, raw = _gk(cl)
+    dbn = db.read_ntt(0, 10)
+    for rep in range(5):
+        pt = np.zeros(N, dtype=np.uint64); pt[rep] = 1
+        q = cl.encrypt(pt)[None]
+        r = server.ProcessRequest(pb.Request([q], gk)).reply[0]
+        assert np.array_equal(r, cl.orc.process_query(dbn, p.dimensions, cl.elts, raw, q)), rep
+    cl2 = _harness(p, seed=4242)
+    gk2, raw2 = _gk(cl2)
+    for rep in range(3):
+        pt = np.zeros(N, dtype=np.uint64); pt[9 - rep] = 1
+        q = cl2.encrypt(pt)[None]
+        r = server.ProcessRequest(pb.Request([q], gk2)).reply[0]
+        assert np.array_equal(r, cl2.orc.process_query(dbn, p.dimensions, cl2.elts, raw2, q)), rep
+        assert oc.integer_decode(cl2.decrypt(r[0]), cl2.orc.t) == vals[9 - rep] * 16
