@@ -8,7 +8,7 @@ LIB := pir_b200/lib/libpirb200.so
 OBJS := $(OBJ)/kernels_ntt.o $(OBJ)/kernels_stream.o $(OBJ)/kernels_cluster.o $(OBJ)/context.o
 HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/pir_b200.h
 
-all: $(LIB) oracle
+all: $(LIB) oracle build/shim_test
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -17,6 +17,11 @@ $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 $(LIB): $(OBJS)
 	@mkdir -p pir_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
+
+# C++ end-to-end test of the pir:: shim (host code in the reference's language over the C ABI)
+build/shim_test: tests/cpp/shim_test.cpp pir_b200/cpp/pir_b200.hpp oracle/pir_oracle.hpp include/pir_b200.h $(LIB)
+	@mkdir -p build
+	g++ -O2 -std=c++17 -march=x86-64-v3 -o $@ tests/cpp/shim_test.cpp -Lpir_b200/lib -lpirb200 -Wl,-rpath,'$$ORIGIN/../pir_b200/lib'
 
 oracle:
 	$(MAKE) -C oracle

@@ -210,7 +210,12 @@ def run_ours(args):
     n_ct = queries.shape[1]
     q_local = queries[rank * ql:(rank + 1) * ql]
     d_q = sharded.to_device(q_local, dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def flush_l2():
+        # read (not write) a buffer larger than L2: everything of ours is evicted and only CLEAN lines are left behind,
+        # so the timed step does not also pay for writing back 126 MB of dirty flush data
+        return flush.view(torch.int64).sum()
 
     def step_dev():
         if world == 1:
@@ -225,7 +230,7 @@ def run_ours(args):
 
     # ---------------- device-resident throughput ----------------
     for _ in range(max(3, args.warmup)):
-        flush.zero_()
+        flush_l2()
         step_dev()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -235,7 +240,7 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for i in range(args.steps):
-        flush.zero_()  # L2 flush between timed iterations, outside the per-step events
+        flush_l2()  # L2 flush between timed iterations, outside the per-step events
         ev[i][0].record()
         out = step_dev()
         ev[i][1].record()
@@ -252,7 +257,7 @@ def run_ours(args):
     srv.set_profiling(True)
     stage_acc = {}
     for i in range(min(args.steps, 10)):
-        flush.zero_()
+        flush_l2()
         step_dev()
         torch.cuda.synchronize()
         for nm, v in srv.stage_ms().items():
@@ -338,7 +343,7 @@ def run_ours(args):
                    "dims": list(params.dimensions), "key_switches_per_query": sum(
                        int(pb.next_power_two(min(N, max(0, sum(params.dimensions) - t * N)))) - 1 for t in range(n_ct)),
                    "reply_cts": srv.ctx.reply_cts, "parallelism": "rows sharded x%d, expansion split by query" % world,
-                   "l2": "256 MiB buffer written between timed iterations (outside the per-step CUDA events)",
+                   "l2": "256 MiB buffer read between timed iterations (evicts L2, leaves clean lines; outside the per-step CUDA events)",
                    "galois_keys": "resident in HBM, uploaded once per client"},
         "p50_latency_ms": statistics.median(step_ms),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(world * ql * n_ct * ctL * 8),

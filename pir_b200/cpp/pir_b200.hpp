@@ -1,0 +1,469 @@
+// pir_b200.hpp — C++17 host-side mirror of the reference's server interface over the C ABI (include/pir_b200.h).
+//
+// Same class names, method names, argument meaning and status codes as OpenMined/PIR's pir::PIRServer
+// (pir/cpp/server.h:43-131), pir::PIRDatabase (pir/cpp/database.h:47-127), CreatePIRParameters
+// (pir/cpp/parameters.h:55-73) and StringEncoder (pir/cpp/string_encoder.h), with SEAL / abseil / protobuf types
+// replaced by plain structs of raw RNS limbs (those libraries are not available in this image):
+//
+//   pir::Ciphertext   std::vector<uint64_t> limbs, layout [2][k][N]  == seal::Ciphertext::data()
+//   pir::GaloisKeys   elts[i] + limbs [n][k][2][k+1][N]               == seal::GaloisKeys (KSwitchKeys layout)
+//   pir::Request      { query: vector<vector<Ciphertext>>, galois_keys }   (payload.proto:28-36)
+//   pir::Response     { reply: vector<vector<Ciphertext>> }                (payload.proto:39-42)
+//   pir::Status / StatusOr<T>   codes as absl::StatusCode: 0 OK, 3 InvalidArgument, 13 Internal
+//
+// Header-only; link with -lpirb200.  All ring arithmetic runs in the CUDA kernels behind the C ABI; nothing here
+// computes on ciphertexts.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <optional>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/pir_b200.h"
+
+namespace pir {
+
+// ---------------------------------------------------------------------------------------------------------------
+struct Status {
+  int code_ = 0;
+  std::string message_;
+  Status() {}
+  Status(int c, std::string m) : code_(c), message_(std::move(m)) {}
+  bool ok() const { return code_ == 0; }
+  int code() const { return code_; }
+  const std::string& message() const { return message_; }
+};
+inline Status OkStatus() { return Status(); }
+inline Status InvalidArgumentError(const std::string& m) { return Status(PIRB_INVALID_ARGUMENT, m); }
+inline Status InternalError(const std::string& m) { return Status(PIRB_INTERNAL, m); }
+inline Status FromRc(int rc) { return rc ? Status(rc, pirb_last_error()) : Status(); }
+
+template <typename T>
+class StatusOr {
+ public:
+  StatusOr(const Status& s) : status_(s) {}          // NOLINT
+  StatusOr(T v) : value_(std::move(v)) {}            // NOLINT
+  bool ok() const { return status_.ok(); }
+  const Status& status() const { return status_; }
+  T& value() { return *value_; }
+  const T& value() const { return *value_; }
+  T& operator*() { return *value_; }
+  T* operator->() { return &*value_; }
+
+ private:
+  Status status_;
+  std::optional<T> value_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t DEFAULT_POLY_MODULUS_DEGREE = 4096;  // parameters.h:40
+
+struct EncryptionParameters {
+  uint32_t poly_modulus_degree = 0;
+  uint64_t plain_modulus = 0;
+  std::vector<uint64_t> coeff_modulus;  // data primes, then the special prime
+};
+
+// parameters.cpp:33-54
+inline EncryptionParameters GenerateEncryptionParams(uint32_t poly_mod_degree = DEFAULT_POLY_MODULUS_DEGREE,
+                                                     uint32_t plain_mod_bit_size = 20) {
+  EncryptionParameters p;
+  p.poly_modulus_degree = poly_mod_degree;
+  p.plain_modulus = pirb_plain_modulus_batching(poly_mod_degree, plain_mod_bit_size);
+  uint64_t buf[PIRB_MAX_MODULI];
+  int n = pirb_bfv_default_coeff_modulus(poly_mod_degree, buf, PIRB_MAX_MODULI);
+  if (n > 0) p.coeff_modulus.assign(buf, buf + n);
+  return p;
+}
+
+// pir/proto/payload.proto:45-69
+struct PIRParameters {
+  uint64_t num_items = 0;
+  uint64_t num_pt = 0;
+  std::vector<uint32_t> dimensions;
+  EncryptionParameters encryption_parameters;
+  uint32_t bytes_per_item = 0;
+  uint32_t items_per_plaintext = 0;
+  uint32_t bits_per_coeff = 0;
+  bool use_ciphertext_multiplication = false;
+};
+
+// string_encoder.{h,cpp}: MSB-first packing of bytes into bits_per_coeff-bit coefficients
+class StringEncoder {
+ public:
+  explicit StringEncoder(const EncryptionParameters& ep)
+      : poly_modulus_degree_(ep.poly_modulus_degree), bits_per_coeff_(pirb_log2((uint32_t)ep.plain_modulus)) {}
+  size_t bits_per_coeff() const { return bits_per_coeff_; }
+  void set_bits_per_coeff(size_t b) { bits_per_coeff_ = b; }
+  size_t num_items_per_plaintext(size_t item_size) const { return poly_modulus_degree_ * bits_per_coeff_ / item_size / 8; }
+  size_t max_bytes_per_plaintext() const { return poly_modulus_degree_ * bits_per_coeff_ / 8; }
+
+  // string_encoder.cpp:58-80, 95-122: coefficients of the concatenation of [begin, end)
+  Status encode(std::vector<std::string>::const_iterator v, std::vector<std::string>::const_iterator end,
+                std::vector<uint64_t>& destination) const {
+    size_t total = 0;
+    for (auto it = v; it != end; ++it) total += it->size();
+    const size_t num_coeff = (size_t)std::ceil(static_cast<double>(total * 8) / bits_per_coeff_);
+    if (num_coeff > poly_modulus_degree_)
+      return InvalidArgumentError("Number of coefficients needed greater than poly modulus degree");
+    destination.assign(num_coeff, 0);
+    size_t ci = 0, cb = bits_per_coeff_;
+    for (; v != end; ++v)
+      for (uint8_t ch : *v) {
+        size_t remain = 8;
+        while (remain > 0) {
+          const size_t n = std::min(cb, remain);
+          destination[ci] = (destination[ci] << n) | (uint64_t)(ch >> (8 - n));
+          ch = (uint8_t)(ch << n);
+          cb -= n;
+          remain -= n;
+          if (cb == 0) { ++ci; cb = bits_per_coeff_; }
+        }
+      }
+    if (cb < bits_per_coeff_ && cb > 0) destination[ci] <<= cb;
+    return OkStatus();
+  }
+  Status encode(const std::string& value, std::vector<uint64_t>& destination) const {
+    std::vector<std::string> one{value};
+    return encode(one.cbegin(), one.cend(), destination);
+  }
+  // string_encoder.cpp:124-158
+  StatusOr<std::string> decode(const std::vector<uint64_t>& pt, size_t length, size_t byte_offset = 0) const {
+    if ((byte_offset + length) > (pt.size() * bits_per_coeff_ / 8))
+      return InvalidArgumentError("Requested decode beyond end of data in polynomial");
+    const size_t start = byte_offset * 8 / bits_per_coeff_;
+    size_t cb = ((start + 1) * bits_per_coeff_) - (byte_offset * 8);
+    if (cb == 0) cb = bits_per_coeff_;
+    std::string result(length, 0);
+    if (!length) return result;
+    size_t ri = 0, remain = 8;
+    for (size_t i = start; i < pt.size(); ++i) {
+      while (cb > 0) {
+        const size_t n = std::min(cb, remain);
+        result[ri] = (char)(((uint8_t)result[ri] << n) | (uint8_t)((pt[i] >> (cb - n)) & ((1u << n) - 1)));
+        cb -= n;
+        remain -= n;
+        if (remain == 0) {
+          if (++ri >= length) return result;
+          remain = 8;
+        }
+      }
+      cb = bits_per_coeff_;
+    }
+    return result;
+  }
+
+ private:
+  size_t poly_modulus_degree_;
+  size_t bits_per_coeff_;
+};
+
+// parameters.cpp:56-107
+inline StatusOr<std::shared_ptr<PIRParameters>> CreatePIRParameters(
+    size_t dbsize, size_t bytes_per_item = 0, size_t dimensions = 1,
+    EncryptionParameters seal_params = GenerateEncryptionParams(), bool use_ciphertext_multiplication = false,
+    size_t bits_per_coeff = 0) {
+  if (seal_params.coeff_modulus.size() < 2 || !seal_params.plain_modulus)
+    return InvalidArgumentError("Error setting encryption parameters: invalid parameters");
+  if (use_ciphertext_multiplication)
+    return InvalidArgumentError("ciphertext-multiplication mode is outside this library's path");
+  StringEncoder encoder(seal_params);
+  auto p = std::make_shared<PIRParameters>();
+  p->num_items = dbsize;
+  p->encryption_parameters = seal_params;
+  if (bits_per_coeff > 0) {
+    if (bits_per_coeff > encoder.bits_per_coeff()) return InvalidArgumentError("Bits per coefficient greater than max");
+    encoder.set_bits_per_coeff(bits_per_coeff);
+    p->bits_per_coeff = (uint32_t)bits_per_coeff;
+  }
+  if (bytes_per_item > 0) {
+    p->bytes_per_item = (uint32_t)bytes_per_item;
+    p->items_per_plaintext = (uint32_t)encoder.num_items_per_plaintext(bytes_per_item);
+    if (p->items_per_plaintext <= 0) return InvalidArgumentError("Cannot fit an item within one plaintext");
+    size_t num_pt = dbsize / p->items_per_plaintext;
+    while (dbsize > num_pt * p->items_per_plaintext) ++num_pt;
+    p->num_pt = num_pt;
+  } else {
+    p->bytes_per_item = (uint32_t)encoder.max_bytes_per_plaintext();
+    p->items_per_plaintext = 1;
+    p->num_pt = dbsize;
+  }
+  p->dimensions.resize(dimensions);
+  pirb_calculate_dimensions((uint32_t)p->num_pt, (uint32_t)dimensions, p->dimensions.data());
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct Ciphertext {
+  std::vector<uint64_t> limbs;  // [2][k][N]
+  bool is_ntt_form = false;
+  uint64_t* data() { return limbs.data(); }
+  const uint64_t* data() const { return limbs.data(); }
+};
+struct GaloisKeys {
+  std::vector<uint32_t> elts;
+  std::vector<uint64_t> limbs;  // [n][k][2][k+1][N], NTT form
+};
+struct Request {
+  std::vector<std::vector<Ciphertext>> query;
+  GaloisKeys galois_keys;
+};
+struct Response {
+  std::vector<std::vector<Ciphertext>> reply;
+};
+
+// utils.cpp:7-14
+inline std::vector<uint32_t> generate_galois_elts(uint64_t N) {
+  std::vector<uint32_t> e(pirb_ceil_log2((uint32_t)N));
+  for (size_t i = 0; i < e.size(); ++i) e[i] = (uint32_t)((N >> i) + 1);
+  return e;
+}
+
+namespace detail {
+struct CtxDeleter { void operator()(pirb_ctx* c) const { pirb_ctx_destroy(c); } };
+struct KeysDeleter { void operator()(pirb_keys* k) const { pirb_keys_destroy(k); } };
+inline std::vector<uint64_t> integer_encode(int64_t value, size_t N, uint64_t t) {  // SEAL IntegerEncoder::encode
+  std::vector<uint64_t> pt(N, 0);
+  const bool neg = value < 0;
+  uint64_t v = neg ? (uint64_t)(-value) : (uint64_t)value;
+  for (size_t i = 0; v; ++i, v >>= 1)
+    if (v & 1) pt[i] = neg ? t - 1 : 1;
+  return pt;
+}
+}  // namespace detail
+
+// ---------------------------------------------------------------------------------------------------------------
+class PIRDatabase {
+ public:
+  static StatusOr<std::shared_ptr<PIRDatabase>> Create(std::shared_ptr<PIRParameters> params, int device = 0) {
+    pirb_params p{};
+    const auto& ep = params->encryption_parameters;
+    if (ep.coeff_modulus.size() > PIRB_MAX_MODULI || params->dimensions.size() > PIRB_MAX_DIMS)
+      return InvalidArgumentError("too many moduli or dimensions");
+    p.poly_modulus_degree = ep.poly_modulus_degree;
+    p.n_moduli = (uint32_t)ep.coeff_modulus.size();
+    std::copy(ep.coeff_modulus.begin(), ep.coeff_modulus.end(), p.coeff_modulus);
+    p.plain_modulus = ep.plain_modulus;
+    p.n_dims = (uint32_t)params->dimensions.size();
+    std::copy(params->dimensions.begin(), params->dimensions.end(), p.dims);
+    p.num_pt = params->num_pt;
+    p.device = device;
+    p.shard_index = 0;
+    p.shard_count = 1;
+    pirb_ctx* ctx = nullptr;
+    Status st = FromRc(pirb_ctx_create(&p, &ctx));
+    if (!st.ok()) return st;
+    return std::shared_ptr<PIRDatabase>(new PIRDatabase(params, ctx));
+  }
+  static StatusOr<std::shared_ptr<PIRDatabase>> Create(const std::vector<std::string>& rawdb,
+                                                       std::shared_ptr<PIRParameters> params, int device = 0) {
+    auto db = Create(params, device);
+    if (!db.ok()) return db.status();
+    Status st = (*db)->populate(rawdb);
+    if (!st.ok()) return st;
+    return db;
+  }
+  static StatusOr<std::shared_ptr<PIRDatabase>> Create(const std::vector<int64_t>& rawdb,
+                                                       std::shared_ptr<PIRParameters> params, int device = 0) {
+    auto db = Create(params, device);
+    if (!db.ok()) return db.status();
+    Status st = (*db)->populate(rawdb);
+    if (!st.ok()) return st;
+    return db;
+  }
+
+  // database.cpp:84-110
+  Status populate(const std::vector<std::string>& rawdb) {
+    if (rawdb.size() != params_->num_items)
+      return InvalidArgumentError("Database size " + std::to_string(rawdb.size()) + " does not match params value " +
+                                  std::to_string(params_->num_items));
+    const size_t N = params_->encryption_parameters.poly_modulus_degree;
+    const size_t ipp = params_->items_per_plaintext;
+    StringEncoder encoder(params_->encryption_parameters);
+    if (params_->bits_per_coeff > 0) encoder.set_bits_per_coeff(params_->bits_per_coeff);
+    const size_t chunk = std::max<size_t>(1, (32u << 20) / (N * 8));
+    std::vector<uint64_t> buf, coeffs;
+    auto raw_it = rawdb.begin();
+    for (size_t start = 0; start < params_->num_pt; start += chunk) {
+      const size_t stop = std::min<size_t>(params_->num_pt, start + chunk);
+      buf.assign((stop - start) * N, 0);
+      for (size_t i = start; i < stop; ++i) {
+        auto end_it = (size_t)(rawdb.end() - raw_it) > ipp ? raw_it + ipp : rawdb.end();
+        Status st = encoder.encode(raw_it, end_it, coeffs);
+        if (!st.ok()) return st;
+        std::copy(coeffs.begin(), coeffs.end(), buf.begin() + (i - start) * N);
+        raw_it = end_it;
+      }
+      Status st = FromRc(pirb_db_load_coeff(ctx_.get(), buf.data(), start, stop - start));
+      if (!st.ok()) return st;
+    }
+    return OkStatus();
+  }
+  // database.cpp:60-82
+  Status populate(const std::vector<int64_t>& rawdb) {
+    if (rawdb.size() != params_->num_items)
+      return InvalidArgumentError("Database size " + std::to_string(rawdb.size()) + " does not match params value " +
+                                  std::to_string(params_->num_items));
+    const size_t N = params_->encryption_parameters.poly_modulus_degree;
+    std::vector<uint64_t> buf(rawdb.size() * N);
+    for (size_t i = 0; i < rawdb.size(); ++i) {
+      auto pt = detail::integer_encode(rawdb[i], N, params_->encryption_parameters.plain_modulus);
+      std::copy(pt.begin(), pt.end(), buf.begin() + i * N);
+    }
+    return FromRc(pirb_db_load_coeff(ctx_.get(), buf.data(), 0, rawdb.size()));
+  }
+
+  // database.cpp:290-316 — the selection vector is transformed to NTT form in place
+  StatusOr<std::vector<Ciphertext>> multiply(std::vector<Ciphertext>& selection_vector) const {
+    const size_t L = pirb_ct_limbs(ctx_.get());
+    std::vector<uint64_t> sv(selection_vector.size() * L);
+    for (size_t i = 0; i < selection_vector.size(); ++i) {
+      if (selection_vector[i].limbs.size() != L) return InvalidArgumentError("bad ciphertext size");
+      std::copy(selection_vector[i].limbs.begin(), selection_vector[i].limbs.end(), sv.begin() + i * L);
+    }
+    const size_t cap = pirb_reply_cts(ctx_.get());
+    std::vector<uint64_t> out(cap * L);
+    uint64_t cnt = 0;
+    Status st = FromRc(pirb_db_multiply(ctx_.get(), sv.data(), selection_vector.size(), out.data(), cap, &cnt));
+    if (!st.ok()) return st;
+    for (size_t i = 0; i < selection_vector.size(); ++i)
+      if (std::memcmp(selection_vector[i].limbs.data(), sv.data() + i * L, L * 8) != 0) {
+        std::copy(sv.begin() + i * L, sv.begin() + (i + 1) * L, selection_vector[i].limbs.begin());
+        selection_vector[i].is_ntt_form = true;
+      }
+    std::vector<Ciphertext> res(cnt);
+    for (size_t i = 0; i < cnt; ++i) res[i].limbs.assign(out.begin() + i * L, out.begin() + (i + 1) * L);
+    return res;
+  }
+
+  size_t size() const { return pirb_db_size(ctx_.get()); }
+
+  // database.cpp:318-332
+  std::vector<uint32_t> calculate_indices(uint32_t index) const {
+    uint32_t pt_index = index / params_->items_per_plaintext;
+    std::vector<uint32_t> results(params_->dimensions.size(), 0);
+    for (int i = (int)results.size() - 1; i >= 0; --i) {
+      results[i] = pt_index % params_->dimensions[i];
+      pt_index = pt_index / params_->dimensions[i];
+    }
+    return results;
+  }
+  size_t calculate_item_offset(uint32_t index) const {
+    const uint32_t pt_index = index / params_->items_per_plaintext;
+    return (index - (pt_index * params_->items_per_plaintext)) * params_->bytes_per_item;
+  }
+  static std::vector<uint32_t> calculate_dimensions(uint32_t db_size, uint32_t num_dimensions) {
+    std::vector<uint32_t> r(num_dimensions);
+    pirb_calculate_dimensions(db_size, num_dimensions, r.data());
+    return r;
+  }
+
+  pirb_ctx* handle() const { return ctx_.get(); }
+  const std::shared_ptr<PIRParameters>& params() const { return params_; }
+
+ private:
+  PIRDatabase(std::shared_ptr<PIRParameters> p, pirb_ctx* c) : params_(std::move(p)), ctx_(c) {}
+  std::shared_ptr<PIRParameters> params_;
+  std::unique_ptr<pirb_ctx, detail::CtxDeleter> ctx_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+class PIRServer {
+ public:
+  // server.cpp:35-42
+  static StatusOr<std::unique_ptr<PIRServer>> Create(std::shared_ptr<PIRDatabase> db,
+                                                     std::shared_ptr<PIRParameters> params) {
+    if (params->num_pt != db->size()) return InvalidArgumentError("database size mismatch");
+    return std::unique_ptr<PIRServer>(new PIRServer(std::move(db), std::move(params)));
+  }
+
+  // server.cpp:44-65: all queries of the request in one batched device call
+  StatusOr<Response> ProcessRequest(const Request& request) const {
+    pirb_ctx* ctx = db_->handle();
+    std::unique_ptr<pirb_keys, detail::KeysDeleter> keys;
+    Status st = LoadKeys(request.galois_keys, keys);
+    if (!st.ok()) return st;
+    Response response;
+    if (request.query.empty()) return response;
+    const size_t L = pirb_ct_limbs(ctx), n_ct = request.query[0].size(), R = pirb_reply_cts(ctx);
+    std::vector<uint64_t> q(request.query.size() * n_ct * L), r(request.query.size() * R * L);
+    for (size_t i = 0; i < request.query.size(); ++i) {
+      if (request.query[i].size() != n_ct || n_ct != pirb_query_cts(ctx))
+        return InvalidArgumentError("Number of ciphertexts doesn't match number of items for oblivious expansion.");
+      for (size_t c = 0; c < n_ct; ++c) {
+        if (request.query[i][c].limbs.size() != L) return InvalidArgumentError("bad ciphertext size");
+        std::copy(request.query[i][c].limbs.begin(), request.query[i][c].limbs.end(), q.begin() + (i * n_ct + c) * L);
+      }
+    }
+    st = FromRc(pirb_answer(ctx, keys.get(), q.data(), (uint32_t)request.query.size(), n_ct, r.data()));
+    if (!st.ok()) return st;
+    response.reply.resize(request.query.size());
+    for (size_t i = 0; i < request.query.size(); ++i) {
+      response.reply[i].resize(R);
+      for (size_t c = 0; c < R; ++c)
+        response.reply[i][c].limbs.assign(r.begin() + (i * R + c) * L, r.begin() + (i * R + c + 1) * L);
+    }
+    return response;
+  }
+
+  // server.cpp:67-76
+  Status substitute_power_x_inplace(Ciphertext& ct, uint32_t power, const GaloisKeys& gal_keys) const {
+    std::unique_ptr<pirb_keys, detail::KeysDeleter> keys;
+    Status st = LoadKeys(gal_keys, keys);
+    if (!st.ok()) return st;
+    return FromRc(pirb_substitute(db_->handle(), keys.get(), ct.data(), power));
+  }
+  // server.cpp:78-103
+  void multiply_inverse_power_of_x(const Ciphertext& encrypted, uint32_t k, Ciphertext& destination) const {
+    destination = encrypted;
+    pirb_mul_inv_pow_x(db_->handle(), encrypted.data(), k, destination.data());
+  }
+  // server.cpp:105-146
+  StatusOr<std::vector<Ciphertext>> oblivious_expansion(const Ciphertext& ct, size_t num_items,
+                                                        const GaloisKeys& gal_keys) const {
+    return Expand(ct.limbs.data(), 1, num_items, 1, gal_keys);
+  }
+  // server.cpp:148-171
+  StatusOr<std::vector<Ciphertext>> oblivious_expansion(const std::vector<Ciphertext>& cts, size_t total_items,
+                                                        const GaloisKeys& gal_keys) const {
+    const size_t L = pirb_ct_limbs(db_->handle());
+    std::vector<uint64_t> in(cts.size() * L);
+    for (size_t i = 0; i < cts.size(); ++i) std::copy(cts[i].limbs.begin(), cts[i].limbs.end(), in.begin() + i * L);
+    return Expand(in.data(), cts.size(), total_items, 0, gal_keys);
+  }
+
+ private:
+  PIRServer(std::shared_ptr<PIRDatabase> db, std::shared_ptr<PIRParameters> params)
+      : db_(std::move(db)), params_(std::move(params)) {}
+  Status LoadKeys(const GaloisKeys& gk, std::unique_ptr<pirb_keys, detail::KeysDeleter>& out) const {
+    pirb_keys* k = nullptr;
+    if (gk.limbs.size() != gk.elts.size() * pirb_key_limbs(db_->handle()))
+      return InvalidArgumentError("Galois key data has the wrong size");
+    Status st = FromRc(pirb_keys_load(db_->handle(), gk.elts.data(), (uint32_t)gk.elts.size(), gk.limbs.data(), &k));
+    out.reset(k);
+    return st;
+  }
+  StatusOr<std::vector<Ciphertext>> Expand(const uint64_t* cts, size_t n_ct, size_t total, int single,
+                                           const GaloisKeys& gal_keys) const {
+    std::unique_ptr<pirb_keys, detail::KeysDeleter> keys;
+    Status st = LoadKeys(gal_keys, keys);
+    if (!st.ok()) return st;
+    const size_t L = pirb_ct_limbs(db_->handle());
+    std::vector<uint64_t> out(std::max<size_t>(1, total) * L);
+    st = FromRc(pirb_expand(db_->handle(), keys.get(), cts, n_ct, total, single, out.data()));
+    if (!st.ok()) return st;
+    std::vector<Ciphertext> res(total);
+    for (size_t i = 0; i < total; ++i) res[i].limbs.assign(out.begin() + i * L, out.begin() + (i + 1) * L);
+    return res;
+  }
+  std::shared_ptr<PIRDatabase> db_;
+  std::shared_ptr<PIRParameters> params_;
+};
+
+}  // namespace pir

@@ -112,7 +112,7 @@ struct pirb_ctx {
   // CUDA graphs of the whole answer path (expansion + multiply), one per (batch size, key handle, partial flag);
   // they read c->qbuf and write c->rbuf, so they stay valid as long as no workspace buffer moves.
   struct GraphEntry { cudaGraphExec_t exec = nullptr; unsigned long long epoch = 0; u64 launches = 0; };
-  std::map<std::tuple<u32, const void*, int>, GraphEntry> graphs;
+  std::map<std::tuple<int, u32, const void*, const void*, const void*>, GraphEntry> graphs;  // (op, Q, keys, in, out)
   bool use_graphs = true;
   DevBuf dbg;            // PIRB_DEBUG_STAMPS=<level>: clock64 phase stamps of that expansion level
   int dbg_level = -1;
@@ -347,12 +347,14 @@ int run_answer(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u32 n_q
   return 0;
 }
 
-// Answer n_queries queries held in c->qbuf into c->rbuf, replaying a captured CUDA graph when one is valid.
-// The first call with a given shape runs eagerly (it sizes every workspace), the second one captures.
-int answer_buffers(pirb_ctx* c, const pirb_keys* keys, u32 n_queries, u64 n_ct, int partial, cudaStream_t st) {
-  if (!c->use_graphs || c->profiling || c->dbg.p)
-    return run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, st);
-  auto key = std::make_tuple(n_queries, (const void*)keys, partial);
+// Run `body(stream)` (a fixed sequence of kernel launches for fixed pointers and shapes), replaying a captured CUDA
+// graph when one is valid for `key`.  The first call with a key runs eagerly (it sizes every workspace), the second
+// one captures, later ones replay.  Any workspace reallocation or key-handle change bumps g_alloc_epoch and
+// invalidates the cache.
+template <typename Body>
+int run_graphed(pirb_ctx* c, const std::tuple<int, u32, const void*, const void*, const void*>& key, cudaStream_t st,
+                Body&& body) {
+  if (!c->use_graphs || c->profiling || c->dbg.p) return body(st);
   auto it = c->graphs.find(key);
   if (it != c->graphs.end() && it->second.exec && it->second.epoch == g_alloc_epoch) {
     c->launches = it->second.launches;
@@ -360,13 +362,18 @@ int answer_buffers(pirb_ctx* c, const pirb_keys* keys, u32 n_queries, u64 n_ct, 
     return 0;
   }
   if (it == c->graphs.end()) {  // first sight of this shape: eager run, remember that we have seen it
+    if (c->graphs.size() > 64) {  // callers that keep changing pointers: do not grow without bound
+      for (auto& kv : c->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      c->graphs.clear();
+    }
     c->graphs[key] = pirb_ctx::GraphEntry();
-    return run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, st);
+    return body(st);
   }
   if (it->second.exec) { cudaGraphExecDestroy(it->second.exec); it->second.exec = nullptr; }
   const unsigned long long epoch_before = g_alloc_epoch;
   CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-  const int rc = run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, st);
+  const int rc = body(st);
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(st, &graph);
   if (rc || e != cudaSuccess || epoch_before != g_alloc_epoch) {
@@ -374,7 +381,7 @@ int answer_buffers(pirb_ctx* c, const pirb_keys* keys, u32 n_queries, u64 n_ct, 
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
     if (rc) return rc;
-    return run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, st);
+    return body(st);
   }
   cudaGraphExec_t exec = nullptr;
   e = cudaGraphInstantiate(&exec, graph, 0);
@@ -382,13 +389,21 @@ int answer_buffers(pirb_ctx* c, const pirb_keys* keys, u32 n_queries, u64 n_ct, 
   if (e != cudaSuccess) {
     cudaGetLastError();
     c->use_graphs = false;
-    return run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, st);
+    return body(st);
   }
   it->second.exec = exec;
   it->second.epoch = g_alloc_epoch;
   it->second.launches = c->launches;
   CU(cudaGraphLaunch(exec, st));
   return 0;
+}
+
+// Answer n_queries queries held in c->qbuf into c->rbuf.
+int answer_buffers(pirb_ctx* c, const pirb_keys* keys, u32 n_queries, u64 n_ct, int partial, cudaStream_t st) {
+  return run_graphed(c, std::make_tuple(partial, n_queries, (const void*)keys, (const void*)c->qbuf.p, (const void*)c->rbuf.p),
+                     st, [&](cudaStream_t s_) {
+                       return run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, s_);
+                     });
 }
 
 }  // namespace
@@ -478,12 +493,20 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
     m.qd = (double)q;
     m.qinv = 1.0 / (double)q;
     if (!T.fw.empty()) {
+      // interleave (w, w/q) pairs: [fw | iw | fin], N double2 each
+      std::vector<double> packed(6ull * N);
+      const std::vector<double>* a3[3] = {&T.fw, &T.iw, &T.fin};
+      const std::vector<double>* b3[3] = {&T.fwi, &T.iwi, &T.fini};
+      for (int t3 = 0; t3 < 3; ++t3)
+        for (u64 n = 0; n < N; ++n) {
+          packed[(t3 * (u64)N + n) * 2] = (*a3[t3])[n];
+          packed[(t3 * (u64)N + n) * 2 + 1] = (*b3[t3])[n];
+        }
       double* dbase = reinterpret_cast<double*>(base + 4ull * N);
-      const std::vector<double>* src[6] = {&T.fw, &T.fwi, &T.iw, &T.iwi, &T.fin, &T.fini};
-      for (int t6 = 0; t6 < 6; ++t6)
-        CU(cudaMemcpy(dbase + (size_t)t6 * N, src[t6]->data(), N * sizeof(double), cudaMemcpyHostToDevice));
-      m.fw = dbase; m.fwi = dbase + N; m.iw = dbase + 2ull * N; m.iwi = dbase + 3ull * N;
-      m.fin = dbase + 4ull * N; m.fini = dbase + 5ull * N;
+      CU(cudaMemcpy(dbase, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice));
+      m.fw = reinterpret_cast<const double2*>(dbase);
+      m.iw = reinterpret_cast<const double2*>(dbase + 2ull * N);
+      m.fin = reinterpret_cast<const double2*>(dbase + 4ull * N);
     }
     if ((int)i < c->k) {
       P.inv_P[i] = hm::invmod_prime(Pq % q, q);
@@ -842,12 +865,15 @@ int pirb_expand_ntt_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_qu
   int rc;
   ExpandPlan* pl = get_plan(c, c->dim_sum, 0, &rc);
   if (!pl) return rc;
-  c->launches = 0;
-  if (c->profiling) cudaEventRecord(c->ev[0], st);
-  RC(run_expand(c, keys, pl, U(d_queries), (int)n_queries, st));
-  LAUNCH(c, launch_ntt_fwd(c->P, c->work.p, U(d_sv_ntt), (int)(c->dim_sum * 2 * c->k), c->k, 0, (int)n_queries,
-                           2 * pl->cap * c->ctL, c->dim_sum * c->ctL, st));
-  return 0;
+  return run_graphed(c, std::make_tuple(2, n_queries, (const void*)keys, (const void*)d_queries, (const void*)d_sv_ntt), st,
+                     [&](cudaStream_t s_) -> int {
+                       c->launches = 0;
+                       if (c->profiling) cudaEventRecord(c->ev[0], s_);
+                       RC(run_expand(c, keys, pl, U(d_queries), (int)n_queries, s_));
+                       LAUNCH(c, launch_ntt_fwd(c->P, c->work.p, U(d_sv_ntt), (int)(c->dim_sum * 2 * c->k), c->k, 0,
+                                                (int)n_queries, 2 * pl->cap * c->ctL, c->dim_sum * c->ctL, s_));
+                       return 0;
+                     });
 }
 
 int pirb_multiply_partial_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_queries, uint64_t* d_partial,
@@ -857,7 +883,12 @@ int pirb_multiply_partial_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_
   if (!n_queries) return 0;
   if (c->loaded != c->pt_count) return fail(PIRB_INVALID_ARGUMENT, "database size mismatch");
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-  const int rc = run_multiply(c, const_cast<u64*>(U(d_sv_ntt)), c->dim_sum * c->ctL, (int)n_queries, U(d_partial), 1, st, true);
+  const int rc = run_graphed(c, std::make_tuple(3, n_queries, (const void*)nullptr, (const void*)d_sv_ntt, (const void*)d_partial),
+                             st, [&](cudaStream_t s_) -> int {
+                               c->launches = 0;
+                               return run_multiply(c, const_cast<u64*>(U(d_sv_ntt)), c->dim_sum * c->ctL, (int)n_queries,
+                                                   U(d_partial), 1, s_, true);
+                             });
   c->ev_valid = c->profiling && rc == 0;
   return rc;
 }

@@ -95,6 +95,75 @@ k_scan(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_
 }
 
 // ---------------------------------------------------------------------------------------------
+// scan, register-pipelined LDG variant: the loads of step i+PD-1 are issued before the multiply-accumulates of
+// step i, so every warp keeps PD-1 steps of database/selection tiles in flight while it computes.
+// ---------------------------------------------------------------------------------------------
+template <int R, int PD, int MODE>
+__global__ void __launch_bounds__(SCAN_NT)
+k_scan_pipe(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
+            const u64* __restrict__ sv, u64 sv_qstride, int n_split, u64* __restrict__ part) {
+  const u32 kN = (u32)P.k * P.N;
+  const u32 limb = blockIdx.x * SCAN_LIMBS + threadIdx.x * 2;
+  const u32 row0 = blockIdx.y * R;
+  const u32 split = blockIdx.z % n_split, qi = blockIdx.z / n_split;
+  const ModC& m = P.m[limb / P.N];
+  const u32 per = (dimL + n_split - 1) / n_split;
+  const u32 i_lo = split * per;
+  const u32 i_hi = min(dimL, i_lo + per);
+  Acc<MODE> acc[R][2][2];
+  const int hb = P.half_bits;
+  const u64 ctL = 2ull * kN;
+  const u64* svq = sv + qi * sv_qstride + limb;
+  const u64* dbr[R];
+  u32 cnt[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const u64 first = (u64)(row0 + r) * dimL;
+    dbr[r] = db + first * kN + limb;
+    cnt[r] = (row0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
+  }
+  ulonglong2 s0[PD], s1[PD], d[PD][R];
+  auto load = [&](int slot, u32 i) {
+    const bool in = i < i_hi;
+    s0[slot] = in ? ldg128(svq + i * ctL) : make_ulonglong2(0, 0);
+    s1[slot] = in ? ldg128(svq + i * ctL + kN) : make_ulonglong2(0, 0);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      d[slot][r] = (in && i < cnt[r]) ? ldg128_stream(dbr[r] + (u64)i * kN) : make_ulonglong2(0, 0);
+  };
+#pragma unroll
+  for (int p = 0; p < PD - 1; ++p) load(p, i_lo + p);
+#pragma unroll 1
+  for (u32 i = i_lo; i < i_hi; i += PD) {
+#pragma unroll
+    for (int p = 0; p < PD; ++p) {
+      load((p + PD - 1) % PD, i + p + PD - 1);
+      const Opnd<MODE> a0x(s0[p].x, hb), a0y(s0[p].y, hb), a1x(s1[p].x, hb), a1y(s1[p].y, hb);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const Opnd<MODE> bx(d[p][r].x, hb), by(d[p][r].y, hb);
+        acc[r][0][0].mac(a0x, bx);
+        acc[r][0][1].mac(a0y, by);
+        acc[r][1][0].mac(a1x, bx);
+        acc[r][1][1].mac(a1y, by);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= n_rows) break;
+    u64* o = part + (((u64)qi * n_split + split) * n_rows + row0 + r) * ctL + limb;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      ulonglong2 v;
+      v.x = acc[r][c][0].reduce(m, hb);
+      v.y = acc[r][c][1].reduce(m, hb);
+      *reinterpret_cast<ulonglong2*>(o + (u64)c * kN) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // scan, TMA variant: the same arithmetic, but database and selection-vector tiles are moved global->shared by the
 // bulk-copy engine (cp.async.bulk, completion on an mbarrier) through a STAGES-deep ring, issued by one producer
 // lane; four consumer warps read the tiles from shared memory and keep the accumulators in registers.  Bytes in
@@ -305,6 +374,20 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
   const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
   dim3 grid(slices, (n_rows + R - 1) / R, n_queries * n_split);
   if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidConfiguration;
+  if (scan_mode() == 2) {
+#define PIPE_CASE(RR, PP)                                                                                          \
+  if (R == RR && U == PP) {                                                                                        \
+    if (mode == MAC_FP64) k_scan_pipe<RR, PP, MAC_FP64><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
+    else if (mode == MAC_INT24) k_scan_pipe<RR, PP, MAC_INT24><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
+    else k_scan_pipe<RR, PP, MAC_WIDE><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
+    return cudaGetLastError();                                                                                     \
+  }
+    PIPE_CASE(1, 2) PIPE_CASE(1, 3) PIPE_CASE(1, 4)
+    PIPE_CASE(2, 2) PIPE_CASE(2, 3) PIPE_CASE(2, 4)
+    PIPE_CASE(4, 2) PIPE_CASE(4, 3)
+#undef PIPE_CASE
+    return cudaErrorInvalidValue;
+  }
   if (scan_mode() == 1) {
     const int G = scan_groups(R);
     const int RG = R / G;

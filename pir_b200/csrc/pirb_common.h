@@ -2,6 +2,8 @@
 #pragma once
 #include <cstdint>
 
+#include <vector_types.h>  // double2
+
 typedef unsigned long long u64;  // == uint64_t on LP64; matches CUDA's 64-bit intrinsics
 typedef uint32_t u32;
 typedef uint8_t u8;
@@ -21,12 +23,10 @@ struct ModC {
   const u64* irps;
   // FP64 engine (moduli <= 44 bits): the same constants as integer-valued doubles, plus x/q companions
   double qd, qinv;         // q and 1/q
-  const double* fw;        // fw[i]  = (double)rp[i]                      forward twiddles, SEAL ordering
-  const double* fwi;       // fwi[i] = rp[i] / q
-  const double* iw;        // iw[g + j] = psi^(-j*N/g)   for gap g = 1,2,4,...,N/2, j < g   (inverse, DIT form)
-  const double* iwi;
-  const double* fin;       // fin[i] = N^{-1} * psi^{-i}   final scaling of the inverse
-  const double* fini;
+  // each table entry is the pair (w, w/q) so one 128-bit load fetches both operands of f64_modmul
+  const double2* fw;       // fw[i].x  = (double)rp[i]                    forward twiddles, SEAL ordering
+  const double2* iw;       // iw[g + j].x = psi^(-j*N/g)  for gap g = 1,2,4,...,N/2, j < g   (inverse, DIT form)
+  const double2* fin;      // fin[i].x = N^{-1} * psi^{-i}                final scaling of the inverse
   double pow_h, pow_h_i;    // 2^h mod q and (2^h mod q)/q     (h = DevParams::half_bits; FP64 Karatsuba recombination)
   double pow_2h, pow_2h_i;  // 2^(2h) mod q and its /q companion
 };

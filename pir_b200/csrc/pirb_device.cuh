@@ -348,8 +348,8 @@ __device__ __forceinline__ u64 f64_to_u64_exact(double d) {  // integer-valued, 
 
 // forward pass (Cooley-Tukey, SEAL ordering) on doubles; same unit geometry as ntt_fwd_pass
 template <int LOGN, int NT, int S0, int R>
-__device__ __forceinline__ void f64_fwd_pass(double* __restrict__ s, const double* __restrict__ tw,
-                                             const double* __restrict__ twi, double q, int tid) {
+__device__ __forceinline__ void f64_fwd_pass(double* __restrict__ s, const double2* __restrict__ tw, double q,
+                                             int tid) {
   constexpr int N = 1 << LOGN;
   constexpr int E = 1 << R;
   constexpr int TL = N >> (S0 + R);
@@ -368,8 +368,8 @@ __device__ __forceinline__ void f64_fwd_pass(double* __restrict__ s, const doubl
       const int mbase = (1 << (S0 + a)) + (hi << a);
 #pragma unroll
       for (int b = 0; b < (1 << a); ++b) {
-        const double w = __ldg(tw + mbase + b);
-        const double wi = __ldg(twi + mbase + b);
+        const double2 w2 = __ldg(tw + mbase + b);
+        const double w = w2.x, wi = w2.y;
 #pragma unroll
         for (int c = 0; c < half; ++c) {
           const int e0 = b * 2 * half + c, e1 = e0 + half;
@@ -387,8 +387,8 @@ __device__ __forceinline__ void f64_fwd_pass(double* __restrict__ s, const doubl
 // For the stage with gap g the twiddle of the pair at in-block offset j is iw[g + j] = psi^(-j*N/g)  (cyclic
 // inverse DFT with root psi^-2); the remaining psi^-i * N^-1 is applied per element at the end (fin table).
 template <int LOGN, int NT, int S0, int R>
-__device__ __forceinline__ void f64_inv_pass(double* __restrict__ s, const double* __restrict__ iw,
-                                             const double* __restrict__ iwi, double q, int tid) {
+__device__ __forceinline__ void f64_inv_pass(double* __restrict__ s, const double2* __restrict__ iw, double q,
+                                             int tid) {
   constexpr int N = 1 << LOGN;
   constexpr int E = 1 << R;
   constexpr int TL = N >> (S0 + R);
@@ -407,8 +407,8 @@ __device__ __forceinline__ void f64_inv_pass(double* __restrict__ s, const doubl
       const int g = dist * TL;
 #pragma unroll
       for (int c = 0; c < dist; ++c) {  // in-block offset j = c*TL + lo
-        const double w = __ldg(iw + g + c * TL + lo);
-        const double wi = __ldg(iwi + g + c * TL + lo);
+        const double2 w2 = __ldg(iw + g + c * TL + lo);
+        const double w = w2.x, wi = w2.y;
 #pragma unroll
         for (int b = 0; b < (1 << a); ++b) {
           const int e0 = b * 2 * dist + c, e1 = e0 + dist;
@@ -442,7 +442,8 @@ __device__ __forceinline__ u64 eng_store_fwd(u64 word, const ModC& m) {  // forw
 template <int ENG>
 __device__ __forceinline__ u64 eng_store_inv(u64 word, int i, const ModC& m) {  // inverse output word -> canonical
   if constexpr (ENG == ENG_FP64) {
-    double t = f64_modmul(__longlong_as_double((long long)word), __ldg(m.fin + i), __ldg(m.fini + i), m.qd);
+    const double2 f2 = __ldg(m.fin + i);
+    double t = f64_modmul(__longlong_as_double((long long)word), f2.x, f2.y, m.qd);
     t = t < 0.0 ? __dadd_rn(t, m.qd) : t;
     return f64_to_u64_exact(t);
   } else {
@@ -463,7 +464,8 @@ __device__ __forceinline__ double f64_negmod(double a, double q) { return a == 0
 template <int ENG>
 __device__ __forceinline__ u64 eng_finish_inv_native(u64 word, int i, const ModC& m) {
   if constexpr (ENG == ENG_FP64) {
-    double t = f64_modmul(__longlong_as_double((long long)word), __ldg(m.fin + i), __ldg(m.fini + i), m.qd);
+    const double2 f2 = __ldg(m.fin + i);
+    double t = f64_modmul(__longlong_as_double((long long)word), f2.x, f2.y, m.qd);
     t = t < 0.0 ? __dadd_rn(t, m.qd) : t;
     return (u64)__double_as_longlong(t);
   } else {
@@ -476,12 +478,12 @@ __device__ __forceinline__ void eng_forward(u64* s, const ModC& m, int tid) {
   if constexpr (ENG == ENG_FP64) {
     constexpr int R0 = ((LOGN - 1) % 3) + 1;
     double* d = reinterpret_cast<double*>(s);
-    f64_fwd_pass<LOGN, NT, 0, R0>(d, m.fw, m.fwi, m.qd, tid);
+    f64_fwd_pass<LOGN, NT, 0, R0>(d, m.fw, m.qd, tid);
     __syncthreads();
-    if constexpr (LOGN > R0) { f64_fwd_pass<LOGN, NT, R0, 3>(d, m.fw, m.fwi, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0 + 3) { f64_fwd_pass<LOGN, NT, R0 + 3, 3>(d, m.fw, m.fwi, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0 + 6) { f64_fwd_pass<LOGN, NT, R0 + 6, 3>(d, m.fw, m.fwi, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0 + 9) { f64_fwd_pass<LOGN, NT, R0 + 9, 3>(d, m.fw, m.fwi, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0) { f64_fwd_pass<LOGN, NT, R0, 3>(d, m.fw, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0 + 3) { f64_fwd_pass<LOGN, NT, R0 + 3, 3>(d, m.fw, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0 + 6) { f64_fwd_pass<LOGN, NT, R0 + 6, 3>(d, m.fw, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0 + 9) { f64_fwd_pass<LOGN, NT, R0 + 9, 3>(d, m.fw, m.qd, tid); __syncthreads(); }
   } else {
     ntt_forward_smem_t<LOGN, NT, ENG == ENG_INT_LAZY>(s, m, tid);
   }
@@ -491,11 +493,11 @@ __device__ __forceinline__ void eng_inverse(u64* s, const ModC& m, int tid) {
   if constexpr (ENG == ENG_FP64) {
     constexpr int R0 = ((LOGN - 1) % 3) + 1;
     double* d = reinterpret_cast<double*>(s);
-    if constexpr (LOGN > R0 + 9) { f64_inv_pass<LOGN, NT, R0 + 9, 3>(d, m.iw, m.iwi, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0 + 6) { f64_inv_pass<LOGN, NT, R0 + 6, 3>(d, m.iw, m.iwi, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0 + 3) { f64_inv_pass<LOGN, NT, R0 + 3, 3>(d, m.iw, m.iwi, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0) { f64_inv_pass<LOGN, NT, R0, 3>(d, m.iw, m.iwi, m.qd, tid); __syncthreads(); }
-    f64_inv_pass<LOGN, NT, 0, R0>(d, m.iw, m.iwi, m.qd, tid);
+    if constexpr (LOGN > R0 + 9) { f64_inv_pass<LOGN, NT, R0 + 9, 3>(d, m.iw, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0 + 6) { f64_inv_pass<LOGN, NT, R0 + 6, 3>(d, m.iw, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0 + 3) { f64_inv_pass<LOGN, NT, R0 + 3, 3>(d, m.iw, m.qd, tid); __syncthreads(); }
+    if constexpr (LOGN > R0) { f64_inv_pass<LOGN, NT, R0, 3>(d, m.iw, m.qd, tid); __syncthreads(); }
+    f64_inv_pass<LOGN, NT, 0, R0>(d, m.iw, m.qd, tid);
     __syncthreads();
   } else {
     ntt_inverse_smem_t<LOGN, NT, ENG == ENG_INT_LAZY>(s, m, tid);

@@ -1,0 +1,131 @@
+// End-to-end test of the C++ shim (pir_b200/cpp/pir_b200.hpp) written like the reference's own tests
+// (pir/cpp/correctness_test.cpp:82-93, pir/cpp/server_test.cpp:98-121, 209-260): client -> PIRServer::ProcessRequest
+// -> client.  The client side (keygen / encrypt / decrypt) and the expected answers come from the CPU oracle
+// (oracle/pir_oracle.hpp), which this test is allowed to use as the checker.
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+#include "../../oracle/pir_oracle.hpp"
+#include "../../pir_b200/cpp/pir_b200.hpp"
+
+#define CHECK(cond, msg)                                            \
+  do {                                                              \
+    if (!(cond)) {                                                  \
+      std::fprintf(stderr, "FAIL %s:%d %s\n", __FILE__, __LINE__, msg); \
+      return 1;                                                     \
+    }                                                               \
+  } while (0)
+
+static int run_case(size_t dbsize, size_t elem_size, size_t d, size_t desired_index) {
+  auto ep = pir::GenerateEncryptionParams(4096, 20);
+  auto params_or = pir::CreatePIRParameters(dbsize, elem_size, d, ep);
+  CHECK(params_or.ok(), "CreatePIRParameters");
+  auto params = *params_or;
+  std::mt19937_64 rng(42);
+  std::vector<std::string> db(dbsize, std::string(params->bytes_per_item, 0));
+  for (auto& s : db)
+    for (auto& ch : s) ch = (char)(rng() & 0xff);
+  auto db_or = pir::PIRDatabase::Create(db, params);
+  CHECK(db_or.ok(), db_or.status().message().c_str());
+  auto server_or = pir::PIRServer::Create(*db_or, params);
+  CHECK(server_or.ok(), "PIRServer::Create");
+  auto& server = *server_or;
+
+  // ---- client side (oracle harness) ----
+  orc::Context octx(ep.poly_modulus_degree, ep.coeff_modulus, ep.plain_modulus);
+  orc::Crypto crypto(octx);
+  orc::Rng r1(7);
+  orc::SecretKey sk = orc::gen_secret_key(octx, r1);
+  orc::PublicKey pk = orc::gen_public_key(octx, sk, r1);
+  pir::GaloisKeys gk;
+  gk.elts = pir::generate_galois_elts(ep.poly_modulus_degree);
+  const size_t key_limbs = octx.k * 2 * (octx.k + 1) * octx.N;
+  gk.limbs.resize(gk.elts.size() * key_limbs);
+  for (size_t i = 0; i < gk.elts.size(); ++i) orc::gen_galois_key(octx, sk, gk.elts[i], r1, gk.limbs.data() + i * key_limbs);
+
+  // query packing as PIRClient::createQueryFor (client.cpp:92-144) for dim_sum <= N
+  const size_t N = octx.N;
+  auto indices = (*db_or)->calculate_indices((uint32_t)desired_index);
+  size_t dim_sum = 0;
+  for (auto v : params->dimensions) dim_sum += v;
+  CHECK(dim_sum < N, "test shape must fit one query ciphertext");
+  const uint64_t m = pirb_next_power_two(dim_sum);
+  const uint64_t m_inv = orc::invmod(m % ep.plain_modulus, orc::Modulus(ep.plain_modulus));
+  std::vector<uint64_t> pt(N, 0);
+  size_t offset = 0;
+  for (size_t i = 0; i < indices.size(); ++i) {
+    pt[offset + indices[i]] = m_inv;
+    offset += params->dimensions[i];
+  }
+  pir::Request req;
+  req.galois_keys = gk;
+  req.query.resize(1);
+  req.query[0].resize(1);
+  req.query[0][0].limbs.resize(octx.ct_limbs());
+  crypto.encrypt(pk, pt.data(), N, r1, req.query[0][0].data());
+
+  auto resp_or = server->ProcessRequest(req);
+  CHECK(resp_or.ok(), resp_or.status().message().c_str());
+  auto& reply = resp_or->reply[0];
+
+  // ---- oracle answer on the same inputs: limbs must be identical ----
+  std::vector<uint64_t> coeffs, db_ntt(params->num_pt * octx.pt_limbs());
+  pir::StringEncoder enc(ep);
+  for (size_t i = 0; i < params->num_pt; ++i) {
+    auto b = db.begin() + i * params->items_per_plaintext;
+    auto e = (size_t)(db.end() - b) > params->items_per_plaintext ? b + params->items_per_plaintext : db.end();
+    CHECK(enc.encode(b, e, coeffs).ok(), "encode");
+    orc::plain_to_ntt(octx, coeffs.data(), coeffs.size(), db_ntt.data() + i * octx.pt_limbs());
+  }
+  orc::GaloisKeys ogk;
+  ogk.elts = gk.elts;
+  ogk.data = gk.limbs;
+  std::vector<uint64_t> want;
+  int rc = orc::process_query(octx, db_ntt.data(), params->num_pt, params->dimensions.data(), params->dimensions.size(),
+                              ogk, req.query[0][0].data(), 1, want);
+  CHECK(rc == 0, "oracle process_query");
+  CHECK(want.size() == reply.size() * octx.ct_limbs(), "reply count");
+  for (size_t i = 0; i < reply.size(); ++i)
+    CHECK(std::memcmp(reply[i].data(), want.data() + i * octx.ct_limbs(), octx.ct_limbs() * 8) == 0,
+          "GPU reply differs from the oracle");
+
+  // ---- client decode (client.cpp:219-255) ----
+  const size_t two_er = 2 * octx.expansion_ratio();
+  std::vector<std::vector<uint64_t>> cts;
+  for (auto& c : reply) cts.push_back(c.limbs);
+  std::vector<std::vector<uint64_t>> pts;
+  for (size_t level = 0; level < d; ++level) {
+    pts.assign(cts.size(), std::vector<uint64_t>(N));
+    for (size_t i = 0; i < cts.size(); ++i) crypto.decrypt(sk, cts[i].data(), pts[i].data());
+    if (pts.size() <= 1) break;
+    std::vector<std::vector<uint64_t>> next(cts.size() / two_er, std::vector<uint64_t>(octx.ct_limbs(), 0));
+    for (size_t i = 0; i < next.size(); ++i) {
+      std::vector<uint64_t> flat(two_er * N);
+      for (size_t e = 0; e < two_er; ++e) std::copy(pts[i * two_er + e].begin(), pts[i * two_er + e].end(), flat.begin() + e * N);
+      orc::reencode_decode(octx, flat.data(), next[i].data());
+    }
+    cts.swap(next);
+  }
+  auto got = enc.decode(pts[0], params->bytes_per_item, (*db_or)->calculate_item_offset((uint32_t)desired_index));
+  CHECK(got.ok(), "decode");
+  CHECK(*got == db[desired_index], "retrieved element differs");
+  std::printf("ok: %zu items x %u B, d=%zu, index %zu: reply (%zu cts) bit-exact vs oracle, element recovered\n", dbsize,
+              params->bytes_per_item, d, desired_index, reply.size());
+  return 0;
+}
+
+int main() {
+  // error behaviour of the factories (server.cpp:37-39)
+  {
+    auto params = *pir::CreatePIRParameters(10, 0, 1);
+    auto db = *pir::PIRDatabase::Create(params);
+    auto s = pir::PIRServer::Create(db, params);
+    CHECK(!s.ok() && s.status().code() == PIRB_INVALID_ARGUMENT, "size mismatch must be InvalidArgument");
+  }
+  if (run_case(10, 0, 1, 7)) return 1;         // server_test.cpp TestProcessRequest shape
+  if (run_case(82, 0, 2, 42)) return 1;        // server_test.cpp TestProcessRequest_2Dim shape (dims [10,9])
+  if (run_case(1200, 64, 1, 777)) return 1;    // correctness_test.cpp:110 shape
+  std::printf("SHIM_TEST_OK\n");
+  return 0;
+}

@@ -441,3 +441,16 @@ def test_repeated_requests_replay_the_captured_graph(srv10):
         r = server.ProcessRequest(pb.Request([q], gk2)).reply[0]
         assert np.array_equal(r, cl2.orc.process_query(dbn, p.dimensions, cl2.elts, raw2, q)), rep
         assert oc.integer_decode(cl2.decrypt(r[0]), cl2.orc.t) == vals[9 - rep] * 16
+
+
+def test_cpp_shim_end_to_end():
+    """pir::PIRServer / pir::PIRDatabase C++ shim (pir_b200/cpp/pir_b200.hpp) over the C ABI: build/shim_test runs the
+    reference-style client -> ProcessRequest -> client round trip and compares reply limbs with the oracle."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "shim_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", root, "build/shim_test"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "SHIM_TEST_OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]

@@ -37,7 +37,10 @@ def main():
     rng = np.random.default_rng(0)
     sv = bench.random_limbs(rng, mods[:k], (args.queries, dimL, 2), N)
     d_sv = sharded.to_device(sv, dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2():  # read a buffer larger than L2: evicts everything and leaves only CLEAN lines behind
+        return flush.view(torch.int64).sum()
     peak, _ = bench.measured_peak()
     nbytes = srv.scan_bytes(args.queries)
     if args.variants:
@@ -71,7 +74,7 @@ def main():
             same = bool(torch.equal(ref, out))
         ts = []
         for _ in range(args.iters):
-            flush.zero_()
+            flush_l2()
             srv.scan(d_sv, want_rows=False)
             ts.append(srv.last_scan_ms())  # CUDA events recorded around the kernel on its launching stream
         ts.sort()
