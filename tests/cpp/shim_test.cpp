@@ -119,8 +119,9 @@ int main() {
   // error behaviour of the factories (server.cpp:37-39)
   {
     auto params = *pir::CreatePIRParameters(10, 0, 1);
-    auto db = *pir::PIRDatabase::Create(params);
-    auto s = pir::PIRServer::Create(db, params);
+    auto db_or = pir::PIRDatabase::Create(params);
+    CHECK(db_or.ok(), db_or.status().message().c_str());
+    auto s = pir::PIRServer::Create(*db_or, params);
     CHECK(!s.ok() && s.status().code() == PIRB_INVALID_ARGUMENT, "size mismatch must be InvalidArgument");
   }
   if (run_case(10, 0, 1, 7)) return 1;         // server_test.cpp TestProcessRequest shape
