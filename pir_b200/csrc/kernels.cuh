@@ -74,6 +74,9 @@ cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peer
 cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64* work, const u64* root_off, int n_trees,
                                int n_queries, u64 q_stride, cudaStream_t st);
 
+// warm L2 with constants that every kernel of a query re-reads (tables, keys)
+cudaError_t launch_prefetch_l2(const void* p, u64 bytes, cudaStream_t st);
+
 // synthetic data: out[p][N] uniform in [0, q_{(p % cycle) + off}) from a counter-based generator
 cudaError_t launch_fill_random(const DevParams& P, u64* out, u64 n_polys, int cycle, int off, u64 seed, cudaStream_t st);
 

@@ -67,6 +67,23 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
     }                                                                                      \
   } while (0)
   PIRB_STAMP(0);
+  // Prologue: pull everything this CTA will read from global memory into L2 now (one 128-byte line per prefetch), so
+  // the key limbs of phase 2 and the source polynomials of phases 1 and 3 are L2 hits when they are needed.
+  {
+    constexpr int LINES = N * 8 / 128;  // lines per polynomial
+    for (int J = 0; J < k; ++J) {
+      const char* kp = reinterpret_cast<const char*>(key + ((u64)(J * 2 + c) * (k + 1) + I) * N);
+      for (int l = tid; l < LINES; l += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + (size_t)l * 128));
+    }
+    for (int J = c; J < k; J += 2) {
+      const char* sp = reinterpret_cast<const char*>(src + (u64)(k + J) * N);
+      for (int l = tid; l < LINES; l += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (size_t)l * 128));
+    }
+    if (I < k) {
+      const char* sp = reinterpret_cast<const char*>(src + (u64)(c * k + I) * N);
+      for (int l = tid; l < LINES; l += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (size_t)l * 128));
+    }
+  }
 
   // ---- phase 1: my digits ----
   for (int J = c; J < k; J += 2) {
@@ -85,7 +102,12 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
     eng_forward<LOGN, NT, ENG>(D, mI, tid);
     PIRB_STAMP(2);
 #pragma unroll
-    for (int i = tid; i < N; i += NT) D[swz(i)] = eng_store_fwd<ENG>(D[swz(i)], mI);
+    for (int i = tid; i < N; i += NT) {
+      if constexpr (ENG == ENG_FP64)  // stay in the FP64 domain: canonical integer-valued double
+        D[swz(i)] = (u64)__double_as_longlong(f64_canon(__longlong_as_double((long long)D[swz(i)]), mI.qd, mI.qinv));
+      else
+        D[swz(i)] = eng_store_fwd<ENG>(D[swz(i)], mI);
+    }
   }
   PIRB_STAMP(3);
   cluster.sync();
@@ -98,29 +120,59 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
     // four coefficients per thread at a time; for every digit all operand loads (shared / distributed shared /
     // global) are issued before the first multiply so their latencies overlap
     constexpr int CH = 4;
+    if constexpr (ENG == ENG_FP64) {
+      // k <= 8 terms: one exact FP64 modular product per term (digit (.) key), summed and canonicalised once.
+      // The key limb's w/q companion is formed on the fly (kv * (1/q)); its 2^-51 relative error keeps the
+      // quotient estimate within 0.51 of the true value, so |product| <= 0.54 q as for table constants.
+      const double qd = mI.qd, qinv = mI.qinv;
 #pragma unroll 1
-    for (int i0 = tid; i0 < N; i0 += CH * NT) {
-      Acc<MODE> acc[CH];
-      int si[CH];
+      for (int i0 = tid; i0 < N; i0 += CH * NT) {
+        double acc[CH];
+        int si[CH];
 #pragma unroll
-      for (int e = 0; e < CH; ++e) si[e] = swz(i0 + e * NT);
-#pragma unroll 1
-      for (int J = 0; J < k; ++J) {
-        const u64* buf = (((J & 1) == c) ? smem : peer) + (size_t)(J >> 1) * N;
-        const u64* kp = key + ((u64)(J * 2 + c) * (k + 1) + I) * N + i0;
-        u64 dv[CH], kv[CH];
+        for (int e = 0; e < CH; ++e) { si[e] = swz(i0 + e * NT); acc[e] = 0.0; }
+#pragma unroll 2
+        for (int J = 0; J < k; ++J) {
+          const u64* buf = (((J & 1) == c) ? smem : peer) + (size_t)(J >> 1) * N;
+          const u64* kp = key + ((u64)(J * 2 + c) * (k + 1) + I) * N + i0;
+          u64 dv[CH], kv[CH];
 #pragma unroll
-        for (int e = 0; e < CH; ++e) {
-          dv[e] = buf[si[e]];
-          kv[e] = __ldg(kp + e * NT);
+          for (int e = 0; e < CH; ++e) {
+            dv[e] = buf[si[e]];
+            kv[e] = __ldg(kp + e * NT);
+          }
+#pragma unroll
+          for (int e = 0; e < CH; ++e) {
+            const double kd = u64_to_f64_exact(kv[e]);
+            const double t = f64_modmul(__longlong_as_double((long long)dv[e]), kd, __dmul_rn(kd, qinv), qd);
+            acc[e] = __dadd_rn(acc[e], t);
+          }
         }
 #pragma unroll
-        for (int e = 0; e < CH; ++e) acc[e].mac(Opnd<MODE>(dv[e], hb), Opnd<MODE>(kv[e], hb));
+        for (int e = 0; e < CH; ++e) A[si[e]] = (u64)__double_as_longlong(f64_canon(acc[e], qd, qinv));
       }
+    } else {
+#pragma unroll 1
+      for (int i0 = tid; i0 < N; i0 += CH * NT) {
+        Acc<MODE> acc[CH];
+        int si[CH];
 #pragma unroll
-      for (int e = 0; e < CH; ++e) {
-        if constexpr (ENG == ENG_FP64 && MODE == MAC_FP64) A[si[e]] = (u64)__double_as_longlong(acc[e].reduce_d(mI));
-        else A[si[e]] = eng_load<ENG>(acc[e].reduce(mI, hb));
+        for (int e = 0; e < CH; ++e) si[e] = swz(i0 + e * NT);
+#pragma unroll 1
+        for (int J = 0; J < k; ++J) {
+          const u64* buf = (((J & 1) == c) ? smem : peer) + (size_t)(J >> 1) * N;
+          const u64* kp = key + ((u64)(J * 2 + c) * (k + 1) + I) * N + i0;
+          u64 dv[CH], kv[CH];
+#pragma unroll
+          for (int e = 0; e < CH; ++e) {
+            dv[e] = buf[si[e]];
+            kv[e] = __ldg(kp + e * NT);
+          }
+#pragma unroll
+          for (int e = 0; e < CH; ++e) acc[e].mac(Opnd<MODE>(dv[e], hb), Opnd<MODE>(kv[e], hb));
+        }
+#pragma unroll
+        for (int e = 0; e < CH; ++e) A[si[e]] = eng_load<ENG>(acc[e].reduce(mI, hb));
       }
     }
     __syncthreads();

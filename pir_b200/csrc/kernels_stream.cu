@@ -630,6 +630,19 @@ cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64* work, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// L2 warm-up of constants (NTT tables, the client's Galois keys): one prefetch per 128-byte line, fire and forget.
+__global__ void __launch_bounds__(256) k_prefetch_l2(const char* __restrict__ p, u64 lines) {
+  const u64 l = (u64)blockIdx.x * 256 + threadIdx.x;
+  if (l < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + l * 128));
+}
+cudaError_t launch_prefetch_l2(const void* p, u64 bytes, cudaStream_t st) {
+  const u64 lines = (bytes + 127) / 128;
+  if (!lines) return cudaSuccess;
+  k_prefetch_l2<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(reinterpret_cast<const char*>(p), lines);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_fill_random(const __grid_constant__ DevParams P, u64* __restrict__ out, int cycle, int off, u64 seed) {
   const u64 poly = blockIdx.x;
