@@ -194,8 +194,10 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
   const u64 q_stride = 2 * pl->cap * c->ctL;
   RC(c->work.ensure((size_t)n_queries * q_stride * sizeof(u64)));
   const u64 nodes = pl->max_nodes * n_queries;
-  RC(c->dig.ensure((size_t)std::max<u64>(nodes, 1) * (c->k + 1) * c->k * c->N * sizeof(u64)));
-  RC(c->acc.ensure((size_t)std::max<u64>(nodes, 1) * 2 * (c->k + 1) * c->N * sizeof(u64)));
+  if (!c->use_cluster) {  // the cluster kernel keeps digits and accumulators in shared memory
+    RC(c->dig.ensure((size_t)std::max<u64>(nodes, 1) * (c->k + 1) * c->k * c->N * sizeof(u64)));
+    RC(c->acc.ensure((size_t)std::max<u64>(nodes, 1) * 2 * (c->k + 1) * c->N * sizeof(u64)));
+  }
   LAUNCH(c, launch_place_roots(c->P, d_query, c->work.p, pl->d_off.p, pl->n_trees, n_queries, q_stride, st));
   for (int j = 0; j < pl->max_logm; ++j) {
     const u32 g = (c->N >> j) + 1;

@@ -95,6 +95,81 @@ k_scan(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_
 }
 
 // ---------------------------------------------------------------------------------------------
+// scan for a BATCH of queries sharing one pass over the database (BASELINE config 4: 64 concurrent queries).
+// A CTA owns R rows x QB queries for a slice of 128 limbs (one limb per thread): every database limb it loads is
+// used for QB queries x 2 ciphertext polynomials, every selection-vector limb for R rows.  Query tiles are the
+// fastest grid dimension, so the CTAs that read the same database tile run together and share it through L2.
+// Slices are the SLOWEST grid dimension: while one 128-limb slice is being processed its selection-vector data for
+// all queries (Q x dimL x 2 KiB) stays in L2 and the slice of the database streams through exactly once.
+//   grid (query tile, row tile * n_split, slice)
+// ---------------------------------------------------------------------------------------------
+constexpr int BATCH_NT = 128;
+
+template <int R, int QB, int MODE>
+__global__ void __launch_bounds__(BATCH_NT)
+k_scan_batch(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
+             const u64* __restrict__ sv, u64 sv_qstride, int n_queries, int n_split, u64* __restrict__ part) {
+  const u32 kN = (u32)P.k * P.N;
+  const u64 ctL = 2ull * kN;
+  const u32 limb = blockIdx.z * BATCH_NT + threadIdx.x;
+  const u32 q0 = blockIdx.x * QB;
+  const u32 n_row_tiles = (n_rows + R - 1) / R;
+  const u32 row0 = (blockIdx.y % n_row_tiles) * R;
+  const u32 split = blockIdx.y / n_row_tiles;
+  const ModC& m = P.m[limb / P.N];
+  const u32 per = (dimL + n_split - 1) / n_split;
+  const u32 i_lo = split * per;
+  const u32 i_hi = min(dimL, i_lo + per);
+  const int hb = P.half_bits;
+  Acc<MODE> acc[R][QB][2];
+  const u64* dbr[R];
+  u32 cnt[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const u64 first = (u64)(row0 + r) * dimL;
+    dbr[r] = db + first * kN + limb;
+    cnt[r] = (row0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
+  }
+  const u64* svq[QB];
+#pragma unroll
+  for (int q = 0; q < QB; ++q) svq[q] = sv + (u64)min(q0 + q, (u32)n_queries - 1) * sv_qstride + limb;
+#pragma unroll 1
+  for (u32 i = i_lo; i < i_hi; ++i) {
+    u64 s[QB][2], d[R];
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      s[q][0] = __ldg(svq[q] + i * ctL);
+      s[q][1] = __ldg(svq[q] + i * ctL + kN);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) d[r] = i < cnt[r] ? __ldg(dbr[r] + (u64)i * kN) : 0;
+    Opnd<MODE> b0(d[0], hb);
+    Opnd<MODE> b1(d[R - 1], hb);
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      const Opnd<MODE> a0(s[q][0], hb), a1(s[q][1], hb);
+      acc[0][q][0].mac(a0, b0);
+      acc[0][q][1].mac(a1, b0);
+      if (R > 1) {
+        acc[R - 1][q][0].mac(a0, b1);
+        acc[R - 1][q][1].mac(a1, b1);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= n_rows) break;
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      if (q0 + q >= (u32)n_queries) break;
+      u64* o = part + (((u64)(q0 + q) * n_split + split) * n_rows + row0 + r) * ctL + limb;
+      o[0] = acc[r][q][0].reduce(m, hb);
+      o[kN] = acc[r][q][1].reduce(m, hb);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // scan, register-pipelined LDG variant: the loads of step i+PD-1 are issued before the multiply-accumulates of
 // step i, so every warp keeps PD-1 steps of database/selection tiles in flight while it computes.
 // ---------------------------------------------------------------------------------------------
@@ -374,6 +449,22 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
   const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
   dim3 grid(slices, (n_rows + R - 1) / R, n_queries * n_split);
   if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidConfiguration;
+  if (n_queries >= env_int("PIRB_SCAN_BATCH_MIN", 4) && scan_mode() == 0) {
+    // batch of queries: share every database tile between QB queries
+    const int QB = env_int("PIRB_SCAN_QB", n_queries >= 4 ? 4 : 2);
+    const int RB = env_int("PIRB_SCAN_RB", n_rows >= 2 ? 2 : 1);
+    dim3 bgrid((n_queries + QB - 1) / QB, ((n_rows + RB - 1) / RB) * n_split, (u32)P.k * P.N / BATCH_NT);
+    if (bgrid.y > 65535 || bgrid.z > 65535) return cudaErrorInvalidConfiguration;
+#define BATCH_CASE(RR, QQ)                                                                                         \
+  if (RB == RR && QB == QQ) {                                                                                      \
+    if (mode == MAC_FP64) k_scan_batch<RR, QQ, MAC_FP64><<<bgrid, BATCH_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_queries, n_split, part); \
+    else if (mode == MAC_INT24) k_scan_batch<RR, QQ, MAC_INT24><<<bgrid, BATCH_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_queries, n_split, part); \
+    else k_scan_batch<RR, QQ, MAC_WIDE><<<bgrid, BATCH_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_queries, n_split, part); \
+    return cudaGetLastError();                                                                                     \
+  }
+    BATCH_CASE(1, 2) BATCH_CASE(1, 4) BATCH_CASE(2, 2) BATCH_CASE(2, 4)
+#undef BATCH_CASE
+  }
   if (scan_mode() == 2) {
 #define PIPE_CASE(RR, PP)                                                                                          \
   if (R == RR && U == PP) {                                                                                        \
