@@ -335,6 +335,15 @@ def run_ours(args):
                              "with the GPU reply: %s" % (len(ts), "identical" if parity else "MISMATCH"),
                    "p50_latency_ms": 1e3 * med, "host_cpus": os.cpu_count()}
 
+    traffic = args.scan_traffic
+    if traffic is None and world == 1 and ql == 1:
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one scan launch, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r1_scan_traffic.json")) as f:
+                t = json.load(f)
+            if t.get("workload") == args.workload:
+                traffic = t["traffic_bytes"]
+        except Exception:  # noqa: BLE001
+            traffic = None
     line = {
         "metric": "pir_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -351,7 +360,7 @@ def run_ours(args):
                 "p50_latency_ms": 1e3 * statistics.median(lat)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": args.scan_traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms,
                      "share_of_step": scan_ms / stage_mean["total"]},
         "stages_ms": stage_mean,
@@ -374,7 +383,7 @@ def main():
     ap.add_argument("--queries-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scan-traffic", type=float, default=None,
-                    help="dram bytes per scan launch from the committed ncu capture (profiles/), if known")
+                    help="dram bytes per scan launch; default: the committed ncu capture in profiles/ for this workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
