@@ -217,9 +217,14 @@ def run_ours(args):
         # so the timed step does not also pay for writing back 126 MB of dirty flush data
         return flush.view(torch.int64).sum()
 
+    if world > 1 and args.p2p:
+        srv.setup_peer_exchange(max_queries=world * ql)
+
     def step_dev():
         if world == 1:
             return srv.answer(d_q)
+        if args.p2p:
+            return srv.answer_batch_distributed_p2p(d_q)
         return srv.answer_batch_distributed(d_q)
 
     def barrier():
@@ -279,7 +284,7 @@ def run_ours(args):
     else:
         def step_e2e():
             d = q_pin.to(dev, non_blocking=True)
-            r = srv.answer_batch_distributed(d)
+            r = srv.answer_batch_distributed_p2p(d) if args.p2p else srv.answer_batch_distributed(d)
             out_pin.copy_(r, non_blocking=True)
             torch.cuda.synchronize()
     for _ in range(3):
@@ -351,7 +356,9 @@ def run_ours(args):
         "config": {"workload": WORKLOADS[args.workload][5], "queries_per_step": world * ql, "num_pt": params.num_pt,
                    "dims": list(params.dimensions), "key_switches_per_query": sum(
                        int(pb.next_power_two(min(N, max(0, sum(params.dimensions) - t * N)))) - 1 for t in range(n_ct)),
-                   "reply_cts": srv.ctx.reply_cts, "parallelism": "rows sharded x%d, expansion split by query" % world,
+                   "reply_cts": srv.ctx.reply_cts, "parallelism": "rows sharded x%d, expansion split by query%s" % (
+                       world, "" if world == 1 else (", partial replies reduced over NVLink peer loads" if args.p2p
+                                                    else ", partial replies gathered with NCCL")),
                    "l2": "256 MiB buffer read between timed iterations (evicts L2, leaves clean lines; outside the per-step CUDA events)",
                    "galois_keys": "resident in HBM, uploaded once per client"},
         "p50_latency_ms": statistics.median(step_ms),
@@ -382,6 +389,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--queries-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--p2p", type=int, default=1,
+                    help="N>1: combine partial replies with peer-memory loads in the reduce kernel (1) or an NCCL gather (0)")
     ap.add_argument("--scan-traffic", type=float, default=None,
                     help="dram bytes per scan launch; default: the committed ncu capture in profiles/ for this workload")
     args = ap.parse_args()

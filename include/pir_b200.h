@@ -127,6 +127,20 @@ int pirb_reduce_finish_dev(pirb_ctx* ctx, const uint64_t* d_partials, uint32_t n
                            uint32_t n_queries, uint64_t* d_replies, void* stream);
 int pirb_reduce_finish_peers_dev(pirb_ctx* ctx, const uint64_t* const* d_peer_ptrs, uint32_t n_parts,
                                  uint32_t n_queries, uint64_t* d_replies, void* stream);
+/* Peer-memory exchange of the partial replies (P2P loads inside the reduce kernel instead of an NCCL
+ * gather).  Every rank creates `n_slots` exchange slots for up to `max_queries` queries and exports the CUDA IPC
+ * handle (64 bytes); after the handles have been exchanged, pirb_xbuf_open maps the peers' buffers.  Partials are
+ * written into a slot with the *_xbuf_dev variants; once every rank has done so (the caller provides the
+ * stream-ordered barrier), pirb_reduce_finish_xbuf_dev adds all ranks' partials mod q — loading the peers' copies over
+ * NVLink inside the kernel — and applies the final inverse NTT for queries [q_first, q_first + q_count). */
+int pirb_xbuf_create(pirb_ctx* ctx, uint32_t max_queries, uint32_t n_slots, uint8_t* ipc_handle_out /*[64]*/);
+int pirb_xbuf_open(pirb_ctx* ctx, const uint8_t* ipc_handles /*[n_ranks][64]*/, uint32_t n_ranks, uint32_t self_rank);
+int pirb_answer_partial_xbuf_dev(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries,
+                                 uint64_t n_ct, uint32_t slot, void* stream);
+int pirb_multiply_partial_xbuf_dev(pirb_ctx* ctx, const uint64_t* d_sv_ntt, uint32_t n_queries, uint32_t slot,
+                                   void* stream);
+int pirb_reduce_finish_xbuf_dev(pirb_ctx* ctx, uint32_t slot, uint32_t q_first, uint32_t q_count, uint64_t* d_replies,
+                                void* stream);
 /* Scan only (the HBM-bound kernel): d_sv_ntt[n_queries][dims[d-1]][2][k][N] NTT form -> rows in NTT form.
  * Used by the bench to time the scan in isolation.  d_rows may be NULL (internal scratch). */
 int pirb_scan_dev(pirb_ctx* ctx, const uint64_t* d_sv_ntt, uint32_t n_queries, uint64_t* d_rows, void* stream);

@@ -68,6 +68,12 @@ SYMBOLS = {
                                          C.c_void_p]),
     "pirb_reduce_finish_peers_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
                                                C.c_void_p]),
+    "pirb_xbuf_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "pirb_xbuf_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "pirb_answer_partial_xbuf_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32,
+                                               C.c_void_p]),
+    "pirb_multiply_partial_xbuf_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "pirb_reduce_finish_xbuf_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "pirb_scan_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "pirb_sync": (C.c_int, [C.c_void_p]),
     "pirb_debug_stamps": (C.c_int, [C.c_void_p, u64p, C.c_uint64]),

@@ -114,6 +114,13 @@ struct pirb_ctx {
   struct GraphEntry { cudaGraphExec_t exec = nullptr; unsigned long long epoch = 0; u64 launches = 0; };
   std::map<std::tuple<int, u32, const void*, const void*, const void*>, GraphEntry> graphs;  // (op, Q, keys, in, out)
   bool use_graphs = true;
+  // peer-memory exchange of partial replies (CUDA IPC over NVLink): own slots + the peers' mapped base pointers
+  u64* xbuf = nullptr;
+  u64 xslot_limbs = 0;
+  u32 xslots = 0;
+  std::vector<void*> xpeer_open;  // mappings to close
+  DevBuf xptrs;                   // device table [n_ranks] of base pointers (own + peers)
+  u32 xranks = 0;
   DevBuf dbg;            // PIRB_DEBUG_STAMPS=<level>: clock64 phase stamps of that expansion level
   int dbg_level = -1;
   bool use_cluster = false;  // one-launch-per-level key switch on thread-block clusters
@@ -600,6 +607,8 @@ void pirb_ctx_destroy(pirb_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   for (auto& kv : c->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (void* pm : c->xpeer_open) cudaIpcCloseMemHandle(pm);
+  if (c->xbuf) cudaFree(c->xbuf);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -914,7 +923,75 @@ int pirb_reduce_finish_peers_dev(pirb_ctx* c, const uint64_t* const* d_peer_ptrs
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   const u64 cts = (u64)n_queries * c->reply_cts;
   RC(c->rbuf.ensure(cts * c->ctL * sizeof(u64)));
-  LAUNCH(c, launch_modadd_reduce_ptrs(c->P, reinterpret_cast<const u64* const*>(d_peer_ptrs), (int)n_parts, c->rbuf.p, cts, st));
+  LAUNCH(c, launch_modadd_reduce_ptrs(c->P, reinterpret_cast<const u64* const*>(d_peer_ptrs), (int)n_parts, 0, c->rbuf.p, cts, st));
+  LAUNCH(c, launch_ntt_inv(c->P, c->rbuf.p, U(d_replies), (int)(cts * 2 * c->k), c->k, 0, 1, 0, 1, 0, 0, st));
+  return 0;
+}
+
+// ---- peer-memory exchange ("direct P2P loads in the reduce kernel") ------------------------------------
+int pirb_xbuf_create(pirb_ctx* c, uint32_t max_queries, uint32_t n_slots, uint8_t* handle_out) {
+  if (!c || !handle_out || !max_queries || !n_slots) return fail(PIRB_INVALID_ARGUMENT, "bad argument");
+  CU(cudaSetDevice(c->device));
+  if (c->xbuf) return fail(PIRB_INVALID_ARGUMENT, "exchange buffer already created");
+  c->xslot_limbs = (u64)max_queries * c->reply_cts * c->ctL;
+  c->xslots = n_slots;
+  CU(cudaMalloc(&c->xbuf, c->xslot_limbs * n_slots * sizeof(u64)));
+  ++g_alloc_epoch;
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->xbuf));
+  static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+  memcpy(handle_out, &h, 64);
+  return 0;
+}
+
+int pirb_xbuf_open(pirb_ctx* c, const uint8_t* handles, uint32_t n_ranks, uint32_t self_rank) {
+  if (!c || !handles || !c->xbuf || self_rank >= n_ranks) return fail(PIRB_INVALID_ARGUMENT, "bad argument");
+  CU(cudaSetDevice(c->device));
+  std::vector<u64*> table(n_ranks);
+  for (u32 r = 0; r < n_ranks; ++r) {
+    if (r == self_rank) { table[r] = c->xbuf; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, 64);
+    void* pm = nullptr;
+    CU(cudaIpcOpenMemHandle(&pm, h, cudaIpcMemLazyEnablePeerAccess));
+    c->xpeer_open.push_back(pm);
+    table[r] = (u64*)pm;
+  }
+  RC(c->xptrs.ensure(n_ranks * sizeof(u64*)));
+  CU(cudaMemcpy(c->xptrs.p, table.data(), n_ranks * sizeof(u64*), cudaMemcpyHostToDevice));
+  c->xranks = n_ranks;
+  return 0;
+}
+
+int pirb_multiply_partial_xbuf_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_queries, uint32_t slot,
+                                   void* stream) {
+  if (!c || !c->xbuf || slot >= c->xslots) return fail(PIRB_INVALID_ARGUMENT, "exchange buffer not set up");
+  if ((u64)n_queries * c->reply_cts * c->ctL > c->xslot_limbs) return fail(PIRB_INVALID_ARGUMENT, "too many queries for the slot");
+  return pirb_multiply_partial_dev(c, d_sv_ntt, n_queries, reinterpret_cast<uint64_t*>(c->xbuf + (u64)slot * c->xslot_limbs),
+                                   stream);
+}
+
+int pirb_answer_partial_xbuf_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_queries,
+                                 uint64_t n_ct, uint32_t slot, void* stream) {
+  if (!c || !c->xbuf || slot >= c->xslots) return fail(PIRB_INVALID_ARGUMENT, "exchange buffer not set up");
+  if ((u64)n_queries * c->reply_cts * c->ctL > c->xslot_limbs) return fail(PIRB_INVALID_ARGUMENT, "too many queries for the slot");
+  return pirb_answer_partial_dev(c, keys, d_queries, n_queries, n_ct,
+                                 reinterpret_cast<uint64_t*>(c->xbuf + (u64)slot * c->xslot_limbs), stream);
+}
+
+// Caller guarantees (stream-ordered barrier, e.g. a tiny NCCL all-reduce) that every rank has finished writing `slot`.
+int pirb_reduce_finish_xbuf_dev(pirb_ctx* c, uint32_t slot, uint32_t q_first, uint32_t q_count, uint64_t* d_replies,
+                                void* stream) {
+  if (!c || !c->xbuf || !c->xranks || slot >= c->xslots || !d_replies) return fail(PIRB_INVALID_ARGUMENT, "exchange buffer not set up");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const u64 cts = (u64)q_count * c->reply_cts;
+  if (!cts) return 0;
+  RC(c->rbuf.ensure(cts * c->ctL * sizeof(u64)));
+  const u64 off = (u64)slot * c->xslot_limbs + (u64)q_first * c->reply_cts * c->ctL;
+  // the partial replies of every rank are loaded through the peer mappings inside the reducing kernel (NVLink P2P)
+  LAUNCH(c, launch_modadd_reduce_ptrs(c->P, reinterpret_cast<const u64* const*>(c->xptrs.p), (int)c->xranks, off, c->rbuf.p,
+                                      cts, st));
   LAUNCH(c, launch_ntt_inv(c->P, c->rbuf.p, U(d_replies), (int)(cts * 2 * c->k), c->k, 0, 1, 0, 1, 0, 0, st));
   return 0;
 }

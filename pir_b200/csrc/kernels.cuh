@@ -67,8 +67,8 @@ cudaError_t launch_dim_mac(const DevParams& P, const u64* pts, u64 pts_qstride, 
 cudaError_t launch_modadd_reduce(const DevParams& P, const u64* in, u64 stride, int n_parts, u64* out, u64 n_cts,
                                  cudaStream_t st);
 // out[i] = sum over peers of *(peers[g] + i) mod q: same, reading each partial through its own (peer) pointer
-cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peers_dev, int n_parts, u64* out,
-                                      u64 n_cts, cudaStream_t st);
+cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peers_dev, int n_parts, u64 offset_limbs,
+                                      u64* out, u64 n_cts, cudaStream_t st);
 
 // copy root ciphertexts of every tree into place: work[qi*q_stride + root_off[t]] = query[qi][t]
 cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64* work, const u64* root_off, int n_trees,

@@ -680,23 +680,24 @@ cudaError_t launch_modadd_reduce(const DevParams& P, const u64* in, u64 stride, 
 // other GPUs' buffers, so the loads travel over NVLink inside the reducing kernel (no staging copy).
 __global__ void __launch_bounds__(256)
 k_modadd_reduce_ptrs(const __grid_constant__ DevParams P, const u64* const* __restrict__ peers, int n_parts,
-                     u64* __restrict__ out, u64 total_limbs) {
+                     u64 offset, u64* __restrict__ out, u64 total_limbs) {
   const u64 i = ((u64)blockIdx.x * 256 + threadIdx.x) * 2;
   if (i >= total_limbs) return;
   const u64 q = P.m[(i / P.N) % P.k].q;
-  ulonglong2 v = *reinterpret_cast<const ulonglong2*>(peers[0] + i);
+  ulonglong2 v = *reinterpret_cast<const ulonglong2*>(peers[0] + offset + i);
   for (int g = 1; g < n_parts; ++g) {
-    const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(peers[g] + i);
+    const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(peers[g] + offset + i);
     v.x = addmod(v.x, w.x, q);
     v.y = addmod(v.y, w.y, q);
   }
   *reinterpret_cast<ulonglong2*>(out + i) = v;
 }
-cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peers_dev, int n_parts, u64* out,
-                                      u64 n_cts, cudaStream_t st) {
+cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peers_dev, int n_parts, u64 offset_limbs,
+                                      u64* out, u64 n_cts, cudaStream_t st) {
   const u64 total = n_cts * 2 * P.k * P.N;
   if (!total) return cudaSuccess;
-  k_modadd_reduce_ptrs<<<(unsigned)((total / 2 + 255) / 256), 256, 0, st>>>(P, peers_dev, n_parts, out, total);
+  k_modadd_reduce_ptrs<<<(unsigned)((total / 2 + 255) / 256), 256, 0, st>>>(P, peers_dev, n_parts, offset_limbs, out,
+                                                                            total);
   return cudaGetLastError();
 }
 

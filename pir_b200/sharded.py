@@ -170,6 +170,42 @@ class ShardServer:
         self._exit()
         return out
 
+    # -- peer-memory exchange (CUDA IPC over NVLink) instead of the NCCL gather of partial replies ------------------
+    def setup_peer_exchange(self, max_queries: int, n_slots: int = 2):
+        """Collective: create this rank's exchange slots, swap IPC handles, map the peers' buffers."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        handle = (C.c_uint8 * 64)()
+        _check(_lib.lib().pirb_xbuf_create(self.ctx.h, max_queries, n_slots, handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle))
+        blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+        _check(_lib.lib().pirb_xbuf_open(self.ctx.h, blob, world, rank))
+        self._xslots, self._xslot = n_slots, 0
+        self._xflag = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def answer_batch_distributed_p2p(self, d_queries_local: torch.Tensor) -> torch.Tensor:
+        """Like answer_batch_distributed, but the partial replies are not gathered: every rank writes them into its
+        own exchange slot and, after a stream-ordered barrier, each rank's reduce kernel loads all ranks' partials
+        for its own queries straight through the peer mappings (NVLink P2P) while adding them mod q."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ql = d_queries_local.shape[0]
+        sv_local = self.expand_ntt(d_queries_local)
+        sv_all = self._empty(world * ql, *sv_local.shape[1:])
+        dist.all_gather_into_tensor(sv_all, sv_local)
+        slot = self._xslot
+        st = self._enter()
+        _check(_lib.lib().pirb_multiply_partial_xbuf_dev(self.ctx.h, _dp(sv_all), world * ql, slot, st))
+        self._exit()
+        dist.all_reduce(self._xflag)  # barrier in stream order: every rank's slot is complete before anyone reads it
+        out = self._empty(ql, self.ctx.reply_cts, 2, self.k, self.N)
+        st = self._enter()
+        _check(_lib.lib().pirb_reduce_finish_xbuf_dev(self.ctx.h, slot, rank * ql, ql, _dp(out), st))
+        self._exit()
+        self._xslot = (slot + 1) % self._xslots
+        return out
+
     def scan(self, d_sv_ntt: torch.Tensor, want_rows=True):
         """[Q][dimL][2][k][N] NTT-form last-dimension selection cts -> rows [Q][n_rows][2][k][N] NTT form."""
         Q = d_sv_ntt.shape[0]

@@ -43,6 +43,12 @@ def main():
         # (2) batch path: rank r expands only query r
         mine = sharded.to_host(srv.answer_batch_distributed(sharded.to_device(queries[rank:rank + 1], dev)))[0]
         ok &= bool(np.array_equal(full[rank], mine))
+        # (3) same, partial replies exchanged through peer memory (CUDA IPC) instead of an NCCL gather; run it three
+        #     times so both exchange slots and their reuse are exercised
+        srv.setup_peer_exchange(max_queries=world)
+        for _ in range(3):
+            p2p = sharded.to_host(srv.answer_batch_distributed_p2p(sharded.to_device(queries[rank:rank + 1], dev)))[0]
+            ok &= bool(np.array_equal(p2p, mine))
         # oracle on the whole database
         want = cl.orc.process_query(oc.db_to_ntt(cl.orc, coeffs), p.dimensions, cl.elts, cl.galois, queries[rank])
         ok &= bool(np.array_equal(mine, want))
