@@ -36,6 +36,8 @@ WORKLOADS = {
     "cfg1": (4096, 64, 1, 4096, 20, "d=1, 4096 x 64 B, N=4096 (BASELINE configs[0])"),
     "cfg4": (1 << 22, 256, 2, 4096, 20, "d=2, 2^22 x 256 B, N=4096 (BASELINE configs[3] database)"),
     "cfg3": (1 << 20, 1024, 2, 8192, 20, "d=2, 2^20 x 1 KiB, N=8192 (BASELINE configs[2] database)"),
+    "cfg5a": (1 << 24, 256, 1, 4096, 20, "d=1, 2^24 x 256 B, N=4096 (BASELINE configs[4], d=1 arm)"),
+    "cfg5b": (1 << 24, 256, 2, 4096, 20, "d=2, 2^24 x 256 B, N=4096 (BASELINE configs[4], d=2 arm)"),
 }
 
 

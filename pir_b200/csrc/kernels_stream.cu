@@ -95,6 +95,108 @@ k_scan(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_
 }
 
 // ---------------------------------------------------------------------------------------------
+// scan, shared-selection variant: G groups of 128 threads in one CTA work on different rows (R rows each) of the same
+// 256-limb slice and share the selection-vector tiles through a double-buffered shared-memory stage, so the L2->SM
+// traffic for the selection vector per database byte drops from 2/R to 2/(R*G) without more registers per thread.
+//   grid (slice, row tile of R*G rows, qi*n_split + split); G*128 threads
+// ---------------------------------------------------------------------------------------------
+template <int R, int G, int U, int MODE>
+__global__ void __launch_bounds__(SCAN_NT * G)
+k_scan_share(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
+             const u64* __restrict__ sv, u64 sv_qstride, int n_split, u64* __restrict__ part) {
+  __shared__ __align__(16) u64 stage[2][U][2][SCAN_LIMBS];  // [buffer][i1][poly][limb]
+  constexpr int NTH = SCAN_NT * G;
+  constexpr int VEC = U * 2 * SCAN_LIMBS / 2;  // 128-bit vectors per stage buffer
+  constexpr int VPT = (VEC + NTH - 1) / NTH;   // vectors each thread moves per chunk
+  const u32 kN = (u32)P.k * P.N;
+  const int g = threadIdx.x / SCAN_NT, t = threadIdx.x % SCAN_NT;
+  const u32 limb0 = blockIdx.x * SCAN_LIMBS;
+  const u32 limb = limb0 + t * 2;
+  const u32 row0 = (blockIdx.y * G + g) * R;
+  const u32 split = blockIdx.z % n_split, qi = blockIdx.z / n_split;
+  const ModC& m = P.m[limb / P.N];
+  const u32 per = (dimL + n_split - 1) / n_split;
+  const u32 i_lo = split * per;
+  const u32 i_hi = min(dimL, i_lo + per);
+  Acc<MODE> acc[R][2][2];
+  const int hb = P.half_bits;
+  const u64 ctL = 2ull * kN;
+  const u64* svq = sv + qi * sv_qstride + limb0;
+  const u64* dbr[R];
+  u32 cnt[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const u64 first = (u64)(row0 + r) * dimL;
+    dbr[r] = db + first * kN + limb;
+    cnt[r] = (row0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
+  }
+  // cooperative fetch of one chunk (U consecutive i1) of selection tiles: vector v -> (u, poly, pair of limbs)
+  auto fetch = [&](u32 i_base, ulonglong2 (&regs)[VPT]) {
+#pragma unroll
+    for (int x = 0; x < VPT; ++x) {
+      const int v = threadIdx.x + x * NTH;
+      const int u = v / SCAN_LIMBS, rem = v % SCAN_LIMBS;  // SCAN_LIMBS vectors per i1 (2 polys x 128 vectors)
+      const int poly = rem / (SCAN_LIMBS / 2), l2 = rem % (SCAN_LIMBS / 2);
+      const u32 i = i_base + u;
+      regs[x] = (v < VEC && i < i_hi) ? ldg128(svq + i * ctL + (u64)poly * kN + l2 * 2) : make_ulonglong2(0, 0);
+    }
+  };
+  auto stash = [&](int buf, const ulonglong2 (&regs)[VPT]) {
+#pragma unroll
+    for (int x = 0; x < VPT; ++x) {
+      const int v = threadIdx.x + x * NTH;
+      if (v < VEC) reinterpret_cast<ulonglong2*>(&stage[buf][0][0][0])[v] = regs[x];
+    }
+  };
+  ulonglong2 nxt[VPT];
+  fetch(i_lo, nxt);
+  stash(0, nxt);
+  __syncthreads();
+  int buf = 0;
+#pragma unroll 1
+  for (u32 i1 = i_lo; i1 < i_hi; i1 += U) {
+    fetch(i1 + U, nxt);  // next chunk's selection tiles travel while this chunk is multiplied
+    ulonglong2 d[U][R];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const u32 i = i1 + u;
+        d[u][r] = (i < i_hi && i < cnt[r]) ? ldg128_stream(dbr[r] + (u64)i * kN) : make_ulonglong2(0, 0);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(&stage[buf][u][0][t * 2]);
+      const ulonglong2 s1 = *reinterpret_cast<const ulonglong2*>(&stage[buf][u][1][t * 2]);
+      const Opnd<MODE> a0x(s0.x, hb), a0y(s0.y, hb), a1x(s1.x, hb), a1y(s1.y, hb);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const Opnd<MODE> bx(d[u][r].x, hb), by(d[u][r].y, hb);
+        acc[r][0][0].mac(a0x, bx);
+        acc[r][0][1].mac(a0y, by);
+        acc[r][1][0].mac(a1x, bx);
+        acc[r][1][1].mac(a1y, by);
+      }
+    }
+    stash(buf ^ 1, nxt);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= n_rows) break;
+    u64* o = part + (((u64)qi * n_split + split) * n_rows + row0 + r) * ctL + limb;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      ulonglong2 v;
+      v.x = acc[r][c][0].reduce(m, hb);
+      v.y = acc[r][c][1].reduce(m, hb);
+      *reinterpret_cast<ulonglong2*>(o + (u64)c * kN) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // scan for a BATCH of queries sharing one pass over the database (BASELINE config 4: 64 concurrent queries).
 // A CTA owns R rows x QB queries for a slice of 128 limbs (one limb per thread): every database limb it loads is
 // used for QB queries x 2 ciphertext polynomials, every selection-vector limb for R rows.  Query tiles are the
@@ -464,6 +566,21 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
   }
     BATCH_CASE(1, 2) BATCH_CASE(1, 4) BATCH_CASE(2, 2) BATCH_CASE(2, 4)
 #undef BATCH_CASE
+  }
+  if (scan_mode() == 3) {
+    const int G = env_int("PIRB_SCAN_G", 2);
+    dim3 sgrid(slices, (n_rows + R * G - 1) / (R * G), n_queries * n_split);
+#define SHARE_CASE(RR, GG, UU)                                                                                     \
+  if (R == RR && G == GG && U == UU) {                                                                             \
+    if (mode == MAC_FP64) k_scan_share<RR, GG, UU, MAC_FP64><<<sgrid, SCAN_NT * GG, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
+    else if (mode == MAC_INT24) k_scan_share<RR, GG, UU, MAC_INT24><<<sgrid, SCAN_NT * GG, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
+    else k_scan_share<RR, GG, UU, MAC_WIDE><<<sgrid, SCAN_NT * GG, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
+    return cudaGetLastError();                                                                                     \
+  }
+    SHARE_CASE(2, 2, 2) SHARE_CASE(2, 4, 2) SHARE_CASE(2, 2, 1) SHARE_CASE(2, 4, 1) SHARE_CASE(1, 4, 2) SHARE_CASE(1, 8, 2)
+    SHARE_CASE(2, 8, 2)
+#undef SHARE_CASE
+    return cudaErrorInvalidValue;
   }
   if (scan_mode() == 2) {
 #define PIPE_CASE(RR, PP)                                                                                          \

@@ -454,3 +454,69 @@ def test_cpp_shim_end_to_end():
         subprocess.check_call(["make", "-C", root, "build/shim_test"])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "SHIM_TEST_OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+
+
+# ------------------------------------------------------------------------------------------------ other engines / sizes
+def _find_ntt_primes(bits, n, count):
+    out, v = [], (1 << bits) - 2 * n + 1
+    while len(out) < count:
+        if ob.is_prime(v):
+            out.append(v)
+        v -= 2 * n
+    return out
+
+
+@pytest.mark.parametrize("n,bits,label", [(4096, 60, "60-bit moduli: corrected integer butterflies + 128-bit MACs"),
+                                           (4096, 50, "50-bit moduli: lazy integer butterflies + 128-bit MACs"),
+                                           (4096, 47, "47-bit moduli: lazy integer butterflies + 24-bit-split MACs"),
+                                           (2048, 40, "N=2048 with two data moduli: FP64 engine at another size"),
+                                           (16384, 44, "N=16384, k=3: FP64 engine, 128 KiB transforms")])
+def test_custom_moduli_exercise_every_engine(n, bits, label):
+    """Parity does not depend on the arithmetic engine: custom coefficient moduli force the integer fallbacks
+    (moduli above 44 bits) and other transform sizes; expansion + multiply must still match the oracle limb for limb.
+    (Noise is irrelevant here: inputs are random ring elements.)"""
+    k = 2 if n != 16384 else 3
+    mods = _find_ntt_primes(bits, n, k + 1)
+    ep = pb.EncryptionParameters(n, ob.plain_modulus_batching(n, 20), mods)
+    p = pb.CreatePIRParameters(23, 0, 2, ep)
+    orc = ob.Oracle(n, mods, ep.plain_modulus)
+    rng = np.random.default_rng(bits)
+    coeffs = rng.integers(0, ep.plain_modulus, (p.num_pt, n), dtype=np.uint64)
+    db = pb.PIRDatabase.Create(p)
+    db.load_coeff(coeffs)
+    want_db = np.stack([orc.plain_to_ntt(c) for c in coeffs])
+    assert np.array_equal(db.read_ntt(0, p.num_pt), want_db), label
+    server = pb.PIRServer.Create(db, p)
+    elts = pb.generate_galois_elts(n)
+    n_lvl = pb.ceil_log2(sum(p.dimensions))
+    elts = elts[:n_lvl]
+    keys = np.ascontiguousarray(np.stack([np.stack([np.stack([np.stack(
+        [rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(k + 1)]) for _ in range(2)]) for _ in range(k)])
+        for _ in elts]))
+    gk = pb.GaloisKeys(elts, keys.reshape(-1))
+    q = np.stack([rng.integers(0, mods[j], n, dtype=np.uint64) for _ in range(2) for j in range(k)]).reshape(1, 2, k, n)
+    got = server.ProcessRequest(pb.Request([q], gk)).reply[0]
+    want = orc.process_query(want_db, p.dimensions, elts, keys.reshape(-1), q)
+    assert got.shape == want.shape and np.array_equal(got, want), label
+
+
+def test_multiply_with_unused_selection_entries_and_empty_database():
+    """database.cpp:183: the scan stops when the database runs out.  dims given by the caller need not be tight:
+    [4,4] over 5 plaintexts leaves rows 2,3 empty and row 1 short; only the touched selection entries become NTT form."""
+    ep = pb.GenerateEncryptionParams(4096, 20)
+    p = pb.PIRParameters(num_items=5, num_pt=5, dimensions=[4, 4], encryption_parameters=ep, bytes_per_item=9728,
+                         items_per_plaintext=1)
+    orc = ob.Oracle(4096, ep.coeff_modulus, ep.plain_modulus)
+    rng = np.random.default_rng(77)
+    coeffs = rng.integers(0, ep.plain_modulus, (5, 4096), dtype=np.uint64)
+    db = pb.PIRDatabase.Create(p)
+    db.load_coeff(coeffs)
+    sv = np.stack([np.stack([rng.integers(0, ep.coeff_modulus[j], 4096, dtype=np.uint64) for _ in range(2)
+                             for j in range(2)]).reshape(2, 2, 4096) for _ in range(8)])
+    want, sv_after = orc.db_multiply(np.stack([orc.plain_to_ntt(c) for c in coeffs]), [4, 4], sv)
+    got_sv = sv.copy()
+    got = db.multiply(got_sv)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got_sv, sv_after)      # entries 2,3 of the first dimension stay in coefficient form
+    empty = pb.PIRDatabase.Create(p)
+    assert empty.multiply(sv.copy()).shape[0] == 0   # reference returns an empty vector (database.cpp:181-183)
