@@ -76,6 +76,12 @@ uint64_t pirb_db_size(const pirb_ctx* ctx);              /* PIRDatabase::size():
  * coeffs[count][N] < t, plaintext indices are GLOBAL; the shard keeps the ones it owns.
  * The centred lift + NTT (transform_to_ntt_inplace(pt, first_parms_id), database.cpp:103-106) run on the GPU. */
 int pirb_db_load_coeff(pirb_ctx* ctx, const uint64_t* coeffs, uint64_t first_pt, uint64_t count);
+/* PIRDatabase::populate(vector<string>) entirely on the device: `items` holds n_items raw items of bytes_per_item
+ * bytes each, starting at GLOBAL item index first_item (which must start a plaintext).  StringEncoder's MSB-first bit
+ * packing (string_encoder.cpp:58-80, 108-122; bits_per_coeff = 0 means trunc(log2 t)), the centred lift and the NTT all
+ * run on the GPU; only the raw bytes cross PCIe. */
+int pirb_db_load_items(pirb_ctx* ctx, const uint8_t* items, uint64_t first_item, uint64_t n_items,
+                       uint32_t bytes_per_item, uint32_t items_per_plaintext, uint32_t bits_per_coeff);
 /* Same, for a database already in NTT form (SEAL ordering): limbs[count][k][N]. */
 int pirb_db_load_ntt(pirb_ctx* ctx, const uint64_t* limbs, uint64_t first_pt, uint64_t count);
 /* Read back NTT-form plaintexts (persistence / tests): out[count][k][N]. */

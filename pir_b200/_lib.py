@@ -49,6 +49,7 @@ SYMBOLS = {
     "pirb_shard_pt_count": (C.c_uint64, [C.c_void_p]),
     "pirb_db_size": (C.c_uint64, [C.c_void_p]),
     "pirb_db_load_coeff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "pirb_db_load_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]),
     "pirb_db_load_ntt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "pirb_db_read_ntt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "pirb_db_fill_random": (C.c_int, [C.c_void_p, C.c_uint64]),

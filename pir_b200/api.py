@@ -300,7 +300,16 @@ class PIRDatabase:
             raise PIRStatusError(INVALID_ARGUMENT, "Database size %d does not match params value %d" %
                                  (len(rawdb), p.num_items))
         N = p.encryption_parameters.poly_modulus_degree
-        if len(rawdb) and isinstance(rawdb[0], (bytes, bytearray, str)):
+        if len(rawdb) and isinstance(rawdb[0], (bytes, bytearray, str)) and \
+                all(len(x) == p.bytes_per_item for x in rawdb):
+            # fixed-size items: ship the raw bytes, pack + lift + NTT on the GPU
+            ipp = p.items_per_plaintext
+            per_chunk = max(ipp, ((64 << 20) // max(1, p.bytes_per_item)) // ipp * ipp)
+            for start in range(0, len(rawdb), per_chunk):
+                chunk = rawdb[start:start + per_chunk]
+                blob = b"".join(x.encode("latin1") if isinstance(x, str) else bytes(x) for x in chunk)
+                self.load_items(blob, start, len(chunk))
+        elif len(rawdb) and isinstance(rawdb[0], (bytes, bytearray, str)):
             enc = StringEncoder(p.encryption_parameters)
             if p.bits_per_coeff > 0:
                 enc.set_bits_per_coeff(p.bits_per_coeff)
@@ -327,6 +336,41 @@ class PIRDatabase:
     def load_coeff(self, coeffs, first_pt=0):
         a = _u64(coeffs).reshape(-1, self.ctx.N)
         _check(_lib.lib().pirb_db_load_coeff(self.ctx.h, _ptr(a), first_pt, a.shape[0]))
+
+    def load_items(self, blob: bytes, first_item: int, n_items: int):
+        """Raw fixed-size items -> packed, lifted, NTT-transformed on the device (pirb_db_load_items)."""
+        p = self.params
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        _check(_lib.lib().pirb_db_load_items(self.ctx.h, _ptr(buf), first_item, n_items, p.bytes_per_item,
+                                             p.items_per_plaintext, p.bits_per_coeff))
+
+    def save(self, path: str, chunk_pt: int = 4096):
+        """Persist this shard's preprocessed (NTT-form) plaintexts: 64-byte header + raw little-endian u64 limbs."""
+        L = _lib.lib()
+        begin, count = int(L.pirb_shard_pt_begin(self.ctx.h)), int(L.pirb_shard_pt_count(self.ctx.h))
+        hdr = np.zeros(8, dtype=np.uint64)
+        hdr[:6] = [0x3142444252495042, self.ctx.N, self.ctx.k, begin, count, self.params.encryption_parameters.plain_modulus]
+        with open(path, "wb") as f:
+            f.write(hdr.tobytes())
+            f.write(np.array(self.params.encryption_parameters.coeff_modulus, dtype=np.uint64).tobytes())
+            for s0 in range(begin, begin + count, chunk_pt):
+                n = min(chunk_pt, begin + count - s0)
+                f.write(self.read_ntt(s0, n).tobytes())
+
+    def load(self, path: str, chunk_pt: int = 4096):
+        """Load a shard file written by save(); the parameters must match."""
+        ep = self.params.encryption_parameters
+        with open(path, "rb") as f:
+            hdr = np.frombuffer(f.read(64), dtype=np.uint64)
+            mods = np.frombuffer(f.read(8 * len(ep.coeff_modulus)), dtype=np.uint64)
+            if int(hdr[0]) != 0x3142444252495042 or int(hdr[1]) != self.ctx.N or int(hdr[2]) != self.ctx.k or \
+                    int(hdr[5]) != ep.plain_modulus or [int(x) for x in mods] != list(ep.coeff_modulus):
+                raise PIRStatusError(INVALID_ARGUMENT, "shard file does not match the parameters")
+            begin, count = int(hdr[3]), int(hdr[4])
+            for s0 in range(begin, begin + count, chunk_pt):
+                n = min(chunk_pt, begin + count - s0)
+                a = np.frombuffer(f.read(n * self.ctx.pt_limbs * 8), dtype=np.uint64)
+                self.load_ntt(a, s0)
 
     def load_ntt(self, limbs, first_pt=0):
         a = _u64(limbs).reshape(-1, self.ctx.pt_limbs)

@@ -650,6 +650,39 @@ int pirb_db_load_coeff(pirb_ctx* c, const uint64_t* coeffs, uint64_t first, uint
   return 0;
 }
 
+int pirb_db_load_items(pirb_ctx* c, const uint8_t* items, uint64_t first_item, uint64_t n_items,
+                       uint32_t bytes_per_item, uint32_t items_per_plaintext, uint32_t bits_per_coeff) {
+  if (!c || !items || !bytes_per_item || !items_per_plaintext) return fail(PIRB_INVALID_ARGUMENT, "bad argument");
+  CU(cudaSetDevice(c->device));
+  if (bits_per_coeff == 0) bits_per_coeff = c->P.ptb;
+  if (bits_per_coeff > c->P.ptb || bits_per_coeff > 32) return fail(PIRB_INVALID_ARGUMENT, "Bits per coefficient greater than max");
+  if (first_item % items_per_plaintext) return fail(PIRB_INVALID_ARGUMENT, "first_item must start a plaintext");
+  const u64 bytes_per_pt = (u64)bytes_per_item * items_per_plaintext;
+  if ((bytes_per_pt * 8 + bits_per_coeff - 1) / bits_per_coeff > c->N)  // string_encoder.cpp:86-93
+    return fail(PIRB_INVALID_ARGUMENT, "Number of coefficients needed greater than poly modulus degree");
+  const u64 first_pt = first_item / items_per_plaintext;
+  const u64 n_pt = (n_items + items_per_plaintext - 1) / items_per_plaintext;
+  u64 lo, hi;
+  RC(clip_to_shard(c, first_pt, n_pt, &lo, &hi));
+  const u64 chunk_max = std::max<u64>(1, (64ull << 20) / (c->N * sizeof(u64)));
+  DevBuf raw;
+  for (u64 p = lo; p < hi;) {
+    const u64 n = std::min(chunk_max, hi - p);
+    const u64 byte_lo = (p - first_pt) * bytes_per_pt;
+    const u64 byte_hi = std::min<u64>(n_items * (u64)bytes_per_item, (p - first_pt + n) * bytes_per_pt);
+    RC(raw.ensure(std::max<u64>(byte_hi - byte_lo, 16)));
+    RC(c->stage.ensure(n * c->N * sizeof(u64)));
+    CU(cudaMemcpyAsync(raw.p, items + byte_lo, byte_hi - byte_lo, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, launch_pack_items(reinterpret_cast<const u8*>(raw.p), c->stage.p, c->N, bits_per_coeff, bytes_per_pt,
+                                byte_hi - byte_lo, n, c->stream));
+    LAUNCH(c, launch_db_preprocess(c->P, c->stage.p, c->db.p + (p - c->pt_begin) * c->ptL, n, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->loaded += n;
+    p += n;
+  }
+  return 0;
+}
+
 int pirb_db_load_ntt(pirb_ctx* c, const uint64_t* limbs, uint64_t first, uint64_t count) {
   if (!c || !limbs) return fail(PIRB_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(c->device));

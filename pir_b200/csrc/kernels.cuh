@@ -74,6 +74,10 @@ cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peer
 cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64* work, const u64* root_off, int n_trees,
                                int n_queries, u64 q_stride, cudaStream_t st);
 
+// StringEncoder packing on the device: raw item bytes -> plaintext coefficients [n_pt][N]
+cudaError_t launch_pack_items(const u8* bytes, u64* coeffs, u32 N, u32 bits, u64 bytes_per_pt, u64 total_bytes,
+                              u64 n_pt, cudaStream_t st);
+
 // warm L2 with constants that every kernel of a query re-reads (tables, keys)
 cudaError_t launch_prefetch_l2(const void* p, u64 bytes, cudaStream_t st);
 

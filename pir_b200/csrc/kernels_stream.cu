@@ -839,6 +839,40 @@ cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64* work, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// StringEncoder::encode on the device (string_encoder.cpp:58-80, 108-122): coefficient c of plaintext p holds bits
+// [c*b, (c+1)*b) (MSB first) of the concatenation of the plaintext's items, zero-padded.  One thread per coefficient.
+__global__ void __launch_bounds__(256)
+k_pack_items(const u8* __restrict__ bytes, u64* __restrict__ coeffs, u32 N, u32 bits, u64 bytes_per_pt,
+             u64 total_bytes) {
+  const u64 pt = blockIdx.y;
+  const u32 c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= N) return;
+  const u64 base = pt * bytes_per_pt;
+  const u64 avail = total_bytes > base ? min(bytes_per_pt, total_bytes - base) : 0;  // the last plaintext may be short
+  const u64 bit0 = (u64)c * bits;
+  u64 v = 0;
+  // gather up to 9 bytes covering the (at most 32) wanted bits
+  const u64 byte0 = bit0 >> 3;
+  const u32 skip = (u32)(bit0 & 7);
+  unsigned __int128 acc = 0;
+  const u32 nbytes = (skip + bits + 7) >> 3;
+  for (u32 i = 0; i < nbytes; ++i) {
+    const u64 idx = byte0 + i;
+    const u8 b = idx < avail ? bytes[base + idx] : 0;
+    acc = (acc << 8) | b;
+  }
+  const u32 tail = nbytes * 8 - skip - bits;
+  v = (u64)((acc >> tail) & (((unsigned __int128)1 << bits) - 1));
+  coeffs[pt * N + c] = v;
+}
+cudaError_t launch_pack_items(const u8* bytes, u64* coeffs, u32 N, u32 bits, u64 bytes_per_pt, u64 total_bytes,
+                              u64 n_pt, cudaStream_t st) {
+  if (!n_pt) return cudaSuccess;
+  k_pack_items<<<dim3((N + 255) / 256, (unsigned)n_pt), 256, 0, st>>>(bytes, coeffs, N, bits, bytes_per_pt, total_bytes);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // L2 warm-up of constants (NTT tables, the client's Galois keys): one prefetch per 128-byte line, fire and forget.
 __global__ void __launch_bounds__(256) k_prefetch_l2(const char* __restrict__ p, u64 lines) {
   const u64 l = (u64)blockIdx.x * 256 + threadIdx.x;

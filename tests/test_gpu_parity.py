@@ -520,3 +520,23 @@ def test_multiply_with_unused_selection_entries_and_empty_database():
     assert np.array_equal(got_sv, sv_after)      # entries 2,3 of the first dimension stay in coefficient form
     empty = pb.PIRDatabase.Create(p)
     assert empty.multiply(sv.copy()).shape[0] == 0   # reference returns an empty vector (database.cpp:181-183)
+
+
+def test_device_populate_and_shard_file_roundtrip(tmp_path):
+    """pirb_db_load_items packs raw item bytes on the device exactly like StringEncoder (string_encoder.cpp:58-122),
+    for several (bytes_per_item, bits_per_coeff) shapes incl. a short last plaintext; save()/load() round-trips."""
+    for n, bits, elem, bpc, dbsize in [(4096, 20, 64, 0, 1200), (4096, 24, 289, 10, 777), (4096, 16, 1, 0, 5000),
+                                       (8192, 20, 1024, 13, 100), (4096, 20, 9728, 0, 3)]:
+        p = _params(dbsize, elem, 1, n, bits, bpc)
+        cl = _harness(p)
+        items = _random_items(p, seed=elem)
+        db = pb.PIRDatabase.Create(items, p)            # device packing path (fixed-size items)
+        assert db.size() == p.num_pt
+        want = oc.db_to_ntt(cl.orc, oc.encode_string_db(cl.params, items))
+        got = db.read_ntt(0, p.num_pt)
+        assert np.array_equal(got, want), (n, bits, elem, bpc, dbsize)
+    path = str(tmp_path / "shard.bin")
+    db.save(path)
+    db2 = pb.PIRDatabase.Create(p)
+    db2.load(path)
+    assert db2.size() == p.num_pt and np.array_equal(db2.read_ntt(0, p.num_pt), got)
