@@ -13,6 +13,8 @@
 // polynomials never touch global memory and a tree level costs one launch instead of three.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -67,6 +69,7 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
     }                                                                                      \
   } while (0)
   PIRB_STAMP(0);
+  asm volatile("griddepcontrol.launch_dependents;");  // the next level may start its own prologue now
   // Prologue: pull everything this CTA will read from global memory into L2 now (one 128-byte line per prefetch), so
   // the key limbs of phase 2 and the source polynomials of phases 1 and 3 are L2 hits when they are needed.
   {
@@ -75,6 +78,9 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
       const char* kp = reinterpret_cast<const char*>(key + ((u64)(J * 2 + c) * (k + 1) + I) * N);
       for (int l = tid; l < LINES; l += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + (size_t)l * 128));
     }
+    // Programmatic dependent launch: everything above (key prefetch, index math) may overlap the tail of the previous
+    // level's kernel; from here on we read what it wrote.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int J = c; J < k; J += 2) {
       const char* sp = reinterpret_cast<const char*>(src + (u64)(k + J) * N);
       for (int l = tid; l < LINES; l += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (size_t)l * 128));
@@ -261,13 +267,16 @@ cudaError_t launch_ks_level_cluster(const DevParams& P, u64* work, const LevelAr
     cfg.blockDim = dim3(CCfg<LN>::NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = csize;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static const bool pdl = !(getenv("PIRB_PDL") && getenv("PIRB_PDL")[0] == '0');
+    cfg.numAttrs = pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kern, P, work, L, key, mode);
   };
   auto by_mode = [&](auto ln, auto lz) -> cudaError_t {

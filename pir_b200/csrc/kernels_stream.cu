@@ -28,8 +28,8 @@ __device__ __forceinline__ ulonglong2 ldg128_stream(const u64* p) {
 constexpr int SCAN_NT = 128;
 constexpr int SCAN_LIMBS = 2 * SCAN_NT;
 
-template <int R, int U, int MODE>
-__global__ void __launch_bounds__(SCAN_NT)
+template <int R, int U, int MODE, int MINB = 1>
+__global__ void __launch_bounds__(SCAN_NT, MINB)
 k_scan(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
        const u64* __restrict__ sv, u64 sv_qstride, int n_split, u64* __restrict__ part) {
   const u32 kN = (u32)P.k * P.N;
@@ -621,6 +621,15 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
 #undef TMA_CASE
 #undef TMA_LAUNCH
     return cudaErrorInvalidValue;
+  }
+  {
+    const int minb = env_int("PIRB_SCAN_MINB", 1);
+    if (R == 2 && U == 2 && mode == MAC_FP64 && minb > 1) {
+      if (minb == 5) k_scan<2, 2, MAC_FP64, 5><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part);
+      else if (minb == 6) k_scan<2, 2, MAC_FP64, 6><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part);
+      else k_scan<2, 2, MAC_FP64, 8><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part);
+      return cudaGetLastError();
+    }
   }
 #define SCAN_CASE(RR, UU)                                                                                          \
   if (R == RR && U == UU) {                                                                                        \

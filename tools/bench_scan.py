@@ -55,7 +55,7 @@ def main():
                                  "PIRB_SCAN_G": str(g), "PIRB_SCAN_U": str(st), "PIRB_SCAN_CTAS_PER_SM": str(cps)})
     ref = None
     srv.set_profiling(True)
-    knobs = ["PIRB_MAC_MODE", "PIRB_SCAN_G", "PIRB_SCAN_QB", "PIRB_SCAN_RB", "PIRB_SCAN_BATCH_MIN", "PIRB_SCAN_R", "PIRB_SCAN_U", "PIRB_SCAN_CTAS_PER_SM", "PIRB_SCAN_SPLIT",
+    knobs = ["PIRB_MAC_MODE", "PIRB_SCAN_MINB", "PIRB_SCAN_G", "PIRB_SCAN_QB", "PIRB_SCAN_RB", "PIRB_SCAN_BATCH_MIN", "PIRB_SCAN_R", "PIRB_SCAN_U", "PIRB_SCAN_CTAS_PER_SM", "PIRB_SCAN_SPLIT",
              "PIRB_SCAN_MODE"]
     for v in variants:
         for kk in knobs:
