@@ -8,6 +8,7 @@ either NCCL all-gather + the fused add-and-inverse-NTT kernel, or peer pointers 
 torch is used only for device memory, streams and torch.distributed — uint64 limbs are carried in int64 tensors.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -157,8 +158,7 @@ class ShardServer:
         if world == 1:
             part = self.multiply_partial(sv_local)
             return self.reduce_finish(part[None], ql)
-        sv_all = self._empty(world * ql, *sv_local.shape[1:])
-        dist.all_gather_into_tensor(sv_all, sv_local)
+        sv_all = self._exchange_selection_vectors(sv_local)
         part = self.multiply_partial(sv_all)                     # [world*ql][reply_cts]...
         gathered = self._empty(world, *part.shape)
         dist.all_gather_into_tensor(gathered, part)
@@ -184,6 +184,35 @@ class ShardServer:
         self._xslots, self._xslot = n_slots, 0
         self._xflag = torch.zeros(1, dtype=torch.int32, device=self.device)
 
+    def _exchange_selection_vectors(self, sv_local: torch.Tensor) -> torch.Tensor:
+        """Every rank needs, of every query: all selection ciphertexts of dimensions 1..d-1 (they multiply every row)
+        but of dimension 0 only the entries of the rows it owns.  For >= 4 ranks the tail is all-gathered and the
+        head is exchanged by ownership (all-to-all), which moves about half of what a full all-gather would."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ql, dim_sum = sv_local.shape[0], sv_local.shape[1]
+        d0 = self.params.dimensions[0]
+        sv_all = self._empty(world * ql, *sv_local.shape[1:])
+        # measured on 8 B200s: the extra all-to-all costs more latency than the halved volume saves at this message
+        # size (10 MB per query), so the plain all-gather is the default; PIRB_SPLIT_EXCHANGE=1 selects the split.
+        if world < 4 or len(self.params.dimensions) == 1 or os.environ.get("PIRB_SPLIT_EXCHANGE") != "1":
+            dist.all_gather_into_tensor(sv_all, sv_local)
+            return sv_all
+        rows = shard_rows(d0, world)
+        tail_local = sv_local[:, d0:].contiguous()
+        tail_all = self._empty(world * ql, dim_sum - d0, *sv_local.shape[2:])
+        dist.all_gather_into_tensor(tail_all, tail_local)
+        per = sv_local[0, 0].numel()
+        send = torch.cat([sv_local[:, lo:hi].reshape(-1) for lo, hi in rows])
+        lo_me, hi_me = rows[rank]
+        recv = self._empty(world * ql * (hi_me - lo_me) * per)
+        dist.all_to_all_single(recv, send, output_split_sizes=[ql * (hi_me - lo_me) * per] * world,
+                               input_split_sizes=[ql * (hi - lo) * per for lo, hi in rows])
+        sv_all[:, d0:] = tail_all
+        if hi_me > lo_me:
+            sv_all[:, lo_me:hi_me] = recv.view(world * ql, hi_me - lo_me, *sv_local.shape[2:])
+        return sv_all  # dimension-0 entries of other ranks' rows stay uninitialised: this shard never reads them
+
     def answer_batch_distributed_p2p(self, d_queries_local: torch.Tensor) -> torch.Tensor:
         """Like answer_batch_distributed, but the partial replies are not gathered: every rank writes them into its
         own exchange slot and, after a stream-ordered barrier, each rank's reduce kernel loads all ranks' partials
@@ -192,8 +221,7 @@ class ShardServer:
         world, rank = dist.get_world_size(), dist.get_rank()
         ql = d_queries_local.shape[0]
         sv_local = self.expand_ntt(d_queries_local)
-        sv_all = self._empty(world * ql, *sv_local.shape[1:])
-        dist.all_gather_into_tensor(sv_all, sv_local)
+        sv_all = self._exchange_selection_vectors(sv_local)
         slot = self._xslot
         st = self._enter()
         _check(_lib.lib().pirb_multiply_partial_xbuf_dev(self.ctx.h, _dp(sv_all), world * ql, slot, st))
