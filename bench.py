@@ -220,7 +220,17 @@ def run_ours(args):
         return flush.view(torch.int64).sum()
 
     if world > 1 and args.p2p:
-        srv.setup_peer_exchange(max_queries=world * ql)
+        # peer-memory exchange needs CUDA IPC between the ranks' devices; if any rank cannot set it up, every rank
+        # falls back to the NCCL gather so the run still produces a number (and says so in config.parallelism)
+        ok = 1
+        try:
+            srv.setup_peer_exchange(max_queries=world * ql)
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            sys.stderr.write("rank %d: peer exchange unavailable (%s); using NCCL gather\n" % (rank, e))
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        args.p2p = int(flag.item())
 
     def step_dev():
         if world == 1:
