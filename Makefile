@@ -8,7 +8,9 @@ LIB := pir_b200/lib/libpirb200.so
 OBJS := $(OBJ)/kernels_ntt.o $(OBJ)/kernels_stream.o $(OBJ)/kernels_cluster.o $(OBJ)/context.o
 HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/pir_b200.h
 
-all: $(LIB) oracle build/shim_test
+WIRE := pir_b200/lib/libpirb_wire.so
+
+all: $(LIB) $(WIRE) oracle build/shim_test
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -18,8 +20,14 @@ $(LIB): $(OBJS)
 	@mkdir -p pir_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
 
+# host-only wire codec (protobuf framing + SEAL 3.5.6 object formats) behind plain-C entry points for the tests
+wire: $(WIRE)
+$(WIRE): pir_b200/cpp/wire_capi.cpp pir_b200/cpp/wire.hpp
+	@mkdir -p pir_b200/lib
+	g++ -O2 -std=c++17 -Wall -Wextra -shared -fPIC -o $@ pir_b200/cpp/wire_capi.cpp
+
 # C++ end-to-end test of the pir:: shim (host code in the reference's language over the C ABI)
-build/shim_test: tests/cpp/shim_test.cpp pir_b200/cpp/pir_b200.hpp oracle/pir_oracle.hpp include/pir_b200.h $(LIB)
+build/shim_test: tests/cpp/shim_test.cpp pir_b200/cpp/pir_b200.hpp pir_b200/cpp/wire.hpp oracle/pir_oracle.hpp include/pir_b200.h $(LIB)
 	@mkdir -p build
 	g++ -O2 -std=c++17 -march=x86-64-v3 -o $@ tests/cpp/shim_test.cpp -Lpir_b200/lib -lpirb200 -Wl,-rpath,'$$ORIGIN/../pir_b200/lib'
 
@@ -28,4 +36,4 @@ oracle:
 
 clean:
 	rm -rf build pir_b200/lib oracle/_build
-.PHONY: all oracle clean
+.PHONY: all oracle wire clean

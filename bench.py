@@ -69,7 +69,9 @@ class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region (NVML every ~1 ms; nvidia-smi -lms as fallback)."""
 
     def __init__(self, gpu_index):
-        self.idx = gpu_index
+        # NVML enumerates physical devices; honour a CUDA_VISIBLE_DEVICES remap of numeric indices
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+        self.idx = int(vis[gpu_index]) if gpu_index < len(vis) else gpu_index
         self.sm, self.mx, self.reasons = [], None, set()
         self.stop_flag = threading.Event()
         self.thread = None

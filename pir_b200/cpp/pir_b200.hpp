@@ -11,6 +11,10 @@
 //   pir::Response     { reply: vector<vector<Ciphertext>> }                (payload.proto:39-42)
 //   pir::Status / StatusOr<T>   codes as absl::StatusCode: 0 OK, 3 InvalidArgument, 13 Internal
 //
+// The reference's wire format is layered on top (wire.hpp): PIRServer::ProcessRequest(const std::string&) takes a
+// serialized pir.Request (protobuf framing + SEAL 3.5.6 objects, seed-compressed keys included) and returns a
+// serialized pir.Response; SerializePIRParameters / ParsePIRParameters do the same for pir.PIRParameters.
+//
 // Header-only; link with -lpirb200.  All ring arithmetic runs in the CUDA kernels behind the C ABI; nothing here
 // computes on ciphertexts.
 #pragma once
@@ -26,6 +30,7 @@
 #include <vector>
 
 #include "../../include/pir_b200.h"
+#include "wire.hpp"
 
 namespace pir {
 
@@ -225,6 +230,108 @@ inline std::vector<uint32_t> generate_galois_elts(uint64_t N) {
   return e;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// wire format (pir/cpp/serialization.h:81-138, pir/proto/payload.proto, parameters.cpp:100-101)
+inline wire::SealParams ToSealParams(const EncryptionParameters& ep) {
+  wire::SealParams p;
+  p.poly_modulus_degree = ep.poly_modulus_degree;
+  p.coeff_modulus = ep.coeff_modulus;
+  p.plain_modulus = ep.plain_modulus;
+  return p;
+}
+inline std::string SerializePIRParameters(const PIRParameters& p) {
+  wire::PIRParametersMsg m;
+  m.num_items = p.num_items;
+  m.num_pt = p.num_pt;
+  m.dimensions = p.dimensions;
+  m.encryption_parameters = wire::SaveEncryptionParameters(ToSealParams(p.encryption_parameters));
+  m.bytes_per_item = p.bytes_per_item;
+  m.items_per_plaintext = p.items_per_plaintext;
+  m.bits_per_coeff = p.bits_per_coeff;
+  m.use_ciphertext_multiplication = p.use_ciphertext_multiplication;
+  return wire::Serialize(m);
+}
+inline StatusOr<std::shared_ptr<PIRParameters>> ParsePIRParameters(const std::string& bytes) {
+  wire::PIRParametersMsg m;
+  if (!wire::Parse(bytes, &m)) return InvalidArgumentError("malformed PIRParameters message");
+  wire::SealParams sp;
+  std::string err;
+  if (!wire::LoadEncryptionParameters(m.encryption_parameters, &sp, &err)) return InvalidArgumentError(err);
+  auto p = std::make_shared<PIRParameters>();
+  p->num_items = m.num_items;
+  p->num_pt = m.num_pt;
+  p->dimensions = m.dimensions;
+  p->encryption_parameters.poly_modulus_degree = sp.poly_modulus_degree;
+  p->encryption_parameters.coeff_modulus = sp.coeff_modulus;
+  p->encryption_parameters.plain_modulus = sp.plain_modulus;
+  p->bytes_per_item = m.bytes_per_item;
+  p->items_per_plaintext = m.items_per_plaintext;
+  p->bits_per_coeff = m.bits_per_coeff;
+  p->use_ciphertext_multiplication = m.use_ciphertext_multiplication;
+  return p;
+}
+// SEALDeserialize<GaloisKeys> (serialization.h:106-121) into the raw-limb key layout of the C ABI
+inline StatusOr<GaloisKeys> DeserializeGaloisKeys(const EncryptionParameters& ep, const std::string& bytes) {
+  wire::KSwitchKeysData K;
+  std::string err;
+  if (!wire::LoadKSwitchKeys(bytes, ToSealParams(ep), &K, &err)) return InvalidArgumentError(err);
+  GaloisKeys gk;
+  const size_t per_digit = 2 * ep.coeff_modulus.size() * (size_t)ep.poly_modulus_degree;
+  for (size_t s = 0; s < K.keys.size(); ++s) {
+    if (K.keys[s].empty()) continue;
+    gk.elts.push_back(wire::galois_elt_of_index((uint32_t)s));
+    for (const auto& ct : K.keys[s]) gk.limbs.insert(gk.limbs.end(), ct.limbs.begin(), ct.limbs.begin() + per_digit);
+  }
+  return gk;
+}
+inline std::string SerializeGaloisKeys(const EncryptionParameters& ep, const GaloisKeys& gk) {
+  const wire::SealParams sp = ToSealParams(ep);
+  const size_t N = ep.poly_modulus_degree, k = ep.coeff_modulus.size() - 1, per_digit = 2 * (k + 1) * N;
+  wire::KSwitchKeysData K;
+  K.parms_id = wire::key_parms_id(sp);
+  K.keys.assign(N, {});
+  for (size_t e = 0; e < gk.elts.size(); ++e) {
+    auto& slot = K.keys[wire::galois_index(gk.elts[e])];
+    slot.resize(k);
+    for (size_t j = 0; j < k; ++j) {
+      slot[j].parms_id = K.parms_id;
+      slot[j].is_ntt_form = true;
+      slot[j].size = 2;
+      slot[j].poly_modulus_degree = N;
+      slot[j].coeff_modulus_size = k + 1;
+      slot[j].limbs.assign(gk.limbs.begin() + (e * k + j) * per_digit, gk.limbs.begin() + (e * k + j + 1) * per_digit);
+    }
+  }
+  return wire::SaveKSwitchKeys(K);
+}
+// SEALSerialize<Ciphertext> / SEALDeserialize<Ciphertext> for data-level ciphertexts [2][k][N]
+inline std::string SerializeCiphertext(const EncryptionParameters& ep, const Ciphertext& ct,
+                                       const wire::parms_id_type* parms_id = nullptr) {
+  const wire::SealParams sp = ToSealParams(ep);
+  wire::CiphertextData d;
+  d.parms_id = parms_id ? *parms_id : wire::data_parms_id(sp);
+  d.is_ntt_form = ct.is_ntt_form;
+  d.poly_modulus_degree = ep.poly_modulus_degree;
+  d.coeff_modulus_size = ep.coeff_modulus.size() - 1;
+  d.size = ct.limbs.size() / (d.poly_modulus_degree * d.coeff_modulus_size);
+  d.limbs = ct.limbs;
+  return wire::SaveCiphertext(d);
+}
+inline StatusOr<Ciphertext> DeserializeCiphertext(const EncryptionParameters& ep, const std::string& bytes,
+                                                  wire::parms_id_type* parms_id = nullptr) {
+  wire::CiphertextData d;
+  std::string err;
+  if (!wire::LoadCiphertext(bytes, ep.poly_modulus_degree, ep.coeff_modulus.data(), ep.coeff_modulus.size() - 1, &d,
+                            &err))
+    return InvalidArgumentError(err);
+  if (d.size != 2) return InvalidArgumentError("ciphertext data is invalid");
+  if (parms_id) *parms_id = d.parms_id;
+  Ciphertext ct;
+  ct.limbs = std::move(d.limbs);
+  ct.is_ntt_form = d.is_ntt_form;
+  return ct;
+}
+
 namespace detail {
 struct CtxDeleter { void operator()(pirb_ctx* c) const { pirb_ctx_destroy(c); } };
 struct KeysDeleter { void operator()(pirb_keys* k) const { pirb_keys_destroy(k); } };
@@ -410,6 +517,45 @@ class PIRServer {
         response.reply[i][c].limbs.assign(r.begin() + (i * R + c) * L, r.begin() + (i * R + c + 1) * L);
     }
     return response;
+  }
+
+  // server.cpp:44-65 on the wire: serialized pir.Request in, serialized pir.Response out.  Deserialization failures
+  // are InvalidArgument (serialization.h:113-115); relin_keys are parsed for validity and otherwise unused
+  // (server.cpp:53-58).  Reply ciphertexts carry the parms_id of the query's first ciphertext.
+  StatusOr<std::string> ProcessRequest(const std::string& serialized_request, bool strict_parms_id = false) const {
+    wire::RequestMsg msg;
+    if (!wire::Parse(serialized_request, &msg)) return InvalidArgumentError("malformed Request message");
+    const EncryptionParameters& ep = params_->encryption_parameters;
+    const wire::SealParams sp = ToSealParams(ep);
+    auto gk = DeserializeGaloisKeys(ep, msg.galois_keys);
+    if (!gk.ok()) return gk.status();
+    std::string err;
+    if (!msg.relin_keys.empty()) {
+      wire::KSwitchKeysData rk;
+      if (!wire::LoadKSwitchKeys(msg.relin_keys, sp, &rk, &err, /*keep_data=*/false)) return InvalidArgumentError(err);
+    }
+    Request req;
+    req.galois_keys = std::move(*gk);
+    wire::parms_id_type pid = wire::data_parms_id(sp), got;
+    bool first = true;
+    for (const auto& q : msg.query) {
+      req.query.emplace_back();
+      for (const auto& blob : q.ct) {
+        auto ct = DeserializeCiphertext(ep, blob, &got);
+        if (!ct.ok()) return ct.status();
+        if (strict_parms_id && got != wire::data_parms_id(sp)) return InvalidArgumentError("ciphertext data is invalid");
+        if (first) { pid = got; first = false; }
+        req.query.back().push_back(std::move(*ct));
+      }
+    }
+    auto resp = ProcessRequest(req);
+    if (!resp.ok()) return resp.status();
+    wire::ResponseMsg out;
+    for (const auto& r : resp->reply) {
+      out.reply.emplace_back();
+      for (const auto& ct : r) out.reply.back().ct.push_back(SerializeCiphertext(ep, ct, &pid));
+    }
+    return wire::Serialize(out);
   }
 
   // server.cpp:67-76

@@ -90,6 +90,98 @@ static int run_case(size_t dbsize, size_t elem_size, size_t d, size_t desired_in
     CHECK(std::memcmp(reply[i].data(), want.data() + i * octx.ct_limbs(), octx.ct_limbs() * 8) == 0,
           "GPU reply differs from the oracle");
 
+  // ---- the same request over the reference's wire format (serialization.h:81-138, payload.proto) ----
+  // Keys travel seed-compressed as the reference client sends them (client.cpp:47-54): replace every key's uniform
+  // polynomial a by the expansion a' of a fresh seed and fix c0 so that it is still a valid key:
+  // c0' = c0 + (a - a') * s (NTT domain).  The server must rebuild a' from the seed alone.
+  {
+    const size_t K1 = octx.k + 1, per_digit = 2 * K1 * N;
+    const pir::wire::SealParams sp = pir::ToSealParams(ep);
+    pir::wire::KSwitchKeysData K;
+    K.parms_id = pir::wire::key_parms_id(sp);
+    K.keys.assign(N, {});
+    std::vector<std::vector<pir::wire::seed_type>> seeds(N);
+    pir::GaloisKeys gk2 = gk;
+    std::vector<uint64_t> a2(K1 * N);
+    for (size_t e = 0; e < gk.elts.size(); ++e) {
+      const uint32_t idx = pir::wire::galois_index(gk.elts[e]);
+      K.keys[idx].resize(octx.k);
+      seeds[idx].resize(octx.k);
+      for (size_t J = 0; J < octx.k; ++J) {
+        for (auto& w : seeds[idx][J]) w = rng();
+        pir::wire::BlakePRNG prng(seeds[idx][J]);
+        pir::wire::sample_poly_uniform(prng, (uint32_t)N, ep.coeff_modulus.data(), K1, a2.data());
+        uint64_t* kj = gk2.limbs.data() + (e * octx.k + J) * per_digit;
+        for (size_t j = 0; j < K1; ++j) {
+          const orc::Modulus& m = octx.mod(j);
+          for (size_t n = 0; n < N; ++n) {
+            uint64_t& c0 = kj[j * N + n];
+            uint64_t& c1 = kj[(K1 + j) * N + n];
+            c0 = orc::addmod(c0, orc::mulmod(orc::submod(c1, a2[j * N + n], m), sk.ntt[j * N + n], m), m);
+            c1 = a2[j * N + n];
+          }
+        }
+        auto& ct = K.keys[idx][J];
+        ct.parms_id = K.parms_id;
+        ct.is_ntt_form = true;
+        ct.size = 2;
+        ct.poly_modulus_degree = N;
+        ct.coeff_modulus_size = K1;
+        ct.limbs.assign(kj, kj + per_digit);
+      }
+    }
+    pir::wire::RequestMsg msg;
+    msg.galois_keys = pir::wire::SaveKSwitchKeys(K, &seeds);
+    CHECK(msg.galois_keys.size() < pir::SerializeGaloisKeys(ep, gk2).size() * 6 / 10, "seeded keys must be ~half the size");
+    {  // relin keys are always sent (client.cpp:49,53-54) and only parsed: one slot of k seeded keys
+      pir::wire::KSwitchKeysData R;
+      R.parms_id = K.parms_id;
+      R.keys.push_back(K.keys[pir::wire::galois_index(gk.elts[0])]);
+      std::vector<std::vector<pir::wire::seed_type>> rs{seeds[pir::wire::galois_index(gk.elts[0])]};
+      msg.relin_keys = pir::wire::SaveKSwitchKeys(R, &rs);
+    }
+    msg.query.emplace_back();
+    msg.query.back().ct.push_back(pir::SerializeCiphertext(ep, req.query[0][0]));
+    const std::string wire_req = pir::wire::Serialize(msg);
+    auto wire_resp = server->ProcessRequest(wire_req);
+    CHECK(wire_resp.ok(), wire_resp.status().message().c_str());
+    pir::wire::ResponseMsg rmsg;
+    CHECK(pir::wire::Parse(*wire_resp, &rmsg) && rmsg.reply.size() == 1, "Response parse");
+    orc::GaloisKeys ogk2;
+    ogk2.elts = gk2.elts;
+    ogk2.data = gk2.limbs;
+    std::vector<uint64_t> want2;
+    CHECK(orc::process_query(octx, db_ntt.data(), params->num_pt, params->dimensions.data(), params->dimensions.size(),
+                             ogk2, req.query[0][0].data(), 1, want2) == 0, "oracle process_query (seeded keys)");
+    CHECK(rmsg.reply[0].ct.size() * octx.ct_limbs() == want2.size(), "wire reply count");
+    for (size_t i = 0; i < rmsg.reply[0].ct.size(); ++i) {
+      pir::wire::parms_id_type pid;
+      auto ct = pir::DeserializeCiphertext(ep, rmsg.reply[0].ct[i], &pid);
+      CHECK(ct.ok(), "reply ciphertext must deserialize");
+      CHECK(pid == pir::wire::data_parms_id(sp), "reply parms_id is the query's");
+      CHECK(std::memcmp(ct->data(), want2.data() + i * octx.ct_limbs(), octx.ct_limbs() * 8) == 0,
+            "wire-path reply differs from the oracle");
+    }
+    // malformed requests are InvalidArgument, as SEALDeserialize failures are (serialization.h:113-115)
+    auto bad1 = server->ProcessRequest(wire_req.substr(0, wire_req.size() / 2));
+    CHECK(!bad1.ok() && bad1.status().code() == PIRB_INVALID_ARGUMENT, "truncated request");
+    pir::wire::RequestMsg m2 = msg;
+    m2.query[0].ct[0][100] ^= 0x40;  // high byte of a limb -> limb >= modulus
+    m2.query[0].ct[0][111] = (char)0xff;
+    auto bad2 = server->ProcessRequest(pir::wire::Serialize(m2));
+    CHECK(!bad2.ok() && bad2.status().code() == PIRB_INVALID_ARGUMENT, "out-of-range ciphertext limb");
+    pir::wire::RequestMsg m3 = msg;
+    m3.galois_keys.clear();
+    auto bad3 = server->ProcessRequest(pir::wire::Serialize(m3));
+    CHECK(!bad3.ok() && bad3.status().code() == PIRB_INVALID_ARGUMENT, "missing galois keys");
+    // PIRParameters over the wire (parameters.cpp:100-101)
+    auto p2 = pir::ParsePIRParameters(pir::SerializePIRParameters(*params));
+    CHECK(p2.ok() && (*p2)->num_pt == params->num_pt && (*p2)->dimensions == params->dimensions &&
+              (*p2)->encryption_parameters.coeff_modulus == ep.coeff_modulus &&
+              (*p2)->encryption_parameters.plain_modulus == ep.plain_modulus &&
+              (*p2)->bytes_per_item == params->bytes_per_item, "PIRParameters wire round trip");
+  }
+
   // ---- client decode (client.cpp:219-255) ----
   const size_t two_er = 2 * octx.expansion_ratio();
   std::vector<std::vector<uint64_t>> cts;
