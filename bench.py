@@ -76,29 +76,44 @@ class ClockSampler:
         self.stop_flag = threading.Event()
         self.thread = None
 
+    def _setup(self):
+        # import + nvmlInit in the caller's thread, before the timed region: a module import inside the sampling
+        # thread holds the GIL for milliseconds and stalls the thread that enqueues the timed steps
+        import pynvml as nv
+        nv.nvmlInit()
+        self.nv = nv
+        self.h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+        self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        self.names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                      "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                      "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                      "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self._sample()
+
+    def _sample(self):
+        self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+        r = self.get_reasons(self.h)
+        for nm, bit in self.names.items():
+            if r & bit:
+                self.reasons.add(nm)
+
     def _run(self):
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
-            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
-                nv.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self.stop_flag.is_set():
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                r = get_reasons(h)
-                for nm, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.001)
+                self._sample()
+                time.sleep(0.002)
         except Exception as e:  # noqa: BLE001
             self.reasons.add("nvml unavailable: %s" % type(e).__name__)
 
     def start(self):
+        try:
+            self._setup()
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add("nvml unavailable: %s" % type(e).__name__)
+            return
+        self.sm = []  # keep only samples taken under load
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
@@ -106,6 +121,11 @@ class ClockSampler:
         self.stop_flag.set()
         if self.thread:
             self.thread.join(timeout=2)
+        if not self.sm and hasattr(self, "nv"):
+            try:
+                self._sample()
+            except Exception:  # noqa: BLE001
+                pass
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
@@ -354,6 +374,24 @@ def run_ours(args):
                              "with the GPU reply: %s" % (len(ts), "identical" if parity else "MISMATCH"),
                    "p50_latency_ms": 1e3 * med, "host_cpus": os.cpu_count()}
 
+    # ---------------- expansion (FP64-pipe-bound): algorithmic FP64 operations of the key switches / stage time -----
+    # per key switch: k(k+1) forward + 2(k+1) inverse transforms of N/2*log2(N) butterflies at 8 FP64 ops, 2k(k+1)N
+    # digit-key products at 8, canonicalisation of the k(k+1) digit transforms at 4 per coefficient, the final
+    # psi^-i/N scaling of the 2(k+1) inverse transforms at 7, the mod-down of 2k polynomials at 20
+    logn = N.bit_length() - 1
+    ks_per_query = sum(int(pb.next_power_two(min(N, max(0, sum(params.dimensions) - t * N)))) - 1 for t in range(n_ct))
+    ops_per_ks = ((k * (k + 1) + 2 * (k + 1)) * (N // 2) * logn * 8 + 2 * k * (k + 1) * N * 8 + k * (k + 1) * N * 4
+                  + 2 * (k + 1) * N * 7 + 2 * k * N * 20)
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp64_peak = 57.7 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_mhz * 1e6 / 1e12
+    exp_ms = stage_mean["expand"]
+    exp_ach = ql * ks_per_query * ops_per_ks / (exp_ms * 1e-3) / 1e12
+    expansion = {"kernel": "k_ks_level_cluster", "bound": "fp64 pipe", "key_switches_per_launch_set": ql * ks_per_query,
+                 "fp64_ops_per_key_switch": ops_per_ks, "achieved": exp_ach, "peak": fp64_peak, "unit": "T FP64 op/s",
+                 "frac": exp_ach / fp64_peak, "ms": exp_ms, "share_of_step": exp_ms / stage_mean["total"],
+                 "peak_source": "57.7 DFMA/clk/SM measured with tools/pipe_bench.cu x SM count x SM clock under load",
+                 "note": "includes the selection-vector exchange when n_gpus > 1"}
+
     traffic = args.scan_traffic
     if traffic is None and world == 1 and ql == 1:
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of one scan launch, from the committed ncu --set full capture
@@ -384,6 +422,7 @@ def run_ours(args):
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms,
                      "share_of_step": scan_ms / stage_mean["total"]},
+        "expansion": expansion,
         "stages_ms": stage_mean,
         "cpu_baseline": cpu,
         "parity_vs_oracle": parity,

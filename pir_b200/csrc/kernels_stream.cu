@@ -272,6 +272,149 @@ k_scan_batch(const __grid_constant__ DevParams P, const u64* __restrict__ db, u6
 }
 
 // ---------------------------------------------------------------------------------------------
+// batched scan, second generation (FP64 MAC only): the compute-bound regime of many queries per database pass.
+// A CTA is RG row groups x 128 threads on one 128-limb slice.  Row group g keeps R rows x QB queries x 2 polynomials of
+// Karatsuba accumulators in registers.  The selection tiles of the CTA's QB queries are staged ONCE per CTA in shared
+// memory, already split into (low, high) halves as doubles (one 128-bit shared load per operand instead of a global
+// load plus two integer->double conversions per row group), double-buffered U columns at a time with one barrier per
+// chunk; each thread streams its own R database limbs through registers one chunk ahead.
+//   per thread and column: 6*R*QB DFMA + 3R (database split) + 2QB (operand sums) + staging; 2QB 128-bit shared loads
+//   grid (query tile, row tile * n_split, slice) — slices slowest, as for k_scan_batch
+// ---------------------------------------------------------------------------------------------
+template <int R, int QB, int RG, int U>
+__global__ void __launch_bounds__(BATCH_NT * RG, (R * QB <= 4 && RG <= 2) ? 2 : 1)
+k_scan_batch2(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
+              const u64* __restrict__ sv, u64 sv_qstride, int n_queries, int n_split, u64* __restrict__ part) {
+  extern __shared__ __align__(16) double2 stage2[];  // [2][U][QB][2][128]
+  constexpr int NTH = BATCH_NT * RG;
+  constexpr int TILE = U * QB * 2 * BATCH_NT;  // operands per chunk
+  constexpr int VPT = (TILE + NTH - 1) / NTH;
+  const u32 kN = (u32)P.k * P.N;
+  const u64 ctL = 2ull * kN;
+  const int g = threadIdx.x / BATCH_NT, t = threadIdx.x % BATCH_NT;
+  const u32 limb0 = blockIdx.z * BATCH_NT, limb = limb0 + t;
+  const u32 q0 = blockIdx.x * QB;
+  const u32 n_row_tiles = (n_rows + R * RG - 1) / (R * RG);
+  const u32 row0 = ((blockIdx.y % n_row_tiles) * RG + g) * R;
+  const u32 split = blockIdx.y / n_row_tiles;
+  const ModC& m = P.m[limb / P.N];
+  const u32 per = (dimL + n_split - 1) / n_split;
+  const u32 i_lo = split * per;
+  const u32 i_hi = min(dimL, i_lo + per);
+  const int hb = P.half_bits;
+  const u32 lo_mask = (1u << hb) - 1u;
+  Acc<MAC_FP64> acc[R][QB][2];
+  const u64* dbr[R];
+  u32 cnt[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const u64 first = (u64)(row0 + r) * dimL;
+    dbr[r] = db + first * kN + limb;
+    cnt[r] = (row0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
+  }
+  // cooperative fetch of a chunk of selection operands: operand v -> (column u, query q, polynomial p, limb l).
+  // Every thread owns the same VPT operand slots for the whole loop, so their global pointers are formed once and
+  // only advanced by U ciphertexts per chunk.
+  const u64* sp[VPT];
+  u32 su[VPT];
+#pragma unroll
+  for (int x = 0; x < VPT; ++x) {
+    const int v = threadIdx.x + x * NTH;
+    const int l = v % BATCH_NT, p = (v / BATCH_NT) % 2, q = (v / (2 * BATCH_NT)) % QB, u = v / (2 * BATCH_NT * QB);
+    const u32 qq = min(q0 + q, (u32)n_queries - 1);
+    su[x] = (v < TILE) ? (u32)u : 0xFFFFFFFFu;  // slots past the tile never load
+    sp[x] = sv + (u64)qq * sv_qstride + (u64)(i_lo + (v < TILE ? u : 0)) * ctL + (u64)p * kN + limb0 + l;
+  }
+  const u64* dp[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    dp[r] = dbr[r] + (u64)i_lo * kN;
+    cnt[r] = min(cnt[r], i_hi);  // one bound per row: column i is live iff i < cnt[r]
+  }
+  auto fetch = [&](u32 i_base, u64 (&regs)[VPT]) {
+#pragma unroll
+    for (int x = 0; x < VPT; ++x) {
+      regs[x] = (su[x] < i_hi - min(i_base, i_hi)) ? __ldg(sp[x]) : 0ull;  // i_base + u < i_hi without overflow
+      sp[x] += (u64)U * ctL;
+    }
+  };
+  auto stash = [&](int buf, const u64 (&regs)[VPT]) {
+#pragma unroll
+    for (int x = 0; x < VPT; ++x) {
+      const int v = threadIdx.x + x * NTH;
+      if (v < TILE)
+        stage2[buf * TILE + v] =
+            make_double2(u32_to_double_exact((u32)regs[x] & lo_mask), u32_to_double_exact((u32)(regs[x] >> hb)));
+    }
+  };
+  auto load_db = [&](u32 i_base, u64 (&d)[U][R]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int r = 0; r < R; ++r) d[u][r] = (i_base + u < cnt[r]) ? __ldg(dp[r] + (u64)u * kN) : 0ull;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dp[r] += (u64)U * kN;
+  };
+  auto compute = [&](int buf, const u64 (&d)[U][R]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double bl[R], bh[R], bs[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        bl[r] = u32_to_double_exact((u32)d[u][r] & lo_mask);
+        bh[r] = u32_to_double_exact((u32)(d[u][r] >> hb));
+        bs[r] = __dadd_rn(bl[r], bh[r]);
+      }
+      const double2* st = stage2 + buf * TILE + u * QB * 2 * BATCH_NT + t;
+#pragma unroll
+      for (int q = 0; q < QB; ++q)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const double2 a = st[(q * 2 + p) * BATCH_NT];
+          const double as = __dadd_rn(a.x, a.y);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            acc[r][q][p].s0 = fma(a.x, bl[r], acc[r][q][p].s0);
+            acc[r][q][p].sk = fma(as, bs[r], acc[r][q][p].sk);
+            acc[r][q][p].s2 = fma(a.y, bh[r], acc[r][q][p].s2);
+          }
+        }
+    }
+  };
+  // two chunks per loop trip with the roles of the register sets swapped, so nothing is copied between trips
+  u64 svr[VPT], da[U][R], dbq[U][R];
+  fetch(i_lo, svr);
+  load_db(i_lo, da);
+  stash(0, svr);
+  __syncthreads();
+#pragma unroll 1
+  for (u32 i1 = i_lo; i1 < i_hi; i1 += 2 * U) {
+    fetch(i1 + U, svr);  // the next chunk's operands travel while this chunk is multiplied
+    load_db(i1 + U, dbq);
+    compute(0, da);
+    stash(1, svr);
+    __syncthreads();
+    if (i1 + U >= i_hi) break;
+    fetch(i1 + 2 * U, svr);
+    load_db(i1 + 2 * U, da);
+    compute(1, dbq);
+    stash(0, svr);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= n_rows) break;
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      if (q0 + q >= (u32)n_queries) break;
+      u64* o = part + (((u64)(q0 + q) * n_split + split) * n_rows + row0 + r) * ctL + limb;
+      o[0] = acc[r][q][0].reduce(m, hb);
+      o[kN] = acc[r][q][1].reduce(m, hb);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // scan, register-pipelined LDG variant: the loads of step i+PD-1 are issued before the multiply-accumulates of
 // step i, so every warp keeps PD-1 steps of database/selection tiles in flight while it computes.
 // ---------------------------------------------------------------------------------------------
@@ -553,6 +696,37 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
   if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidConfiguration;
   if (n_queries >= env_int("PIRB_SCAN_BATCH_MIN", 4) && scan_mode() == 0) {
     // batch of queries: share every database tile between QB queries
+    if (mode == MAC_FP64 && env_int("PIRB_SCAN_BATCH_V", 2) == 2) {
+      const int R2 = env_int("PIRB_B2_R", n_rows >= 2 ? 2 : 1);
+      const int QB2 = env_int("PIRB_B2_QB", 2);
+      const int U2 = env_int("PIRB_B2_U", 2);  // measured: 2 rows x 2 queries, 4 row groups, 2 columns per barrier
+      int RG2 = env_int("PIRB_B2_RG", 4);
+      while (RG2 > 1 && (u32)(R2 * RG2) > n_rows + R2 - 1) RG2 >>= 1;  // do not idle whole row groups on small shards
+      const u32 tiles = (n_rows + R2 * RG2 - 1) / (R2 * RG2);
+      dim3 g2((n_queries + QB2 - 1) / QB2, tiles * n_split, (u32)P.k * P.N / BATCH_NT);
+      if (g2.y > 65535 || g2.z > 65535) return cudaErrorInvalidConfiguration;
+      const size_t smem2 = (size_t)2 * U2 * QB2 * 2 * BATCH_NT * sizeof(double2);
+#define B2_CASE(RR, QQ, GG, UU)                                                                                    \
+  if (R2 == RR && QB2 == QQ && RG2 == GG && U2 == UU) {                                                            \
+    auto kern = k_scan_batch2<RR, QQ, GG, UU>;                                                                     \
+    if (smem2 > 48 * 1024) {                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);         \
+      if (e != cudaSuccess) return e;                                                                              \
+    }                                                                                                              \
+    kern<<<g2, BATCH_NT * GG, smem2, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_queries, n_split, part); \
+    return cudaGetLastError();                                                                                     \
+  }
+      B2_CASE(2, 4, 1, 1) B2_CASE(2, 4, 2, 1) B2_CASE(2, 4, 3, 1) B2_CASE(2, 3, 3, 1) B2_CASE(2, 4, 4, 1) B2_CASE(2, 4, 2, 2) B2_CASE(2, 4, 4, 2)
+      B2_CASE(2, 2, 1, 2) B2_CASE(1, 2, 1, 2) B2_CASE(1, 2, 2, 2) B2_CASE(1, 2, 4, 2)
+      B2_CASE(2, 2, 2, 2) B2_CASE(2, 2, 2, 4) B2_CASE(2, 2, 4, 3) B2_CASE(2, 2, 4, 4) B2_CASE(2, 2, 3, 2) B2_CASE(2, 2, 3, 4) B2_CASE(4, 2, 2, 4)
+      B2_CASE(2, 2, 1, 1) B2_CASE(2, 2, 2, 1) B2_CASE(2, 2, 4, 1) B2_CASE(2, 2, 4, 2) B2_CASE(2, 2, 8, 2) B2_CASE(2, 2, 8, 1)
+      B2_CASE(1, 4, 1, 1) B2_CASE(1, 4, 2, 1) B2_CASE(1, 4, 4, 1) B2_CASE(1, 4, 8, 1) B2_CASE(1, 4, 4, 2)
+      B2_CASE(1, 2, 1, 1) B2_CASE(1, 2, 2, 1) B2_CASE(1, 2, 4, 1)
+      B2_CASE(4, 2, 1, 1) B2_CASE(4, 2, 2, 1) B2_CASE(4, 2, 4, 1) B2_CASE(4, 2, 2, 2)
+      B2_CASE(3, 2, 2, 1) B2_CASE(3, 2, 4, 1) B2_CASE(2, 3, 2, 1) B2_CASE(2, 3, 4, 1)
+#undef B2_CASE
+      // unlisted shape: fall through to the first-generation kernel
+    }
     const int QB = env_int("PIRB_SCAN_QB", n_queries >= 4 ? 4 : 2);
     const int RB = env_int("PIRB_SCAN_RB", n_rows >= 2 ? 2 : 1);
     dim3 bgrid((n_queries + QB - 1) / QB, ((n_rows + RB - 1) / RB) * n_split, (u32)P.k * P.N / BATCH_NT);

@@ -193,9 +193,12 @@ class ShardServer:
         ql, dim_sum = sv_local.shape[0], sv_local.shape[1]
         d0 = self.params.dimensions[0]
         sv_all = self._empty(world * ql, *sv_local.shape[1:])
-        # measured on 8 B200s: the extra all-to-all costs more latency than the halved volume saves at this message
-        # size (10 MB per query), so the plain all-gather is the default; PIRB_SPLIT_EXCHANGE=1 selects the split.
-        if world < 4 or len(self.params.dimensions) == 1 or os.environ.get("PIRB_SPLIT_EXCHANGE") != "1":
+        # measured on 8 B200s: at 10 MB per rank (config 2) the extra all-to-all costs more latency than the halved
+        # volume saves, at 85-680 MB per rank (configs 3/4) the exchange is bandwidth-bound and the split wins.
+        # PIRB_SPLIT_EXCHANGE=1/0 forces the choice.
+        env = os.environ.get("PIRB_SPLIT_EXCHANGE")
+        split = env == "1" or (env is None and sv_local.numel() * 8 >= (64 << 20))
+        if world < 2 or len(self.params.dimensions) == 1 or not split:
             dist.all_gather_into_tensor(sv_all, sv_local)
             return sv_all
         rows = shard_rows(d0, world)

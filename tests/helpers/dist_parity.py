@@ -43,6 +43,11 @@ def main():
         # (2) batch path: rank r expands only query r
         mine = sharded.to_host(srv.answer_batch_distributed(sharded.to_device(queries[rank:rank + 1], dev)))[0]
         ok &= bool(np.array_equal(full[rank], mine))
+        # (2b) the ownership-aware exchange of the selection vectors (chosen automatically for large messages)
+        os.environ["PIRB_SPLIT_EXCHANGE"] = "1"
+        split = sharded.to_host(srv.answer_batch_distributed(sharded.to_device(queries[rank:rank + 1], dev)))[0]
+        del os.environ["PIRB_SPLIT_EXCHANGE"]
+        ok &= bool(np.array_equal(split, mine))
         # (3) same, partial replies exchanged through peer memory (CUDA IPC) instead of an NCCL gather; run it three
         #     times so both exchange slots and their reuse are exercised
         srv.setup_peer_exchange(max_queries=world)

@@ -422,6 +422,37 @@ def test_scan_selects_database_rows_at_baseline_size():
     assert np.array_equal((ra + rb) % q[None, None, :, None], rs)
 
 
+@pytest.mark.parametrize("n,bits,dbsize,d,nq", [(4096, 20, 82, 2, 4), (4096, 20, 82, 2, 7), (4096, 20, 300, 2, 5),
+                                                (4096, 20, 37, 1, 6), (8192, 20, 50, 2, 4), (4096, 24, 1639, 2, 9)])
+def test_batched_scan_matches_single_query_scan_and_oracle(n, bits, dbsize, d, nq):
+    """Batches of >= 4 queries share one pass over the database (k_scan_batch2): every query's rows must equal what
+    the single-query kernel returns for it, and the oracle's selection-vector x database row (database.cpp:185-194).
+    Shapes cover a short last row, d=1 (one row), odd batch sizes (a half-empty query tile) and N=8192."""
+    import torch
+    from pir_b200 import sharded
+    ep = pb.GenerateEncryptionParams(n, bits)
+    p = pb.CreatePIRParameters(dbsize, 0, d, ep)
+    sh = sharded.ShardServer(p, device=0)
+    sh.db.fill_random(11)
+    k = len(ep.coeff_modulus) - 1
+    dimL = p.dimensions[-1]
+    rng = np.random.default_rng(3)
+    q = [int(x) for x in ep.coeff_modulus[:k]]
+    sv = np.stack([rng.integers(0, q[j], (nq, dimL, 2, n), dtype=np.uint64) for j in range(k)], axis=3)
+    d_sv = torch.from_numpy(np.ascontiguousarray(sv).view(np.int64)).cuda()
+    batch = sh.scan(d_sv).cpu().numpy().view(np.uint64)
+    for i in range(nq):
+        single = sh.scan(d_sv[i:i + 1]).cpu().numpy().view(np.uint64)[0]
+        assert np.array_equal(batch[i], single), i
+    orc = ob.Oracle(n, list(ep.coeff_modulus), ep.plain_modulus)
+    n_rows = batch.shape[1]
+    for i, r in [(0, 0), (nq - 1, n_rows - 1), (nq // 2, n_rows // 2)]:
+        first = r * dimL
+        cnt = min(dimL, p.num_pt - first)
+        want = orc.scan_row(sh.db.read_ntt(first, cnt), sv[i, :cnt])
+        assert np.array_equal(batch[i, r], want), (i, r)
+
+
 def test_repeated_requests_replay_the_captured_graph(srv10):
     """The first ProcessRequest of a shape runs eagerly, the second captures a CUDA graph, later ones replay it:
     every reply must still match the oracle, also after the client (key handle) changes."""

@@ -25,13 +25,14 @@ def main():
     ap.add_argument("--queries", type=int, default=1)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--variants", default="")
+    ap.add_argument("--shards", type=int, default=1, help="time the scan of shard 0 of this many row shards")
     args = ap.parse_args()
     params = bench.make_params(args.workload)
     ep = params.encryption_parameters
     N, mods = ep.poly_modulus_degree, ep.coeff_modulus
     k = len(mods) - 1
     dev = torch.device("cuda", 0)
-    srv = sharded.ShardServer(params, device=0)
+    srv = sharded.ShardServer(params, device=0, shard_index=0, shard_count=args.shards)
     srv.db.fill_random(1)
     dimL = params.dimensions[-1]
     rng = np.random.default_rng(0)
@@ -55,7 +56,7 @@ def main():
                                  "PIRB_SCAN_G": str(g), "PIRB_SCAN_U": str(st), "PIRB_SCAN_CTAS_PER_SM": str(cps)})
     ref = None
     srv.set_profiling(True)
-    knobs = ["PIRB_MAC_MODE", "PIRB_SCAN_MINB", "PIRB_SCAN_G", "PIRB_SCAN_QB", "PIRB_SCAN_RB", "PIRB_SCAN_BATCH_MIN", "PIRB_SCAN_R", "PIRB_SCAN_U", "PIRB_SCAN_CTAS_PER_SM", "PIRB_SCAN_SPLIT",
+    knobs = ["PIRB_SCAN_BATCH_V", "PIRB_B2_R", "PIRB_B2_QB", "PIRB_B2_RG", "PIRB_B2_U", "PIRB_MAC_MODE", "PIRB_SCAN_MINB", "PIRB_SCAN_G", "PIRB_SCAN_QB", "PIRB_SCAN_RB", "PIRB_SCAN_BATCH_MIN", "PIRB_SCAN_R", "PIRB_SCAN_U", "PIRB_SCAN_CTAS_PER_SM", "PIRB_SCAN_SPLIT",
              "PIRB_SCAN_MODE"]
     for v in variants:
         for kk in knobs:

@@ -25,11 +25,47 @@ __global__ void k(u64* out, u32 seed) {
       if (OP == 6) { asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b));
                      asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[c]) : "d"(da), "d"(db)); }
       if (OP == 7) asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(w[c]) : "r"(a + i), "r"(b));
+      if (OP == 8) asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d[c]) : "f"(f[c] + (float)i));
+      if (OP == 9) { asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d[c]) : "f"(__uint_as_float(w[c] + i)));
+                     asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(da) : "d"(db), "d"(db)); }
     }
   }
   u64 s = 0;
   for (int c = 0; c < CH; ++c) s += acc[c] + (u64)d[c] + (u64)f[c] + w[c];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// shared-memory read bandwidth: every thread reads VEC-byte words at consecutive addresses (conflict-free)
+template <int VEC>
+__global__ void ksmem(u64* out) {
+  __shared__ __align__(16) u64 buf[4096];
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) buf[i] = i;
+  __syncthreads();
+  u64 s = 0;
+  const int words = VEC / 8;
+  for (int i = 0; i < ITERS; ++i) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int idx = ((threadIdx.x + (i + c) * 32) * words) & 4095;
+      const unsigned addr = (unsigned)__cvta_generic_to_shared(&buf[VEC == 16 ? (idx & ~1) : idx]);
+      if (VEC == 16) { u64 x, y; asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(addr)); s += x ^ y; }
+      else { u64 x; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(x) : "r"(addr)); s += x; }
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int VEC>
+void run_smem(const char* name, int sms) {
+  u64* out; cudaMalloc(&out, sizeof(u64) * sms * 8 * 1024);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  ksmem<VEC><<<sms * 2, 1024>>>(out);
+  cudaEventRecord(e0);
+  ksmem<VEC><<<sms * 2, 1024>>>(out);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  double bytes = (double)sms * 2 * 1024 * ITERS * CH * VEC;
+  printf("%-28s %8.3f ms  %7.1f B/clk/SM\n", name, ms, bytes / (ms * 1e-3) / (clk * 1e3) / sms);
+  cudaFree(out);
 }
 template <int OP>
 void run(const char* name, int sms, double mult) {
@@ -55,5 +91,9 @@ int main() {
   run<4>("cvt.f64.u32 (I2F)", sms, 1);
   run<5>("fma.f32 (FFMA)", sms, 1);
   run<6>("IMAD.WIDE + DFMA interleaved", sms, 2);
+  run<8>("cvt.f64.f32 (F2F)", sms, 1);
+  run<9>("F2F + DFMA interleaved", sms, 2);
+  run_smem<8>("LDS.64 conflict-free", sms);
+  run_smem<16>("LDS.128 conflict-free", sms);
   return 0;
 }
