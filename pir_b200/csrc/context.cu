@@ -62,7 +62,9 @@ struct DevBuf {
 // trees of all ciphertexts (server.cpp:148-171) and of all queries of a batch run level by level.
 struct ExpandPlan {
   u64 total_items = 0;
-  int n_trees = 0;
+  int n_trees = 0;               // trees of this plan (a sub-range of the query's ciphertexts for a d=1 shard)
+  int t_first = 0;               // first query ciphertext expanded by this plan
+  int n_ct_in = 0;               // ciphertexts per query in the input array
   std::vector<u64> items, base;  // per tree: outputs kept, first ct index in S
   std::vector<int> logm;
   u64 cap = 0;  // ciphertext slots in S (and in T)
@@ -103,7 +105,7 @@ struct pirb_ctx {
   cudaStream_t stream = nullptr;
   std::vector<DevBuf> tables;
   DevBuf db, stage, work, dig, acc, part, bufA[2], pts, qbuf, rbuf, svbuf;
-  std::map<std::pair<u64, int>, std::unique_ptr<ExpandPlan>> plans;
+  std::map<std::tuple<u64, int, int, int>, std::unique_ptr<ExpandPlan>> plans;  // (items, single, first tree, trees)
   bool profiling = false;
   cudaEvent_t ev[PIRB_N_STAGES + 1] = {};
   bool ev_valid = false;
@@ -147,23 +149,29 @@ u32 inv_mod_2n(u32 g, u32 N) {
   return x & (2 * N - 1);
 }
 
-ExpandPlan* get_plan(pirb_ctx* c, u64 total_items, int single, int* rc) {
+// t_first / t_count select a sub-range of the query's ciphertexts (t_count < 0: all of them).  A row shard of a
+// d=1 database only multiplies the selection entries of its own plaintexts, so it expands only the trees that
+// cover them; their outputs are stored compactly from slot 0.
+ExpandPlan* get_plan(pirb_ctx* c, u64 total_items, int single, int* rc, int t_first = 0, int t_count = -1) {
   *rc = 0;
-  auto key = std::make_pair(total_items, single);
+  const u64 N = c->N;
+  const int n_all = single ? 1 : (int)(total_items / N + 1);
+  if (t_count < 0) { t_first = 0; t_count = n_all; }
+  auto key = std::make_tuple(total_items, single, t_first, t_count);
   auto it = c->plans.find(key);
   if (it != c->plans.end()) return it->second.get();
   auto pl = std::make_unique<ExpandPlan>();
-  const u64 N = c->N;
   pl->total_items = total_items;
-  pl->n_trees = single ? 1 : (int)(total_items / N + 1);
-  u64 remaining = total_items;
-  for (int t = 0; t < pl->n_trees; ++t) {
-    u64 it_ = single ? total_items : (remaining < N ? remaining : N);
+  pl->n_trees = t_count;
+  pl->t_first = t_first;
+  pl->n_ct_in = n_all;
+  for (int t = t_first; t < t_first + t_count; ++t) {
+    const u64 before = (u64)t * N;
+    u64 it_ = single ? total_items : (total_items > before ? std::min<u64>(N, total_items - before) : 0);
     pl->items.push_back(it_);
     pl->logm.push_back((int)hm::ceil_log2((uint32_t)it_));
-    pl->base.push_back((u64)t * N);
+    pl->base.push_back((u64)(t - t_first) * N);
     pl->max_logm = std::max(pl->max_logm, pl->logm.back());
-    remaining = remaining >= N ? remaining - N : 0;
   }
   pl->cap = pl->base.back() + hm::next_power_two(pl->items.back());
   const u64 Soff = 0, Toff = pl->cap * c->ctL;
@@ -205,7 +213,8 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
     RC(c->dig.ensure((size_t)std::max<u64>(nodes, 1) * (c->k + 1) * c->k * c->N * sizeof(u64)));
     RC(c->acc.ensure((size_t)std::max<u64>(nodes, 1) * 2 * (c->k + 1) * c->N * sizeof(u64)));
   }
-  LAUNCH(c, launch_place_roots(c->P, d_query, c->work.p, pl->d_off.p, pl->n_trees, n_queries, q_stride, st));
+  LAUNCH(c, launch_place_roots(c->P, d_query + (u64)pl->t_first * c->ctL, (u64)pl->n_ct_in * c->ctL, c->work.p,
+                               pl->d_off.p, pl->n_trees, n_queries, q_stride, st));
   for (int j = 0; j < pl->max_logm; ++j) {
     const u32 g = (c->N >> j) + 1;
     if (!keys) return fail(PIRB_INTERNAL, "Galois keys required");
@@ -244,14 +253,17 @@ int choose_split(u64 base_ctas, u32 len, int sm_count) {
 // DatabaseMultiplier::multiply on the device.  d_sv: [n_queries] x (sv_qstride limbs apart) x [dim_sum][2][k][N]
 // coefficient form; transformed to NTT form in place.  d_out: [n_queries][reply_cts][2][k][N]; coefficient form,
 // or (partial != 0) the NTT-form sum over this shard's rows, to be reduced across shards.
+// sv_item0 / sv_items: index of the first selection ciphertext stored at d_sv and how many are stored (a d=1 shard
+// only holds the expansion of its own trees).
 int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_out, int partial, cudaStream_t st,
-                 bool sv_is_ntt = false) {
+                 bool sv_is_ntt = false, u64 sv_item0 = 0, u64 sv_items = ~0ull) {
+  if (sv_items == ~0ull) sv_items = c->dim_sum;
   const int d = c->d, k = c->k;
   const u64 ctL = c->ctL;
   const DevParams& P = c->P;
   if (c->profiling) cudaEventRecord(c->ev[1], st);
   if (!sv_is_ntt)
-    LAUNCH(c, launch_ntt_fwd(P, d_sv, d_sv, (int)(c->dim_sum * 2 * k), k, 0, n_queries, sv_qstride, sv_qstride, st));
+    LAUNCH(c, launch_ntt_fwd(P, d_sv, d_sv, (int)(sv_items * 2 * k), k, 0, n_queries, sv_qstride, sv_qstride, st));
   if (c->profiling) cudaEventRecord(c->ev[2], st);
 
   const u64 out_cts = c->reply_cts;
@@ -267,7 +279,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   if (d == 1) {
     dimL = c->top_hi - c->top_lo;
     n_rows = 1;
-    sv_last = d_sv + (u64)c->top_lo * ctL;
+    sv_last = d_sv + ((u64)c->top_lo - sv_item0) * ctL;
   } else {
     dimL = c->dims[d - 1];
     n_rows = (u32)((c->pt_count + dimL - 1) / dimL);
@@ -346,12 +358,21 @@ int run_answer(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u32 n_q
   }
   if (c->loaded != c->pt_count) return fail(PIRB_INVALID_ARGUMENT, "database size mismatch");  // server.cpp:37-39
   int rc;
-  ExpandPlan* pl = get_plan(c, c->dim_sum, 0, &rc);
+  // a row shard of a one-dimensional database expands only the query ciphertexts that cover its plaintexts
+  int t_first = 0, t_count = -1;
+  if (c->d == 1 && partial && c->top_hi > c->top_lo && (c->top_lo > 0 || c->top_hi < c->dims[0])) {
+    t_first = (int)(c->top_lo / c->N);
+    t_count = (int)((c->top_hi - 1) / c->N) - t_first + 1;
+  }
+  ExpandPlan* pl = get_plan(c, c->dim_sum, 0, &rc, t_first, t_count);
   if (!pl) return rc;
   c->launches = 0;
   if (c->profiling) cudaEventRecord(c->ev[0], st);
   RC(run_expand(c, keys, pl, d_queries, (int)n_queries, st));
-  RC(run_multiply(c, c->work.p, 2 * pl->cap * c->ctL, (int)n_queries, d_out, partial, st));
+  u64 sv_items = 0;
+  for (size_t t = 0; t < pl->items.size(); ++t) sv_items = std::max(sv_items, pl->base[t] + pl->items[t]);
+  RC(run_multiply(c, c->work.p, 2 * pl->cap * c->ctL, (int)n_queries, d_out, partial, st, false, (u64)pl->t_first * c->N,
+                  t_count < 0 ? c->dim_sum : sv_items));
   c->ev_valid = c->profiling;
   return 0;
 }
@@ -484,7 +505,7 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   for (u32 i = 0; i < prm->n_moduli; ++i) {
     const u64 q = prm->coeff_modulus[i];
     hm::Tables T = hm::build_tables(q, logn);
-    RC(c->tables[i].ensure(10ull * N * sizeof(u64)));
+    RC(c->tables[i].ensure(12ull * N * sizeof(u64)));
     u64* base = c->tables[i].p;
     CU(cudaMemcpy(base, T.rp.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(base + N, T.rps.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
@@ -516,6 +537,10 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
       m.fw = reinterpret_cast<const double2*>(dbase);
       m.iw = reinterpret_cast<const double2*>(dbase + 2ull * N);
       m.fin = reinterpret_cast<const double2*>(dbase + 4ull * N);
+      CU(cudaMemcpy(dbase + 6ull * N, T.fw.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(dbase + 7ull * N, T.iw.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+      m.fw1 = dbase + 6ull * N;
+      m.iw1 = dbase + 7ull * N;
     }
     if ((int)i < c->k) {
       P.inv_P[i] = hm::invmod_prime(Pq % q, q);

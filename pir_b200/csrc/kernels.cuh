@@ -71,8 +71,8 @@ cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peer
                                       u64* out, u64 n_cts, cudaStream_t st);
 
 // copy root ciphertexts of every tree into place: work[qi*q_stride + root_off[t]] = query[qi][t]
-cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64* work, const u64* root_off, int n_trees,
-                               int n_queries, u64 q_stride, cudaStream_t st);
+cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64 query_qstride, u64* work, const u64* root_off,
+                               int n_trees, int n_queries, u64 q_stride, cudaStream_t st);
 
 // StringEncoder packing on the device: raw item bytes -> plaintext coefficients [n_pt][N]
 cudaError_t launch_pack_items(const u8* bytes, u64* coeffs, u32 N, u32 bits, u64 bytes_per_pt, u64 total_bytes,

@@ -59,6 +59,20 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
   const ModC& mI = P.m[I];
   const int nd = (k + 1) / 2;  // digit buffers per CTA
   u64* A = smem + (size_t)nd * N;
+  // FP64 engine, N <= 4096: the twiddle table of the running transform is staged in shared memory by one bulk
+  // asynchronous copy (forward table while the digits are gathered, inverse table while the key products are
+  // formed), so no butterfly pass waits on an L2 round trip for its twiddles
+  constexpr bool TWS = (ENG == ENG_FP64) && (LOGN <= 12);
+  double* TWb = reinterpret_cast<double*>(A + N);
+  u64* twbar = A + 2 * (size_t)N;
+  if constexpr (TWS) {
+    if (tid == 0) {
+      mbar_init(twbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(twbar, N * 8);
+      bulk_g2s_plain(TWb, mI.fw1, N * 8, twbar);
+    }
+  }
 #define PIRB_STAMP(slot)                                                                   \
   do {                                                                                     \
     if (L.dbg && tid == 0) {                                                               \
@@ -105,7 +119,12 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
     }
     __syncthreads();
     PIRB_STAMP(1);
-    eng_forward<LOGN, NT, ENG>(D, mI, tid);
+    if constexpr (TWS) {
+      mbar_wait(twbar, 0);
+      f64_forward_all<LOGN, NT>(reinterpret_cast<double*>(D), TwShared{TWb, mI.qinv}, mI.qd, tid);
+    } else {
+      eng_forward<LOGN, NT, ENG>(D, mI, tid);
+    }
     PIRB_STAMP(2);
 #pragma unroll
     for (int i = tid; i < N; i += NT) {
@@ -113,6 +132,14 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
         D[swz(i)] = (u64)__double_as_longlong(f64_canon(__longlong_as_double((long long)D[swz(i)]), mI.qd, mI.qinv));
       else
         D[swz(i)] = eng_store_fwd<ENG>(D[swz(i)], mI);
+    }
+  }
+  if constexpr (TWS) {
+    // every forward pass has ended with a block barrier: the table buffer is free for the inverse twiddles
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(twbar, N * 8);
+      bulk_g2s_plain(TWb, mI.iw1, N * 8, twbar);
     }
   }
   PIRB_STAMP(3);
@@ -183,7 +210,12 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
     }
     __syncthreads();
     PIRB_STAMP(5);
-    eng_inverse<LOGN, NT, ENG>(A, mI, tid);
+    if constexpr (TWS) {
+      mbar_wait(twbar, 1);
+      f64_inverse_all<LOGN, NT>(reinterpret_cast<double*>(A), TwShared{TWb, mI.qinv}, mI.qd, tid);
+    } else {
+      eng_inverse<LOGN, NT, ENG>(A, mI, tid);
+    }
     PIRB_STAMP(6);
 #pragma unroll
     for (int i = tid; i < N; i += NT) A[swz(i)] = eng_finish_inv_native<ENG>(A[swz(i)], i, mI);
@@ -232,9 +264,14 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
   cluster.sync();  // keep shared memory alive until every peer has finished reading it
 }
 
+static size_t ks_cluster_smem(const DevParams& P) {
+  const bool tws = P.ntt_engine == ENG_FP64 && P.logn <= 12;  // + staged twiddle table and its mbarrier
+  return (size_t)((P.k + 1) / 2 + 1 + (tws ? 1 : 0)) * P.N * sizeof(u64) + (tws ? 16 : 0);
+}
+
 bool ks_cluster_supported(const DevParams& P) {
   const int k = P.k;
-  const size_t smem = (size_t)((k + 1) / 2 + 1) * P.N * sizeof(u64);
+  const size_t smem = ks_cluster_smem(P);
   return 2 * (k + 1) <= 16 && smem <= 227 * 1024 && P.logn >= 11 && P.logn <= 14;
 }
 
@@ -244,7 +281,7 @@ cudaError_t launch_ks_level_cluster(const DevParams& P, u64* work, const LevelAr
   if (!nodes) return cudaSuccess;
   const int k = P.k;
   const unsigned csize = 2 * (k + 1);
-  const size_t smem = (size_t)((k + 1) / 2 + 1) * P.N * sizeof(u64);
+  const size_t smem = ks_cluster_smem(P);
   auto go = [&](auto ln, auto lz, auto mm) -> cudaError_t {
     constexpr int LN = decltype(ln)::value;
     constexpr int LZ = decltype(lz)::value;

@@ -494,33 +494,6 @@ constexpr int TMA_L = 256;              // limbs per tile (2 KiB)
 constexpr int TMA_CONSUMERS = 128;
 constexpr int TMA_NT = TMA_CONSUMERS + 32;
 
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(u64* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar, u64 policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-
 // G consumer groups of 128 threads share the selection-vector tiles of a stage; group g owns rows g*RG .. g*RG+RG-1
 // of the CTA's R = G*RG rows, so L2->SM traffic per database byte is (R + 2) / R.
 template <int RG, int G, int STAGES, int MODE>
@@ -1003,21 +976,21 @@ cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peer
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_place_roots(const u64* __restrict__ query, u64* __restrict__ work, const u64* __restrict__ root_off, int n_trees,
-              u64 q_stride, u64 ctL) {
+k_place_roots(const u64* __restrict__ query, u64 query_qstride, u64* __restrict__ work,
+              const u64* __restrict__ root_off, int n_trees, u64 q_stride, u64 ctL) {
   const u32 tq = blockIdx.y;
   const u32 ti = tq % n_trees, qi = tq / n_trees;
   const u64 i = ((u64)blockIdx.x * 256 + threadIdx.x) * 2;
   if (i >= ctL) return;
-  const ulonglong2 v = ldg128(query + (u64)tq * ctL + i);
+  const ulonglong2 v = ldg128(query + qi * query_qstride + (u64)ti * ctL + i);
   *reinterpret_cast<ulonglong2*>(work + qi * q_stride + root_off[ti] + i) = v;
 }
-cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64* work, const u64* root_off, int n_trees,
-                               int n_queries, u64 q_stride, cudaStream_t st) {
+cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64 query_qstride, u64* work, const u64* root_off,
+                               int n_trees, int n_queries, u64 q_stride, cudaStream_t st) {
   if (!n_trees || !n_queries) return cudaSuccess;
   const u64 ctL = 2ull * P.k * P.N;
-  k_place_roots<<<dim3((unsigned)((ctL / 2 + 255) / 256), n_trees * n_queries), 256, 0, st>>>(query, work, root_off,
-                                                                                            n_trees, q_stride, ctL);
+  k_place_roots<<<dim3((unsigned)((ctL / 2 + 255) / 256), n_trees * n_queries), 256, 0, st>>>(
+      query, query_qstride, work, root_off, n_trees, q_stride, ctL);
   return cudaGetLastError();
 }
 

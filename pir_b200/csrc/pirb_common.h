@@ -27,6 +27,8 @@ struct ModC {
   const double2* fw;       // fw[i].x  = (double)rp[i]                    forward twiddles, SEAL ordering
   const double2* iw;       // iw[g + j].x = psi^(-j*N/g)  for gap g = 1,2,4,...,N/2, j < g   (inverse, DIT form)
   const double2* fin;      // fin[i].x = N^{-1} * psi^{-i}                final scaling of the inverse
+  const double* fw1;       // w-only copies of fw / iw (N doubles each): bulk-copied into shared memory by the
+  const double* iw1;       // cluster key-switch kernel, which forms w/q on the fly
   double pow_h, pow_h_i;    // 2^h mod q and (2^h mod q)/q     (h = DevParams::half_bits; FP64 Karatsuba recombination)
   double pow_2h, pow_2h_i;  // 2^(2h) mod q and its /q companion
 };

@@ -347,9 +347,28 @@ __device__ __forceinline__ u64 f64_to_u64_exact(double d) {  // integer-valued, 
 }
 
 // forward pass (Cooley-Tukey, SEAL ordering) on doubles; same unit geometry as ntt_fwd_pass
-template <int LOGN, int NT, int S0, int R>
-__device__ __forceinline__ void f64_fwd_pass(double* __restrict__ s, const double2* __restrict__ tw, double q,
-                                             int tid) {
+// Twiddle sources of the FP64 passes: the (w, w/q) pair table in global memory, or a w-only table staged in shared
+// memory whose companion is formed on the fly (w * (1/q): relative error 2^-52, so the quotient estimate of
+// f64_modmul stays within 0.5 + |y| 2^-51 of the true quotient and every bound above holds with 0.57 q per stage).
+struct TwGlobal {
+  const double2* t;
+  __device__ __forceinline__ void get(int i, double& w, double& wi) const {
+    const double2 v = __ldg(t + i);
+    w = v.x;
+    wi = v.y;
+  }
+};
+struct TwShared {
+  const double* t;
+  double qinv;
+  __device__ __forceinline__ void get(int i, double& w, double& wi) const {
+    w = t[i];
+    wi = __dmul_rn(w, qinv);
+  }
+};
+
+template <int LOGN, int NT, int S0, int R, class TW>
+__device__ __forceinline__ void f64_fwd_pass(double* __restrict__ s, const TW tw, double q, int tid) {
   constexpr int N = 1 << LOGN;
   constexpr int E = 1 << R;
   constexpr int TL = N >> (S0 + R);
@@ -368,8 +387,8 @@ __device__ __forceinline__ void f64_fwd_pass(double* __restrict__ s, const doubl
       const int mbase = (1 << (S0 + a)) + (hi << a);
 #pragma unroll
       for (int b = 0; b < (1 << a); ++b) {
-        const double2 w2 = __ldg(tw + mbase + b);
-        const double w = w2.x, wi = w2.y;
+        double w, wi;
+        tw.get(mbase + b, w, wi);
 #pragma unroll
         for (int c = 0; c < half; ++c) {
           const int e0 = b * 2 * half + c, e1 = e0 + half;
@@ -386,9 +405,8 @@ __device__ __forceinline__ void f64_fwd_pass(double* __restrict__ s, const doubl
 // inverse pass: decimation-in-time butterflies (X + W*Y, X - W*Y) on the bit-reversed input, gaps increasing.
 // For the stage with gap g the twiddle of the pair at in-block offset j is iw[g + j] = psi^(-j*N/g)  (cyclic
 // inverse DFT with root psi^-2); the remaining psi^-i * N^-1 is applied per element at the end (fin table).
-template <int LOGN, int NT, int S0, int R>
-__device__ __forceinline__ void f64_inv_pass(double* __restrict__ s, const double2* __restrict__ iw, double q,
-                                             int tid) {
+template <int LOGN, int NT, int S0, int R, class TW>
+__device__ __forceinline__ void f64_inv_pass(double* __restrict__ s, const TW iw, double q, int tid) {
   constexpr int N = 1 << LOGN;
   constexpr int E = 1 << R;
   constexpr int TL = N >> (S0 + R);
@@ -407,8 +425,8 @@ __device__ __forceinline__ void f64_inv_pass(double* __restrict__ s, const doubl
       const int g = dist * TL;
 #pragma unroll
       for (int c = 0; c < dist; ++c) {  // in-block offset j = c*TL + lo
-        const double2 w2 = __ldg(iw + g + c * TL + lo);
-        const double w = w2.x, wi = w2.y;
+        double w, wi;
+        iw.get(g + c * TL + lo, w, wi);
 #pragma unroll
         for (int b = 0; b < (1 << a); ++b) {
           const int e0 = b * 2 * dist + c, e1 = e0 + dist;
@@ -473,35 +491,72 @@ __device__ __forceinline__ u64 eng_finish_inv_native(u64 word, int i, const ModC
   }
 }
 
+template <int LOGN, int NT, class TW>
+__device__ __forceinline__ void f64_forward_all(double* d, const TW tw, double q, int tid) {
+  constexpr int R0 = ((LOGN - 1) % 3) + 1;
+  f64_fwd_pass<LOGN, NT, 0, R0>(d, tw, q, tid);
+  __syncthreads();
+  if constexpr (LOGN > R0) { f64_fwd_pass<LOGN, NT, R0, 3>(d, tw, q, tid); __syncthreads(); }
+  if constexpr (LOGN > R0 + 3) { f64_fwd_pass<LOGN, NT, R0 + 3, 3>(d, tw, q, tid); __syncthreads(); }
+  if constexpr (LOGN > R0 + 6) { f64_fwd_pass<LOGN, NT, R0 + 6, 3>(d, tw, q, tid); __syncthreads(); }
+  if constexpr (LOGN > R0 + 9) { f64_fwd_pass<LOGN, NT, R0 + 9, 3>(d, tw, q, tid); __syncthreads(); }
+}
+template <int LOGN, int NT, class TW>
+__device__ __forceinline__ void f64_inverse_all(double* d, const TW iw, double q, int tid) {
+  constexpr int R0 = ((LOGN - 1) % 3) + 1;
+  if constexpr (LOGN > R0 + 9) { f64_inv_pass<LOGN, NT, R0 + 9, 3>(d, iw, q, tid); __syncthreads(); }
+  if constexpr (LOGN > R0 + 6) { f64_inv_pass<LOGN, NT, R0 + 6, 3>(d, iw, q, tid); __syncthreads(); }
+  if constexpr (LOGN > R0 + 3) { f64_inv_pass<LOGN, NT, R0 + 3, 3>(d, iw, q, tid); __syncthreads(); }
+  if constexpr (LOGN > R0) { f64_inv_pass<LOGN, NT, R0, 3>(d, iw, q, tid); __syncthreads(); }
+  f64_inv_pass<LOGN, NT, 0, R0>(d, iw, q, tid);
+  __syncthreads();
+}
 template <int LOGN, int NT, int ENG>
 __device__ __forceinline__ void eng_forward(u64* s, const ModC& m, int tid) {
-  if constexpr (ENG == ENG_FP64) {
-    constexpr int R0 = ((LOGN - 1) % 3) + 1;
-    double* d = reinterpret_cast<double*>(s);
-    f64_fwd_pass<LOGN, NT, 0, R0>(d, m.fw, m.qd, tid);
-    __syncthreads();
-    if constexpr (LOGN > R0) { f64_fwd_pass<LOGN, NT, R0, 3>(d, m.fw, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0 + 3) { f64_fwd_pass<LOGN, NT, R0 + 3, 3>(d, m.fw, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0 + 6) { f64_fwd_pass<LOGN, NT, R0 + 6, 3>(d, m.fw, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0 + 9) { f64_fwd_pass<LOGN, NT, R0 + 9, 3>(d, m.fw, m.qd, tid); __syncthreads(); }
-  } else {
-    ntt_forward_smem_t<LOGN, NT, ENG == ENG_INT_LAZY>(s, m, tid);
-  }
+  if constexpr (ENG == ENG_FP64) f64_forward_all<LOGN, NT>(reinterpret_cast<double*>(s), TwGlobal{m.fw}, m.qd, tid);
+  else ntt_forward_smem_t<LOGN, NT, ENG == ENG_INT_LAZY>(s, m, tid);
 }
 template <int LOGN, int NT, int ENG>
 __device__ __forceinline__ void eng_inverse(u64* s, const ModC& m, int tid) {
-  if constexpr (ENG == ENG_FP64) {
-    constexpr int R0 = ((LOGN - 1) % 3) + 1;
-    double* d = reinterpret_cast<double*>(s);
-    if constexpr (LOGN > R0 + 9) { f64_inv_pass<LOGN, NT, R0 + 9, 3>(d, m.iw, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0 + 6) { f64_inv_pass<LOGN, NT, R0 + 6, 3>(d, m.iw, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0 + 3) { f64_inv_pass<LOGN, NT, R0 + 3, 3>(d, m.iw, m.qd, tid); __syncthreads(); }
-    if constexpr (LOGN > R0) { f64_inv_pass<LOGN, NT, R0, 3>(d, m.iw, m.qd, tid); __syncthreads(); }
-    f64_inv_pass<LOGN, NT, 0, R0>(d, m.iw, m.qd, tid);
-    __syncthreads();
-  } else {
-    ntt_inverse_smem_t<LOGN, NT, ENG == ENG_INT_LAZY>(s, m, tid);
-  }
+  if constexpr (ENG == ENG_FP64) f64_inverse_all<LOGN, NT>(reinterpret_cast<double*>(s), TwGlobal{m.iw}, m.qd, tid);
+  else ntt_inverse_smem_t<LOGN, NT, ENG == ENG_INT_LAZY>(s, m, tid);
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier + bulk asynchronous copy (cp.async.bulk, the non-tensor TMA path) helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar, u64 policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s_plain(void* dst, const void* src, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // Galois automorphism x -> x^g in coefficient form, as a gather: value of sigma_g(a) at index n.

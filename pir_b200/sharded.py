@@ -154,12 +154,23 @@ class ShardServer:
         import torch.distributed as dist
         world, rank = dist.get_world_size(), dist.get_rank()
         ql = d_queries_local.shape[0]
-        sv_local = self.expand_ntt(d_queries_local)
-        if world == 1:
-            part = self.multiply_partial(sv_local)
-            return self.reduce_finish(part[None], ql)
-        sv_all = self._exchange_selection_vectors(sv_local)
-        part = self.multiply_partial(sv_all)                     # [world*ql][reply_cts]...
+        if world > 1 and len(self.params.dimensions) == 1:
+            # one-dimensional database: the selection vector is as large as the database, so it is never exchanged;
+            # the (tiny) query ciphertexts are, and every rank expands only the trees that cover its own plaintexts
+            q_all = self._gather_queries(d_queries_local)
+            # expansion workspace per query: two ping-pong regions over this shard's trees; bound it to ~48 GB a call
+            lo, hi = shard_rows(self.params.dimensions[0], self.shard_count)[self.shard_index]
+            trees = max(1, (max(hi, lo + 1) - 1) // self.N - lo // self.N + 1)
+            per_query = 2 * trees * self.N * 2 * self.k * self.N * 8
+            chunk = max(1, (48 << 30) // per_query)
+            part = torch.cat([self.answer_partial(q_all[i:i + chunk]) for i in range(0, q_all.shape[0], chunk)])
+        else:
+            sv_local = self.expand_ntt(d_queries_local)
+            if world == 1:
+                part = self.multiply_partial(sv_local)
+                return self.reduce_finish(part[None], ql)
+            sv_all = self._exchange_selection_vectors(sv_local)
+            part = self.multiply_partial(sv_all)                 # [world*ql][reply_cts]...
         gathered = self._empty(world, *part.shape)
         dist.all_gather_into_tensor(gathered, part)
         own = gathered[:, rank * ql:(rank + 1) * ql]             # view: [world][ql][reply_cts]...
@@ -183,6 +194,13 @@ class ShardServer:
         _check(_lib.lib().pirb_xbuf_open(self.ctx.h, blob, world, rank))
         self._xslots, self._xslot = n_slots, 0
         self._xflag = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _gather_queries(self, d_queries_local: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        q_all = self._empty(world * d_queries_local.shape[0], *d_queries_local.shape[1:])
+        dist.all_gather_into_tensor(q_all, d_queries_local.contiguous())
+        return q_all
 
     def _exchange_selection_vectors(self, sv_local: torch.Tensor) -> torch.Tensor:
         """Every rank needs, of every query: all selection ciphertexts of dimensions 1..d-1 (they multiply every row)
@@ -223,9 +241,12 @@ class ShardServer:
         import torch.distributed as dist
         world, rank = dist.get_world_size(), dist.get_rank()
         ql = d_queries_local.shape[0]
+        if len(self.params.dimensions) == 1:
+            # one ciphertext of partial reply per query: nothing worth a peer-memory exchange (see the gather path)
+            return self.answer_batch_distributed(d_queries_local)
+        slot = self._xslot
         sv_local = self.expand_ntt(d_queries_local)
         sv_all = self._exchange_selection_vectors(sv_local)
-        slot = self._xslot
         st = self._enter()
         _check(_lib.lib().pirb_multiply_partial_xbuf_dev(self.ctx.h, _dp(sv_all), world * ql, slot, st))
         self._exit()

@@ -360,7 +360,9 @@ def test_end_to_end_correctness(n, bits, elem, bpc, dbsize, d, indices):
 
 
 # ------------------------------------------------------------------------------------------------ sharding on one GPU
-@pytest.mark.parametrize("dbsize,d,shards", [(82, 2, 2), (82, 2, 3), (200, 1, 4), (50, 3, 2), (9, 2, 4)])
+# (9000, 1, 4): a one-dimensional database over three query ciphertexts; shards expand only the trees that cover their
+# plaintexts (shard 2 starts inside the second tree, shard 3 spans the second and third)
+@pytest.mark.parametrize("dbsize,d,shards", [(82, 2, 2), (82, 2, 3), (200, 1, 4), (50, 3, 2), (9, 2, 4), (9000, 1, 4)])
 def test_row_sharded_partials_reduce_to_unsharded_answer(dbsize, d, shards):
     import torch
     from pir_b200 import sharded
