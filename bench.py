@@ -345,6 +345,8 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     scan_ms = statistics.mean(stage_acc["scan"])
     nq_scan = ql if world == 1 else world * ql
+    if world > 1 and len(params.dimensions) == 1:
+        nq_scan = getattr(srv, "last_partial_batch", nq_scan)  # d=1: the stage times describe the last chunk of queries
     scan_bytes = srv.scan_bytes(nq_scan)
     achieved = scan_bytes / (scan_ms * 1e-3) / 1e9
     stage_mean = {nm: statistics.mean(v) for nm, v in stage_acc.items()}

@@ -690,6 +690,7 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
     return cudaGetLastError();                                                                                     \
   }
       B2_CASE(2, 4, 1, 1) B2_CASE(2, 4, 2, 1) B2_CASE(2, 4, 3, 1) B2_CASE(2, 3, 3, 1) B2_CASE(2, 4, 4, 1) B2_CASE(2, 4, 2, 2) B2_CASE(2, 4, 4, 2)
+      B2_CASE(4, 1, 4, 2) B2_CASE(4, 1, 4, 4) B2_CASE(4, 1, 2, 2) B2_CASE(4, 1, 2, 4) B2_CASE(3, 1, 4, 4) B2_CASE(3, 2, 3, 2)
       B2_CASE(2, 2, 1, 2) B2_CASE(1, 2, 1, 2) B2_CASE(1, 2, 2, 2) B2_CASE(1, 2, 4, 2)
       B2_CASE(2, 2, 2, 2) B2_CASE(2, 2, 2, 4) B2_CASE(2, 2, 4, 3) B2_CASE(2, 2, 4, 4) B2_CASE(2, 2, 3, 2) B2_CASE(2, 2, 3, 4) B2_CASE(4, 2, 2, 4)
       B2_CASE(2, 2, 1, 1) B2_CASE(2, 2, 2, 1) B2_CASE(2, 2, 4, 1) B2_CASE(2, 2, 4, 2) B2_CASE(2, 2, 8, 2) B2_CASE(2, 2, 8, 1)

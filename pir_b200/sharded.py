@@ -163,6 +163,7 @@ class ShardServer:
             trees = max(1, (max(hi, lo + 1) - 1) // self.N - lo // self.N + 1)
             per_query = 2 * trees * self.N * 2 * self.k * self.N * 8
             chunk = max(1, (48 << 30) // per_query)
+            self.last_partial_batch = (q_all.shape[0] - 1) % chunk + 1  # queries in the last library call
             part = torch.cat([self.answer_partial(q_all[i:i + chunk]) for i in range(0, q_all.shape[0], chunk)])
         else:
             sv_local = self.expand_ntt(d_queries_local)
