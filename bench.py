@@ -416,6 +416,7 @@ def run_ours(args):
                    "l2": "256 MiB buffer read between timed iterations (evicts L2, leaves clean lines; outside the per-step CUDA events)",
                    "galois_keys": "resident in HBM, uploaded once per client"},
         "p50_latency_ms": statistics.median(step_ms),
+        "step_ms": [round(x, 4) for x in step_ms],
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(world * ql * n_ct * ctL * 8),
                 "d2h_bytes_per_step": int(world * ql * srv.ctx.reply_cts * ctL * 8),
                 "p50_latency_ms": 1e3 * statistics.median(lat)},

@@ -104,7 +104,7 @@ struct pirb_ctx {
   u64 loaded = 0;
   cudaStream_t stream = nullptr;
   std::vector<DevBuf> tables;
-  DevBuf db, stage, work, dig, acc, part, bufA[2], pts, qbuf, rbuf, svbuf;
+  DevBuf db, stage, work, dig, acc, xch, part, bufA[2], pts, qbuf, rbuf, svbuf;
   std::map<std::tuple<u64, int, int, int>, std::unique_ptr<ExpandPlan>> plans;  // (items, single, first tree, trees)
   bool profiling = false;
   cudaEvent_t ev[PIRB_N_STAGES + 1] = {};
@@ -209,7 +209,9 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
   const u64 q_stride = 2 * pl->cap * c->ctL;
   RC(c->work.ensure((size_t)n_queries * q_stride * sizeof(u64)));
   const u64 nodes = pl->max_nodes * n_queries;
-  if (!c->use_cluster) {  // the cluster kernel keeps digits and accumulators in shared memory
+  if (c->use_cluster) {
+    RC(c->xch.ensure((size_t)std::max<u64>(nodes, 1) * 2 * c->N * sizeof(u64)));
+  } else {  // the cluster kernel keeps digits and accumulators in shared memory
     RC(c->dig.ensure((size_t)std::max<u64>(nodes, 1) * (c->k + 1) * c->k * c->N * sizeof(u64)));
     RC(c->acc.ensure((size_t)std::max<u64>(nodes, 1) * 2 * (c->k + 1) * c->N * sizeof(u64)));
   }
@@ -228,7 +230,9 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
     L.ginv = inv_mod_2n(g, c->N);
     L.q_stride = q_stride;
     L.n_queries = n_queries;
+    L.xch = c->xch.p;
     L.dbg = !c->dbg.p ? nullptr : (c->dbg_level == -2 ? c->dbg.p + (size_t)j * 65536 : (j == c->dbg_level ? c->dbg.p : nullptr));
+    L.dbg_clock = (c->dbg_level >= 0 && getenv("PIRB_STAMP_CLOCK")) ? atoi(getenv("PIRB_STAMP_CLOCK")) : 0;
     const int n_nodes = (n_queries * L.n_trees) << j;
     if (c->use_cluster) {
       LAUNCH(c, launch_ks_level_cluster(c->P, c->work.p, L, key, 0, st));
@@ -782,7 +786,11 @@ int pirb_substitute(pirb_ctx* c, const pirb_keys* keys, uint64_t* ct, uint32_t p
   L.q_stride = 0;
   L.n_queries = 1;
   L.dbg = nullptr;
+  L.dbg_clock = 0;
+  L.xch = nullptr;
   if (c->use_cluster) {
+    RC(c->xch.ensure((size_t)2 * c->N * sizeof(u64)));
+    L.xch = c->xch.p;
     LAUNCH(c, launch_ks_level_cluster(c->P, c->work.p, L, key, 1, st));
   } else {
     LAUNCH(c, launch_ks_digits(c->P, c->work.p, L, c->dig.p, st));

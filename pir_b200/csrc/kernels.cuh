@@ -17,7 +17,10 @@ struct LevelArgs {
   u32 ginv;      // inverse of the Galois element (N>>j)+1 modulo 2N
   u64 q_stride;  // limbs between consecutive queries' workspaces
   int n_queries;
+  u64* xch;      // cluster kernel: [node][2][N] scratch through which the special-prime accumulators reach the
+                 // other CTAs of the cluster (L2 moves them faster than distributed shared memory does)
   u64* dbg;      // optional per-CTA phase timestamps (clock64), 8 slots per CTA; nullptr in production
+  int dbg_clock; // 1: slots 0 and 7 are clock64 too (single-level probe); 0: globaltimer (level-to-level gaps)
 };
 
 // generic batched transforms on [n_polys][N] arrays; modulus of poly p is m[(p % cycle) + off].

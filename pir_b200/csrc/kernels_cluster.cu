@@ -77,7 +77,7 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
   do {                                                                                     \
     if (L.dbg && tid == 0) {                                                               \
       u64 t_;                                                                              \
-      if ((slot) == 0 || (slot) == 7) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+      if (((slot) == 0 || (slot) == 7) && !L.dbg_clock) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
       else t_ = clock64();                                                                 \
       L.dbg[(u64)blockIdx.x * 8 + (slot)] = t_;                                            \
     }                                                                                      \
@@ -216,52 +216,93 @@ k_ks_level_cluster(const __grid_constant__ DevParams P, u64* __restrict__ work, 
     } else {
       eng_inverse<LOGN, NT, ENG>(A, mI, tid);
     }
-    PIRB_STAMP(6);
+    if (!(L.dbg_clock & 2)) PIRB_STAMP(6);
+    if (I == k) {
+      // special-prime accumulator: hand it to the readers through global memory.  Distributed shared memory moves
+      // ~21 B/clk per source SM and each of these CTAs feeds k readers; the same 8 B per coefficient through L2 is
+      // several times faster.  barrier.cluster (release/acquire) orders these stores before the readers' loads.
+      u64* xo = L.xch + ((u64)z * 2 + c) * N;
 #pragma unroll
-    for (int i = tid; i < N; i += NT) A[swz(i)] = eng_finish_inv_native<ENG>(A[swz(i)], i, mI);
+      for (int i = tid; i < N; i += NT) xo[i] = eng_finish_inv_native<ENG>(A[swz(i)], i, mI);
+    } else {
+#pragma unroll
+      for (int i = tid; i < N; i += NT) A[swz(i)] = eng_finish_inv_native<ENG>(A[swz(i)], i, mI);
+      if constexpr (TWS) {
+        // the twiddle buffer is free again: stage this CTA's source polynomial there (coalesced loads), so that the
+        // Galois gather sigma_g(c0) of phase 3 is a shared-memory permutation instead of scattered global sectors
+        const u64* sp = src + (u64)(c * k + I) * N;
+        u64* SB = reinterpret_cast<u64*>(TWb);
+#pragma unroll
+        for (int i = tid; i < N; i += NT) SB[i] = sp[i];
+      }
+    }
   }
   cluster.sync();
+  if (L.dbg_clock & 2) PIRB_STAMP(6);  // PIRB_STAMP_CLOCK=3: slot 6 after the barrier, to split the tail
 
   // ---- phase 3: mod-down by P, add sigma_g(c0), expansion butterfly ----
   if (I < k) {
     const int j = I;
     const u64 q = mI.q, Pq = P.m[k].q;
-    const u64* lastA = cluster.map_shared_rank(A, 2 * k + c);
+    const u64* lastA = L.xch + ((u64)z * 2 + c) * N;
+    const u64* SB = reinterpret_cast<const u64*>(TWb);
     u64* dstE = work + qi * L.q_stride + L.dst_off[ti] + kk * ctL;
     const u64* sp = src + (u64)(c * k + j) * N;
     const u32 s1 = (2 * N - (1u << L.j)) & (2 * N - 1);
+    // Source and destination live in the same workspace, so the compiler must keep every load behind the previous
+    // element's stores; gather all operands of CH elements first (distributed shared memory, shared memory, global)
+    // and only then compute and store, so their latencies overlap instead of adding up.
+    constexpr int CH = 4;
+#pragma unroll 1
+    for (int i0 = tid; i0 < N; i0 += CH * NT) {
+      u64 la[CH], av[CH], pv[CH], gv[CH];
 #pragma unroll
-    for (int i = tid; i < N; i += NT) {
-      const int si = swz(i);
-      u64 c0;
-      if constexpr (ENG == ENG_FP64) {
-        // mod-down by P on the FP64 pipe: ((a - ((l + P/2 mod P) mod q - P/2 mod q)) * P^-1) mod q
-        const double qd = mI.qd;
-        double l = __dadd_rn(__longlong_as_double((long long)lastA[si]), P.half_P_d);
-        l = l >= P.m[k].qd ? __dadd_rn(l, -P.m[k].qd) : l;
-        const double r = f64_submod(f64_canon(l, qd, mI.qinv), P.half_P_mod_d[j], qd);
-        const double dd = f64_submod(__longlong_as_double((long long)A[si]), r, qd);
-        double md = f64_modmul(dd, P.inv_P_d[j], P.inv_P_di[j], qd);
-        md = md < 0.0 ? __dadd_rn(md, qd) : md;
-        c0 = f64_to_u64_exact(md);
-      } else {
-        c0 = mod_down_c(A[si], lastA[si], P, j, Pq);
+      for (int e = 0; e < CH; ++e) {
+        const int i = i0 + e * NT, si = swz(i);
+        la[e] = __ldcg(lastA + i);
+        av[e] = A[si];
+        if constexpr (TWS) {
+          gv[e] = (c == 0) ? galois_gather(SB, i, L.ginv, N, q) : 0;
+          pv[e] = (mode == 1) ? 0 : SB[i];
+        } else {
+          gv[e] = (c == 0) ? galois_gather(sp, i, L.ginv, N, q) : 0;
+          pv[e] = (mode == 1) ? 0 : sp[i];
+        }
       }
-      if (c == 0) c0 = addmod(galois_gather(sp, i, L.ginv, N, q), c0, q);
-      if (mode == 1) {
-        dstE[(u64)(c * k + j) * N + i] = c0;
-      } else {
-        const u64 p = sp[i];
-        dstE[(u64)(c * k + j) * N + i] = addmod(p, c0, q);
-        const u32 r = i + s1;
-        u64 d = submod(p, c0, q);
-        if (r & N) d = negmod(d, q);
-        (dstE + ((u64)ctL << L.j))[(u64)(c * k + j) * N + (r & (N - 1))] = d;
+#pragma unroll
+      for (int e = 0; e < CH; ++e) {
+        const int i = i0 + e * NT;
+        u64 c0;
+        if constexpr (ENG == ENG_FP64) {
+          // mod-down by P on the FP64 pipe: ((a - ((l + P/2 mod P) mod q - P/2 mod q)) * P^-1) mod q
+          const double qd = mI.qd;
+          double l = __dadd_rn(__longlong_as_double((long long)la[e]), P.half_P_d);
+          l = l >= P.m[k].qd ? __dadd_rn(l, -P.m[k].qd) : l;
+          const double r = f64_submod(f64_canon(l, qd, mI.qinv), P.half_P_mod_d[j], qd);
+          const double dd = f64_submod(__longlong_as_double((long long)av[e]), r, qd);
+          double md = f64_modmul(dd, P.inv_P_d[j], P.inv_P_di[j], qd);
+          md = md < 0.0 ? __dadd_rn(md, qd) : md;
+          c0 = f64_to_u64_exact(md);
+        } else {
+          c0 = mod_down_c(av[e], la[e], P, j, Pq);
+        }
+        if (c == 0) c0 = addmod(gv[e], c0, q);
+        if (mode == 1) {
+          dstE[(u64)(c * k + j) * N + i] = c0;
+        } else {
+          const u64 p = pv[e];
+          dstE[(u64)(c * k + j) * N + i] = addmod(p, c0, q);
+          const u32 r = i + s1;
+          u64 d = submod(p, c0, q);
+          if (r & N) d = negmod(d, q);
+          (dstE + ((u64)ctL << L.j))[(u64)(c * k + j) * N + (r & (N - 1))] = d;
+        }
       }
     }
   }
   PIRB_STAMP(7);
-  cluster.sync();  // keep shared memory alive until every peer has finished reading it
+  // no CTA's shared memory is read remotely after the second cluster barrier (the partner's digit reads of phase 2
+  // are complete, the special-prime accumulators travel through global memory), so every CTA may exit on its own
 }
 
 static size_t ks_cluster_smem(const DevParams& P) {

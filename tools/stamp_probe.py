@@ -19,6 +19,8 @@ buf = np.zeros(n, dtype=np.uint64)
 _lib.lib().pirb_debug_stamps(srv.ctx.h, buf.ctypes.data_as(_lib.u64p), n)
 st = buf.reshape(-1, 8).astype(np.int64)
 names = {1: "fwd NTT", 2: "canon", 3: "cluster.sync", 4: "MAC", 5: "inv NTT"}
+if os.environ.get("PIRB_STAMP_CLOCK"):
+    names = {0: "prologue+gather", **names, 6: "fin+sync+phase3"}
 for i, nm in names.items():
     d = st[:, i + 1] - st[:, i]
     print("%-14s mean %8.0f  min %8d  max %8d cycles" % (nm, d.mean(), d.min(), d.max()))
