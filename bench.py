@@ -22,7 +22,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -66,31 +65,34 @@ def synth_inputs(params, n_queries, seed):
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (NVML every ~1 ms; nvidia-smi -lms as fallback)."""
+    """SM clock + throttle reasons sampled DURING the timed region, from the enqueuing thread itself: all timed steps
+    are enqueued first (the host runs ahead of the GPU), then NVML is polled until the last step's end event has
+    completed.  NVML queries take a driver lock that can stall kernel launches for milliseconds, so they must not run
+    concurrently with the enqueue loop (a sampling thread did exactly that and added 4-9 ms to single steps)."""
 
     def __init__(self, gpu_index):
         # NVML enumerates physical devices; honour a CUDA_VISIBLE_DEVICES remap of numeric indices
         vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
         self.idx = int(vis[gpu_index]) if gpu_index < len(vis) else gpu_index
         self.sm, self.mx, self.reasons = [], None, set()
-        self.stop_flag = threading.Event()
-        self.thread = None
-
-    def _setup(self):
-        # import + nvmlInit in the caller's thread, before the timed region: a module import inside the sampling
-        # thread holds the GIL for milliseconds and stalls the thread that enqueues the timed steps
-        import pynvml as nv
-        nv.nvmlInit()
-        self.nv = nv
-        self.h = nv.nvmlDeviceGetHandleByIndex(self.idx)
-        self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
-        self.names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                      "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                      "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                      "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-        self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
-            nv.nvmlDeviceGetCurrentClocksThrottleReasons
-        self._sample()
+        self.nv = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                          "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                          "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                          "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self._sample()      # resolves every NVML entry point now, outside the timed region
+            self.sm = []
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.reasons.add("nvml unavailable: %s" % type(e).__name__)
 
     def _sample(self):
         self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
@@ -99,33 +101,20 @@ class ClockSampler:
             if r & bit:
                 self.reasons.add(nm)
 
-    def _run(self):
-        try:
-            while not self.stop_flag.is_set():
-                self._sample()
-                time.sleep(0.002)
-        except Exception as e:  # noqa: BLE001
-            self.reasons.add("nvml unavailable: %s" % type(e).__name__)
-
-    def start(self):
-        try:
-            self._setup()
-        except Exception as e:  # noqa: BLE001
-            self.reasons.add("nvml unavailable: %s" % type(e).__name__)
+    def sample_until(self, done_event):
+        """Poll while the GPU is still working through the enqueued timed steps (at least one sample)."""
+        if self.nv is None:
             return
-        self.sm = []  # keep only samples taken under load
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
-
-    def stop(self):
-        self.stop_flag.set()
-        if self.thread:
-            self.thread.join(timeout=2)
-        if not self.sm and hasattr(self, "nv"):
-            try:
+        try:
+            while True:
                 self._sample()
-            except Exception:  # noqa: BLE001
-                pass
+                if done_event.query():
+                    break
+                time.sleep(0.0005)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add("nvml unavailable: %s" % type(e).__name__)
+
+    def result(self):
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
@@ -268,14 +257,11 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
+    out = None
     for _ in range(max(3, args.warmup)):
         flush_l2()
-        step_dev()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.005)
+        out = step_dev()  # held like in the timed loop, so the caching allocator already owns both reply buffers
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for i in range(args.steps):
@@ -283,8 +269,10 @@ def run_ours(args):
         ev[i][0].record()
         out = step_dev()
         ev[i][1].record()
+    if sampler is not None:
+        sampler.sample_until(ev[-1][1])  # clocks under load: the queue of timed steps is still executing
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.result() if sampler is not None else None
     launches = srv.launch_count() * args.steps
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
