@@ -103,6 +103,8 @@ struct pirb_ctx {
   u64 pt_begin = 0, pt_count = 0;            // owned plaintexts (global indices)
   u64 loaded = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;          // second branch of the answer graph (work off the critical path)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<DevBuf> tables;
   DevBuf db, stage, work, dig, acc, xch, part, bufA[2], pts, qbuf, rbuf, svbuf;
   std::map<std::tuple<u64, int, int, int>, std::unique_ptr<ExpandPlan>> plans;  // (items, single, first tree, trees)
@@ -266,12 +268,30 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   const u64 ctL = c->ctL;
   const DevParams& P = c->P;
   if (c->profiling) cudaEventRecord(c->ev[1], st);
-  if (!sv_is_ntt)
-    LAUNCH(c, launch_ntt_fwd(P, d_sv, d_sv, (int)(sv_items * 2 * k), k, 0, n_queries, sv_qstride, sv_qstride, st));
+  // database.cpp:190,222: the selection vector goes to NTT form.  Only the last dimension's entries are needed by the
+  // scan; for d >= 2 the others are transformed on a side branch (a second stream, captured as a parallel branch of the
+  // answer graph) that joins the main one before the first upper-dimension multiply.
+  bool forked = false;
+  if (!sv_is_ntt) {
+    u64 head = 0;
+    for (int e = 0; e < d - 1; ++e) head += c->dims[e];
+    if (d >= 2 && sv_item0 == 0 && sv_items == c->dim_sum && head > 0 && c->side) {
+      CU(cudaEventRecord(c->ev_fork, st));
+      CU(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+      LAUNCH(c, launch_ntt_fwd(P, d_sv, d_sv, (int)(head * 2 * k), k, 0, n_queries, sv_qstride, sv_qstride, c->side));
+      CU(cudaEventRecord(c->ev_join, c->side));
+      forked = true;
+      LAUNCH(c, launch_ntt_fwd(P, d_sv + head * ctL, d_sv + head * ctL, (int)((sv_items - head) * 2 * k), k, 0, n_queries,
+                               sv_qstride, sv_qstride, st));
+    } else {
+      LAUNCH(c, launch_ntt_fwd(P, d_sv, d_sv, (int)(sv_items * 2 * k), k, 0, n_queries, sv_qstride, sv_qstride, st));
+    }
+  }
   if (c->profiling) cudaEventRecord(c->ev[2], st);
 
   const u64 out_cts = c->reply_cts;
   if (c->pt_count == 0 || c->loaded == 0) {
+    if (forked) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     // empty shard: contributes the additive identity
     CU(cudaMemsetAsync(d_out, 0, (size_t)n_queries * out_cts * ctL * sizeof(u64), st));
     if (c->profiling) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
@@ -313,6 +333,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   LAUNCH(c, launch_ntt_inv(P, c->part.p, c->bufA[0].p, (int)(n_rows * 2 * k), k, 0, n_split, (u64)n_rows * ctL,
                            n_queries, (u64)n_split * n_rows * ctL, (u64)n_rows * ctL, st));
   if (c->profiling) cudaEventRecord(c->ev[4], st);
+  if (forked) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
   // ---- upper dimensions (database.cpp:196-235) ----
   u32 n_entries = n_rows;
   u32 w = 1;
@@ -623,6 +644,9 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
     CU(cudaMemset(c->dbg.p, 0, 8 << 20));
   }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
   *out = c.release();
   return 0;
@@ -639,6 +663,9 @@ void pirb_ctx_destroy(pirb_ctx* c) {
   for (void* pm : c->xpeer_open) cudaIpcCloseMemHandle(pm);
   if (c->xbuf) cudaFree(c->xbuf);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
 }
 
