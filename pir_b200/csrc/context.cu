@@ -453,12 +453,25 @@ int run_graphed(pirb_ctx* c, const std::tuple<int, u32, const void*, const void*
   return 0;
 }
 
-// Answer n_queries queries held in c->qbuf into c->rbuf.
-int answer_buffers(pirb_ctx* c, const pirb_keys* keys, u32 n_queries, u64 n_ct, int partial, cudaStream_t st) {
-  return run_graphed(c, std::make_tuple(partial, n_queries, (const void*)keys, (const void*)c->qbuf.p, (const void*)c->rbuf.p),
-                     st, [&](cudaStream_t s_) {
-                       return run_answer(c, keys, c->qbuf.p, n_queries, n_ct, c->rbuf.p, partial, s_);
-                     });
+// Answer n_queries queries held at d_in (device-accessible) into d_out (device-accessible).
+int answer_buffers(pirb_ctx* c, const pirb_keys* keys, u32 n_queries, u64 n_ct, int partial, cudaStream_t st,
+                   const u64* d_in = nullptr, u64* d_out = nullptr) {
+  if (!d_in) d_in = c->qbuf.p;
+  if (!d_out) d_out = c->rbuf.p;
+  return run_graphed(c, std::make_tuple(partial, n_queries, (const void*)keys, (const void*)d_in, (const void*)d_out), st,
+                     [&](cudaStream_t s_) { return run_answer(c, keys, d_in, n_queries, n_ct, d_out, partial, s_); });
+}
+
+// Page-locked host memory is addressable from kernels under unified addressing: the first kernel of the answer path
+// can read the queries from it and the last one can write the replies into it, so a caller that passes pinned buffers
+// pays no staging copies (and no extra launch latencies) on either side.
+bool host_buffer_is_device_accessible(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost && a.devicePointer == p;
 }
 
 }  // namespace
@@ -918,11 +931,16 @@ int pirb_answer(pirb_ctx* c, const pirb_keys* keys, const uint64_t* queries, uin
   cudaStream_t st = c->stream;
   const size_t qbytes = (size_t)n_queries * n_ct * c->ctL * sizeof(u64);
   const size_t rbytes = (size_t)n_queries * c->reply_cts * c->ctL * sizeof(u64);
-  RC(c->qbuf.ensure(std::max<size_t>(qbytes, 256)));
-  RC(c->rbuf.ensure(std::max<size_t>(rbytes, 256)));
-  CU(cudaMemcpyAsync(c->qbuf.p, queries, qbytes, cudaMemcpyHostToDevice, st));
-  RC(answer_buffers(c, keys, n_queries, n_ct, 0, st));
-  CU(cudaMemcpyAsync(replies, c->rbuf.p, rbytes, cudaMemcpyDeviceToHost, st));
+  static const bool zero_copy = !(getenv("PIRB_ZERO_COPY") && getenv("PIRB_ZERO_COPY")[0] == '0');
+  const bool q_direct = zero_copy && host_buffer_is_device_accessible(queries);
+  const bool r_direct = zero_copy && host_buffer_is_device_accessible(replies);
+  if (!q_direct) {
+    RC(c->qbuf.ensure(std::max<size_t>(qbytes, 256)));
+    CU(cudaMemcpyAsync(c->qbuf.p, queries, qbytes, cudaMemcpyHostToDevice, st));
+  }
+  if (!r_direct) RC(c->rbuf.ensure(std::max<size_t>(rbytes, 256)));
+  RC(answer_buffers(c, keys, n_queries, n_ct, 0, st, q_direct ? U(queries) : nullptr, r_direct ? U(replies) : nullptr));
+  if (!r_direct) CU(cudaMemcpyAsync(replies, c->rbuf.p, rbytes, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return 0;
 }

@@ -312,6 +312,28 @@ def test_process_request_batch_and_zero(srv10):
         assert oc.integer_decode(cl.decrypt(r[0]), cl.orc.t) == exp
 
 
+def test_process_request_pinned_host_buffers_zero_copy(srv10):
+    """Page-locked host buffers are read and written in place by the kernels (no staging copies); the replies must be
+    the ones the staged path produces, call after call (the second and later calls replay a captured graph)."""
+    import torch
+    p, cl, vals, db, server = srv10
+    gk, raw = _gk(cl)
+    q_pin = torch.empty((1, 2, cl.orc.k, N), dtype=torch.int64).pin_memory()
+    out_pin = torch.empty((1, server.ctx.reply_cts, 2, cl.orc.k, N), dtype=torch.int64).pin_memory()
+    q_np, out_np = q_pin.numpy().view(np.uint64), out_pin.numpy().view(np.uint64)
+    dbn = db.read_ntt(0, 10)
+    for idx in (3, 7, 3, 9):
+        pt = np.zeros(N, dtype=np.uint64); pt[idx] = 1
+        q = cl.encrypt(pt)[None]
+        q_np[...] = q
+        out_np[...] = 0
+        server.ProcessRequest(pb.Request([q_np], gk), out=out_np)
+        want = cl.orc.process_query(dbn, p.dimensions, cl.elts, raw, q)
+        assert np.array_equal(out_np[0], want), idx
+        staged = server.ProcessRequest(pb.Request([q.copy()], gk)).reply[0]
+        assert np.array_equal(staged, want), idx
+
+
 def test_process_request_2dim():
     # server_test.cpp:209-260
     p = _params(82, 7680, 2)
