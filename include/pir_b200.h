@@ -107,7 +107,8 @@ int pirb_expand(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* cts, uint6
 int pirb_db_multiply(pirb_ctx* ctx, uint64_t* sv, uint64_t n_sv, uint64_t* out, uint64_t out_cap_cts,
                      uint64_t* out_count);
 /* PIRServer::processQuery for every query of a request (server.cpp:60-63, 173-195): expansion + multiply.
- * queries[n_queries][n_ct][2][k][N] -> replies[n_queries][reply_cts][2][k][N].  Host buffers. */
+ * queries[n_queries][n_ct][2][k][N] -> replies[n_queries][reply_cts][2][k][N].  Host buffers; page-locked ones
+ * (cudaHostAlloc / cudaHostRegister) are read and written in place by the kernels, pageable ones are staged. */
 int pirb_answer(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* queries, uint32_t n_queries, uint64_t n_ct,
                 uint64_t* replies);
 
