@@ -411,3 +411,76 @@ def test_encryption_parameters_roundtrip(lib):
     assert (gn.value, gm.value, gt.value) == (N, 3, T) and np.array_equal(mods[:3], MODS)
     assert lib.pirw_encryption_parameters_load(buf(blob[:30]), C.c_size_t(30), C.byref(gn), mods.ctypes.data_as(u64p),
                                                8, C.byref(gm), C.byref(gt)) == 3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# untrusted input: a server parses these bytes straight off the network
+# ---------------------------------------------------------------------------------------------------------------
+def test_mutated_objects_never_crash_the_loaders(lib):
+    """Random byte flips, truncations and splices of valid objects must come back as OK or InvalidArgument (3) —
+    never a crash, an over-read or an unbounded allocation."""
+    rng = np.random.default_rng(11)
+    k = 2
+    pid = np.zeros(4, dtype=np.uint64)
+    out, n = u8p(), C.c_size_t()
+    limbs = rand_limbs(rng, MODS[:k], (2,))
+    assert lib.pirw_ct_save(limbs.ctypes.data_as(u64p), 2, N, k, pid.ctypes.data_as(u64p), 0, None, C.byref(out),
+                            C.byref(n)) == 0
+    ct_blob = take(lib, out, n)
+    elts = np.array([N + 1, N // 2 + 1, 3], dtype=np.uint32)
+    klimbs = rand_limbs(rng, MODS, (len(elts), k, 2))
+    seeds = rng.integers(0, 1 << 63, size=(len(elts), k, 8), dtype=np.uint64)
+    assert lib.pirw_galois_keys_save(N, MODS.ctypes.data_as(u64p), 3, C.c_uint64(T), elts.ctypes.data_as(u32p),
+                                     len(elts), klimbs.ctypes.data_as(u64p), seeds.ctypes.data_as(u64p), C.byref(out),
+                                     C.byref(n)) == 0
+    key_blob = take(lib, out, n)
+    assert lib.pirw_encryption_parameters_save(N, MODS.ctypes.data_as(u64p), 3, C.c_uint64(T), C.byref(out),
+                                               C.byref(n)) == 0
+    ep_blob = take(lib, out, n)
+
+    got_ct = np.zeros_like(limbs)
+    pid2 = np.zeros(4, dtype=np.uint64)
+    ntt, seeded = C.c_int(), C.c_int()
+    got_e = np.zeros(8, dtype=np.uint32)
+    got_k = np.zeros((8, k, 2, 3, N), dtype=np.uint64)
+    cnt = C.c_uint32()
+    gn, gm, gt = C.c_uint32(), C.c_uint32(), C.c_uint64()
+    mods = np.zeros(8, dtype=np.uint64)
+
+    def mutate(blob):
+        b = bytearray(blob)
+        kind = rng.integers(0, 4)
+        if kind == 0:      # flip bytes, biased to the structural first 200 bytes
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(0, min(len(b), 200))) if rng.random() < 0.7 else int(rng.integers(0, len(b)))
+                b[pos] = int(rng.integers(0, 256))
+        elif kind == 1:    # truncate
+            b = b[:int(rng.integers(0, len(b)))]
+        elif kind == 2:    # overwrite a length / count field with an extreme value
+            extremes = [0, 1, 2**31, 2**32 - 1, 2**63, 2**64 - 1]
+            pos = int(rng.integers(0, max(1, min(len(b) - 8, 160))))
+            b[pos:pos + 8] = struct.pack("<Q", extremes[int(rng.integers(0, len(extremes)))])
+        else:              # splice another object's bytes into the middle
+            pos = int(rng.integers(0, len(b)))
+            b = b[:pos] + bytearray(ep_blob) + b[pos:]
+        return bytes(b)
+
+    for _ in range(300):
+        bad = mutate(ct_blob)
+        assert lib.pirw_ct_load(buf(bad), C.c_size_t(len(bad)), N, MODS.ctypes.data_as(u64p), k,
+                                got_ct.ctypes.data_as(u64p), pid2.ctypes.data_as(u64p), C.byref(ntt),
+                                C.byref(seeded)) in (0, 3)
+    for _ in range(60):
+        bad = mutate(key_blob)
+        assert lib.pirw_galois_keys_load(buf(bad), C.c_size_t(len(bad)), N, MODS.ctypes.data_as(u64p), 3,
+                                         C.c_uint64(T), 8, got_e.ctypes.data_as(u32p), got_k.ctypes.data_as(u64p),
+                                         C.byref(cnt)) in (0, 3)
+    for _ in range(300):
+        bad = mutate(ep_blob)
+        assert lib.pirw_encryption_parameters_load(buf(bad), C.c_size_t(len(bad)), C.byref(gn),
+                                                   mods.ctypes.data_as(u64p), 8, C.byref(gm), C.byref(gt)) in (0, 3)
+    for kind, good in [(1, b"\x0a\x05\x0a\x03abc\x12\x01k"), (3, b"\x08\x05\x12\x02\x29\x28\x20\x07")]:
+        for _ in range(300):
+            bad = mutate(good * 3)
+            rc, _ = roundtrip(lib, kind, bad)
+            assert rc in (0, 3)
