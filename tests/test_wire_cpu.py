@@ -484,3 +484,12 @@ def test_mutated_objects_never_crash_the_loaders(lib):
             bad = mutate(good * 3)
             rc, _ = roundtrip(lib, kind, bad)
             assert rc in (0, 3)
+
+
+def test_wire_end_to_end_against_the_oracle_cpp():
+    """tests/cpp/wire_test.cpp: protobuf-framed request with seed-compressed keys -> raw limbs -> oracle answer ->
+    serialized reply -> decrypt.  No GPU involved; the oracle is the checker."""
+    exe = os.path.join(ROOT, "build", "wire_test")
+    subprocess.check_call(["make", "-C", ROOT, "build/wire_test"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "WIRE_TEST_OK" in out.stdout, out.stdout + out.stderr
