@@ -156,6 +156,67 @@ int main() {
   uint64_t value = 0;
   for (size_t i = 0; i < 63; ++i) value += dec[i] << i;
   CHECK(value == 10 * index, "decrypted reply must be the selected database entry");
+  // ---- the reference's own serialization tests, restated (pir/cpp/serialization_test.cpp) ----
+  {
+    // TestResponseSerialization (:62-78): encode 987654321, encrypt, save into a Response, reload, decrypt
+    std::vector<uint64_t> ipt(N, 0), back(N);
+    for (uint64_t v = 987654321ull, b = 0; v; v >>= 1, ++b)
+      if (v & 1) ipt[b] = 1;
+    w::CiphertextData c1;
+    c1.parms_id = w::data_parms_id(sp);
+    c1.size = 2;
+    c1.poly_modulus_degree = N;
+    c1.coeff_modulus_size = k;
+    c1.limbs.resize(octx.ct_limbs());
+    crypto.encrypt(pk, ipt.data(), N, rng, c1.limbs.data());
+    w::ResponseMsg rp;
+    rp.reply.emplace_back();
+    rp.reply.back().ct.push_back(w::SaveCiphertext(c1));
+    w::ResponseMsg rp2;
+    CHECK(w::Parse(w::Serialize(rp), &rp2) && rp2.reply.size() == 1 && rp2.reply[0].ct.size() == 1, "reload size");
+    w::CiphertextData c2;
+    CHECK(w::LoadCiphertext(rp2.reply[0].ct[0], N, mods.data(), k, &c2, &err), err.c_str());
+    crypto.decrypt(sk, c2.limbs.data(), back.data());
+    CHECK(back == ipt, "TestResponseSerialization: reloaded plaintext differs");
+
+    // TestRequestSerialization_IndividualMethods (:80-113): galois_keys_local (not seed-compressed) + relin keys;
+    // after the round trip every Galois element must be present (has_key)
+    w::KSwitchKeysData L;
+    L.parms_id = w::key_parms_id(sp);
+    L.keys.assign(N, {});
+    for (uint32_t g : elts) L.keys[w::galois_index(g)] = K.keys[w::galois_index(g)];
+    w::RequestMsg rq;
+    rq.query.emplace_back();
+    rq.query.back().ct.push_back(w::SaveCiphertext(c1));
+    rq.galois_keys = w::SaveKSwitchKeys(L);  // full ciphertexts, no seeds
+    w::KSwitchKeysData RL;
+    RL.parms_id = L.parms_id;
+    RL.keys.push_back(K.keys[w::galois_index(elts[1])]);
+    rq.relin_keys = w::SaveKSwitchKeys(RL);
+    w::RequestMsg rq2;
+    CHECK(w::Parse(w::Serialize(rq), &rq2), "request parse");
+    w::KSwitchKeysData L2, RL2;
+    CHECK(w::LoadKSwitchKeys(rq2.galois_keys, sp, &L2, &err), err.c_str());
+    for (uint32_t g : elts) {
+      const uint32_t idx = w::galois_index(g);
+      CHECK(idx < L2.keys.size() && L2.keys[idx].size() == k, "has_key");
+      for (size_t J = 0; J < k; ++J)
+        CHECK(!L2.keys[idx][J].was_seeded && L2.keys[idx][J].limbs == K.keys[idx][J].limbs, "key limbs round trip");
+    }
+    CHECK(w::LoadKSwitchKeys(rq2.relin_keys, sp, &RL2, &err) && RL2.keys.size() == 1, "relin keys reload");
+    CHECK(rq.galois_keys.size() > 18 * req.galois_keys.size() / 10, "seed compression must halve the key bytes");
+
+    // TestRequestSerialization_Shortcut (:115-132): SaveRequest(cts) leaves both key fields empty
+    w::RequestMsg sc;
+    sc.query.emplace_back();
+    sc.query.back().ct.push_back(w::SaveCiphertext(c1));
+    w::RequestMsg sc2;
+    CHECK(w::Parse(w::Serialize(sc), &sc2), "shortcut parse");
+    CHECK(sc2.query.size() == 1 && sc2.galois_keys.empty() && sc2.relin_keys.empty(), "shortcut: no keys");
+    // a server must refuse it: there is nothing to expand with (server.cpp:46-48 fails to deserialize "")
+    w::KSwitchKeysData none;
+    CHECK(!w::LoadKSwitchKeys(sc2.galois_keys, sp, &none, &err), "empty galois_keys must not load");
+  }
   std::printf("WIRE_TEST_OK: seeded keys expanded, query answered by the oracle, reply decrypts to %llu\n",
               (unsigned long long)value);
   return 0;
