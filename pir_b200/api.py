@@ -484,6 +484,14 @@ class PIRServer:
         resp.reply = [out[i] for i in range(n_q)]
         return resp
 
+    def ProcessRequestBytes(self, serialized_request: bytes) -> bytes:
+        """server.cpp:44-65 on the wire: a serialized pir.Request (protobuf framing, SEAL 3.5.6 objects, seed-compressed
+        keys included) in, a serialized pir.Response out.  InvalidArgument on any deserialization failure
+        (serialization.h:113-115).  The codec is host-side (pir_b200/wire.py); the answer is ProcessRequest's."""
+        from . import wire
+        request = wire.parse_request(serialized_request, self.params)
+        return wire.serialize_response(self.ProcessRequest(request), self.params, parms_id=request.parms_id)
+
     def substitute_power_x_inplace(self, ct: np.ndarray, power: int, gal_keys: GaloisKeys):
         """server.cpp:67-76"""
         keys = self._keys(gal_keys)

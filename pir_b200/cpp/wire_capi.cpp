@@ -184,3 +184,73 @@ int pirw_encryption_parameters_load(const uint8_t* in, size_t in_len, uint32_t* 
 }
 
 }  // extern "C"
+
+// ---- message walking for host languages without a protobuf runtime (pir_b200/wire.py) ----
+namespace {
+struct ParsedMsg {
+  std::vector<CiphertextsMsg> groups;  // Request.query or Response.reply
+  std::string galois_keys, relin_keys;
+};
+}  // namespace
+
+extern "C" {
+
+// kind: 1 Request, 2 Response.  Returns an opaque handle through *out (release with pirw_msg_free).
+int pirw_msg_parse(int kind, const uint8_t* in, size_t in_len, void** out) {
+  auto* m = new ParsedMsg();
+  bool ok = false;
+  const std::string_view sv((const char*)in, in_len);
+  if (kind == 1) {
+    RequestMsg r;
+    ok = Parse(sv, &r);
+    if (ok) { m->groups = std::move(r.query); m->galois_keys = std::move(r.galois_keys); m->relin_keys = std::move(r.relin_keys); }
+  } else if (kind == 2) {
+    ResponseMsg r;
+    ok = Parse(sv, &r);
+    if (ok) m->groups = std::move(r.reply);
+  }
+  if (!ok) { delete m; g_err = "malformed protobuf message"; return 3; }
+  *out = m;
+  return 0;
+}
+void pirw_msg_free(void* h) { delete (ParsedMsg*)h; }
+uint32_t pirw_msg_groups(const void* h) { return (uint32_t)((const ParsedMsg*)h)->groups.size(); }
+uint32_t pirw_msg_group_size(const void* h, uint32_t g) {
+  const auto* m = (const ParsedMsg*)h;
+  return g < m->groups.size() ? (uint32_t)m->groups[g].ct.size() : 0;
+}
+// Borrowed pointers, valid until pirw_msg_free.
+int pirw_msg_ct(const void* h, uint32_t g, uint32_t i, const uint8_t** p, size_t* len) {
+  const auto* m = (const ParsedMsg*)h;
+  if (g >= m->groups.size() || i >= m->groups[g].ct.size()) { g_err = "index out of range"; return 3; }
+  *p = (const uint8_t*)m->groups[g].ct[i].data();
+  *len = m->groups[g].ct[i].size();
+  return 0;
+}
+int pirw_msg_keys(const void* h, int which, const uint8_t** p, size_t* len) {  // which: 2 galois_keys, 3 relin_keys
+  const auto* m = (const ParsedMsg*)h;
+  const std::string& s = which == 2 ? m->galois_keys : m->relin_keys;
+  *p = (const uint8_t*)s.data();
+  *len = s.size();
+  return 0;
+}
+// Response from n_groups x per_group serialized ciphertexts of equal length laid out back to back.
+int pirw_response_build(const uint8_t* cts, uint32_t n_groups, uint32_t per_group, size_t ct_len, uint8_t** out,
+                        size_t* out_len) {
+  ResponseMsg m;
+  for (uint32_t q = 0; q < n_groups; ++q) {
+    m.reply.emplace_back();
+    for (uint32_t c = 0; c < per_group; ++c)
+      m.reply.back().ct.emplace_back((const char*)cts + ((size_t)q * per_group + c) * ct_len, ct_len);
+  }
+  return give(Serialize(m), out, out_len);
+}
+// Structural check of a KSwitchKeys blob without keeping its data (relin_keys are parsed and otherwise unused).
+int pirw_kswitch_keys_check(const uint8_t* in, size_t in_len, uint32_t N, const uint64_t* moduli, uint32_t n_moduli,
+                            uint64_t t) {
+  KSwitchKeysData K;
+  return LoadKSwitchKeys(std::string_view((const char*)in, in_len), make_params(N, moduli, n_moduli, t), &K, &g_err,
+                         false) ? 0 : 3;
+}
+
+}  // extern "C"

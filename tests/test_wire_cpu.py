@@ -493,3 +493,67 @@ def test_wire_end_to_end_against_the_oracle_cpp():
     subprocess.check_call(["make", "-C", ROOT, "build/wire_test"], stdout=subprocess.DEVNULL)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "WIRE_TEST_OK" in out.stdout, out.stdout + out.stderr
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pir_b200/wire.py: the Python mirror's view of the same codec (host-side only, no GPU)
+# ---------------------------------------------------------------------------------------------------------------
+def test_python_wire_request_response_roundtrip(pb):
+    import pir_b200 as pbm
+    from pir_b200 import wire
+    ep = pbm.GenerateEncryptionParams(4096, 20)
+    p = pbm.CreatePIRParameters(5000, 0, 1, ep)          # 2 query ciphertexts per query
+    k, n = len(ep.coeff_modulus) - 1, ep.poly_modulus_degree
+    rng = np.random.default_rng(21)
+    mods = [int(q) for q in ep.coeff_modulus]
+    queries = [np.ascontiguousarray(np.stack([rng.integers(0, mods[j], (2, 2, n), dtype=np.uint64) for j in range(k)],
+                                             axis=2)) for _ in range(3)]   # [n_ct=2][2][k][N] each
+    elts = pbm.generate_galois_elts(n)
+    keys = np.ascontiguousarray(np.stack([rng.integers(0, mods[j], (len(elts), k, 2, n), dtype=np.uint64)
+                                          for j in range(k + 1)], axis=3))
+    gk = pbm.GaloisKeys(elts, keys.reshape(-1))
+    relin = wire.save_galois_keys(pbm.GaloisKeys([3], keys[:1].reshape(-1)), ep)
+    blob = wire.serialize_request(queries, gk, p, relin_keys=relin)
+    # the protobuf runtime reads the same structure out of it
+    ref = pb["Request"]()
+    ref.ParseFromString(blob)
+    assert len(ref.query) == 3 and all(len(q.ct) == 2 for q in ref.query)
+    assert ref.relin_keys == relin and len(ref.galois_keys) > len(elts) * k * 2 * (k + 1) * n * 8
+    req = wire.parse_request(blob, p)
+    assert len(req.query) == 3
+    for a, b in zip(req.query, queries):
+        assert np.array_equal(a, b)
+    order = np.argsort(elts)
+    assert req.galois_keys.elts == [int(elts[i]) for i in order]
+    assert np.array_equal(req.galois_keys.data.reshape(len(elts), -1), keys[order].reshape(len(elts), -1))
+    assert np.array_equal(req.parms_id, wire.data_parms_id(ep))
+    # responses
+    resp = pbm.Response([np.ascontiguousarray(np.stack([rng.integers(0, mods[j], (1, 2, n), dtype=np.uint64)
+                                                        for j in range(k)], axis=2)) for _ in range(3)])
+    rb = wire.serialize_response(resp, p, parms_id=req.parms_id)
+    ref_r = pb["Response"]()
+    ref_r.ParseFromString(rb)
+    assert len(ref_r.reply) == 3 and all(len(r.ct) == 1 for r in ref_r.reply)
+    back = wire.parse_response(rb, p)
+    for a, b in zip(back.reply, resp.reply):
+        assert np.array_equal(a, b)
+    # malformed input surfaces as the reference's InvalidArgument
+    for bad in [blob[:len(blob) // 3], b"\x12\x03abc", rb]:
+        with pytest.raises(pbm.PIRStatusError) as e:
+            wire.parse_request(bad, p)
+        assert e.value.code == pbm.INVALID_ARGUMENT
+
+
+def test_python_wire_pir_parameters(pb):
+    import pir_b200 as pbm
+    from pir_b200 import wire
+    ep = pbm.GenerateEncryptionParams(4096, 24)
+    p = pbm.CreatePIRParameters(1 << 16, 288, 2, ep)
+    blob = wire.serialize_pir_parameters(p)
+    ref = pb["PIRParameters"]()
+    ref.ParseFromString(blob)
+    assert (ref.num_items, ref.num_pt, list(ref.dimensions), ref.bytes_per_item, ref.items_per_plaintext) == \
+        (1 << 16, 1639, [41, 40], 288, p.items_per_plaintext)
+    ep2 = wire.load_encryption_parameters(ref.encryption_parameters)
+    assert (ep2.poly_modulus_degree, ep2.plain_modulus, list(ep2.coeff_modulus)) == \
+        (4096, ep.plain_modulus, list(ep.coeff_modulus))
