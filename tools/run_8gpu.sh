@@ -2,14 +2,14 @@
 run() {  # name, visible devices, n, port, extra args...
   name=$1; vis=$2; n=$3; port=$4; shift 4
   CUDA_VISIBLE_DEVICES=$vis timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
-      bench.py --gpus $n --warmup 3 --no-cpu-baseline "$@" 2> gpurun_out/cfgs8c_$name.err | tail -1 > gpurun_out/cfgs8c_$name.json
+      bench.py --gpus $n --warmup 3 --no-cpu-baseline "$@" 2> gpurun_out/run8_$name.err | tail -1 > gpurun_out/run8_$name.json
   python - <<PY
 import json
 try:
-    d = json.loads(open("gpurun_out/cfgs8c_$name.json").read())
+    d = json.loads(open("gpurun_out/run8_$name.json").read())
     print("$name", "value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"], 1), d.get("stages_ms"))
 except Exception as e:
-    print("$name FAILED", e); print(open("gpurun_out/cfgs8c_$name.err").read()[-1500:])
+    print("$name FAILED", e); print(open("gpurun_out/run8_$name.err").read()[-1500:])
 PY
 }
 ALL=0,1,2,3,4,5,6,7
