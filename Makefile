@@ -10,7 +10,7 @@ HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/pir_b200.h
 
 WIRE := pir_b200/lib/libpirb_wire.so
 
-all: $(LIB) $(WIRE) oracle build/shim_test build/wire_test
+all: $(LIB) $(WIRE) oracle build/shim_test build/wire_test build/device_math_host_test
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -35,6 +35,11 @@ build/shim_test: tests/cpp/shim_test.cpp pir_b200/cpp/pir_b200.hpp pir_b200/cpp/
 build/wire_test: tests/cpp/wire_test.cpp pir_b200/cpp/wire.hpp oracle/pir_oracle.hpp
 	@mkdir -p build
 	g++ -O2 -std=c++17 -march=x86-64-v3 -Wall -o $@ tests/cpp/wire_test.cpp
+
+# the device arithmetic (pirb_device.cuh) compiled for the HOST and checked against 128-bit integers and the oracle
+build/device_math_host_test: tests/cpp/device_math_host_test.cpp $(HDRS) oracle/pir_oracle.hpp
+	@mkdir -p build
+	g++ -O2 -std=c++17 -march=x86-64-v3 -ffp-contract=off -I/usr/local/cuda/include -Wno-attributes -o $@ tests/cpp/device_math_host_test.cpp
 
 oracle:
 	$(MAKE) -C oracle
