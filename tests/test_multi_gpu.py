@@ -69,6 +69,67 @@ def test_row_sharding_math_gloo_world2():
     assert all(ret.get(r) for r in range(world)), dict(ret)
 
 
+def _gloo_worker_d1(rank, world, port, ret):
+    """d=1 over two query ciphertexts: a shard expands only the trees that cover its own plaintexts (what
+    run_answer does for a one-dimensional shard), scans them, and the NTT-form partials add up mod q."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle import client as oc
+    from pir_b200.sharded import shard_rows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_items, N = 4200, 4096
+        p = oc.create_pir_parameters(n_items, 0, 1, N, 20)       # dims [4200]: trees of 4096 and 104 items
+        cl = oc.HarnessClient(p, seed=8)
+        rng = np.random.default_rng(3)
+        # a random NTT-form database is enough here: the property is linearity over the plaintext index
+        mods = [int(q) for q in cl.orc.moduli[:cl.orc.k]]
+        db = np.ascontiguousarray(np.stack([rng.integers(0, mods[j], (n_items, N), dtype=np.uint64)
+                                            for j in range(cl.orc.k)], axis=1))
+        idx = 4150                                                 # lives in the second tree
+        q = cl.create_query(idx)                                   # [2][2][k][N]
+        lo, hi = shard_rows(n_items, world)[rank]
+        t_first, t_last = lo // N, (hi - 1) // N
+        sv = {}
+        for t in range(t_first, t_last + 1):                       # only this shard's trees
+            items = min(N, n_items - t * N)
+            out = cl.orc.expand(q[t], items, cl.elts, cl.galois, single=True)
+            for i in range(items):
+                sv[t * N + i] = out[i]
+        assert all(i in sv for i in range(lo, hi))
+        sub_sv = np.stack([cl.orc.ct_to_ntt(sv[i]) for i in range(lo, hi)])
+        part = cl.orc.scan_row(db[lo:hi], sub_sv)                  # NTT-form partial reply of this shard
+        t = torch.from_numpy(part.view(np.int64).copy())
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        m = np.array(mods, dtype=np.uint64)[None, :, None]
+        total = np.zeros_like(part)
+        for g in gathered:
+            total = (total + g.numpy().view(np.uint64)) % m
+        got = cl.orc.ct_from_ntt(total)
+        want = cl.orc.process_query(db, p.dimensions, cl.elts, cl.galois, q)[0]
+        ret[rank] = bool(np.array_equal(got, want))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_one_dimensional_tree_sharding_math_gloo_world2():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_gloo_worker_d1, args=(r, world, port, ret)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(600)
+        assert pr.exitcode == 0
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
 def test_shard_rows_cover_and_match_library_split():
     sys.path.insert(0, ROOT)
     from pir_b200.sharded import shard_rows
