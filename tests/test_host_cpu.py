@@ -105,3 +105,20 @@ def test_string_encoder_matches_oracle_and_reference_shapes():
         enc.encode(b"x" * 9729)
     value = b"This is a string test for random VALUES@!#"  # string_encoder_test.cpp:73-83
     assert enc.decode(enc.encode(value))[:len(value)] == value
+
+
+def test_boundary_headers_compile_strictly(tmp_path):
+    """include/pir_b200.h is plain C99 (the C ABI a foreign-function binding would parse); the C++ shim and the wire
+    codec compile warning-free with -Wall -Wextra -pedantic."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    c = tmp_path / "t.c"
+    c.write_text('#include "include/pir_b200.h"\nint main(void) { return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", root, str(c)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "pir_b200/cpp/pir_b200.hpp"\n#include "pir_b200/cpp/wire.hpp"\nint main() { return 0; }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", root,
+                        str(cpp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
