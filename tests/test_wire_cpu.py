@@ -557,3 +557,36 @@ def test_python_wire_pir_parameters(pb):
     ep2 = wire.load_encryption_parameters(ref.encryption_parameters)
     assert (ep2.poly_modulus_degree, ep2.plain_modulus, list(ep2.coeff_modulus)) == \
         (4096, ep.plain_modulus, list(ep.coeff_modulus))
+
+
+def test_process_request_bytes_composition_with_the_oracle_as_engine():
+    """PIRServer.ProcessRequestBytes = parse -> ProcessRequest -> serialize.  Here ProcessRequest is played by the CPU
+    oracle (a stand-in object; the GPU tests cover the real one), so the wire composition is checked end to end on the
+    CPU: a harness client's query travels as bytes, the reply comes back as bytes and decrypts to the right item."""
+    import pir_b200 as pbm
+    from oracle import client as oc
+    from pir_b200 import wire
+    ep = pbm.GenerateEncryptionParams(4096, 20)
+    p = pbm.CreatePIRParameters(10, 0, 1, ep)
+    hp = oc.PIRParameters(p.num_items, p.num_pt, list(p.dimensions), p.bytes_per_item, p.items_per_plaintext,
+                          p.bits_per_coeff, ep.poly_modulus_degree, ep.plain_modulus, list(ep.coeff_modulus))
+    cl = oc.HarnessClient(hp, seed=4)
+    rng = np.random.default_rng(9)
+    items = [rng.integers(0, 256, p.bytes_per_item, dtype=np.uint8).tobytes() for _ in range(p.num_items)]
+    db_ntt = oc.db_to_ntt(cl.orc, oc.encode_string_db(hp, items))
+
+    class OracleServer:
+        params = p
+
+        def ProcessRequest(self, request):
+            gk = request.galois_keys
+            return pbm.Response([cl.orc.process_query(db_ntt, p.dimensions, gk.elts, gk.data, q)
+                                 for q in request.query])
+
+    idxs = [3, 8]
+    blob = wire.serialize_request([cl.create_query(i) for i in idxs], pbm.GaloisKeys(cl.elts, cl.galois), p)
+    reply_bytes = pbm.PIRServer.ProcessRequestBytes(OracleServer(), blob)
+    resp = wire.parse_response(reply_bytes, p)
+    assert len(resp.reply) == 2
+    got = cl.process_response_strings(idxs, resp.reply)
+    assert got == [items[i] for i in idxs]
