@@ -477,9 +477,12 @@ class PIRServer:
         shape = (n_q, self.ctx.reply_cts, 2, self.ctx.k, self.ctx.N)
         if out is None:
             out = np.empty(shape, dtype=np.uint64)
-        elif out.dtype != np.uint64 or out.size != int(np.prod(shape)) or not out.flags["C_CONTIGUOUS"]:
+        elif out.dtype != np.uint64 or out.size != n_q * self.ctx.reply_cts * self.ctx.ct_limbs or \
+                not out.flags["C_CONTIGUOUS"]:
             raise PIRStatusError(INVALID_ARGUMENT, "bad output buffer")
-        _check(_lib.lib().pirb_answer(self.ctx.h, keys.h, _ptr(q), n_q, n_ct, _ptr(out)))
+        # q and out are locals that outlive the call, so plain addresses are enough (ndarray.ctypes.data_as costs 4 us)
+        _check(_lib.lib().pirb_answer(self.ctx.h, keys.h, C.c_void_p(q.ctypes.data), n_q, n_ct,
+                                      C.c_void_p(out.ctypes.data)))
         out = out.reshape(shape)
         resp.reply = [out[i] for i in range(n_q)]
         return resp

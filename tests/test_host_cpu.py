@@ -122,3 +122,39 @@ def test_boundary_headers_compile_strictly(tmp_path):
     r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", root,
                         str(cpp)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_process_request_marshalling_with_a_stub_library(monkeypatch):
+    """Host-side argument marshalling of PIRServer.ProcessRequest without a device: the C entry point is replaced by a
+    stub that records what it is given (addresses of the caller's own buffers, counts) — no compute involved."""
+    import types
+    from pir_b200 import api
+    ep = pb.GenerateEncryptionParams(4096, 24)
+    p = pb.CreatePIRParameters(1 << 16, 288, 2, ep)
+    srv = api.PIRServer.__new__(api.PIRServer)
+    srv.params = p
+    srv.ctx = types.SimpleNamespace(ct_limbs=2 * 2 * 4096, query_cts=1, reply_cts=8, k=2, N=4096, h=None)
+    gk = pb.GaloisKeys([3], np.zeros(8, dtype=np.uint64))
+    srv._key_cache = (gk, types.SimpleNamespace(h=None))
+    seen = {}
+
+    class Stub:
+        def pirb_answer(self, h, kh, qp, nq, nct, op):
+            seen.update(q=qp.value, o=op.value, n=(nq, nct))
+            return 0
+
+    monkeypatch.setattr(api._lib, "lib", lambda: Stub())
+    q = np.zeros((1, 2, 2, 4096), dtype=np.uint64)
+    out = np.zeros((2, 8, 2, 2, 4096), dtype=np.uint64)
+    r = srv.ProcessRequest(pb.Request([q, q.copy()], gk), out=out)
+    assert seen["o"] == out.ctypes.data and seen["n"] == (2, 1)
+    assert [x.shape for x in r.reply] == [(8, 2, 2, 4096)] * 2 and r.reply[1].ctypes.data == out[1].ctypes.data
+    r = srv.ProcessRequest(pb.Request([q], gk), out=out[:1])
+    assert seen["q"] == q.ctypes.data and seen["n"] == (1, 1)          # a single contiguous query is not copied
+    assert srv.ProcessRequest(pb.Request([q], gk)).reply[0].shape == (8, 2, 2, 4096)
+    with pytest.raises(pb.PIRStatusError) as e:
+        srv.ProcessRequest(pb.Request([q], gk), out=np.zeros(5, dtype=np.uint64))
+    assert e.value.code == pb.INVALID_ARGUMENT
+    with pytest.raises(pb.PIRStatusError):                             # wrong number of query ciphertexts
+        srv.ProcessRequest(pb.Request([np.zeros((2, 2, 2, 4096), dtype=np.uint64)], gk))
+    assert srv.ProcessRequest(pb.Request([], gk)).reply == []
