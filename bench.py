@@ -407,7 +407,11 @@ def run_ours(args):
         "step_ms": [round(x, 4) for x in step_ms],
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(world * ql * n_ct * ctL * 8),
                 "d2h_bytes_per_step": int(world * ql * srv.ctx.reply_cts * ctL * 8),
-                "p50_latency_ms": 1e3 * statistics.median(lat)},
+                "p50_latency_ms": 1e3 * statistics.median(lat),
+                "transfer": ("pinned host buffers; the first kernel reads the queries and the last one writes the "
+                             "replies over PCIe in place, inside the timed region (PIRB_ZERO_COPY=0: staged "
+                             "cudaMemcpyAsync both ways)") if world == 1 else
+                            "pinned host buffers, cudaMemcpyAsync H2D of the queries and D2H of the replies every step"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
