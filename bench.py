@@ -309,6 +309,26 @@ def run_ours(args):
             r = srv.answer_batch_distributed_p2p(d) if args.p2p else srv.answer_batch_distributed(d)
             out_pin.copy_(r, non_blocking=True)
             torch.cuda.synchronize()
+    def time_e2e(n):
+        for _ in range(3):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step_e2e()
+        barrier()
+        return time.perf_counter() - t0
+
+    # single GPU: also the explicitly staged variant (cudaMemcpyAsync H2D + D2H around the kernels) for comparison
+    staged_qps = None
+    if world == 1:
+        prev = os.environ.get("PIRB_ZERO_COPY")
+        os.environ["PIRB_ZERO_COPY"] = "0"
+        staged_qps = ql * args.steps / time_e2e(args.steps)
+        if prev is None:
+            del os.environ["PIRB_ZERO_COPY"]
+        else:
+            os.environ["PIRB_ZERO_COPY"] = prev
     for _ in range(3):
         step_e2e()
     barrier()
@@ -408,6 +428,7 @@ def run_ours(args):
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(world * ql * n_ct * ctL * 8),
                 "d2h_bytes_per_step": int(world * ql * srv.ctx.reply_cts * ctL * 8),
                 "p50_latency_ms": 1e3 * statistics.median(lat),
+                "staged_copies_value": staged_qps,
                 "transfer": ("pinned host buffers; the first kernel reads the queries and the last one writes the "
                              "replies over PCIe in place, inside the timed region (PIRB_ZERO_COPY=0: staged "
                              "cudaMemcpyAsync both ways)") if world == 1 else

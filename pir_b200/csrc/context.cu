@@ -931,7 +931,8 @@ int pirb_answer(pirb_ctx* c, const pirb_keys* keys, const uint64_t* queries, uin
   cudaStream_t st = c->stream;
   const size_t qbytes = (size_t)n_queries * n_ct * c->ctL * sizeof(u64);
   const size_t rbytes = (size_t)n_queries * c->reply_cts * c->ctL * sizeof(u64);
-  static const bool zero_copy = !(getenv("PIRB_ZERO_COPY") && getenv("PIRB_ZERO_COPY")[0] == '0');
+  const char* zc = getenv("PIRB_ZERO_COPY");  // read per call so that a caller can compare both paths in one process
+  const bool zero_copy = !(zc && zc[0] == '0');
   const bool q_direct = zero_copy && host_buffer_is_device_accessible(queries);
   const bool r_direct = zero_copy && host_buffer_is_device_accessible(replies);
   if (!q_direct) {
