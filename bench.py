@@ -289,6 +289,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         for nm, v in srv.stage_ms().items():
             stage_acc.setdefault(nm, []).append(v)
+    srv.set_profiling(False)  # back to graph replay: the end-to-end leg below must run the product's normal path
     qps = world * ql * args.steps / (total_ms / 1e3)
 
     # ---------------- end to end through the reference-facing call, host buffers ----------------
