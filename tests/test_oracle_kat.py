@@ -388,3 +388,20 @@ def test_end_to_end_correctness(n, bits, elem, bpc, dbsize, d, indices):
     replies = [cl.orc.process_query(db, p.dimensions, cl.elts, cl.galois, cl.create_query(i)) for i in indices]
     got = cl.process_response_strings(indices, replies)
     assert got == [items[i] for i in indices]
+
+
+# ------------------------------------------------------------------ the oracle frozen against itself
+def test_oracle_outputs_match_the_committed_digests():
+    """tests/golden/oracle_digests.json: SHA-256 of the oracle's substitution / shift / expansion / reply for inputs
+    derived from SHAKE-256 (pure integer pipeline).  The oracle defines "bit-exact" for the CUDA path, so a change in
+    oracle/ that moves a single limb must be deliberate: regenerate with tests/golden/make_oracle_digests.py."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_digests", os.path.join(here, "golden",
+                                                                                      "make_oracle_digests.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(here, "golden", "oracle_digests.json")) as f:
+        want = json.load(f)
+    for name, *args in mod.CASES:
+        assert mod.run_case(name, *args) == want[name], name
