@@ -38,9 +38,27 @@ def limbs(tag, shape_prefix, mods, n):
     return np.ascontiguousarray(a)
 
 
-def run_case(name, items, size, d, n, bits, index):
-    """Pure integer pipeline: every input is a SHAKE-derived ring element (no noise sampling, no floating point), so
-    the digests only depend on the oracle's arithmetic."""
+class OracleBackend:
+    """The four operations whose outputs are frozen, answered by the CPU oracle."""
+
+    def __init__(self, orc, p, db, elts, keys):
+        self.orc, self.p, self.db, self.elts, self.keys = orc, p, db, elts, keys
+
+    def substitute(self, ct, power):
+        return self.orc.substitute(ct, power, self.elts, self.keys)
+
+    def shift(self, ct, k):
+        return self.orc.mul_inv_pow_x(ct, k)
+
+    def expand(self, cts, total):
+        return np.stack(self.orc.expand(cts, total, self.elts, self.keys))
+
+    def answer(self, query):
+        return self.orc.process_query(self.db, self.p.dimensions, self.elts, self.keys, query)
+
+
+def case_inputs(name, items, size, d, n, bits):
+    """Pure integer inputs: SHAKE-derived ring elements (no noise sampling, no floating point)."""
     p = oc.create_pir_parameters(items, size, d, n, bits)
     orc = oc.HarnessClient(p, seed=1).orc                    # only used for its Oracle handle
     k, mods = orc.k, [int(q) for q in orc.moduli]
@@ -49,13 +67,21 @@ def run_case(name, items, size, d, n, bits, index):
     n_ct = p.dim_sum // n + 1
     query = limbs(name + "/query", (n_ct, 2), mods[:k], n)            # [n_ct][2][k][N]
     db = limbs(name + "/db", (p.num_pt,), mods[:k], n)                # NTT-form database
-    sv = orc.expand(query, p.dim_sum, elts, keys.reshape(-1))
-    reply = orc.process_query(db, p.dimensions, elts, keys.reshape(-1), query)
-    sub = orc.substitute(query[0], elts[0], elts, keys.reshape(-1))
-    shifted = orc.mul_inv_pow_x(query[0], 5 + index)
-    return {"inputs": digest(np.concatenate([keys.reshape(-1), query.reshape(-1), db.reshape(-1)])),
-            "substitute": digest(sub), "multiply_inverse_power_of_x": digest(shifted),
-            "selection_vector": digest(np.stack(sv)), "reply": digest(reply), "reply_cts": int(reply.shape[0])}
+    return p, orc, elts, keys, query, db
+
+
+def run_case(name, items, size, d, n, bits, index, make_backend=None):
+    """Digests of one case.  make_backend(p, db, elts, keys_flat) -> object with substitute / shift / expand / answer;
+    default: the oracle.  The GPU parity suite passes the CUDA path and must reproduce the same digests."""
+    p, orc, elts, keys, query, db = case_inputs(name, items, size, d, n, bits)
+    flat = keys.reshape(-1)
+    be = make_backend(p, db, elts, flat) if make_backend else OracleBackend(orc, p, db, elts, flat)
+    reply = be.answer(query)
+    return {"inputs": digest(np.concatenate([flat, query.reshape(-1), db.reshape(-1)])),
+            "substitute": digest(be.substitute(query[0], elts[0])),
+            "multiply_inverse_power_of_x": digest(be.shift(query[0], 5 + index)),
+            "selection_vector": digest(be.expand(query, p.dim_sum)),
+            "reply": digest(reply), "reply_cts": int(reply.shape[0])}
 
 
 def main():

@@ -2,6 +2,9 @@
 oracle on the same seeded inputs — bit-exact on all limbs — plus decrypt-level checks against the reference's
 known-answer vectors and size-independent properties at BASELINE.json's sizes.
 """
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -475,6 +478,55 @@ def test_batched_scan_matches_single_query_scan_and_oracle(n, bits, dbsize, d, n
         cnt = min(dimL, p.num_pt - first)
         want = orc.scan_row(sh.db.read_ntt(first, cnt), sv[i, :cnt])
         assert np.array_equal(batch[i, r], want), (i, r)
+
+
+# ------------------------------------------------------------------------------------------------ golden fixtures
+def _load_digest_module():
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_digests",
+                                                  os.path.join(here, "golden", "make_oracle_digests.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(here, "golden", "oracle_digests.json")) as f:
+        return mod, json.load(f)
+
+
+class _CudaBackend:
+    """substitute / shift / expand / answer through the product API, for tests/golden/make_oracle_digests.run_case"""
+
+    def __init__(self, hp, db_limbs, elts, keys_flat):
+        ep = pb.EncryptionParameters(hp.poly_modulus_degree, hp.plain_modulus, list(hp.coeff_modulus))
+        self.p = pb.PIRParameters(num_items=hp.num_items, num_pt=hp.num_pt, dimensions=list(hp.dimensions),
+                                  encryption_parameters=ep, bytes_per_item=hp.bytes_per_item,
+                                  items_per_plaintext=hp.items_per_plaintext, bits_per_coeff=hp.bits_per_coeff)
+        self.db = pb.PIRDatabase.Create(self.p)
+        self.db.load_ntt(db_limbs)
+        self.server = pb.PIRServer.Create(self.db, self.p)
+        self.gk = pb.GaloisKeys(elts, keys_flat)
+
+    def substitute(self, ct, power):
+        got = ct.copy()
+        self.server.substitute_power_x_inplace(got, power, self.gk)
+        return got
+
+    def shift(self, ct, k):
+        return self.server.multiply_inverse_power_of_x(ct, k)
+
+    def expand(self, cts, total):
+        return self.server.oblivious_expansion(cts, total, self.gk)
+
+    def answer(self, query):
+        return self.server.ProcessRequest(pb.Request([query], self.gk)).reply[0]
+
+
+def test_cuda_path_reproduces_the_committed_golden_digests():
+    """tests/golden/oracle_digests.json freezes the oracle's substitution / shift / expansion / reply for SHAKE-derived
+    inputs; the CUDA path must produce byte-identical objects (same SHA-256) for N=4096 d=1/d=2, t 24-bit and N=8192."""
+    mod, want = _load_digest_module()
+    for name, *args in mod.CASES:
+        got = mod.run_case(name, *args, make_backend=_CudaBackend)
+        assert got == want[name], name
 
 
 def test_repeated_requests_replay_the_captured_graph(srv10):
