@@ -451,20 +451,22 @@ class PIRDatabase {
 
   size_t size() const { return pirb_db_size(ctx_.get()); }
 
-  // database.cpp:318-332
-  std::vector<uint32_t> calculate_indices(uint32_t index) const {
-    uint32_t pt_index = index / params_->items_per_plaintext;
-    std::vector<uint32_t> results(params_->dimensions.size(), 0);
+  // database.cpp:318-332 (the parameter-only forms need no device and are what the instance methods use)
+  static std::vector<uint32_t> calculate_indices(const PIRParameters& p, uint32_t index) {
+    uint32_t pt_index = index / p.items_per_plaintext;
+    std::vector<uint32_t> results(p.dimensions.size(), 0);
     for (int i = (int)results.size() - 1; i >= 0; --i) {
-      results[i] = pt_index % params_->dimensions[i];
-      pt_index = pt_index / params_->dimensions[i];
+      results[i] = pt_index % p.dimensions[i];
+      pt_index = pt_index / p.dimensions[i];
     }
     return results;
   }
-  size_t calculate_item_offset(uint32_t index) const {
-    const uint32_t pt_index = index / params_->items_per_plaintext;
-    return (index - (pt_index * params_->items_per_plaintext)) * params_->bytes_per_item;
+  static size_t calculate_item_offset(const PIRParameters& p, uint32_t index) {
+    const uint32_t pt_index = index / p.items_per_plaintext;
+    return (index - (pt_index * p.items_per_plaintext)) * p.bytes_per_item;
   }
+  std::vector<uint32_t> calculate_indices(uint32_t index) const { return calculate_indices(*params_, index); }
+  size_t calculate_item_offset(uint32_t index) const { return calculate_item_offset(*params_, index); }
   static std::vector<uint32_t> calculate_dimensions(uint32_t db_size, uint32_t num_dimensions) {
     std::vector<uint32_t> r(num_dimensions);
     pirb_calculate_dimensions(db_size, num_dimensions, r.data());

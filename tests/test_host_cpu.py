@@ -158,3 +158,12 @@ def test_process_request_marshalling_with_a_stub_library(monkeypatch):
     with pytest.raises(pb.PIRStatusError):                             # wrong number of query ciphertexts
         srv.ProcessRequest(pb.Request([np.zeros((2, 2, 2, 4096), dtype=np.uint64)], gk))
     assert srv.ProcessRequest(pb.Request([], gk)).reply == []
+
+
+def test_cpp_shim_host_side_tables():
+    """tests/cpp/shim_host_test.cpp: the reference's parameters / string-encoder / index tables through the C++ shim."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", root, "build/shim_host_test"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([os.path.join(root, "build", "shim_host_test")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "SHIM_HOST_TEST_OK" in out.stdout, out.stdout + out.stderr
