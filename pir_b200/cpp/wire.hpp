@@ -426,25 +426,53 @@ struct In {
     return true;
   }
 };
-// Serialization::SEALHeader {u16 magic, u8 zero, u8 compr_mode, u32 size, u64 reserved}
-inline void put_header(std::string& out, uint32_t total_size) {
+// Serialization::SEALHeader as of SEAL 3.5 (the version deps.bzl pins), 16 bytes:
+//   {u16 magic = 0xA15E, u8 header_size = 0x10, u8 version_major = 3, u8 version_minor = 5, u8 compr_mode,
+//    u16 reserved = 0, u64 size}
+// SEAL 3.5's IsValidHeader wants exactly that (magic, header size, matching major.minor, known compr_mode); its
+// LoadHeader falls back to legacy_headers::SEALHeader_3_4 {u16 magic, u8 zero = 0, u8 compr_mode, u32 size,
+// u64 reserved} when the 3.5 check fails, and so does get_header below.  Restated from the published sources; not
+// byte-verified against a SEAL build (none is available here).
+constexpr uint8_t SEAL_HEADER_SIZE_BYTE = 0x10;
+constexpr uint8_t SEAL_VERSION_MAJOR = 3;
+constexpr uint8_t SEAL_VERSION_MINOR = 5;
+inline void put_header(std::string& out, uint64_t total_size) {
   put<uint16_t>(out, SEAL_MAGIC);
-  put<uint8_t>(out, 0);
+  put<uint8_t>(out, SEAL_HEADER_SIZE_BYTE);
+  put<uint8_t>(out, SEAL_VERSION_MAJOR);
+  put<uint8_t>(out, SEAL_VERSION_MINOR);
   put<uint8_t>(out, 0);  // compr_mode_type::none (the reference builds SEAL with SEAL_USE_ZLIB=OFF)
-  put<uint32_t>(out, total_size);
-  put<uint64_t>(out, 0);
+  put<uint16_t>(out, 0);
+  put<uint64_t>(out, total_size);
 }
 // reads a header and returns the sub-range [after header, header start + size)
 inline bool get_header(In& in, In* body, std::string* err) {
   const char* start = in.p;
-  uint16_t magic; uint8_t zero, compr; uint32_t size; uint64_t reserved;
-  if (!in.get(&magic) || !in.get(&zero) || !in.get(&compr) || !in.get(&size) || !in.get(&reserved)) {
+  uint8_t raw[SEAL_HEADER_BYTES];
+  if (!in.raw(raw, sizeof(raw))) {
     *err = "truncated SEAL header";
     return false;
   }
-  if (magic != SEAL_MAGIC || zero != 0) { *err = "loaded SEALHeader is invalid"; return false; }
+  uint16_t magic;
+  std::memcpy(&magic, raw, 2);
+  if (magic != SEAL_MAGIC) { *err = "loaded SEALHeader is invalid"; return false; }
+  uint8_t compr;
+  uint64_t size;
+  if (raw[2] == SEAL_HEADER_SIZE_BYTE) {  // SEAL 3.5 layout
+    if (raw[3] != SEAL_VERSION_MAJOR || raw[4] != SEAL_VERSION_MINOR) { *err = "incompatible SEAL version in SEALHeader"; return false; }
+    compr = raw[5];
+    std::memcpy(&size, raw + 8, 8);
+  } else if (raw[2] == 0) {  // legacy SEAL 3.4 layout
+    compr = raw[3];
+    uint32_t size32;
+    std::memcpy(&size32, raw + 4, 4);
+    size = size32;
+  } else {
+    *err = "loaded SEALHeader is invalid";
+    return false;
+  }
   if (compr != 0) { *err = "unsupported compression mode"; return false; }
-  if (size < SEAL_HEADER_BYTES || (size_t)(in.end - start) < size) { *err = "SEAL object size exceeds the buffer"; return false; }
+  if (size < SEAL_HEADER_BYTES || (uint64_t)(in.end - start) < size) { *err = "SEAL object size exceeds the buffer"; return false; }
   body->p = in.p;
   body->end = start + size;
   in.p = start + size;
@@ -513,7 +541,7 @@ inline void SaveCiphertextMembers(std::string& out, const CiphertextData& ct, co
   detail::put<uint64_t>(out, ct.coeff_modulus_size);
   detail::put<double>(out, ct.scale);
   const uint64_t count = seed ? ct.poly_modulus_degree * ct.coeff_modulus_size : ct.limbs.size();
-  detail::put_header(out, (uint32_t)(SEAL_HEADER_BYTES + 8 + count * 8));  // nested IntArray<u64>
+  detail::put_header(out, (uint64_t)(SEAL_HEADER_BYTES + 8 + count * 8));  // nested IntArray<u64>
   detail::put<uint64_t>(out, count);
   out.append((const char*)ct.limbs.data(), count * 8);
   if (seed) out.append((const char*)seed->data(), sizeof(seed_type));
@@ -522,7 +550,7 @@ inline std::string SaveCiphertext(const CiphertextData& ct, const seed_type* see
   std::string body;
   SaveCiphertextMembers(body, ct, seed);
   std::string out;
-  detail::put_header(out, (uint32_t)(SEAL_HEADER_BYTES + body.size()));
+  detail::put_header(out, (uint64_t)(SEAL_HEADER_BYTES + body.size()));
   out += body;
   return out;
 }
@@ -592,7 +620,7 @@ inline std::string SaveKSwitchKeys(const KSwitchKeysData& k, const std::vector<s
     for (size_t j = 0; j < k.keys[s].size(); ++j) body += SaveCiphertext(k.keys[s][j], seeds ? &(*seeds)[s][j] : nullptr);
   }
   std::string out;
-  detail::put_header(out, (uint32_t)(SEAL_HEADER_BYTES + body.size()));
+  detail::put_header(out, (uint64_t)(SEAL_HEADER_BYTES + body.size()));
   out += body;
   return out;
 }
@@ -630,13 +658,13 @@ inline std::string SaveEncryptionParameters(const SealParams& p) {
   detail::put<uint64_t>(body, p.poly_modulus_degree);
   detail::put<uint64_t>(body, p.coeff_modulus.size());
   auto put_modulus = [&](uint64_t q) {
-    detail::put_header(body, (uint32_t)(SEAL_HEADER_BYTES + 8));
+    detail::put_header(body, (uint64_t)(SEAL_HEADER_BYTES + 8));
     detail::put<uint64_t>(body, q);
   };
   for (uint64_t q : p.coeff_modulus) put_modulus(q);
   put_modulus(p.plain_modulus);
   std::string out;
-  detail::put_header(out, (uint32_t)(SEAL_HEADER_BYTES + body.size()));
+  detail::put_header(out, (uint64_t)(SEAL_HEADER_BYTES + body.size()));
   out += body;
   return out;
 }

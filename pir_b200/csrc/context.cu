@@ -5,6 +5,7 @@
 //   PIRServer::processQuery (server.cpp:173-195) -> oblivious_expansion (server.cpp:105-171)
 //   -> PIRDatabase::multiply / DatabaseMultiplier::multiply (database.cpp:170-258, 290-316)
 //   -> CiphertextReencoder::Encode (ct_reencoder.cpp:40-71)
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -39,15 +40,20 @@ int fail(int code, const std::string& msg) {
     if (rc_) return rc_;  \
   } while (0)
 
-unsigned long long g_alloc_epoch = 0;  // bumped whenever a workspace buffer moves: captured graphs become stale
+// Captured graphs hold raw workspace pointers, so every context counts the moves of ITS buffers (alloc_epoch) and a
+// graph is replayed only while that count is unchanged.  Buffers that no graph of a context depends on (plan offset
+// tables, key handles: a new one never replaces a captured one) count into a process-wide dummy.
+unsigned long long g_unowned_epoch = 0;
+std::atomic<unsigned long long> g_next_key_id{1};
 
 struct DevBuf {
   u64* p = nullptr;
   size_t bytes = 0;
+  unsigned long long* epoch = &g_unowned_epoch;  // the owning context's alloc_epoch
   ~DevBuf() { if (p) cudaFree(p); }
   int ensure(size_t b) {
     if (b <= bytes) return 0;
-    ++g_alloc_epoch;
+    ++*epoch;
     if (p) { cudaFree(p); p = nullptr; bytes = 0; }
     cudaError_t e = cudaMalloc(&p, b);
     if (e != cudaSuccess) {
@@ -78,6 +84,7 @@ struct ExpandPlan {
 }  // namespace
 
 struct pirb_keys {
+  unsigned long long id = g_next_key_id.fetch_add(1);  // never reused: captured graphs are keyed on it, not on the pointer
   std::vector<u32> elts;
   DevBuf d;  // [n][k][2][k+1][N]
   u64 key_limbs = 0;
@@ -101,10 +108,28 @@ struct pirb_ctx {
   u64 dim_sum = 0, reply_cts = 1, rest = 1;  // rest = prod dims[1..]
   u32 top_lo = 0, top_hi = 0;                // owned slice of dims[0]
   u64 pt_begin = 0, pt_count = 0;            // owned plaintexts (global indices)
+  // which of the owned plaintexts have been loaded (re-loading a range is idempotent); `loaded` = how many
+  std::vector<u8> have;
   u64 loaded = 0;
+  void mark_loaded(u64 first_local, u64 n) {
+    if (have.size() < pt_count) have.resize(pt_count, 0);
+    for (u64 i = first_local; i < first_local + n; ++i)
+      if (!have[i]) { have[i] = 1; ++loaded; }
+  }
+  u64 loaded_prefix() const {  // plaintexts loaded contiguously from the start of the shard
+    if (loaded == pt_count) return pt_count;
+    u64 i = 0;
+    while (i < have.size() && have[i]) ++i;
+    return i;
+  }
+  unsigned long long alloc_epoch = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;          // second branch of the answer graph (work off the critical path)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // end of the last *_dev call: the next one (possibly on another caller stream) waits on it, because all calls share
+  // the context's workspaces
+  cudaEvent_t ev_last = nullptr;
+  bool ev_last_valid = false;
   std::vector<DevBuf> tables;
   DevBuf db, stage, work, dig, acc, xch, part, bufA[2], pts, qbuf, rbuf, svbuf;
   std::map<std::tuple<u64, int, int, int>, std::unique_ptr<ExpandPlan>> plans;  // (items, single, first tree, trees)
@@ -116,7 +141,7 @@ struct pirb_ctx {
   // CUDA graphs of the whole answer path (expansion + multiply), one per (batch size, key handle, partial flag);
   // they read c->qbuf and write c->rbuf, so they stay valid as long as no workspace buffer moves.
   struct GraphEntry { cudaGraphExec_t exec = nullptr; unsigned long long epoch = 0; u64 launches = 0; };
-  std::map<std::tuple<int, u32, const void*, const void*, const void*>, GraphEntry> graphs;  // (op, Q, keys, in, out)
+  std::map<std::tuple<int, u32, unsigned long long, const void*, const void*>, GraphEntry> graphs;  // (op, Q, key id, in, out)
   bool use_graphs = true;
   // peer-memory exchange of partial replies (CUDA IPC over NVLink): own slots + the peers' mapped base pointers
   u64* xbuf = nullptr;
@@ -128,6 +153,11 @@ struct pirb_ctx {
   DevBuf dbg;            // PIRB_DEBUG_STAMPS=<level>: clock64 phase stamps of that expansion level
   int dbg_level = -1;
   bool use_cluster = false;  // one-launch-per-level key switch on thread-block clusters
+  pirb_ctx() {
+    for (DevBuf* b : {&db, &stage, &work, &dig, &acc, &xch, &part, &bufA[0], &bufA[1], &pts, &qbuf, &rbuf, &svbuf, &xptrs,
+                      &dbg})
+      b->epoch = &alloc_epoch;
+  }
 };
 
 namespace {
@@ -247,15 +277,6 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
   return 0;
 }
 
-int choose_split(u64 base_ctas, u32 len, int sm_count) {
-  const u64 want = (u64)sm_count * 4;
-  int s = 1;
-  if (base_ctas < want) s = (int)((want + base_ctas - 1) / base_ctas);
-  const int max_split = (int)((len + 3) / 4);
-  if (s > max_split) s = max_split;
-  return s < 1 ? 1 : s;
-}
-
 // DatabaseMultiplier::multiply on the device.  d_sv: [n_queries] x (sv_qstride limbs apart) x [dim_sum][2][k][N]
 // coefficient form; transformed to NTT form in place.  d_out: [n_queries][reply_cts][2][k][N]; coefficient form,
 // or (partial != 0) the NTT-form sum over this shard's rows, to be reduced across shards.
@@ -290,7 +311,11 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   if (c->profiling) cudaEventRecord(c->ev[2], st);
 
   const u64 out_cts = c->reply_cts;
-  if (c->pt_count == 0 || c->loaded == 0) {
+  // the reference multiplies whatever the database holds (database.cpp:183 stops at db_.end()); here that is the
+  // contiguously loaded prefix of the shard — a database with unloaded gaps is an error, not uninitialised memory
+  const u64 npt = c->loaded_prefix();
+  if (npt != c->loaded) return fail(PIRB_INVALID_ARGUMENT, "database has unloaded gaps");
+  if (npt == 0) {
     if (forked) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     // empty shard: contributes the additive identity
     CU(cudaMemsetAsync(d_out, 0, (size_t)n_queries * out_cts * ctL * sizeof(u64), st));
@@ -306,7 +331,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
     sv_last = d_sv + ((u64)c->top_lo - sv_item0) * ctL;
   } else {
     dimL = c->dims[d - 1];
-    n_rows = (u32)((c->pt_count + dimL - 1) / dimL);
+    n_rows = (u32)((npt + dimL - 1) / dimL);
     u64 off = 0;
     for (int e = 0; e < d - 1; ++e) off += c->dims[e];
     sv_last = d_sv + off * ctL;
@@ -315,7 +340,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   scan_config(P, dimL, n_rows, n_queries, c->sm_count, &n_split);
   c->scan_split = n_split;
   RC(c->part.ensure((size_t)n_queries * n_split * n_rows * ctL * sizeof(u64)));
-  LAUNCH(c, launch_scan(P, c->db.p, c->pt_count, dimL, n_rows, sv_last, sv_qstride, n_queries, n_split, c->part.p, st));
+  LAUNCH(c, launch_scan(P, c->db.p, npt, dimL, n_rows, sv_last, sv_qstride, n_queries, n_split, c->part.p, st));
   if (c->profiling) cudaEventRecord(c->ev[3], st);
   if (d == 1) {
     if (partial) {
@@ -348,7 +373,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
     RC(c->pts.ensure((size_t)n_queries * n_cts_in * c->two_er * c->ptL * sizeof(u64)));
     LAUNCH(c, launch_reencode_ntt(P, c->bufA[cur].p, c->pts.p, (int)(n_queries * n_cts_in), st));
     const u32 slices = (u32)(c->ptL / 256);
-    const int ns = choose_split((u64)slices * w_out * n_groups * n_queries, dim, c->sm_count);
+    const int ns = dim_mac_config(P, (u64)slices * w_out * n_groups * n_queries, dim, c->sm_count);
     RC(c->part.ensure((size_t)n_queries * ns * n_groups * w_out * ctL * sizeof(u64)));
     LAUNCH(c, launch_dim_mac(P, c->pts.p, n_cts_in * c->two_er * c->ptL, d_sv + sv_off * ctL, sv_qstride, n_queries, dim,
                              n_entries, n_groups, w_out, ns, c->part.p, st));
@@ -404,14 +429,14 @@ int run_answer(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u32 n_q
 
 // Run `body(stream)` (a fixed sequence of kernel launches for fixed pointers and shapes), replaying a captured CUDA
 // graph when one is valid for `key`.  The first call with a key runs eagerly (it sizes every workspace), the second
-// one captures, later ones replay.  Any workspace reallocation or key-handle change bumps g_alloc_epoch and
-// invalidates the cache.
+// one captures, later ones replay.  Any workspace reallocation bumps the context's alloc_epoch and invalidates the
+// cache; key handles enter the cache key by their never-reused id.
 template <typename Body>
-int run_graphed(pirb_ctx* c, const std::tuple<int, u32, const void*, const void*, const void*>& key, cudaStream_t st,
+int run_graphed(pirb_ctx* c, const std::tuple<int, u32, unsigned long long, const void*, const void*>& key, cudaStream_t st,
                 Body&& body) {
   if (!c->use_graphs || c->profiling || c->dbg.p) return body(st);
   auto it = c->graphs.find(key);
-  if (it != c->graphs.end() && it->second.exec && it->second.epoch == g_alloc_epoch) {
+  if (it != c->graphs.end() && it->second.exec && it->second.epoch == c->alloc_epoch) {
     c->launches = it->second.launches;
     CU(cudaGraphLaunch(it->second.exec, st));
     return 0;
@@ -426,12 +451,12 @@ int run_graphed(pirb_ctx* c, const std::tuple<int, u32, const void*, const void*
     return body(st);
   }
   if (it->second.exec) { cudaGraphExecDestroy(it->second.exec); it->second.exec = nullptr; }
-  const unsigned long long epoch_before = g_alloc_epoch;
+  const unsigned long long epoch_before = c->alloc_epoch;
   CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
   const int rc = body(st);
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(st, &graph);
-  if (rc || e != cudaSuccess || epoch_before != g_alloc_epoch) {
+  if (rc || e != cudaSuccess || epoch_before != c->alloc_epoch) {
     // argument error, or a workspace had to grow during capture: fall back to an eager run (and try again next time)
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
@@ -447,7 +472,7 @@ int run_graphed(pirb_ctx* c, const std::tuple<int, u32, const void*, const void*
     return body(st);
   }
   it->second.exec = exec;
-  it->second.epoch = g_alloc_epoch;
+  it->second.epoch = c->alloc_epoch;
   it->second.launches = c->launches;
   CU(cudaGraphLaunch(exec, st));
   return 0;
@@ -458,9 +483,22 @@ int answer_buffers(pirb_ctx* c, const pirb_keys* keys, u32 n_queries, u64 n_ct, 
                    const u64* d_in = nullptr, u64* d_out = nullptr) {
   if (!d_in) d_in = c->qbuf.p;
   if (!d_out) d_out = c->rbuf.p;
-  return run_graphed(c, std::make_tuple(partial, n_queries, (const void*)keys, (const void*)d_in, (const void*)d_out), st,
+  return run_graphed(c, std::make_tuple(partial, n_queries, keys ? keys->id : 0ull, (const void*)d_in, (const void*)d_out), st,
                      [&](cudaStream_t s_) { return run_answer(c, keys, d_in, n_queries, n_ct, d_out, partial, s_); });
 }
+
+// All *_dev entry points work on the context's single set of workspaces, whatever stream the caller passes: each call
+// first makes its stream wait for the end of the previous call and records its own end.
+struct DevCallOrder {
+  pirb_ctx* c;
+  cudaStream_t st;
+  DevCallOrder(pirb_ctx* c_, cudaStream_t st_) : c(c_), st(st_) {
+    if (c->ev_last_valid) cudaStreamWaitEvent(st, c->ev_last, 0);
+  }
+  ~DevCallOrder() {
+    if (cudaEventRecord(c->ev_last, st) == cudaSuccess) c->ev_last_valid = true;
+  }
+};
 
 // Page-locked host memory is addressable from kernels under unified addressing: the first kernel of the answer path
 // can read the queries from it and the last one can write the replies into it, so a caller that passes pinned buffers
@@ -540,6 +578,7 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   const u64 Pq = prm->coeff_modulus[c->k];
   P.half_P = Pq >> 1;
   c->tables.resize(prm->n_moduli);
+  for (auto& tb : c->tables) tb.epoch = &c->alloc_epoch;
   for (u32 i = 0; i < prm->n_moduli; ++i) {
     const u64 q = prm->coeff_modulus[i];
     hm::Tables T = hm::build_tables(q, logn);
@@ -632,6 +671,9 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
     P.mac_mode = 0;
     P.mac_max_terms = 1u << 30;
   }
+  // 128-bit accumulation of products below q_max^2 wraps after 2^(128 - 2*bits) terms (64 terms for 61-bit moduli)
+  P.wide_max_terms = 1u << std::min(30, 128 - 2 * max_bits);
+  if (P.mac_mode == 0) P.mac_max_terms = P.wide_max_terms;
   c->two_er = e;
   for (int i = 1; i < c->d; ++i) c->reply_cts *= e;
 
@@ -660,6 +702,7 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
   for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
   *out = c.release();
   return 0;
@@ -679,6 +722,7 @@ void pirb_ctx_destroy(pirb_ctx* c) {
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_last) cudaEventDestroy(c->ev_last);
   delete c;
 }
 
@@ -713,7 +757,7 @@ int pirb_db_load_coeff(pirb_ctx* c, const uint64_t* coeffs, uint64_t first, uint
                        c->stream));
     LAUNCH(c, launch_db_preprocess(c->P, c->stage.p, c->db.p + (p - c->pt_begin) * c->ptL, n, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->loaded += n;
+    c->mark_loaded(p - c->pt_begin, n);
     p += n;
   }
   return 0;
@@ -746,7 +790,7 @@ int pirb_db_load_items(pirb_ctx* c, const uint8_t* items, uint64_t first_item, u
                                 byte_hi - byte_lo, n, c->stream));
     LAUNCH(c, launch_db_preprocess(c->P, c->stage.p, c->db.p + (p - c->pt_begin) * c->ptL, n, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->loaded += n;
+    c->mark_loaded(p - c->pt_begin, n);
     p += n;
   }
   return 0;
@@ -760,7 +804,7 @@ int pirb_db_load_ntt(pirb_ctx* c, const uint64_t* limbs, uint64_t first, uint64_
   if (hi > lo) {
     CU(cudaMemcpy(c->db.p + (lo - c->pt_begin) * c->ptL, limbs + (lo - first) * c->ptL, (hi - lo) * c->ptL * sizeof(u64),
                   cudaMemcpyHostToDevice));
-    c->loaded += hi - lo;
+    c->mark_loaded(lo - c->pt_begin, hi - lo);
   }
   return 0;
 }
@@ -777,9 +821,10 @@ int pirb_db_read_ntt(const pirb_ctx* c, uint64_t* out, uint64_t first, uint64_t 
 int pirb_db_fill_random(pirb_ctx* c, uint64_t seed) {
   if (!c) return fail(PIRB_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(c->device));
-  LAUNCH(c, launch_fill_random(c->P, c->db.p, c->pt_count * (u64)c->k, c->k, 0, seed + c->pt_begin, c->stream));
+  // keyed by the GLOBAL plaintext index: the shards of a database are slices of the unsharded fill with the same seed
+  LAUNCH(c, launch_fill_random(c->P, c->db.p, c->pt_count * (u64)c->k, c->k, 0, seed, c->pt_begin * (u64)c->k, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  c->loaded = c->pt_count;
+  c->mark_loaded(0, c->pt_count);
   return 0;
 }
 
@@ -800,8 +845,7 @@ int pirb_keys_load(pirb_ctx* c, const uint32_t* elts, uint32_t n, const uint64_t
 void pirb_keys_destroy(pirb_keys* kz) {
   if (!kz) return;
   cudaSetDevice(kz->device);
-  ++g_alloc_epoch;  // graphs that captured this handle's device pointer must not be replayed
-  delete kz;
+  delete kz;  // graphs captured with this handle are keyed on its id, which is never handed out again
 }
 
 int pirb_substitute(pirb_ctx* c, const pirb_keys* keys, uint64_t* ct, uint32_t power) {
@@ -955,6 +999,7 @@ static int answer_dev_common(pirb_ctx* c, const pirb_keys* keys, const u64* d_qu
   const size_t rbytes = (size_t)n_queries * c->reply_cts * c->ctL * sizeof(u64);
   RC(c->qbuf.ensure(std::max<size_t>(qbytes, 256)));
   RC(c->rbuf.ensure(std::max<size_t>(rbytes, 256)));
+  DevCallOrder order(c, st);
   // the captured graph works on the context's own buffers; the caller's tensors are copied in and out
   CU(cudaMemcpyAsync(c->qbuf.p, d_queries, qbytes, cudaMemcpyDeviceToDevice, st));
   RC(answer_buffers(c, keys, n_queries, n_ct, partial, st));
@@ -988,7 +1033,8 @@ int pirb_expand_ntt_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_qu
   int rc;
   ExpandPlan* pl = get_plan(c, c->dim_sum, 0, &rc);
   if (!pl) return rc;
-  return run_graphed(c, std::make_tuple(2, n_queries, (const void*)keys, (const void*)d_queries, (const void*)d_sv_ntt), st,
+  DevCallOrder order(c, st);
+  return run_graphed(c, std::make_tuple(2, n_queries, keys ? keys->id : 0ull, (const void*)d_queries, (const void*)d_sv_ntt), st,
                      [&](cudaStream_t s_) -> int {
                        c->launches = 0;
                        if (c->profiling) cudaEventRecord(c->ev[0], s_);
@@ -1006,7 +1052,8 @@ int pirb_multiply_partial_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_
   if (!n_queries) return 0;
   if (c->loaded != c->pt_count) return fail(PIRB_INVALID_ARGUMENT, "database size mismatch");
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-  const int rc = run_graphed(c, std::make_tuple(3, n_queries, (const void*)nullptr, (const void*)d_sv_ntt, (const void*)d_partial),
+  DevCallOrder order(c, st);
+  const int rc = run_graphed(c, std::make_tuple(3, n_queries, 0ull, (const void*)d_sv_ntt, (const void*)d_partial),
                              st, [&](cudaStream_t s_) -> int {
                                c->launches = 0;
                                return run_multiply(c, const_cast<u64*>(U(d_sv_ntt)), c->dim_sum * c->ctL, (int)n_queries,
@@ -1022,6 +1069,7 @@ int pirb_reduce_finish_dev(pirb_ctx* c, const uint64_t* d_partials, uint32_t n_p
   CU(cudaSetDevice(c->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   const u64 cts = (u64)n_queries * c->reply_cts;
+  DevCallOrder order(c, st);
   // the mod-q add of the partials is fused into the load side of the final inverse NTT
   LAUNCH(c, launch_ntt_inv(c->P, U(d_partials), U(d_replies), (int)(cts * 2 * c->k), c->k, 0, (int)n_parts, part_stride, 1, 0,
                            0, st));
@@ -1035,6 +1083,7 @@ int pirb_reduce_finish_peers_dev(pirb_ctx* c, const uint64_t* const* d_peer_ptrs
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   const u64 cts = (u64)n_queries * c->reply_cts;
   RC(c->rbuf.ensure(cts * c->ctL * sizeof(u64)));
+  DevCallOrder order(c, st);
   LAUNCH(c, launch_modadd_reduce_ptrs(c->P, reinterpret_cast<const u64* const*>(d_peer_ptrs), (int)n_parts, 0, c->rbuf.p, cts, st));
   LAUNCH(c, launch_ntt_inv(c->P, c->rbuf.p, U(d_replies), (int)(cts * 2 * c->k), c->k, 0, 1, 0, 1, 0, 0, st));
   return 0;
@@ -1048,7 +1097,7 @@ int pirb_xbuf_create(pirb_ctx* c, uint32_t max_queries, uint32_t n_slots, uint8_
   c->xslot_limbs = (u64)max_queries * c->reply_cts * c->ctL;
   c->xslots = n_slots;
   CU(cudaMalloc(&c->xbuf, c->xslot_limbs * n_slots * sizeof(u64)));
-  ++g_alloc_epoch;
+  ++c->alloc_epoch;
   cudaIpcMemHandle_t h;
   CU(cudaIpcGetMemHandle(&h, c->xbuf));
   static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
@@ -1100,6 +1149,7 @@ int pirb_reduce_finish_xbuf_dev(pirb_ctx* c, uint32_t slot, uint32_t q_first, ui
   const u64 cts = (u64)q_count * c->reply_cts;
   if (!cts) return 0;
   RC(c->rbuf.ensure(cts * c->ctL * sizeof(u64)));
+  DevCallOrder order(c, st);
   const u64 off = (u64)slot * c->xslot_limbs + (u64)q_first * c->reply_cts * c->ctL;
   // the partial replies of every rank are loaded through the peer mappings inside the reducing kernel (NVLink P2P)
   LAUNCH(c, launch_modadd_reduce_ptrs(c->P, reinterpret_cast<const u64* const*>(c->xptrs.p), (int)c->xranks, off, c->rbuf.p,
@@ -1123,6 +1173,7 @@ int pirb_scan_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_queries, uin
     RC(c->part.ensure((size_t)n_queries * n_split * n_rows * c->ctL * sizeof(u64)));
     dst = c->part.p;
   }
+  DevCallOrder order(c, st);
   if (c->profiling) cudaEventRecord(c->ev[2], st);
   LAUNCH(c, launch_scan(c->P, c->db.p, c->pt_count, dimL, n_rows, U(d_sv_ntt), (u64)dimL * c->ctL, (int)n_queries, n_split,
                         dst, st));

@@ -62,6 +62,7 @@ cudaError_t launch_reencode_ntt(const DevParams& P, const u64* cts, u64* pts, in
 
 // upper-dimension MAC (SURVEY §3.1 HOT LOOP 3):
 // part[qi][split][g][x][2][k][N] = sum_{i in split, i < cnt(g)} sv[qi][i][c] (.) pts[qi][(g*dim+i)][x]
+int dim_mac_config(const DevParams& P, u64 base_ctas, u32 len, int sm_count);  // n_split for launch_dim_mac
 cudaError_t launch_dim_mac(const DevParams& P, const u64* pts, u64 pts_qstride, const u64* sv, u64 sv_qstride,
                            int n_queries, u32 dim, u32 n_entries_in, u32 n_groups, u32 w_out, int n_split, u64* part,
                            cudaStream_t st);
@@ -84,7 +85,9 @@ cudaError_t launch_pack_items(const u8* bytes, u64* coeffs, u32 N, u32 bits, u64
 // warm L2 with constants that every kernel of a query re-reads (tables, keys)
 cudaError_t launch_prefetch_l2(const void* p, u64 bytes, cudaStream_t st);
 
-// synthetic data: out[p][N] uniform in [0, q_{(p % cycle) + off}) from a counter-based generator
-cudaError_t launch_fill_random(const DevParams& P, u64* out, u64 n_polys, int cycle, int off, u64 seed, cudaStream_t st);
+// synthetic data: out[p][N] uniform in [0, q_{(p % cycle) + off}) from a counter-based generator keyed by the global
+// polynomial index poly0 + p (poly0 must be a multiple of cycle)
+cudaError_t launch_fill_random(const DevParams& P, u64* out, u64 n_polys, int cycle, int off, u64 seed, u64 poly0,
+                               cudaStream_t st);
 
 }  // namespace pirb

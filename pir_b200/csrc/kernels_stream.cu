@@ -12,6 +12,11 @@
 
 namespace pirb {
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 __device__ __forceinline__ ulonglong2 ldg128(const u64* p) { return __ldg(reinterpret_cast<const ulonglong2*>(p)); }
 // streaming 128-bit load that does not allocate in L1 (database limbs are read exactly once)
 __device__ __forceinline__ ulonglong2 ldg128_stream(const u64* p) {
@@ -611,10 +616,6 @@ k_scan_tma(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 
   }
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
 
 // tuning knobs (overridable through the environment for sweeps): rows per CTA, unroll, generic MAC
 static int scan_mode() { return env_int("PIRB_SCAN_MODE", 0); }  // 0 = LDG kernel (default), 1 = TMA bulk-copy ring
@@ -646,7 +647,7 @@ void scan_config(const DevParams& P, u32 dimL, u32 n_rows, int n_queries, int sm
   const int max_split = (int)((dimL + 7) / 8);  // keep at least 8 database tiles per CTA
   if (s > max_split) s = max_split;
   // exact lazy accumulation chains have a maximum length (pirb_device.cuh)
-  const u32 max_terms = mode >= MAC_FP64 ? P.mac_max_terms : (mode == MAC_INT24 ? PIRB_SMALL_MAX_TERMS : (1u << 30));
+  const u32 max_terms = mode >= MAC_FP64 ? P.mac_max_terms : (mode == MAC_INT24 ? PIRB_SMALL_MAX_TERMS : P.wide_max_terms);
   const int min_split = (int)((dimL + max_terms - 1) / max_terms);
   if (s < min_split) s = min_split;
   s = env_int("PIRB_SCAN_SPLIT", s);
@@ -663,6 +664,7 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
     const u32 chain = (dimL + n_split - 1) / n_split;
     if (mode >= MAC_FP64 && chain > P.mac_max_terms) mode = P.mac_mode >= 1 && P.half_bits <= 24 ? MAC_INT24 : MAC_WIDE;
     if (mode == MAC_INT24 && chain > PIRB_SMALL_MAX_TERMS) mode = MAC_WIDE;
+    if (mode == MAC_WIDE && chain > P.wide_max_terms) return cudaErrorInvalidValue;  // scan_config splits finer than this
   }
   const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
   dim3 grid(slices, (n_rows + R - 1) / R, n_queries * n_split);
@@ -793,6 +795,7 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
 // ---------------------------------------------------------------------------------------------
 // upper-dimension MAC: grid (slice, x = output ct of the group, (qi*n_groups + g)*n_split + split)
 // ---------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(SCAN_NT)
 k_dim_mac(const __grid_constant__ DevParams P, const u64* __restrict__ pts, u64 pts_qstride,
           const u64* __restrict__ sv, u64 sv_qstride, u32 dim, u32 n_entries_in, u32 n_groups, u32 w_out, int n_split,
@@ -808,7 +811,8 @@ k_dim_mac(const __grid_constant__ DevParams P, const u64* __restrict__ pts, u64 
   const u32 cnt = min(dim, n_entries_in - g * dim);
   const u32 per = (dim + n_split - 1) / n_split;
   const u32 i_lo = split * per, i_hi = min(cnt, i_lo + per);
-  u64 alo[2][2] = {{0, 0}, {0, 0}}, ahi[2][2] = {{0, 0}, {0, 0}};
+  const int hb = P.half_bits;
+  Acc<MODE> acc[2][2];
   const u64* svq = sv + qi * sv_qstride + limb;
   const u64* pq = pts + qi * pts_qstride + ((u64)g * dim * w_out + x) * kN + limb;
 #pragma unroll 4
@@ -816,19 +820,39 @@ k_dim_mac(const __grid_constant__ DevParams P, const u64* __restrict__ pts, u64 
     const ulonglong2 s0 = ldg128(svq + i * ctL);
     const ulonglong2 s1 = ldg128(svq + i * ctL + kN);
     const ulonglong2 d = ldg128_stream(pq + (u64)i * w_out * kN);
-    mac128(alo[0][0], ahi[0][0], s0.x, d.x);
-    mac128(alo[0][1], ahi[0][1], s0.y, d.y);
-    mac128(alo[1][0], ahi[1][0], s1.x, d.x);
-    mac128(alo[1][1], ahi[1][1], s1.y, d.y);
+    const Opnd<MODE> bx(d.x, hb), by(d.y, hb);
+    acc[0][0].mac(Opnd<MODE>(s0.x, hb), bx);
+    acc[0][1].mac(Opnd<MODE>(s0.y, hb), by);
+    acc[1][0].mac(Opnd<MODE>(s1.x, hb), bx);
+    acc[1][1].mac(Opnd<MODE>(s1.y, hb), by);
   }
   u64* o = part + ((((u64)qi * n_split + split) * n_groups + g) * w_out + x) * ctL + limb;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     ulonglong2 v;
-    v.x = barrett128(alo[c][0], ahi[c][0], m.q, m.ratio_hi, m.ratio_lo);
-    v.y = barrett128(alo[c][1], ahi[c][1], m.q, m.ratio_hi, m.ratio_lo);
+    v.x = acc[c][0].reduce(m, hb);
+    v.y = acc[c][1].reduce(m, hb);
     *reinterpret_cast<ulonglong2*>(o + (u64)c * kN) = v;
   }
+}
+
+static u32 mac_chain_limit(const DevParams& P, int mode) {
+  return mode >= MAC_FP64 ? P.mac_max_terms : (mode == MAC_INT24 ? PIRB_SMALL_MAX_TERMS : P.wide_max_terms);
+}
+
+// split of an upper dimension's sum over `len` entries: enough CTAs to fill the GPU, and never a lazy accumulation
+// chain longer than the exact range of the context's multiply-accumulate mode (pirb_device.cuh)
+int dim_mac_config(const DevParams& P, u64 base_ctas, u32 len, int sm_count) {
+  const u64 want = (u64)sm_count * 4;
+  int s = 1;
+  if (base_ctas < want) s = (int)((want + base_ctas - 1) / base_ctas);
+  const int max_split = (int)((len + 3) / 4);
+  if (s > max_split) s = max_split;
+  const int mode = std::min(P.mac_mode, env_int("PIRB_MAC_MODE", 2));
+  const u32 max_terms = mac_chain_limit(P, mode);
+  const int min_split = (int)((len + max_terms - 1) / max_terms);
+  if (s < min_split) s = min_split;
+  return s < 1 ? 1 : s;
 }
 
 cudaError_t launch_dim_mac(const DevParams& P, const u64* pts, u64 pts_qstride, const u64* sv, u64 sv_qstride,
@@ -838,8 +862,14 @@ cudaError_t launch_dim_mac(const DevParams& P, const u64* pts, u64 pts_qstride, 
   const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
   dim3 grid(slices, w_out, (unsigned)n_queries * n_groups * n_split);
   if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidConfiguration;
-  k_dim_mac<<<grid, SCAN_NT, 0, st>>>(P, pts, pts_qstride, sv, sv_qstride, dim, n_entries_in, n_groups, w_out,
-                                      n_split, part);
+  const int mode = std::min(P.mac_mode, env_int("PIRB_MAC_MODE", 2));
+  if ((dim + n_split - 1) / n_split > mac_chain_limit(P, mode)) return cudaErrorInvalidValue;
+  if (mode == MAC_FP64)
+    k_dim_mac<MAC_FP64><<<grid, SCAN_NT, 0, st>>>(P, pts, pts_qstride, sv, sv_qstride, dim, n_entries_in, n_groups, w_out, n_split, part);
+  else if (mode == MAC_INT24)
+    k_dim_mac<MAC_INT24><<<grid, SCAN_NT, 0, st>>>(P, pts, pts_qstride, sv, sv_qstride, dim, n_entries_in, n_groups, w_out, n_split, part);
+  else
+    k_dim_mac<MAC_WIDE><<<grid, SCAN_NT, 0, st>>>(P, pts, pts_qstride, sv, sv_qstride, dim, n_entries_in, n_groups, w_out, n_split, part);
   return cudaGetLastError();
 }
 
@@ -1040,20 +1070,22 @@ cudaError_t launch_prefetch_l2(const void* p, u64 bytes, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_fill_random(const __grid_constant__ DevParams P, u64* __restrict__ out, int cycle, int off, u64 seed) {
+k_fill_random(const __grid_constant__ DevParams P, u64* __restrict__ out, int cycle, int off, u64 seed, u64 poly0) {
   const u64 poly = blockIdx.x;
   const u64 q = P.m[(poly % cycle) + off].q;
   for (u32 n = threadIdx.x; n < P.N; n += 256) {
-    u64 x = seed + (poly * P.N + n) * 0x9e3779b97f4a7c15ULL;  // splitmix64 finaliser as a counter-based hash
+    // counter = GLOBAL polynomial index: a row shard holds exactly the limbs the unsharded database holds there
+    u64 x = seed + ((poly0 + poly) * P.N + n) * 0x9e3779b97f4a7c15ULL;  // splitmix64 finaliser as a counter-based hash
     x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
     x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
     x ^= x >> 31;
     out[poly * P.N + n] = x % q;
   }
 }
-cudaError_t launch_fill_random(const DevParams& P, u64* out, u64 n_polys, int cycle, int off, u64 seed, cudaStream_t st) {
+cudaError_t launch_fill_random(const DevParams& P, u64* out, u64 n_polys, int cycle, int off, u64 seed, u64 poly0,
+                               cudaStream_t st) {
   if (!n_polys) return cudaSuccess;
-  k_fill_random<<<(unsigned)n_polys, 256, 0, st>>>(P, out, cycle, off, seed);
+  k_fill_random<<<(unsigned)n_polys, 256, 0, st>>>(P, out, cycle, off, seed, poly0);
   return cudaGetLastError();
 }
 

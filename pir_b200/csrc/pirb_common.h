@@ -56,6 +56,7 @@ struct DevParams {
   int mac_mode;                     // lazy MAC flavour the moduli allow: 0 wide (any), 1 int24 (< 2^48), 2 fp64 (<= 44 bit)
   int half_bits;                    // h: operand split position for the fp64 MAC (ceil(max modulus bits / 2))
   u32 mac_max_terms;                // longest exact accumulation chain for mac_mode
+  u32 wide_max_terms;               // ... and for the 128-bit accumulator: floor(2^128 / q_max^2), capped at 2^30
   u8 re_poly[PIRB_MAX_REENC];       // re-encode chunk e -> source poly (0/1)
   u8 re_mod[PIRB_MAX_REENC];        //                  -> source modulus j
   u8 re_shift[PIRB_MAX_REENC];      //                  -> right shift

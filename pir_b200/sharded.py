@@ -259,6 +259,58 @@ class ShardServer:
         self._xslot = (slot + 1) % self._xslots
         return out
 
+    # -- one entry point for the multi-GPU step, whatever the transport ------------------------------------------
+    def setup_distributed(self, queries_per_rank: int, prefer: str = "nvlink") -> str:
+        """Collective.  Chooses how selection vectors and partial replies travel between the ranks and sets it up;
+        returns a description for the bench line.  Falls back to NCCL collectives on every rank if any rank cannot
+        map its peers' memory."""
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        self._dist_mode = "nccl"
+        if prefer == "nvlink" and len(self.params.dimensions) > 1:
+            ok = 1
+            try:
+                self.setup_peer_exchange(max_queries=world * queries_per_rank)
+            except Exception as e:  # noqa: BLE001
+                ok = 0
+                import sys
+                sys.stderr.write("rank %d: peer exchange unavailable (%s); using NCCL gather\n" % (dist.get_rank(), e))
+            flag = torch.tensor([ok], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()):
+                self._dist_mode = "p2p"
+        if self._dist_mode == "p2p":
+            return "selection vectors all-gathered with NCCL, partial replies reduced over NVLink peer loads"
+        return "selection vectors and partial replies gathered with NCCL"
+
+    def answer_dist(self, d_queries_local: torch.Tensor) -> torch.Tensor:
+        if getattr(self, "_dist_mode", "nccl") == "p2p":
+            return self.answer_batch_distributed_p2p(d_queries_local)
+        return self.answer_batch_distributed(d_queries_local)
+
+    def answer_dist_host(self, q_pinned: torch.Tensor, out_pinned: torch.Tensor):
+        """End-to-end variant: this rank's queries start in (pinned) host memory and its replies end there."""
+        d = q_pinned.to(self.device, non_blocking=True)
+        out_pinned.copy_(self.answer_dist(d), non_blocking=True)
+        torch.cuda.synchronize(self.device)
+
+    def profile_stages(self, step, flush=None, n=5):
+        """Mean per-stage device times (CUDA events recorded by the library on its launching stream) over n extra
+        steps.  Profiling inserts events between kernels, so those steps run eagerly instead of as one graph."""
+        self.set_profiling(True)
+        acc = {}
+        try:
+            for _ in range(n):
+                if flush is not None:
+                    flush()
+                step()
+                torch.cuda.synchronize(self.device)
+                for nm, v in self.stage_ms().items():
+                    acc.setdefault(nm, []).append(v)
+        finally:
+            self.set_profiling(False)
+        return {nm: sum(v) / len(v) for nm, v in acc.items()}
+
     def scan(self, d_sv_ntt: torch.Tensor, want_rows=True):
         """[Q][dimL][2][k][N] NTT-form last-dimension selection cts -> rows [Q][n_rows][2][k][N] NTT form."""
         Q = d_sv_ntt.shape[0]
@@ -276,6 +328,50 @@ def shard_rows(dim0: int, shard_count: int):
     """Row ranges [lo, hi) of dims[0] per shard — the same split the C library makes (context.cu)."""
     per = -(-dim0 // shard_count)
     return [(min(dim0, per * s), min(dim0, per * s + per)) for s in range(shard_count)]
+
+
+def sampled_parity(srv: "ShardServer", orc, params, elts, keys, query: np.ndarray, reply: np.ndarray):
+    """Parity of one d=2 query at sizes where the oracle cannot process the whole database: (1) the FULL expansion and
+    selection-vector NTT against the oracle; (2) the scan at full size, checked on the first, a middle and the last
+    (possibly short) row against the oracle's scan of those rows of the device database; (3) the upper dimension
+    recomputed by the oracle (re-encode, plaintext NTT, multiply, add, inverse NTT: ct_reencoder.cpp:40-71,
+    database.cpp:213-254) from ALL of the device's row results, against the reply.  srv must be unsharded.
+    Returns (ok, description).  TEST INFRASTRUCTURE: the oracle is only ever the checker."""
+    dims = list(params.dimensions)
+    if len(dims) != 2:
+        return None, "sampled parity only implemented for d=2"
+    d0, dimL = dims
+    dim_sum = d0 + dimL
+    q = np.ascontiguousarray(query)
+    d_q = to_device(q[None], srv.device)
+    sv_gpu_t = srv.expand_ntt(d_q)[0]                                   # [dim_sum][2][k][N], NTT form
+    sv = orc.expand(q, dim_sum, elts, np.ascontiguousarray(keys).reshape(-1))
+    sv_ntt = np.stack([orc.ct_to_ntt(c) for c in sv])
+    ok_exp = bool(np.array_equal(to_host(sv_gpu_t), sv_ntt))
+    rows_gpu = to_host(srv.scan(sv_gpu_t[d0:][None].contiguous()))[0]   # [n_rows][2][k][N], NTT form
+    n_rows = rows_gpu.shape[0]
+    ok_rows = True
+    picked = sorted({0, n_rows // 2, n_rows - 1})
+    for r in picked:
+        cnt = min(dimL, params.num_pt - r * dimL)
+        db_row = srv.db.read_ntt(r * dimL, cnt)
+        want = orc.scan_row(db_row, sv_ntt[d0:d0 + cnt])
+        ok_rows = ok_rows and bool(np.array_equal(rows_gpu[r], want))
+    two_er = reply.shape[0]
+    pts = np.empty((n_rows, two_er, orc.k, orc.N), dtype=np.uint64)
+    for r in range(n_rows):
+        enc = orc.reencode(orc.ct_from_ntt(rows_gpu[r]))
+        for x in range(two_er):
+            pts[r, x] = orc.plain_to_ntt(enc[x])
+    ok_up = True
+    for x in range(two_er):
+        acc = orc.scan_row(np.ascontiguousarray(pts[:, x]), sv_ntt[:n_rows])
+        ok_up = ok_up and bool(np.array_equal(orc.ct_from_ntt(acc), reply[x]))
+    desc = ("query 0 vs the oracle: full expansion + selection-vector NTT %s; scan rows %s of %d at full size %s; "
+            "upper dimension recomputed by the oracle from all device rows %s" % (
+                "identical" if ok_exp else "MISMATCH", picked, n_rows, "identical" if ok_rows else "MISMATCH",
+                "identical" if ok_up else "MISMATCH"))
+    return bool(ok_exp and ok_rows and ok_up), desc
 
 
 def to_device(a: np.ndarray, device) -> torch.Tensor:

@@ -284,13 +284,14 @@ def test_ciphertext_save_load_roundtrip_and_layout(lib):
     assert lib.pirw_ct_save(limbs.ctypes.data_as(u64p), 2, N, k, pid.ctypes.data_as(u64p), 0, None, C.byref(out),
                             C.byref(n)) == 0
     blob = take(lib, out, n)
-    # header {magic 0xA15E, 0, compr none, total size, reserved}; members; nested IntArray header + count + limbs
+    # SEAL 3.5 header {magic 0xA15E, header size 0x10, version 3.5, compr none, reserved, u64 total size}; members;
+    # nested IntArray header + count + limbs
     assert len(blob) == 16 + 32 + 1 + 8 * 3 + 8 + 16 + 8 + limbs.nbytes
-    magic, zero, compr, size, reserved = struct.unpack_from("<HBBIQ", blob, 0)
-    assert (magic, zero, compr, size, reserved) == (0xA15E, 0, 0, len(blob), 0)
+    magic, hsize, vmaj, vmin, compr, reserved, size = struct.unpack_from("<HBBBBHQ", blob, 0)
+    assert (magic, hsize, vmaj, vmin, compr, reserved, size) == (0xA15E, 0x10, 3, 5, 0, 0, len(blob))
     assert blob[16:48] == pid.tobytes() and blob[48] == 0
     assert struct.unpack_from("<QQQd", blob, 49) == (2, N, k, 1.0)
-    assert struct.unpack_from("<HBBIQQ", blob, 81) == (0xA15E, 0, 0, 16 + 8 + limbs.nbytes, 0, limbs.size)
+    assert struct.unpack_from("<HBBBBHQQ", blob, 81) == (0xA15E, 0x10, 3, 5, 0, 0, 16 + 8 + limbs.nbytes, limbs.size)
     assert blob[105:] == limbs.tobytes()
     got = np.zeros_like(limbs)
     pid2 = np.zeros(4, dtype=np.uint64)
@@ -298,6 +299,21 @@ def test_ciphertext_save_load_roundtrip_and_layout(lib):
     assert lib.pirw_ct_load(buf(blob), C.c_size_t(len(blob)), N, MODS.ctypes.data_as(u64p), k,
                             got.ctypes.data_as(u64p), pid2.ctypes.data_as(u64p), C.byref(ntt), C.byref(seeded)) == 0
     assert np.array_equal(got, limbs) and np.array_equal(pid, pid2) and ntt.value == 0 and seeded.value == 0
+    # the loader also accepts the legacy SEAL 3.4 header {magic, 0, compr, u32 size, u64 reserved}, as SEAL 3.5's
+    # LoadHeader does, and rejects a foreign version or header size
+    def legacy(b, off):
+        size = struct.unpack_from("<Q", b, off + 8)[0]
+        return b[:off] + struct.pack("<HBBIQ", 0xA15E, 0, 0, size, 0) + b[off + 16:]
+    old = legacy(legacy(blob, 81), 0)
+    got2 = np.zeros_like(limbs)
+    assert lib.pirw_ct_load(buf(old), C.c_size_t(len(old)), N, MODS.ctypes.data_as(u64p), k,
+                            got2.ctypes.data_as(u64p), pid2.ctypes.data_as(u64p), C.byref(ntt), C.byref(seeded)) == 0
+    assert np.array_equal(got2, limbs)
+    for off, val in ((2, 0x18), (3, 4), (4, 6)):
+        bad = bytearray(blob)
+        bad[off] = val
+        assert lib.pirw_ct_load(buf(bytes(bad)), C.c_size_t(len(bad)), N, MODS.ctypes.data_as(u64p), k,
+                                got2.ctypes.data_as(u64p), pid2.ctypes.data_as(u64p), C.byref(ntt), C.byref(seeded)) != 0
     # malformed inputs are InvalidArgument (serialization.h:113-115), never a crash
     bad_magic = b"\x00" + blob[1:]
     too_big = bytearray(blob)
