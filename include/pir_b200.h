@@ -148,6 +148,34 @@ int pirb_multiply_partial_xbuf_dev(pirb_ctx* ctx, const uint64_t* d_sv_ntt, uint
                                    void* stream);
 int pirb_reduce_finish_xbuf_dev(pirb_ctx* ctx, uint32_t slot, uint32_t q_first, uint32_t q_count, uint64_t* d_replies,
                                 void* stream);
+/* Row-sharded serving with the exchange done by the kernels themselves over NVLink peer memory (replaces
+ * the NCCL gathers of the flow above for databases of d >= 2 dimensions).  Every rank (= context with shard_index r of
+ * shard_count) owns ONE exchange block — flags, two selection-vector slots, two partial-reply slots — that all peers
+ * map.  pirb_dist_create allocates it (max_local_queries = queries a rank brings to a step; sub_batch = local queries
+ * per pipelined sub-batch, 0 = default) and returns its CUDA IPC handle (ranks in separate processes: exchange the
+ * handles, then pirb_dist_open_ipc) and its base pointer (contexts of one process on peer-accessible devices:
+ * pirb_dist_attach with everybody's base pointers).  pirb_dist_answer* then runs one step: this rank's n_local
+ * queries (ALL ranks must call it with the same n_local, in lockstep) -> this rank's replies.  The rank expands its own
+ * queries; the selection-vector NTT kernel stores its output directly into every peer's slot (first-dimension entries
+ * only at the row's owner) and raises per-sub-batch flags; every rank multiplies all ranks' queries against its rows
+ * as soon as a sub-batch has arrived from everyone; the partial replies are added mod q by loads from the peers'
+ * partial slots inside the reduce kernel and go through the final inverse NTT (database.cpp:250-254).  A flag that
+ * does not arrive within the timeout (PIRB_DIST_TIMEOUT_MS, default 20 s) makes pirb_dist_status return 13. */
+int pirb_dist_create(pirb_ctx* ctx, uint32_t max_local_queries, uint32_t sub_batch, uint8_t* ipc_handle_out /*[64] or NULL*/,
+                     void** base_out /* or NULL */);
+int pirb_dist_open_ipc(pirb_ctx* ctx, const uint8_t* ipc_handles /*[n_ranks][64]*/, uint32_t n_ranks, uint32_t self_rank);
+int pirb_dist_attach(pirb_ctx* ctx, void* const* peer_bases /*[n_ranks]*/, uint32_t n_ranks, uint32_t self_rank);
+/* device-accessible buffers, asynchronous on `stream` (NULL: the context's stream) */
+int pirb_dist_answer_dev(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_local, uint64_t n_ct,
+                         uint64_t* d_replies, void* stream);
+/* host buffers (page-locked ones are used in place), synchronous; returns pirb_dist_status */
+int pirb_dist_answer(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* queries, uint32_t n_local, uint64_t n_ct,
+                     uint64_t* replies);
+int pirb_dist_status(pirb_ctx* ctx);
+/* device times of the last profiled step: 0 expansion, 1 exchange tail after the expansion, 2 start -> first sub-batch
+ * of every rank has arrived, 3 multiplies, 4 partial-reply reduce + inverse NTT, 5 whole step */
+int pirb_dist_stage_ms(pirb_ctx* ctx, float* out_ms /*[6]*/);
+
 /* Scan only (the HBM-bound kernel): d_sv_ntt[n_queries][dims[d-1]][2][k][N] NTT form -> rows in NTT form.
  * Used by the bench to time the scan in isolation.  d_rows may be NULL (internal scratch). */
 int pirb_scan_dev(pirb_ctx* ctx, const uint64_t* d_sv_ntt, uint32_t n_queries, uint64_t* d_rows, void* stream);

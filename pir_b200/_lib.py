@@ -16,6 +16,7 @@ PIRB_MAX_MODULI = 9
 PIRB_MAX_DIMS = 8
 PIRB_N_STAGES = 6
 STAGE_NAMES = ("expand", "sv_ntt", "scan", "row_intt", "upper_dims", "total")
+DIST_STAGE_NAMES = ("expand", "exchange_tail", "first_subbatch_arrived", "multiply", "reduce", "total")
 
 
 class pirb_params(C.Structure):
@@ -75,6 +76,13 @@ SYMBOLS = {
                                                C.c_void_p]),
     "pirb_multiply_partial_xbuf_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "pirb_reduce_finish_xbuf_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "pirb_dist_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pirb_dist_open_ipc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "pirb_dist_attach": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32]),
+    "pirb_dist_answer_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "pirb_dist_answer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]),
+    "pirb_dist_status": (C.c_int, [C.c_void_p]),
+    "pirb_dist_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pirb_scan_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "pirb_sync": (C.c_int, [C.c_void_p]),
     "pirb_debug_stamps": (C.c_int, [C.c_void_p, u64p, C.c_uint64]),

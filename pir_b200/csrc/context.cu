@@ -150,12 +150,35 @@ struct pirb_ctx {
   std::vector<void*> xpeer_open;  // mappings to close
   DevBuf xptrs;                   // device table [n_ranks] of base pointers (own + peers)
   u32 xranks = 0;
+  // Multi-GPU exchange over NVLink peer memory (pirb_dist_*): one block per rank that every peer maps:
+  //   [ flags: err | sv[n_sub][n_ranks] | part[n_sub][n_ranks] ] [ sv slot 0 | sv slot 1 ] [ partial slot 0 | slot 1 ]
+  struct Dist {
+    bool ready = false, ipc = false;
+    u32 n_ranks = 0, rank = 0, max_local = 0, n_sub = 0, sub_q = 0;  // sub_q = local queries per sub-batch
+    u32 rows_per_rank = 0;
+    u64 sv_qstride = 0;                       // limbs per query in a selection-vector slot (compact layout)
+    u64 flag_limbs = 0, sv_slot_limbs = 0, part_slot_limbs = 0;
+    u64* base = nullptr;
+    size_t bytes = 0;
+    std::vector<u64*> peer_base;
+    std::vector<void*> opened;                // IPC mappings to close
+    DevBuf peer_table;
+    u64 step = 0;
+    cudaStream_t prod = nullptr, xfer = nullptr, cons = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_prod = nullptr, ev_xfer = nullptr, ev_done[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_exp;          // per sub-batch: expansion finished (prod -> xfer)
+    bool done_valid[2] = {false, false}, xfer_valid = false;
+    cudaEvent_t prof[6] = {};                 // step start, expansion end, exchange end, multiply start/end, step end
+    bool prof_valid = false;
+    u64 timeout_ns = 20ull * 1000 * 1000 * 1000;
+    u64 launches = 0;
+  } dist;
   DevBuf dbg;            // PIRB_DEBUG_STAMPS=<level>: clock64 phase stamps of that expansion level
   int dbg_level = -1;
   bool use_cluster = false;  // one-launch-per-level key switch on thread-block clusters
   pirb_ctx() {
     for (DevBuf* b : {&db, &stage, &work, &dig, &acc, &xch, &part, &bufA[0], &bufA[1], &pts, &qbuf, &rbuf, &svbuf, &xptrs,
-                      &dbg})
+                      &dbg, &dist.peer_table})
       b->epoch = &alloc_epoch;
   }
 };
@@ -236,9 +259,14 @@ ExpandPlan* get_plan(pirb_ctx* c, u64 total_items, int single, int* rc, int t_fi
 
 // Expansion of n_queries x n_trees root ciphertexts (contiguous at d_query) into c->work.
 // Result: work[qi*q_stride + i*ctL] for i < total_items (S region), coefficient form.
+// lvl_lo / lvl_hi and q_first / q_count restrict the call to tree levels [lvl_lo, lvl_hi) of queries
+// [q_first, q_first + q_count) of the batch (the workspaces are always sized for the whole batch): the multi-GPU flow
+// runs the small top levels for all queries at once and the wide bottom levels per sub-batch.
 int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_query, int n_queries,
-               cudaStream_t st) {
+               cudaStream_t st, int lvl_lo = 0, int lvl_hi = -1, int q_first = 0, int q_count = -1) {
   const u64 q_stride = 2 * pl->cap * c->ctL;
+  if (lvl_hi < 0) lvl_hi = pl->max_logm;
+  if (q_count < 0) q_count = n_queries - q_first;
   RC(c->work.ensure((size_t)n_queries * q_stride * sizeof(u64)));
   const u64 nodes = pl->max_nodes * n_queries;
   if (c->use_cluster) {
@@ -247,9 +275,11 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
     RC(c->dig.ensure((size_t)std::max<u64>(nodes, 1) * (c->k + 1) * c->k * c->N * sizeof(u64)));
     RC(c->acc.ensure((size_t)std::max<u64>(nodes, 1) * 2 * (c->k + 1) * c->N * sizeof(u64)));
   }
-  LAUNCH(c, launch_place_roots(c->P, d_query + (u64)pl->t_first * c->ctL, (u64)pl->n_ct_in * c->ctL, c->work.p,
-                               pl->d_off.p, pl->n_trees, n_queries, q_stride, st));
-  for (int j = 0; j < pl->max_logm; ++j) {
+  u64* work = c->work.p + (u64)q_first * q_stride;
+  if (lvl_lo == 0)
+    LAUNCH(c, launch_place_roots(c->P, d_query + ((u64)q_first * pl->n_ct_in + pl->t_first) * c->ctL,
+                                 (u64)pl->n_ct_in * c->ctL, work, pl->d_off.p, pl->n_trees, q_count, q_stride, st));
+  for (int j = lvl_lo; j < lvl_hi; ++j) {
     const u32 g = (c->N >> j) + 1;
     if (!keys) return fail(PIRB_INTERNAL, "Galois keys required");
     const u64* key = keys->find(g);
@@ -261,17 +291,17 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
     L.j = j;
     L.ginv = inv_mod_2n(g, c->N);
     L.q_stride = q_stride;
-    L.n_queries = n_queries;
+    L.n_queries = q_count;
     L.xch = c->xch.p;
     L.dbg = !c->dbg.p ? nullptr : (c->dbg_level == -2 ? c->dbg.p + (size_t)j * 65536 : (j == c->dbg_level ? c->dbg.p : nullptr));
     L.dbg_clock = (c->dbg_level >= 0 && getenv("PIRB_STAMP_CLOCK")) ? atoi(getenv("PIRB_STAMP_CLOCK")) : 0;
-    const int n_nodes = (n_queries * L.n_trees) << j;
+    const int n_nodes = (q_count * L.n_trees) << j;
     if (c->use_cluster) {
-      LAUNCH(c, launch_ks_level_cluster(c->P, c->work.p, L, key, 0, st));
+      LAUNCH(c, launch_ks_level_cluster(c->P, work, L, key, 0, st));
     } else {
-      LAUNCH(c, launch_ks_digits(c->P, c->work.p, L, c->dig.p, st));
+      LAUNCH(c, launch_ks_digits(c->P, work, L, c->dig.p, st));
       LAUNCH(c, launch_ks_mac_intt(c->P, c->dig.p, key, c->acc.p, n_nodes, st));
-      LAUNCH(c, launch_ks_combine(c->P, c->work.p, L, c->acc.p, 0, st));
+      LAUNCH(c, launch_ks_combine(c->P, work, L, c->acc.p, 0, st));
     }
   }
   return 0;
@@ -282,8 +312,10 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
 // or (partial != 0) the NTT-form sum over this shard's rows, to be reduced across shards.
 // sv_item0 / sv_items: index of the first selection ciphertext stored at d_sv and how many are stored (a d=1 shard
 // only holds the expansion of its own trees).
+// compact_rows != 0: the per-query selection vector holds only this shard's rows of the first dimension (compact_rows
+// slots, own row r at slot r - top_lo) followed by the other dimensions — the layout of the multi-GPU exchange slots.
 int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_out, int partial, cudaStream_t st,
-                 bool sv_is_ntt = false, u64 sv_item0 = 0, u64 sv_items = ~0ull) {
+                 bool sv_is_ntt = false, u64 sv_item0 = 0, u64 sv_items = ~0ull, u32 compact_rows = 0) {
   if (sv_items == ~0ull) sv_items = c->dim_sum;
   const int d = c->d, k = c->k;
   const u64 ctL = c->ctL;
@@ -332,8 +364,8 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   } else {
     dimL = c->dims[d - 1];
     n_rows = (u32)((npt + dimL - 1) / dimL);
-    u64 off = 0;
-    for (int e = 0; e < d - 1; ++e) off += c->dims[e];
+    u64 off = compact_rows ? compact_rows : c->dims[0];
+    for (int e = 1; e < d - 1; ++e) off += c->dims[e];
     sv_last = d_sv + off * ctL;
   }
   int n_split;
@@ -367,8 +399,8 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
     const u32 dim = (l == 0) ? (c->top_hi - c->top_lo) : c->dims[l];
     const u32 n_groups = (n_entries + dim - 1) / dim;
     const u32 w_out = w * c->two_er;
-    u64 sv_off = (l == 0) ? c->top_lo : 0;
-    for (int e = 0; e < l; ++e) sv_off += c->dims[e];
+    u64 sv_off = (l == 0) ? (compact_rows ? 0 : c->top_lo) : (compact_rows ? compact_rows : c->dims[0]);
+    for (int e = 1; e < l; ++e) sv_off += c->dims[e];
     const u64 n_cts_in = (u64)n_entries * w;  // per query, contiguous
     RC(c->pts.ensure((size_t)n_queries * n_cts_in * c->two_er * c->ptL * sizeof(u64)));
     LAUNCH(c, launch_reencode_ntt(P, c->bufA[cur].p, c->pts.p, (int)(n_queries * n_cts_in), st));
@@ -717,6 +749,18 @@ void pirb_ctx_destroy(pirb_ctx* c) {
   for (auto& kv : c->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* pm : c->xpeer_open) cudaIpcCloseMemHandle(pm);
+  {
+    pirb_ctx::Dist& D = c->dist;
+    for (void* pm : D.opened) cudaIpcCloseMemHandle(pm);
+    if (D.base) cudaFree(D.base);
+    for (cudaStream_t s_ : {D.prod, D.xfer, D.cons})
+      if (s_) cudaStreamDestroy(s_);
+    for (cudaEvent_t e_ : {D.ev_in, D.ev_prod, D.ev_xfer, D.ev_done[0], D.ev_done[1]})
+      if (e_) cudaEventDestroy(e_);
+    for (cudaEvent_t e_ : D.ev_exp) cudaEventDestroy(e_);
+    for (cudaEvent_t e_ : D.prof)
+      if (e_) cudaEventDestroy(e_);
+  }
   if (c->xbuf) cudaFree(c->xbuf);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->side) cudaStreamDestroy(c->side);
@@ -1155,6 +1199,284 @@ int pirb_reduce_finish_xbuf_dev(pirb_ctx* c, uint32_t slot, uint32_t q_first, ui
   LAUNCH(c, launch_modadd_reduce_ptrs(c->P, reinterpret_cast<const u64* const*>(c->xptrs.p), (int)c->xranks, off, c->rbuf.p,
                                       cts, st));
   LAUNCH(c, launch_ntt_inv(c->P, c->rbuf.p, U(d_replies), (int)(cts * 2 * c->k), c->k, 0, 1, 0, 1, 0, 0, st));
+  return 0;
+}
+
+// ---- row-sharded serving with the exchange done by the kernels over NVLink peer memory ----------------
+// Per step and rank (all ranks run the same number of local queries in lockstep):
+//   producer stream  oblivious expansion of the rank's own queries: top levels for all of them at once, the wide
+//                    bottom levels per sub-batch;
+//   transfer stream  per sub-batch: selection-vector NTT whose stores land in every peer's slot (first-dimension
+//                    entries only at the row's owner), then a flag in every peer's block;
+//   consumer stream  per sub-batch: wait for all ranks' flags, scan + re-encode + upper dimensions of the shard's rows
+//                    for the n_ranks * sub_q queries of the sub-batch, partial replies into the own partial slot, flag;
+//                    finally, per sub-batch: wait for all ranks' partial flags, mod-q add of the peers' partials for
+//                    the own queries (loads over NVLink inside the kernel) and the final inverse NTT.
+// Two slots alternate between steps; a rank reuses a slot only after its own consumer has finished the step that last
+// used it, which (through the partial flags) implies every peer has finished reading that slot too.
+static int dist_layout(pirb_ctx* c, u32 max_local, u32 sub_q) {
+  pirb_ctx::Dist& D = c->dist;
+  D.n_ranks = c->prm.shard_count;
+  D.rank = c->prm.shard_index;
+  D.max_local = max_local;
+  D.sub_q = sub_q;
+  D.n_sub = (max_local + sub_q - 1) / sub_q;
+  D.rows_per_rank = (c->dims[0] + D.n_ranks - 1) / D.n_ranks;
+  u64 rest = 0;
+  for (int e = 1; e < c->d; ++e) rest += c->dims[e];
+  D.sv_qstride = ((u64)D.rows_per_rank + rest) * c->ctL;
+  D.flag_limbs = ((1 + 2ull * D.n_sub * D.n_ranks) + 15) / 16 * 16;
+  const u64 slot_queries = (u64)D.n_sub * D.sub_q * D.n_ranks;
+  D.sv_slot_limbs = slot_queries * D.sv_qstride;
+  D.part_slot_limbs = slot_queries * c->reply_cts * c->ctL;
+  D.bytes = (D.flag_limbs + 2 * D.sv_slot_limbs + 2 * D.part_slot_limbs) * sizeof(u64);
+  return 0;
+}
+static u64 dist_flag_off(const pirb_ctx::Dist& D, int kind, u32 sub, u32 src) {  // kind 0: selection vectors, 1: partials
+  return 1 + ((u64)kind * D.n_sub + sub) * D.n_ranks + src;
+}
+static u64 dist_sv_off(const pirb_ctx::Dist& D, int slot) { return D.flag_limbs + (u64)slot * D.sv_slot_limbs; }
+static u64 dist_part_off(const pirb_ctx::Dist& D, int slot) {
+  return D.flag_limbs + 2 * D.sv_slot_limbs + (u64)slot * D.part_slot_limbs;
+}
+
+int pirb_dist_create(pirb_ctx* c, uint32_t max_local_queries, uint32_t sub_batch, uint8_t* ipc_handle_out,
+                     void** base_out) {
+  if (!c || !max_local_queries) return fail(PIRB_INVALID_ARGUMENT, "bad argument");
+  if (c->d < 2) return fail(PIRB_INVALID_ARGUMENT, "the peer-memory exchange serves databases of two or more dimensions");
+  CU(cudaSetDevice(c->device));
+  pirb_ctx::Dist& D = c->dist;
+  if (D.base) return fail(PIRB_INVALID_ARGUMENT, "exchange block already created");
+  if (!sub_batch) {  // default: up to four sub-batches per step, never more than there are ranks
+    const u32 n_sub = std::max<u32>(1, std::min<u32>(std::min<u32>(4, c->prm.shard_count), max_local_queries));
+    sub_batch = (max_local_queries + n_sub - 1) / n_sub;
+  }
+  RC(dist_layout(c, max_local_queries, std::min(sub_batch, max_local_queries)));
+  CU(cudaMalloc(&D.base, D.bytes));
+  CU(cudaMemset(D.base, 0, D.flag_limbs * sizeof(u64)));
+  int lo = 0, hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
+  CU(cudaStreamCreateWithPriority(&D.prod, cudaStreamNonBlocking, hi));
+  CU(cudaStreamCreateWithPriority(&D.xfer, cudaStreamNonBlocking, hi));
+  CU(cudaStreamCreateWithPriority(&D.cons, cudaStreamNonBlocking, lo));
+  for (cudaEvent_t* e : {&D.ev_in, &D.ev_prod, &D.ev_xfer, &D.ev_done[0], &D.ev_done[1]})
+    CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  D.ev_exp.resize(D.n_sub);
+  for (auto& e : D.ev_exp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : D.prof) CU(cudaEventCreate(&e));
+  if (const char* e = getenv("PIRB_DIST_TIMEOUT_MS")) D.timeout_ns = (u64)atoll(e) * 1000000ull;
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, D.base));
+    memcpy(ipc_handle_out, &h, 64);
+  }
+  if (base_out) *base_out = D.base;
+  return 0;
+}
+
+static int dist_finish_attach(pirb_ctx* c, const std::vector<u64*>& table) {
+  pirb_ctx::Dist& D = c->dist;
+  D.peer_base = table;
+  RC(D.peer_table.ensure(table.size() * sizeof(u64*)));
+  CU(cudaMemcpy(D.peer_table.p, table.data(), table.size() * sizeof(u64*), cudaMemcpyHostToDevice));
+  D.ready = true;
+  return 0;
+}
+
+int pirb_dist_open_ipc(pirb_ctx* c, const uint8_t* handles, uint32_t n_ranks, uint32_t self_rank) {
+  if (!c || !handles || !c->dist.base) return fail(PIRB_INVALID_ARGUMENT, "exchange block not created");
+  if (n_ranks != c->prm.shard_count || self_rank != c->prm.shard_index)
+    return fail(PIRB_INVALID_ARGUMENT, "ranks must match the context's shard index/count");
+  CU(cudaSetDevice(c->device));
+  std::vector<u64*> table(n_ranks);
+  for (u32 r = 0; r < n_ranks; ++r) {
+    if (r == self_rank) { table[r] = c->dist.base; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, 64);
+    void* pm = nullptr;
+    CU(cudaIpcOpenMemHandle(&pm, h, cudaIpcMemLazyEnablePeerAccess));
+    c->dist.opened.push_back(pm);
+    table[r] = (u64*)pm;
+  }
+  c->dist.ipc = true;
+  return dist_finish_attach(c, table);
+}
+
+int pirb_dist_attach(pirb_ctx* c, void* const* peer_bases, uint32_t n_ranks, uint32_t self_rank) {
+  if (!c || !peer_bases || !c->dist.base) return fail(PIRB_INVALID_ARGUMENT, "exchange block not created");
+  if (n_ranks != c->prm.shard_count || self_rank != c->prm.shard_index)
+    return fail(PIRB_INVALID_ARGUMENT, "ranks must match the context's shard index/count");
+  if (peer_bases[self_rank] != c->dist.base) return fail(PIRB_INVALID_ARGUMENT, "own entry must be this context's block");
+  CU(cudaSetDevice(c->device));
+  std::vector<u64*> table(n_ranks);
+  for (u32 r = 0; r < n_ranks; ++r) {
+    table[r] = (u64*)peer_bases[r];
+    cudaPointerAttributes a;
+    CU(cudaPointerGetAttributes(&a, peer_bases[r]));
+    if (a.type != cudaMemoryTypeDevice) return fail(PIRB_INVALID_ARGUMENT, "peer block is not device memory");
+    if (a.device != c->device) {  // same process, another GPU: direct peer access over NVLink
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, c->device, a.device));
+      if (!can) return fail(PIRB_INTERNAL, "no peer access between devices " + std::to_string(c->device) + " and " + std::to_string(a.device));
+      cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+      cudaGetLastError();
+    }
+  }
+  return dist_finish_attach(c, table);
+}
+
+// one step of the flow above; d_queries / d_replies are device-accessible (device memory or page-locked host memory)
+static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u32 n_local, u64 n_ct, u64* d_replies,
+                     cudaStream_t user) {
+  pirb_ctx::Dist& D = c->dist;
+  if (!D.ready) return fail(PIRB_INVALID_ARGUMENT, "exchange block not attached (pirb_dist_open_ipc / pirb_dist_attach)");
+  if (!n_local || n_local > D.max_local) return fail(PIRB_INVALID_ARGUMENT, "local batch size out of range");
+  if (n_ct != c->dim_sum / c->N + 1)
+    return fail(PIRB_INVALID_ARGUMENT, "Number of ciphertexts doesn't match number of items for oblivious expansion.");
+  if (c->loaded != c->pt_count) return fail(PIRB_INVALID_ARGUMENT, "database size mismatch");
+  int rc;
+  ExpandPlan* pl = get_plan(c, c->dim_sum, 0, &rc);
+  if (!pl) return rc;
+  const u64 seq = ++D.step;
+  const int slot = (int)(seq & 1);
+  const u32 W = D.n_ranks, SB = D.sub_q;
+  const u32 n_sub = (n_local + SB - 1) / SB;
+  const u64 q_stride = 2 * pl->cap * c->ctL;
+  u64* const* peers = reinterpret_cast<u64* const*>(D.peer_table.p);
+  u64* err = D.base;  // flag word 0
+  c->launches = 0;
+  const bool prof = c->profiling;
+
+  // order: behind the caller's stream, behind the previous user of this slot, behind the last read of c->work
+  CU(cudaEventRecord(D.ev_in, user));
+  CU(cudaStreamWaitEvent(D.prod, D.ev_in, 0));
+  CU(cudaStreamWaitEvent(D.cons, D.ev_in, 0));
+  if (D.done_valid[slot]) CU(cudaStreamWaitEvent(D.prod, D.ev_done[slot], 0));
+  if (D.xfer_valid) CU(cudaStreamWaitEvent(D.prod, D.ev_xfer, 0));
+  if (prof) cudaEventRecord(D.prof[0], D.prod);
+
+  // top levels for the whole local batch while they are too narrow to fill the GPU per sub-batch
+  int split = 0;
+  while (split < pl->max_logm && ((u64)SB * pl->n_trees << split) * 2 * (c->k + 1) < 2ull * c->sm_count) ++split;
+  if (n_sub == 1) split = pl->max_logm;
+  RC(run_expand(c, keys, pl, d_queries, (int)n_local, D.prod, 0, split, 0, (int)n_local));
+  for (u32 sb = 0; sb < n_sub; ++sb) {
+    const u32 q0 = sb * SB, qn = std::min(SB, n_local - q0);
+    if (split < pl->max_logm) RC(run_expand(c, keys, pl, d_queries, (int)n_local, D.prod, split, pl->max_logm, (int)q0, (int)qn));
+    CU(cudaEventRecord(D.ev_exp[sb], D.prod));
+    CU(cudaStreamWaitEvent(D.xfer, D.ev_exp[sb], 0));
+    PushArgs A;
+    A.peers = peers;
+    A.n_ranks = W;
+    A.d0 = c->dims[0];
+    A.rows_per_rank = D.rows_per_rank;
+    A.slot_off = dist_sv_off(D, slot);
+    A.g_first = ((u64)sb * W + D.rank) * SB;
+    A.dst_qstride = D.sv_qstride;
+    LAUNCH(c, launch_ntt_fwd_push(c->P, c->work.p + (u64)q0 * q_stride, q_stride, (u32)c->dim_sum, qn, A, D.xfer));
+    LAUNCH(c, launch_signal(peers, W, dist_flag_off(D, 0, sb, D.rank), seq, D.xfer));
+  }
+  if (prof) cudaEventRecord(D.prof[1], D.prod);
+  CU(cudaEventRecord(D.ev_xfer, D.xfer));
+  D.xfer_valid = true;
+  if (prof) cudaEventRecord(D.prof[2], D.xfer);
+
+  // consumer: every sub-batch holds W * SB queries (rank-major), contiguous in the slot
+  for (u32 sb = 0; sb < n_sub; ++sb) {
+    const u32 qn = std::min(SB, n_local - sb * SB);
+    LAUNCH(c, launch_wait(D.base + dist_flag_off(D, 0, sb, 0), W, seq, D.timeout_ns, err, D.cons));
+    if (prof && sb == 0) cudaEventRecord(D.prof[3], D.cons);
+    const u64 g0 = (u64)sb * W * SB;
+    if (qn == SB) {
+      RC(run_multiply(c, D.base + dist_sv_off(D, slot) + g0 * D.sv_qstride, D.sv_qstride, (int)(W * SB),
+                      D.base + dist_part_off(D, slot) + g0 * c->reply_cts * c->ctL, 1, D.cons, true, 0, ~0ull,
+                      D.rows_per_rank));
+    } else {  // ragged last sub-batch: the ranks' queries are not contiguous, one multiply per rank
+      for (u32 r = 0; r < W; ++r)
+        RC(run_multiply(c, D.base + dist_sv_off(D, slot) + (g0 + (u64)r * SB) * D.sv_qstride, D.sv_qstride, (int)qn,
+                        D.base + dist_part_off(D, slot) + (g0 + (u64)r * SB) * c->reply_cts * c->ctL, 1, D.cons, true, 0,
+                        ~0ull, D.rows_per_rank));
+    }
+    LAUNCH(c, launch_signal(peers, W, dist_flag_off(D, 1, sb, D.rank), seq, D.cons));
+  }
+  if (prof) cudaEventRecord(D.prof[4], D.cons);
+  for (u32 sb = 0; sb < n_sub; ++sb) {
+    const u32 q0 = sb * SB, qn = std::min(SB, n_local - q0);
+    LAUNCH(c, launch_wait(D.base + dist_flag_off(D, 1, sb, 0), W, seq, D.timeout_ns, err, D.cons));
+    const u64 cts = (u64)qn * c->reply_cts;
+    RC(c->rbuf.ensure((size_t)D.max_local * c->reply_cts * c->ctL * sizeof(u64)));
+    const u64 off = dist_part_off(D, slot) + (((u64)sb * W + D.rank) * SB) * c->reply_cts * c->ctL;
+    LAUNCH(c, launch_modadd_reduce_ptrs(c->P, reinterpret_cast<const u64* const*>(D.peer_table.p), (int)W, off,
+                                        c->rbuf.p + (u64)q0 * c->reply_cts * c->ctL, cts, D.cons));
+    LAUNCH(c, launch_ntt_inv(c->P, c->rbuf.p + (u64)q0 * c->reply_cts * c->ctL, d_replies + (u64)q0 * c->reply_cts * c->ctL,
+                             (int)(cts * 2 * c->k), c->k, 0, 1, 0, 1, 0, 0, D.cons));
+  }
+  if (prof) cudaEventRecord(D.prof[5], D.cons);
+  D.prof_valid = prof;
+  CU(cudaEventRecord(D.ev_done[slot], D.cons));
+  D.done_valid[slot] = true;
+  CU(cudaStreamWaitEvent(user, D.ev_done[slot], 0));
+  CU(cudaStreamWaitEvent(user, D.ev_xfer, 0));
+  D.launches = c->launches;
+  return 0;
+}
+
+int pirb_dist_answer_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_local, uint64_t n_ct,
+                         uint64_t* d_replies, void* stream) {
+  if (!c || !d_queries || !d_replies) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  DevCallOrder order(c, st);
+  return dist_step(c, keys, U(d_queries), n_local, n_ct, U(d_replies), st);
+}
+
+int pirb_dist_answer(pirb_ctx* c, const pirb_keys* keys, const uint64_t* queries, uint32_t n_local, uint64_t n_ct,
+                     uint64_t* replies) {
+  if (!c || !queries || !replies) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const size_t qbytes = (size_t)n_local * n_ct * c->ctL * sizeof(u64);
+  const size_t rbytes = (size_t)n_local * c->reply_cts * c->ctL * sizeof(u64);
+  // page-locked buffers are read / written in place by the first / last kernels, pageable ones are staged
+  const bool q_direct = host_buffer_is_device_accessible(queries);
+  const bool r_direct = host_buffer_is_device_accessible(replies);
+  DevCallOrder order(c, st);
+  if (!q_direct) {
+    RC(c->qbuf.ensure(std::max<size_t>(qbytes, 256)));
+    CU(cudaMemcpyAsync(c->qbuf.p, queries, qbytes, cudaMemcpyHostToDevice, st));
+  }
+  if (!r_direct) RC(c->svbuf.ensure(std::max<size_t>(rbytes, 256)));
+  RC(dist_step(c, keys, q_direct ? U(queries) : c->qbuf.p, n_local, n_ct, r_direct ? U(replies) : c->svbuf.p, st));
+  if (!r_direct) CU(cudaMemcpyAsync(replies, c->svbuf.p, rbytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return pirb_dist_status(c);
+}
+
+int pirb_dist_status(pirb_ctx* c) {
+  if (!c || !c->dist.base) return fail(PIRB_INVALID_ARGUMENT, "exchange block not created");
+  CU(cudaSetDevice(c->device));
+  u64 e = 0;
+  CU(cudaMemcpy(&e, c->dist.base, sizeof(u64), cudaMemcpyDeviceToHost));
+  if (e) return fail(PIRB_INTERNAL, "peer exchange timed out waiting for a rank's flag at step " + std::to_string(e));
+  return 0;
+}
+
+// stage: 0 expansion (producer stream), 1 tail of the exchange after the expansion, 2 wait for the first sub-batch of
+// all ranks, 3 multiplies, 4 partial-reply reduce + inverse NTT, 5 whole step
+int pirb_dist_stage_ms(pirb_ctx* c, float* out) {
+  if (!c || !out) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  pirb_ctx::Dist& D = c->dist;
+  if (!D.prof_valid) return fail(PIRB_INVALID_ARGUMENT, "no profiled distributed step recorded");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(D.prof[5]));
+  CU(cudaEventSynchronize(D.prof[2]));
+  CU(cudaEventElapsedTime(out + 0, D.prof[0], D.prof[1]));
+  CU(cudaEventElapsedTime(out + 1, D.prof[1], D.prof[2]));
+  CU(cudaEventElapsedTime(out + 2, D.prof[0], D.prof[3]));
+  CU(cudaEventElapsedTime(out + 3, D.prof[3], D.prof[4]));
+  CU(cudaEventElapsedTime(out + 4, D.prof[4], D.prof[5]));
+  CU(cudaEventElapsedTime(out + 5, D.prof[0], D.prof[5]));
   return 0;
 }
 

@@ -78,6 +78,26 @@ cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peer
 cudaError_t launch_place_roots(const DevParams& P, const u64* query, u64 query_qstride, u64* work, const u64* root_off,
                                int n_trees, int n_queries, u64 q_stride, cudaStream_t st);
 
+// ---- cross-GPU exchange over NVLink peer memory (kernels_dist.cu) ----
+// Every rank owns one exchange block (flags, selection-vector slots, partial-reply slots) that all peers map.
+struct PushArgs {
+  u64* const* peers;   // device array [n_ranks]: base pointers of the ranks' exchange blocks (own included)
+  u32 n_ranks;
+  u32 d0;              // dims[0]
+  u32 rows_per_rank;   // ceil(d0 / n_ranks): rank r owns rows [r * rows_per_rank, ...) of the first dimension
+  u64 slot_off;        // limb offset of the destination slot inside every rank's block
+  u64 g_first;         // position of this launch's first query in the slot's query order
+  u64 dst_qstride;     // limbs per query in the slot: (rows_per_rank + dims[1] + ... + dims[d-1]) * ct_limbs
+};
+// forward NTT of the first n_entries selection ciphertexts of n_queries queries (in: coefficient form, in_qstride limbs
+// apart) with the outputs stored into the peers' slots in the compact layout [own rows of dim 0 | dims 1..]
+cudaError_t launch_ntt_fwd_push(const DevParams& P, const u64* in, u64 in_qstride, u32 n_entries, u32 n_queries,
+                                const PushArgs& A, cudaStream_t st);
+// flag[off] = value in every rank's block (release, system scope), ordered after the stream's earlier kernels
+cudaError_t launch_signal(u64* const* peers_dev, u32 n_ranks, u64 flag_off_limbs, u64 value, cudaStream_t st);
+// spin until flags[0..n_ranks) >= value (acquire, system scope); after timeout_ns sets *err and returns
+cudaError_t launch_wait(const u64* flags, u32 n_ranks, u64 value, u64 timeout_ns, u64* err, cudaStream_t st);
+
 // StringEncoder packing on the device: raw item bytes -> plaintext coefficients [n_pt][N]
 cudaError_t launch_pack_items(const u8* bytes, u64* coeffs, u32 N, u32 bits, u64 bytes_per_pt, u64 total_bytes,
                               u64 n_pt, cudaStream_t st);

@@ -1,0 +1,143 @@
+// kernels_dist.cu — the cross-GPU exchange of the row-sharded answer path, done by the kernels themselves over
+// NVLink peer memory.  No collective library is on the data path.
+//
+//   k_ntt_fwd_push   transform_to_ntt_inplace of the expanded selection vector (database.cpp:190,222) whose OUTPUT
+//                    stores go straight into the peers' mapped exchange buffers: first-dimension entries only to the
+//                    rank that owns the row, entries of the other dimensions to every rank (they multiply every row).
+//   k_signal         after a producer kernel: publish a sequence number in every peer's flag block (release, system
+//                    scope).  Stream order puts it behind the producer's stores.
+//   k_wait           before a consumer kernel: spin (acquire, system scope) until every rank's flag has reached the
+//                    sequence number; bounded by a timeout that raises an error word instead of hanging the GPU.
+#include <set>
+#include <type_traits>
+#include <utility>
+
+#include "kernels.cuh"
+#include "pirb_device.cuh"
+
+namespace pirb {
+
+template <int LOGN>
+struct DCfg {
+  static constexpr int N = 1 << LOGN;
+  static constexpr int NT = (N / 8 < 512) ? N / 8 : 512;
+  static constexpr size_t SMEM = sizeof(u64) * N;
+};
+
+// grid (polynomial p of the selection vector: entry e = p / 2k, query qi of the sub-batch)
+template <int LOGN, int ENG>
+__global__ void __launch_bounds__(DCfg<LOGN>::NT, LOGN <= 13 ? 2 : 1)
+k_ntt_fwd_push(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64 in_qstride, const PushArgs A) {
+  constexpr int N = DCfg<LOGN>::N, NT = DCfg<LOGN>::NT;
+  extern __shared__ u64 s[];
+  const int tid = threadIdx.x;
+  const u32 p = blockIdx.x, qi = blockIdx.y;
+  const u32 two_k = 2 * P.k;
+  const u32 e = p / two_k, within = p % two_k;
+  const ModC& m = P.m[within % P.k];
+  const u64* src = in + (u64)qi * in_qstride + (u64)p * N;
+#pragma unroll
+  for (int i = tid; i < N; i += NT) s[swz(i)] = eng_load<ENG>(src[i]);
+  __syncthreads();
+  eng_forward<LOGN, NT, ENG>(s, m, tid);
+  // destination(s): compact per-query layout [own rows of dimension 0 | dimensions 1..] in every rank's buffer
+  u32 r_lo, r_hi;
+  u64 ce;  // compact entry index at the destination
+  if (e < A.d0) {
+    r_lo = e / A.rows_per_rank;
+    r_hi = r_lo + 1;
+    ce = e - r_lo * A.rows_per_rank;
+  } else {
+    r_lo = 0;
+    r_hi = A.n_ranks;
+    ce = A.rows_per_rank + (e - A.d0);
+  }
+  const u64 off = A.slot_off + (A.g_first + qi) * A.dst_qstride + ce * two_k * N + (u64)within * N;
+  for (u32 r = r_lo; r < r_hi; ++r) {
+    u64* dst = A.peers[r] + off;
+#pragma unroll
+    for (int i = tid; i < N; i += NT) dst[i] = eng_store_fwd<ENG>(s[swz(i)], m);
+  }
+}
+
+template <int V>
+using IntC = std::integral_constant<int, V>;
+
+cudaError_t launch_ntt_fwd_push(const DevParams& P, const u64* in, u64 in_qstride, u32 n_entries, u32 n_queries,
+                                const PushArgs& A, cudaStream_t st) {
+  if (!n_entries || !n_queries) return cudaSuccess;
+  auto go = [&](auto ln, auto eng) -> cudaError_t {
+    constexpr int LN = decltype(ln)::value;
+    constexpr int EN = decltype(eng)::value;
+    auto kern = k_ntt_fwd_push<LN, EN>;
+    if (DCfg<LN>::SMEM > 48 * 1024) {
+      static std::set<std::pair<int, const void*>> configured;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      const auto key = std::make_pair(dev, reinterpret_cast<const void*>(kern));
+      if (!configured.count(key)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DCfg<LN>::SMEM);
+        if (e != cudaSuccess) return e;
+        configured.insert(key);
+      }
+    }
+    kern<<<dim3(n_entries * 2 * P.k, n_queries), DCfg<LN>::NT, DCfg<LN>::SMEM, st>>>(P, in, in_qstride, A);
+    return cudaGetLastError();
+  };
+#define PIRB_CASE(LN)                                              \
+  case LN:                                                         \
+    switch (P.ntt_engine) {                                        \
+      case ENG_FP64: return go(IntC<LN>{}, IntC<ENG_FP64>{});      \
+      case ENG_INT_LAZY: return go(IntC<LN>{}, IntC<ENG_INT_LAZY>{}); \
+      default: return go(IntC<LN>{}, IntC<ENG_INT>{});             \
+    }
+  switch (P.logn) {
+    PIRB_CASE(11)
+    PIRB_CASE(12)
+    PIRB_CASE(13)
+    PIRB_CASE(14)
+    default: return cudaErrorInvalidValue;
+  }
+#undef PIRB_CASE
+}
+
+// ---------------------------------------------------------------------------------------------
+// flags: u64 words in every rank's exchange block, flag[kind][sub][source rank]; values only grow (the step number),
+// so nothing is ever reset and a late reader can never see a stale "ready".
+__global__ void k_signal(u64* const* __restrict__ peers, u32 n_ranks, u64 flag_off, u64 value) {
+  const u32 r = threadIdx.x;
+  if (r >= n_ranks) return;
+  __threadfence_system();  // everything this GPU wrote before (previous kernels of the stream included) is visible first
+  u64* f = peers[r] + flag_off;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(value) : "memory");
+}
+cudaError_t launch_signal(u64* const* peers_dev, u32 n_ranks, u64 flag_off_limbs, u64 value, cudaStream_t st) {
+  k_signal<<<1, 32, 0, st>>>(peers_dev, n_ranks, flag_off_limbs, value);
+  return cudaGetLastError();
+}
+
+__global__ void k_wait(const u64* __restrict__ flags, u32 n_ranks, u64 value, u64 timeout_ns, u64* __restrict__ err) {
+  const u32 r = threadIdx.x;
+  bool ok = true;
+  if (r < n_ranks) {
+    u64 t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      u64 v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+      if (v >= value) break;
+      u64 t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) { ok = false; break; }
+      __nanosleep(200);
+    }
+  }
+  if (!ok) atomicExch((unsigned long long*)err, value ? value : 1ull);  // the host reports it; results are void
+  __threadfence_system();
+}
+cudaError_t launch_wait(const u64* flags, u32 n_ranks, u64 value, u64 timeout_ns, u64* err, cudaStream_t st) {
+  k_wait<<<1, 32, 0, st>>>(flags, n_ranks, value, timeout_ns, err);
+  return cudaGetLastError();
+}
+
+}  // namespace pirb
