@@ -172,10 +172,12 @@ struct pirb_ctx {
     bool prof_valid = false;
     u64 timeout_ns = 20ull * 1000 * 1000 * 1000;
     u64 launches = 0;
+    u32 sized_for = 0;                        // largest local batch the workspaces have been sized for
   } dist;
   DevBuf dbg;            // PIRB_DEBUG_STAMPS=<level>: clock64 phase stamps of that expansion level
   int dbg_level = -1;
   bool use_cluster = false;  // one-launch-per-level key switch on thread-block clusters
+  bool dry = false;          // see LAUNCH
   pirb_ctx() {
     for (DevBuf* b : {&db, &stage, &work, &dig, &acc, &xch, &part, &bufA[0], &bufA[1], &pts, &qbuf, &rbuf, &svbuf, &xptrs,
                       &dbg, &dist.peer_table})
@@ -185,11 +187,14 @@ struct pirb_ctx {
 
 namespace {
 
+// (ctx)->dry: sizing pass — walk the same code path, grow every workspace it needs, launch nothing
 #define LAUNCH(ctx, call)                                                                            \
   do {                                                                                               \
-    cudaError_t e_ = (call);                                                                         \
-    ++(ctx)->launches;                                                                               \
-    if (e_ != cudaSuccess) return fail(PIRB_INTERNAL, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    if (!(ctx)->dry) {                                                                               \
+      cudaError_t e_ = (call);                                                                       \
+      ++(ctx)->launches;                                                                             \
+      if (e_ != cudaSuccess) return fail(PIRB_INTERNAL, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    }                                                                                                \
   } while (0)
 
 // uint64_t (unsigned long) <-> u64 (unsigned long long): same representation on LP64
@@ -320,7 +325,8 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   const int d = c->d, k = c->k;
   const u64 ctL = c->ctL;
   const DevParams& P = c->P;
-  if (c->profiling) cudaEventRecord(c->ev[1], st);
+  const bool prof = c->profiling && !c->dry;
+  if (prof) cudaEventRecord(c->ev[1], st);
   // database.cpp:190,222: the selection vector goes to NTT form.  Only the last dimension's entries are needed by the
   // scan; for d >= 2 the others are transformed on a side branch (a second stream, captured as a parallel branch of the
   // answer graph) that joins the main one before the first upper-dimension multiply.
@@ -328,7 +334,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   if (!sv_is_ntt) {
     u64 head = 0;
     for (int e = 0; e < d - 1; ++e) head += c->dims[e];
-    if (d >= 2 && sv_item0 == 0 && sv_items == c->dim_sum && head > 0 && c->side) {
+    if (d >= 2 && sv_item0 == 0 && sv_items == c->dim_sum && head > 0 && c->side && !c->dry) {
       CU(cudaEventRecord(c->ev_fork, st));
       CU(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
       LAUNCH(c, launch_ntt_fwd(P, d_sv, d_sv, (int)(head * 2 * k), k, 0, n_queries, sv_qstride, sv_qstride, c->side));
@@ -340,7 +346,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
       LAUNCH(c, launch_ntt_fwd(P, d_sv, d_sv, (int)(sv_items * 2 * k), k, 0, n_queries, sv_qstride, sv_qstride, st));
     }
   }
-  if (c->profiling) cudaEventRecord(c->ev[2], st);
+  if (prof) cudaEventRecord(c->ev[2], st);
 
   const u64 out_cts = c->reply_cts;
   // the reference multiplies whatever the database holds (database.cpp:183 stops at db_.end()); here that is the
@@ -350,8 +356,8 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   if (npt == 0) {
     if (forked) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     // empty shard: contributes the additive identity
-    CU(cudaMemsetAsync(d_out, 0, (size_t)n_queries * out_cts * ctL * sizeof(u64), st));
-    if (c->profiling) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
+    if (!c->dry) CU(cudaMemsetAsync(d_out, 0, (size_t)n_queries * out_cts * ctL * sizeof(u64), st));
+    if (prof) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
     return 0;
   }
   // ---- last dimension: scan against the database ----
@@ -373,7 +379,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   c->scan_split = n_split;
   RC(c->part.ensure((size_t)n_queries * n_split * n_rows * ctL * sizeof(u64)));
   LAUNCH(c, launch_scan(P, c->db.p, npt, dimL, n_rows, sv_last, sv_qstride, n_queries, n_split, c->part.p, st));
-  if (c->profiling) cudaEventRecord(c->ev[3], st);
+  if (prof) cudaEventRecord(c->ev[3], st);
   if (d == 1) {
     if (partial) {
       for (int qi = 0; qi < n_queries; ++qi)
@@ -382,14 +388,14 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
       LAUNCH(c, launch_ntt_inv(P, c->part.p, d_out, 2 * k, k, 0, n_split, (u64)n_rows * ctL, n_queries,
                                (u64)n_split * n_rows * ctL, ctL, st));
     }
-    if (c->profiling) { cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
+    if (prof) { cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
     return 0;
   }
   // rows -> coefficient form (database.cpp:250-254)
   RC(c->bufA[0].ensure((size_t)n_queries * n_rows * ctL * sizeof(u64)));
   LAUNCH(c, launch_ntt_inv(P, c->part.p, c->bufA[0].p, (int)(n_rows * 2 * k), k, 0, n_split, (u64)n_rows * ctL,
                            n_queries, (u64)n_split * n_rows * ctL, (u64)n_rows * ctL, st));
-  if (c->profiling) cudaEventRecord(c->ev[4], st);
+  if (prof) cudaEventRecord(c->ev[4], st);
   if (forked) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
   // ---- upper dimensions (database.cpp:196-235) ----
   u32 n_entries = n_rows;
@@ -427,7 +433,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
     w = w_out;
     cur ^= 1;
   }
-  if (c->profiling) cudaEventRecord(c->ev[5], st);
+  if (prof) cudaEventRecord(c->ev[5], st);
   return 0;
 }
 
@@ -1338,22 +1344,32 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
   int rc;
   ExpandPlan* pl = get_plan(c, c->dim_sum, 0, &rc);
   if (!pl) return rc;
-  const u64 seq = ++D.step;
-  const int slot = (int)(seq & 1);
   const u32 W = D.n_ranks, SB = D.sub_q;
+  if (!c->dry && D.sized_for < n_local) {
+    // first step of this size: grow every workspace NOW (cudaMalloc synchronises the device, which must not happen
+    // between a wait kernel and the launches of the peers it waits for when several ranks share one host thread)
+    c->dry = true;
+    const int rc_dry = dist_step(c, keys, d_queries, n_local, n_ct, d_replies, user);
+    c->dry = false;
+    if (rc_dry) return rc_dry;
+    D.sized_for = n_local;
+  }
+  const bool dry = c->dry;
+  const u64 seq = dry ? D.step + 1 : ++D.step;
+  const int slot = (int)(seq & 1);
   const u32 n_sub = (n_local + SB - 1) / SB;
   const u64 q_stride = 2 * pl->cap * c->ctL;
   u64* const* peers = reinterpret_cast<u64* const*>(D.peer_table.p);
   u64* err = D.base;  // flag word 0
   c->launches = 0;
-  const bool prof = c->profiling;
+  const bool prof = c->profiling && !dry;
 
   // order: behind the caller's stream, behind the previous user of this slot, behind the last read of c->work
-  CU(cudaEventRecord(D.ev_in, user));
-  CU(cudaStreamWaitEvent(D.prod, D.ev_in, 0));
-  CU(cudaStreamWaitEvent(D.cons, D.ev_in, 0));
-  if (D.done_valid[slot]) CU(cudaStreamWaitEvent(D.prod, D.ev_done[slot], 0));
-  if (D.xfer_valid) CU(cudaStreamWaitEvent(D.prod, D.ev_xfer, 0));
+  if (!dry) CU(cudaEventRecord(D.ev_in, user));
+  if (!dry) CU(cudaStreamWaitEvent(D.prod, D.ev_in, 0));
+  if (!dry) CU(cudaStreamWaitEvent(D.cons, D.ev_in, 0));
+  if (!dry && D.done_valid[slot]) CU(cudaStreamWaitEvent(D.prod, D.ev_done[slot], 0));
+  if (!dry && D.xfer_valid) CU(cudaStreamWaitEvent(D.prod, D.ev_xfer, 0));
   if (prof) cudaEventRecord(D.prof[0], D.prod);
 
   // top levels for the whole local batch while they are too narrow to fill the GPU per sub-batch
@@ -1364,8 +1380,8 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
   for (u32 sb = 0; sb < n_sub; ++sb) {
     const u32 q0 = sb * SB, qn = std::min(SB, n_local - q0);
     if (split < pl->max_logm) RC(run_expand(c, keys, pl, d_queries, (int)n_local, D.prod, split, pl->max_logm, (int)q0, (int)qn));
-    CU(cudaEventRecord(D.ev_exp[sb], D.prod));
-    CU(cudaStreamWaitEvent(D.xfer, D.ev_exp[sb], 0));
+    if (!dry) CU(cudaEventRecord(D.ev_exp[sb], D.prod));
+    if (!dry) CU(cudaStreamWaitEvent(D.xfer, D.ev_exp[sb], 0));
     PushArgs A;
     A.peers = peers;
     A.n_ranks = W;
@@ -1378,8 +1394,8 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
     LAUNCH(c, launch_signal(peers, W, dist_flag_off(D, 0, sb, D.rank), seq, D.xfer));
   }
   if (prof) cudaEventRecord(D.prof[1], D.prod);
-  CU(cudaEventRecord(D.ev_xfer, D.xfer));
-  D.xfer_valid = true;
+  if (!dry) CU(cudaEventRecord(D.ev_xfer, D.xfer));
+  if (!dry) D.xfer_valid = true;
   if (prof) cudaEventRecord(D.prof[2], D.xfer);
 
   // consumer: every sub-batch holds W * SB queries (rank-major), contiguous in the slot
@@ -1413,12 +1429,12 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
                              (int)(cts * 2 * c->k), c->k, 0, 1, 0, 1, 0, 0, D.cons));
   }
   if (prof) cudaEventRecord(D.prof[5], D.cons);
-  D.prof_valid = prof;
-  CU(cudaEventRecord(D.ev_done[slot], D.cons));
-  D.done_valid[slot] = true;
-  CU(cudaStreamWaitEvent(user, D.ev_done[slot], 0));
-  CU(cudaStreamWaitEvent(user, D.ev_xfer, 0));
-  D.launches = c->launches;
+  if (!dry) D.prof_valid = prof;
+  if (!dry) CU(cudaEventRecord(D.ev_done[slot], D.cons));
+  if (!dry) D.done_valid[slot] = true;
+  if (!dry) CU(cudaStreamWaitEvent(user, D.ev_done[slot], 0));
+  if (!dry) CU(cudaStreamWaitEvent(user, D.ev_xfer, 0));
+  if (!dry) D.launches = c->launches;
   return 0;
 }
 

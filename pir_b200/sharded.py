@@ -260,39 +260,87 @@ class ShardServer:
         return out
 
     # -- one entry point for the multi-GPU step, whatever the transport ------------------------------------------
-    def setup_distributed(self, queries_per_rank: int, prefer: str = "nvlink") -> str:
+    def setup_distributed(self, queries_per_rank: int, prefer: str = "nvlink", sub_batch: int = 0) -> str:
         """Collective.  Chooses how selection vectors and partial replies travel between the ranks and sets it up;
-        returns a description for the bench line.  Falls back to NCCL collectives on every rank if any rank cannot
-        map its peers' memory."""
+        returns a description for the bench line.  "nvlink": the library's own kernels store / load peer memory
+        (pirb_dist_*; the process group is only used here, to swap the CUDA IPC handles).  Falls back to NCCL
+        collectives on every rank if any rank cannot map its peers' memory, and for one-dimensional databases."""
         import torch.distributed as dist
-        world = dist.get_world_size()
+        world, rank = dist.get_world_size(), dist.get_rank()
         self._dist_mode = "nccl"
         if prefer == "nvlink" and len(self.params.dimensions) > 1:
-            ok = 1
+            ok, err = 1, ""
+            handle = (C.c_uint8 * 64)()
+            try:
+                _check(_lib.lib().pirb_dist_create(self.ctx.h, queries_per_rank, sub_batch, handle, None))
+            except Exception as e:  # noqa: BLE001
+                ok, err = 0, str(e)
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle) if ok else None)
+            if all(h is not None for h in handles):
+                blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+                try:
+                    _check(_lib.lib().pirb_dist_open_ipc(self.ctx.h, blob, world, rank))
+                except Exception as e:  # noqa: BLE001
+                    ok, err = 0, str(e)
+            else:
+                ok = 0
+            flag = torch.tensor([ok], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()):
+                self._dist_mode = "nvlink"
+                return ("selection vectors stored into the peers' memory by the NTT kernel, partial replies added mod q "
+                        "by peer loads in the reduce kernel (NVLink, per-sub-batch flags, no collective on the data path)")
+            if not ok:
+                import sys
+                sys.stderr.write("rank %d: peer-memory exchange unavailable (%s); using NCCL\n" % (rank, err))
+        if prefer != "nccl-gather" and len(self.params.dimensions) > 1:
             try:
                 self.setup_peer_exchange(max_queries=world * queries_per_rank)
-            except Exception as e:  # noqa: BLE001
+                ok = 1
+            except Exception:  # noqa: BLE001
                 ok = 0
-                import sys
-                sys.stderr.write("rank %d: peer exchange unavailable (%s); using NCCL gather\n" % (dist.get_rank(), e))
             flag = torch.tensor([ok], device=self.device)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()):
                 self._dist_mode = "p2p"
-        if self._dist_mode == "p2p":
-            return "selection vectors all-gathered with NCCL, partial replies reduced over NVLink peer loads"
+                return "selection vectors all-gathered with NCCL, partial replies reduced over NVLink peer loads"
         return "selection vectors and partial replies gathered with NCCL"
 
     def answer_dist(self, d_queries_local: torch.Tensor) -> torch.Tensor:
-        if getattr(self, "_dist_mode", "nccl") == "p2p":
+        """This rank's queries [ql][n_ct][2][k][N] -> this rank's replies; every rank calls it in lockstep."""
+        mode = getattr(self, "_dist_mode", "nccl")
+        if mode == "nvlink":
+            ql, n_ct = d_queries_local.shape[0], d_queries_local.shape[1]
+            out = self._empty(ql, self.ctx.reply_cts, 2, self.k, self.N)
+            st = self._enter()
+            _check(_lib.lib().pirb_dist_answer_dev(self.ctx.h, self.keys.h if self.keys else None, _dp(d_queries_local),
+                                                   ql, n_ct, _dp(out), st))
+            self._exit()
+            return out
+        if mode == "p2p":
             return self.answer_batch_distributed_p2p(d_queries_local)
         return self.answer_batch_distributed(d_queries_local)
 
     def answer_dist_host(self, q_pinned: torch.Tensor, out_pinned: torch.Tensor):
         """End-to-end variant: this rank's queries start in (pinned) host memory and its replies end there."""
+        if getattr(self, "_dist_mode", "nccl") == "nvlink":
+            # the C ABI's host-buffer entry point: page-locked buffers are read / written in place by the kernels
+            _check(_lib.lib().pirb_dist_answer(self.ctx.h, self.keys.h if self.keys else None,
+                                               C.c_void_p(q_pinned.data_ptr()), q_pinned.shape[0], q_pinned.shape[1],
+                                               C.c_void_p(out_pinned.data_ptr())))
+            return
         d = q_pinned.to(self.device, non_blocking=True)
         out_pinned.copy_(self.answer_dist(d), non_blocking=True)
         torch.cuda.synchronize(self.device)
+
+    def dist_status(self):
+        _check(_lib.lib().pirb_dist_status(self.ctx.h))
+
+    def dist_stage_ms(self):
+        out = (C.c_float * 6)()
+        _check(_lib.lib().pirb_dist_stage_ms(self.ctx.h, out))
+        return dict(zip(_lib.DIST_STAGE_NAMES, [float(x) for x in out]))
 
     def profile_stages(self, step, flush=None, n=5):
         """Mean per-stage device times (CUDA events recorded by the library on its launching stream) over n extra
@@ -305,7 +353,8 @@ class ShardServer:
                     flush()
                 step()
                 torch.cuda.synchronize(self.device)
-                for nm, v in self.stage_ms().items():
+                st = self.dist_stage_ms() if getattr(self, "_dist_mode", "") == "nvlink" else self.stage_ms()
+                for nm, v in st.items():
                     acc.setdefault(nm, []).append(v)
         finally:
             self.set_profiling(False)
@@ -322,6 +371,55 @@ class ShardServer:
         _check(_lib.lib().pirb_scan_dev(self.ctx.h, _dp(d_sv_ntt), Q, _dp(out) if want_rows else None, st))
         self._exit()
         return out
+
+
+class ShardGroup:
+    """All row shards of one database inside ONE process: a context per shard (on `devices[i]`; several shards may share
+    a device), their exchange blocks attached to each other by pointer (peer access between devices).  The same
+    kernels and flags as the one-process-per-GPU flow — this is what a C++ host drives through pirb_dist_attach."""
+
+    def __init__(self, params: PIRParameters, devices, queries_per_rank: int, sub_batch: int = 0):
+        self.world = len(devices)
+        self.shards = [ShardServer(params, device=d, shard_index=i, shard_count=self.world) for i, d in enumerate(devices)]
+        bases = (C.c_void_p * self.world)()
+        for i, sh in enumerate(self.shards):
+            b = C.c_void_p()
+            _check(_lib.lib().pirb_dist_create(sh.ctx.h, queries_per_rank, sub_batch, None, C.byref(b)))
+            bases[i] = b.value
+        for i, sh in enumerate(self.shards):
+            _check(_lib.lib().pirb_dist_attach(sh.ctx.h, bases, self.world, i))
+            sh._dist_mode = "nvlink"
+
+    def fill_random(self, seed):
+        for sh in self.shards:
+            sh.db.fill_random(seed)
+
+    def load_coeff(self, coeffs, first_pt=0):
+        for sh in self.shards:
+            sh.load_coeff(coeffs, first_pt)
+
+    def set_keys(self, gks):
+        """gks: one GaloisKeys for everybody, or one per rank (the keys of the client whose queries that rank expands)."""
+        for i, sh in enumerate(self.shards):
+            sh.set_keys(gks[i] if isinstance(gks, (list, tuple)) else gks)
+
+    def answer(self, queries_per_rank):
+        """queries_per_rank[i]: device tensor [ql][n_ct][2][k][N] on shard i's device -> list of reply tensors.
+        Every rank's step is enqueued before anything is waited for (the ranks wait for each other on the device)."""
+        outs = []
+        for sh, q in zip(self.shards, queries_per_rank):
+            ql, n_ct = q.shape[0], q.shape[1]
+            out = sh._empty(ql, sh.ctx.reply_cts, 2, sh.k, sh.N)
+            st = sh._enter()  # no join with the caller's stream until every rank's step has been enqueued
+            _check(_lib.lib().pirb_dist_answer_dev(sh.ctx.h, sh.keys.h if sh.keys else None, _dp(q), ql, n_ct, _dp(out), st))
+            outs.append(out)
+        for sh in self.shards:
+            sh._exit()
+        for sh in self.shards:
+            torch.cuda.synchronize(sh.device)
+        for sh in self.shards:
+            sh.dist_status()
+        return outs
 
 
 def shard_rows(dim0: int, shard_count: int):

@@ -54,6 +54,20 @@ def main():
         for _ in range(3):
             p2p = sharded.to_host(srv.answer_batch_distributed_p2p(sharded.to_device(queries[rank:rank + 1], dev)))[0]
             ok &= bool(np.array_equal(p2p, mine))
+        # (4) the exchange done by the library's own kernels over peer memory (pirb_dist_*, CUDA IPC between the
+        #     processes): two local queries per rank in sub-batches of one, three steps
+        if d >= 2:
+            mode = srv.setup_distributed(2, prefer="nvlink", sub_batch=1)
+            ok &= srv._dist_mode == "nvlink"
+            two = np.stack([queries[rank], queries[(rank + 1) % world]])
+            for _ in range(3):
+                nv = sharded.to_host(srv.answer_dist(sharded.to_device(two, dev)))
+                srv.dist_status()
+                ok &= bool(np.array_equal(nv[0], mine)) and bool(np.array_equal(nv[1], full[(rank + 1) % world]))
+            pin_q = torch.from_numpy(two.view(np.int64)).pin_memory()
+            pin_r = torch.empty((2,) + nv.shape[1:], dtype=torch.int64).pin_memory()
+            srv.answer_dist_host(pin_q, pin_r)                      # host-buffer entry point of the C ABI
+            ok &= bool(np.array_equal(pin_r.numpy().view(np.uint64), nv))
         # oracle on the whole database
         want = cl.orc.process_query(oc.db_to_ntt(cl.orc, coeffs), p.dimensions, cl.elts, cl.galois, queries[rank])
         ok &= bool(np.array_equal(mine, want))

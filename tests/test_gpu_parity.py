@@ -647,3 +647,40 @@ def test_device_populate_and_shard_file_roundtrip(tmp_path):
     db2 = pb.PIRDatabase.Create(p)
     db2.load(path)
     assert db2.size() == p.num_pt and np.array_equal(db2.read_ntt(0, p.num_pt), got)
+
+
+# ------------------------------------------------------------------------------------------------ NVLink exchange flow
+@pytest.mark.parametrize("dbsize,world,ql,sub", [(82, 2, 2, 1), (82, 3, 3, 2), (300, 4, 4, 0), (43, 8, 1, 0), (300, 2, 5, 2)])
+def test_peer_memory_exchange_flow_matches_oracle(dbsize, world, ql, sub):
+    """pirb_dist_*: the row-sharded flow whose exchange is done by the kernels over peer memory (selection-vector NTT
+    storing into every rank's slot, per-sub-batch flags, partial replies added by peer loads).  All ranks live in this
+    process and on this one GPU (ShardGroup), which exercises exactly the kernels, flags and slot arithmetic of the
+    one-process-per-GPU deployment.  Every rank's replies must equal the oracle's ProcessRequest on the unsharded
+    database, limb for limb; two steps, so both exchange slots and the flag sequence numbers are used.  Shapes cover
+    a short last row, ranks with fewer rows than others, an empty shard (8 ranks over 8 rows of which the last holds
+    one plaintext), ragged sub-batches and more ranks than sub-batches."""
+    import torch
+    from pir_b200 import sharded
+    n = 4096
+    ep = pb.GenerateEncryptionParams(n, 20)
+    p = pb.CreatePIRParameters(dbsize, 0, 2, ep)
+    mods = list(ep.coeff_modulus)
+    k = len(mods) - 1
+    rng = np.random.default_rng(dbsize * 31 + world)
+    grp = sharded.ShardGroup(p, [0] * world, ql, sub)
+    coeffs = rng.integers(0, ep.plain_modulus, (p.num_pt, n), dtype=np.uint64)
+    grp.load_coeff(coeffs)
+    orc = ob.Oracle(n, mods, ep.plain_modulus)
+    db_ntt = np.stack([orc.plain_to_ntt(c) for c in coeffs])
+    elts = [(n >> i) + 1 for i in range(12)]
+    keys = np.stack([rng.integers(0, q, (len(elts), k, 2, n), dtype=np.uint64) for q in mods], axis=3)
+    grp.set_keys(pb.GaloisKeys(elts, keys.reshape(-1)))
+    n_ct = sum(p.dimensions) // n + 1
+    for step in range(2):
+        queries = np.stack([rng.integers(0, q, (world, ql, n_ct, 2, n), dtype=np.uint64) for q in mods[:k]], axis=4)
+        outs = grp.answer([sharded.to_device(queries[r], "cuda:0") for r in range(world)])
+        for r in range(world):
+            got = sharded.to_host(outs[r])
+            for i in range(ql):
+                want = orc.process_query(db_ntt, p.dimensions, elts, keys.reshape(-1), queries[r, i])
+                assert np.array_equal(got[i], want), (step, r, i)
