@@ -165,6 +165,11 @@ int pirb_dist_create(pirb_ctx* ctx, uint32_t max_local_queries, uint32_t sub_bat
                      void** base_out /* or NULL */);
 int pirb_dist_open_ipc(pirb_ctx* ctx, const uint8_t* ipc_handles /*[n_ranks][64]*/, uint32_t n_ranks, uint32_t self_rank);
 int pirb_dist_attach(pirb_ctx* ctx, void* const* peer_bases /*[n_ranks]*/, uint32_t n_ranks, uint32_t self_rank);
+/* Optional, needed when several ranks are driven by ONE host thread (contexts of one process): sizes every workspace
+ * for steps of n_local queries and runs one warm-up step in which the rank exchanges only with itself, so that no
+ * allocation, module load or attribute change (all of which may synchronise the device) happens between one rank's
+ * wait for a flag and the launches of the rank that raises it.  Call it on every rank before the first step. */
+int pirb_dist_prepare(pirb_ctx* ctx, const pirb_keys* keys, uint32_t n_local);
 /* device-accessible buffers, asynchronous on `stream` (NULL: the context's stream) */
 int pirb_dist_answer_dev(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_local, uint64_t n_ct,
                          uint64_t* d_replies, void* stream);

@@ -79,6 +79,7 @@ SYMBOLS = {
     "pirb_dist_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "pirb_dist_open_ipc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
     "pirb_dist_attach": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32]),
+    "pirb_dist_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "pirb_dist_answer_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
     "pirb_dist_answer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]),
     "pirb_dist_status": (C.c_int, [C.c_void_p]),

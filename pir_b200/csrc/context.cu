@@ -163,7 +163,9 @@ struct pirb_ctx {
     std::vector<u64*> peer_base;
     std::vector<void*> opened;                // IPC mappings to close
     DevBuf peer_table;
+    DevBuf self_table;                        // every entry = own block: the solo warm-up step exchanges with itself
     u64 step = 0;
+    u32 warmed_for = 0;
     cudaStream_t prod = nullptr, xfer = nullptr, cons = nullptr;
     cudaEvent_t ev_in = nullptr, ev_prod = nullptr, ev_xfer = nullptr, ev_done[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_exp;          // per sub-batch: expansion finished (prod -> xfer)
@@ -180,7 +182,7 @@ struct pirb_ctx {
   bool dry = false;          // see LAUNCH
   pirb_ctx() {
     for (DevBuf* b : {&db, &stage, &work, &dig, &acc, &xch, &part, &bufA[0], &bufA[1], &pts, &qbuf, &rbuf, &svbuf, &xptrs,
-                      &dbg, &dist.peer_table})
+                      &dbg, &dist.peer_table, &dist.self_table})
       b->epoch = &alloc_epoch;
   }
 };
@@ -1285,6 +1287,9 @@ static int dist_finish_attach(pirb_ctx* c, const std::vector<u64*>& table) {
   D.peer_base = table;
   RC(D.peer_table.ensure(table.size() * sizeof(u64*)));
   CU(cudaMemcpy(D.peer_table.p, table.data(), table.size() * sizeof(u64*), cudaMemcpyHostToDevice));
+  std::vector<u64*> self(table.size(), D.base);
+  RC(D.self_table.ensure(self.size() * sizeof(u64*)));
+  CU(cudaMemcpy(D.self_table.p, self.data(), self.size() * sizeof(u64*), cudaMemcpyHostToDevice));
   D.ready = true;
   return 0;
 }
@@ -1333,8 +1338,11 @@ int pirb_dist_attach(pirb_ctx* c, void* const* peer_bases, uint32_t n_ranks, uin
 }
 
 // one step of the flow above; d_queries / d_replies are device-accessible (device memory or page-locked host memory)
+// solo: the warm-up form of a step — the rank exchanges only with itself (every table entry is its own block) and the
+// flags keep their value (sequence number 0 is always "arrived"), so it needs no peer to make progress: it loads every
+// kernel of the flow and sets their attributes before the first real step.
 static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u32 n_local, u64 n_ct, u64* d_replies,
-                     cudaStream_t user) {
+                     cudaStream_t user, bool solo = false) {
   pirb_ctx::Dist& D = c->dist;
   if (!D.ready) return fail(PIRB_INVALID_ARGUMENT, "exchange block not attached (pirb_dist_open_ipc / pirb_dist_attach)");
   if (!n_local || n_local > D.max_local) return fail(PIRB_INVALID_ARGUMENT, "local batch size out of range");
@@ -1355,11 +1363,11 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
     D.sized_for = n_local;
   }
   const bool dry = c->dry;
-  const u64 seq = dry ? D.step + 1 : ++D.step;
-  const int slot = (int)(seq & 1);
+  const u64 seq = solo ? 0 : (dry ? D.step + 1 : ++D.step);
+  const int slot = (int)((solo ? D.step + 1 : seq) & 1);
   const u32 n_sub = (n_local + SB - 1) / SB;
   const u64 q_stride = 2 * pl->cap * c->ctL;
-  u64* const* peers = reinterpret_cast<u64* const*>(D.peer_table.p);
+  u64* const* peers = reinterpret_cast<u64* const*>(solo ? D.self_table.p : D.peer_table.p);
   u64* err = D.base;  // flag word 0
   c->launches = 0;
   const bool prof = c->profiling && !dry;
@@ -1423,7 +1431,7 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
     const u64 cts = (u64)qn * c->reply_cts;
     RC(c->rbuf.ensure((size_t)D.max_local * c->reply_cts * c->ctL * sizeof(u64)));
     const u64 off = dist_part_off(D, slot) + (((u64)sb * W + D.rank) * SB) * c->reply_cts * c->ctL;
-    LAUNCH(c, launch_modadd_reduce_ptrs(c->P, reinterpret_cast<const u64* const*>(D.peer_table.p), (int)W, off,
+    LAUNCH(c, launch_modadd_reduce_ptrs(c->P, reinterpret_cast<const u64* const*>(peers), (int)W, off,
                                         c->rbuf.p + (u64)q0 * c->reply_cts * c->ctL, cts, D.cons));
     LAUNCH(c, launch_ntt_inv(c->P, c->rbuf.p + (u64)q0 * c->reply_cts * c->ctL, d_replies + (u64)q0 * c->reply_cts * c->ctL,
                              (int)(cts * 2 * c->k), c->k, 0, 1, 0, 1, 0, 0, D.cons));
@@ -1436,6 +1444,23 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
   if (!dry) CU(cudaStreamWaitEvent(user, D.ev_xfer, 0));
   if (!dry) D.launches = c->launches;
   return 0;
+}
+
+int pirb_dist_prepare(pirb_ctx* c, const pirb_keys* keys, uint32_t n_local) {
+  if (!c || !keys) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  pirb_ctx::Dist& D = c->dist;
+  if (!D.ready) return fail(PIRB_INVALID_ARGUMENT, "exchange block not attached");
+  if (D.warmed_for >= n_local && D.sized_for >= n_local) return 0;
+  const u64 n_ct = c->dim_sum / c->N + 1;
+  // scratch queries (zeros are valid residues) and scratch replies
+  RC(c->qbuf.ensure(std::max<size_t>((size_t)n_local * n_ct * c->ctL * sizeof(u64), 256)));
+  RC(c->svbuf.ensure(std::max<size_t>((size_t)n_local * c->reply_cts * c->ctL * sizeof(u64), 256)));
+  CU(cudaMemsetAsync(c->qbuf.p, 0, (size_t)n_local * n_ct * c->ctL * sizeof(u64), c->stream));
+  RC(dist_step(c, keys, c->qbuf.p, n_local, n_ct, c->svbuf.p, c->stream, true));
+  CU(cudaStreamSynchronize(c->stream));
+  D.warmed_for = n_local;
+  return pirb_dist_status(c);
 }
 
 int pirb_dist_answer_dev(pirb_ctx* c, const pirb_keys* keys, const uint64_t* d_queries, uint32_t n_local, uint64_t n_ct,

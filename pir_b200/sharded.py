@@ -406,13 +406,15 @@ class ShardGroup:
     def answer(self, queries_per_rank):
         """queries_per_rank[i]: device tensor [ql][n_ct][2][k][N] on shard i's device -> list of reply tensors.
         Every rank's step is enqueued before anything is waited for (the ranks wait for each other on the device)."""
-        outs = []
+        # everything that may synchronise a device (allocations, first launches) happens before the first rank's step
+        # is enqueued: one host thread drives all ranks, and a rank's wait kernels spin until its peers' launches exist
+        outs = [sh._empty(q.shape[0], sh.ctx.reply_cts, 2, sh.k, sh.N) for sh, q in zip(self.shards, queries_per_rank)]
         for sh, q in zip(self.shards, queries_per_rank):
+            _check(_lib.lib().pirb_dist_prepare(sh.ctx.h, sh.keys.h, q.shape[0]))
+        for sh, q, out in zip(self.shards, queries_per_rank, outs):
             ql, n_ct = q.shape[0], q.shape[1]
-            out = sh._empty(ql, sh.ctx.reply_cts, 2, sh.k, sh.N)
             st = sh._enter()  # no join with the caller's stream until every rank's step has been enqueued
             _check(_lib.lib().pirb_dist_answer_dev(sh.ctx.h, sh.keys.h if sh.keys else None, _dp(q), ql, n_ct, _dp(out), st))
-            outs.append(out)
         for sh in self.shards:
             sh._exit()
         for sh in self.shards:
