@@ -5,7 +5,7 @@ NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall 
 SRC := pir_b200/csrc
 OBJ := build/obj
 LIB := pir_b200/lib/libpirb200.so
-OBJS := $(OBJ)/kernels_ntt.o $(OBJ)/kernels_stream.o $(OBJ)/kernels_cluster.o $(OBJ)/kernels_dist.o $(OBJ)/context.o
+OBJS := $(OBJ)/kernels_ntt.o $(OBJ)/kernels_stream.o $(OBJ)/kernels_cluster.o $(OBJ)/kernels_dist.o $(OBJ)/kernels_tc.o $(OBJ)/context.o
 HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/pir_b200.h
 
 WIRE := pir_b200/lib/libpirb_wire.so

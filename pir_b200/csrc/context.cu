@@ -115,6 +115,7 @@ struct pirb_ctx {
     if (have.size() < pt_count) have.resize(pt_count, 0);
     for (u64 i = first_local; i < first_local + n; ++i)
       if (!have[i]) { have[i] = 1; ++loaded; }
+    tc.built = false;  // the byte-planar copy follows the database
   }
   u64 loaded_prefix() const {  // plaintexts loaded contiguously from the start of the shard
     if (loaded == pt_count) return pt_count;
@@ -180,9 +181,19 @@ struct pirb_ctx {
   int dbg_level = -1;
   bool use_cluster = false;  // one-launch-per-level key switch on thread-block clusters
   bool dry = false;          // see LAUNCH
+  // batched scan on the tensor cores (kernels_tc.cu): byte-planar copy of the shard, built on first use
+  struct Tc {
+    int min_queries = 4;     // batches of at least this many queries take the tensor-core scan (0 = never)
+    bool built = false;
+    TcGeom g = {};
+    u32 dimL = 0, n_rows = 0;
+    u64 npt = 0;
+    DevBuf dbT, svT;
+    int* err = nullptr;      // mapped host memory: raised by the kernel if its pipeline times out
+  } tc;
   pirb_ctx() {
     for (DevBuf* b : {&db, &stage, &work, &dig, &acc, &xch, &part, &bufA[0], &bufA[1], &pts, &qbuf, &rbuf, &svbuf, &xptrs,
-                      &dbg, &dist.peer_table, &dist.self_table})
+                      &dbg, &dist.peer_table, &dist.self_table, &tc.dbT, &tc.svT})
       b->epoch = &alloc_epoch;
   }
 };
@@ -377,10 +388,40 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
     sv_last = d_sv + off * ctL;
   }
   int n_split;
-  scan_config(P, dimL, n_rows, n_queries, c->sm_count, &n_split);
-  c->scan_split = n_split;
-  RC(c->part.ensure((size_t)n_queries * n_split * n_rows * ctL * sizeof(u64)));
-  LAUNCH(c, launch_scan(P, c->db.p, npt, dimL, n_rows, sv_last, sv_qstride, n_queries, n_split, c->part.p, st));
+  const bool use_tc = d >= 2 && c->tc.min_queries > 0 && n_queries >= c->tc.min_queries && tc_supported(P, dimL);
+  if (use_tc) {
+    // batch of queries: dense u8 contraction per coefficient slot on the tensor cores
+    pirb_ctx::Tc& T = c->tc;
+    if (T.err && *T.err) return fail(PIRB_INTERNAL, "tensor-core scan: pipeline timed out in an earlier call");
+    if (!T.built || T.dimL != dimL || T.n_rows != n_rows || T.npt != npt) {
+      tc_geometry(P, dimL, n_rows, &T.g);
+      RC(T.dbT.ensure(T.g.db_bytes));
+      if (!c->dry) {
+        cudaError_t e_ = launch_tc_pack_db(P, c->db.p, npt, dimL, n_rows, T.g, reinterpret_cast<u8*>(T.dbT.p), st);
+        if (e_ != cudaSuccess) return fail(PIRB_INTERNAL, std::string("launch_tc_pack_db: ") + cudaGetErrorString(e_));
+        T.built = true;
+        T.dimL = dimL;
+        T.n_rows = n_rows;
+        T.npt = npt;
+      }
+    }
+    u32 qt, n_qt;
+    const u64 sv_bytes = tc_sv_bytes(P, T.g, (u32)n_queries, &qt, &n_qt);
+    if (sv_bytes > T.svT.bytes) {
+      RC(T.svT.ensure(sv_bytes));
+      CU(cudaMemsetAsync(T.svT.p, 0, sv_bytes, st));  // the K padding is never written afterwards
+    }
+    n_split = 1;
+    c->scan_split = 1;
+    RC(c->part.ensure((size_t)n_queries * n_rows * ctL * sizeof(u64)));
+    LAUNCH(c, launch_tc_scan(P, T.g, reinterpret_cast<const u8*>(T.dbT.p), dimL, n_rows, sv_last, sv_qstride, (u32)n_queries,
+                             reinterpret_cast<u8*>(T.svT.p), T.err, c->sm_count, c->part.p, st));
+  } else {
+    scan_config(P, dimL, n_rows, n_queries, c->sm_count, &n_split);
+    c->scan_split = n_split;
+    RC(c->part.ensure((size_t)n_queries * n_split * n_rows * ctL * sizeof(u64)));
+    LAUNCH(c, launch_scan(P, c->db.p, npt, dimL, n_rows, sv_last, sv_qstride, n_queries, n_split, c->part.p, st));
+  }
   if (prof) cudaEventRecord(c->ev[3], st);
   if (d == 1) {
     if (partial) {
@@ -733,6 +774,17 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
     c->use_cluster = ks_cluster_supported(c->P) && !(e && *e == '0');
   }
   if (const char* e = getenv("PIRB_GRAPHS")) c->use_graphs = atoi(e) != 0;
+  if (const char* e = getenv("PIRB_TC_MIN")) c->tc.min_queries = atoi(e);  // 0 disables the tensor-core scan
+  {
+    int* herr = nullptr;
+    if (cudaHostAlloc(&herr, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+      *herr = 0;
+      c->tc.err = herr;
+    } else {
+      cudaGetLastError();
+      c->tc.min_queries = 0;
+    }
+  }
   if (const char* e = getenv("PIRB_DEBUG_STAMPS")) {
     c->dbg_level = atoi(e);
     RC(c->dbg.ensure(8 << 20));
@@ -756,6 +808,7 @@ void pirb_ctx_destroy(pirb_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   for (auto& kv : c->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (c->tc.err) cudaFreeHost(c->tc.err);
   for (void* pm : c->xpeer_open) cudaIpcCloseMemHandle(pm);
   {
     pirb_ctx::Dist& D = c->dist;
@@ -1560,6 +1613,7 @@ int pirb_sync(pirb_ctx* c) {
   if (!c) return fail(PIRB_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->tc.err && *c->tc.err) return fail(PIRB_INTERNAL, "tensor-core scan: pipeline timed out");
   return 0;
 }
 

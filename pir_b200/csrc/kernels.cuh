@@ -98,6 +98,27 @@ cudaError_t launch_signal(u64* const* peers_dev, u32 n_ranks, u64 flag_off_limbs
 // spin until flags[0..n_ranks) >= value (acquire, system scope); after timeout_ns sets *err and returns
 cudaError_t launch_wait(const u64* flags, u32 n_ranks, u64 value, u64 timeout_ns, u64* err, cudaStream_t st);
 
+// ---- batched scan on the tensor cores (kernels_tc.cu) ----
+struct TcGeom {
+  u32 nb;       // byte limbs per residue (5 or 6)
+  u32 rpt;      // database rows per 128-lane MMA tile = 128 / nb
+  u32 ntiles;   // MMA tiles per coefficient slot
+  u32 Kp;       // dimL rounded up to a multiple of 16 (TMA row pitch)
+  u32 kch;      // 128-byte K chunks
+  u64 db_bytes; // size of the byte-planar database copy
+};
+bool tc_supported(const DevParams& P, u32 dimL);
+void tc_geometry(const DevParams& P, u32 dimL, u32 n_rows, TcGeom* g);
+u64 tc_sv_bytes(const DevParams& P, const TcGeom& g, u32 n_queries, u32* qt_out, u32* n_qt_out);
+// u64 database [pt][k][N] -> byte-planar K-major copy dbT (db_bytes)
+cudaError_t launch_tc_pack_db(const DevParams& P, const u64* db, u64 num_pt, u32 dimL, u32 n_rows, const TcGeom& g,
+                              u8* dbT, cudaStream_t st);
+// part[q][row][2][k][N] = sum_i1 sv[q][i1] (.) db[row*dimL + i1] mod q for a batch of queries (svT: scratch of
+// tc_sv_bytes; err_flag: device-visible int raised if the kernel's internal pipeline times out)
+cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u32 dimL, u32 n_rows, const u64* sv,
+                           u64 sv_qstride, u32 n_queries, u8* svT, int* err_flag, int sm_count, u64* part,
+                           cudaStream_t st);
+
 // StringEncoder packing on the device: raw item bytes -> plaintext coefficients [n_pt][N]
 cudaError_t launch_pack_items(const u8* bytes, u64* coeffs, u32 N, u32 bits, u64 bytes_per_pt, u64 total_bytes,
                               u64 n_pt, cudaStream_t st);

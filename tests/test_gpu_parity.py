@@ -650,15 +650,17 @@ def test_device_populate_and_shard_file_roundtrip(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------ NVLink exchange flow
-@pytest.mark.parametrize("dbsize,world,ql,sub", [(82, 2, 2, 1), (82, 3, 3, 2), (300, 4, 4, 0), (43, 8, 1, 0), (300, 2, 5, 2)])
+@pytest.mark.parametrize("dbsize,world,ql,sub", [(82, 2, 2, 1), (82, 3, 3, 2), (300, 4, 4, 0), (3, 4, 1, 0), (300, 2, 5, 2)])
 def test_peer_memory_exchange_flow_matches_oracle(dbsize, world, ql, sub):
     """pirb_dist_*: the row-sharded flow whose exchange is done by the kernels over peer memory (selection-vector NTT
     storing into every rank's slot, per-sub-batch flags, partial replies added by peer loads).  All ranks live in this
     process and on this one GPU (ShardGroup), which exercises exactly the kernels, flags and slot arithmetic of the
     one-process-per-GPU deployment.  Every rank's replies must equal the oracle's ProcessRequest on the unsharded
     database, limb for limb; two steps, so both exchange slots and the flag sequence numbers are used.  Shapes cover
-    a short last row, ranks with fewer rows than others, an empty shard (8 ranks over 8 rows of which the last holds
-    one plaintext), ragged sub-batches and more ranks than sub-batches."""
+    a short last row, ranks with fewer rows than others, empty shards (4 ranks over 2 rows), ragged sub-batches and more
+    ranks than sub-batches.  (At most 4 ranks share the GPU here: every rank brings 3 library streams, and streams
+    beyond CUDA_DEVICE_MAX_CONNECTIONS = 8 hardware queues per device can be serialised behind a spinning wait
+    kernel — one rank per GPU, the deployment, is far below that.)"""
     import torch
     from pir_b200 import sharded
     n = 4096
