@@ -325,6 +325,51 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
   return 0;
 }
 
+// Last-dimension scan of n_queries selection vectors against the shard into c->part ([q][split][row][2][k][N]):
+// the HBM-bound streaming kernel for single queries, the tensor-core contraction for batches.
+int run_scan(pirb_ctx* c, const u64* sv_last, u64 sv_qstride, int n_queries, u32 dimL, u32 n_rows, u64 npt, bool allow_tc,
+             int* n_split_out, cudaStream_t st) {
+  const DevParams& P = c->P;
+  const u64 ctL = c->ctL;
+  int n_split;
+  const bool use_tc = allow_tc && c->tc.min_queries > 0 && n_queries >= c->tc.min_queries && tc_supported(P, dimL);
+  if (use_tc) {
+    // batch of queries: dense u8 contraction per coefficient slot on the tensor cores
+    pirb_ctx::Tc& T = c->tc;
+    if (T.err && *T.err) return fail(PIRB_INTERNAL, "tensor-core scan: pipeline timed out in an earlier call");
+    if (!T.built || T.dimL != dimL || T.n_rows != n_rows || T.npt != npt) {
+      tc_geometry(P, dimL, n_rows, &T.g);
+      RC(T.dbT.ensure(T.g.db_bytes));
+      if (!c->dry) {
+        cudaError_t e_ = launch_tc_pack_db(P, c->db.p, npt, dimL, n_rows, T.g, reinterpret_cast<u8*>(T.dbT.p), st);
+        if (e_ != cudaSuccess) return fail(PIRB_INTERNAL, std::string("launch_tc_pack_db: ") + cudaGetErrorString(e_));
+        T.built = true;
+        T.dimL = dimL;
+        T.n_rows = n_rows;
+        T.npt = npt;
+      }
+    }
+    u32 qt, n_qt;
+    const u64 sv_bytes = tc_sv_bytes(P, T.g, (u32)n_queries, &qt, &n_qt);
+    if (sv_bytes > T.svT.bytes) {
+      RC(T.svT.ensure(sv_bytes));
+      CU(cudaMemsetAsync(T.svT.p, 0, sv_bytes, st));  // the K padding is never written afterwards
+    }
+    n_split = 1;
+    c->scan_split = 1;
+    RC(c->part.ensure((size_t)n_queries * n_rows * ctL * sizeof(u64)));
+    LAUNCH(c, launch_tc_scan(P, T.g, reinterpret_cast<const u8*>(T.dbT.p), dimL, n_rows, sv_last, sv_qstride, (u32)n_queries,
+                             reinterpret_cast<u8*>(T.svT.p), T.err, c->sm_count, c->part.p, st));
+  } else {
+    scan_config(P, dimL, n_rows, n_queries, c->sm_count, &n_split);
+    c->scan_split = n_split;
+    RC(c->part.ensure((size_t)n_queries * n_split * n_rows * ctL * sizeof(u64)));
+    LAUNCH(c, launch_scan(P, c->db.p, npt, dimL, n_rows, sv_last, sv_qstride, n_queries, n_split, c->part.p, st));
+  }
+  *n_split_out = n_split;
+  return 0;
+}
+
 // DatabaseMultiplier::multiply on the device.  d_sv: [n_queries] x (sv_qstride limbs apart) x [dim_sum][2][k][N]
 // coefficient form; transformed to NTT form in place.  d_out: [n_queries][reply_cts][2][k][N]; coefficient form,
 // or (partial != 0) the NTT-form sum over this shard's rows, to be reduced across shards.
@@ -388,40 +433,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
     sv_last = d_sv + off * ctL;
   }
   int n_split;
-  const bool use_tc = d >= 2 && c->tc.min_queries > 0 && n_queries >= c->tc.min_queries && tc_supported(P, dimL);
-  if (use_tc) {
-    // batch of queries: dense u8 contraction per coefficient slot on the tensor cores
-    pirb_ctx::Tc& T = c->tc;
-    if (T.err && *T.err) return fail(PIRB_INTERNAL, "tensor-core scan: pipeline timed out in an earlier call");
-    if (!T.built || T.dimL != dimL || T.n_rows != n_rows || T.npt != npt) {
-      tc_geometry(P, dimL, n_rows, &T.g);
-      RC(T.dbT.ensure(T.g.db_bytes));
-      if (!c->dry) {
-        cudaError_t e_ = launch_tc_pack_db(P, c->db.p, npt, dimL, n_rows, T.g, reinterpret_cast<u8*>(T.dbT.p), st);
-        if (e_ != cudaSuccess) return fail(PIRB_INTERNAL, std::string("launch_tc_pack_db: ") + cudaGetErrorString(e_));
-        T.built = true;
-        T.dimL = dimL;
-        T.n_rows = n_rows;
-        T.npt = npt;
-      }
-    }
-    u32 qt, n_qt;
-    const u64 sv_bytes = tc_sv_bytes(P, T.g, (u32)n_queries, &qt, &n_qt);
-    if (sv_bytes > T.svT.bytes) {
-      RC(T.svT.ensure(sv_bytes));
-      CU(cudaMemsetAsync(T.svT.p, 0, sv_bytes, st));  // the K padding is never written afterwards
-    }
-    n_split = 1;
-    c->scan_split = 1;
-    RC(c->part.ensure((size_t)n_queries * n_rows * ctL * sizeof(u64)));
-    LAUNCH(c, launch_tc_scan(P, T.g, reinterpret_cast<const u8*>(T.dbT.p), dimL, n_rows, sv_last, sv_qstride, (u32)n_queries,
-                             reinterpret_cast<u8*>(T.svT.p), T.err, c->sm_count, c->part.p, st));
-  } else {
-    scan_config(P, dimL, n_rows, n_queries, c->sm_count, &n_split);
-    c->scan_split = n_split;
-    RC(c->part.ensure((size_t)n_queries * n_split * n_rows * ctL * sizeof(u64)));
-    LAUNCH(c, launch_scan(P, c->db.p, npt, dimL, n_rows, sv_last, sv_qstride, n_queries, n_split, c->part.p, st));
-  }
+  RC(run_scan(c, sv_last, sv_qstride, n_queries, dimL, n_rows, npt, d >= 2, &n_split, st));
   if (prof) cudaEventRecord(c->ev[3], st);
   if (d == 1) {
     if (partial) {
@@ -1581,19 +1593,14 @@ int pirb_scan_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_queries, uin
   if (!c->pt_count) return 0;
   const u32 dimL = c->d == 1 ? (c->top_hi - c->top_lo) : c->dims[c->d - 1];
   const u32 n_rows = c->d == 1 ? 1 : (u32)((c->pt_count + dimL - 1) / dimL);
-  int n_split;
-  scan_config(c->P, dimL, n_rows, (int)n_queries, c->sm_count, &n_split);
-  c->scan_split = n_split;
-  u64* dst = U(d_rows);
-  if (!dst || n_split != 1) {
-    RC(c->part.ensure((size_t)n_queries * n_split * n_rows * c->ctL * sizeof(u64)));
-    dst = c->part.p;
-  }
   DevCallOrder order(c, st);
   if (c->profiling) cudaEventRecord(c->ev[2], st);
-  LAUNCH(c, launch_scan(c->P, c->db.p, c->pt_count, dimL, n_rows, U(d_sv_ntt), (u64)dimL * c->ctL, (int)n_queries, n_split,
-                        dst, st));
+  int n_split;
+  c->launches = 0;
+  RC(run_scan(c, U(d_sv_ntt), (u64)dimL * c->ctL, (int)n_queries, dimL, n_rows, c->pt_count, c->d >= 2, &n_split, st));
   if (c->profiling) cudaEventRecord(c->ev[3], st);
+  if (d_rows && n_split == 1)
+    CU(cudaMemcpyAsync(d_rows, c->part.p, (size_t)n_queries * n_rows * c->ctL * sizeof(u64), cudaMemcpyDeviceToDevice, st));
   if (d_rows && n_split != 1) {
     for (u32 qi = 0; qi < n_queries; ++qi)
       LAUNCH(c, launch_modadd_reduce(c->P, c->part.p + (u64)qi * n_split * n_rows * c->ctL, (u64)n_rows * c->ctL,
