@@ -158,6 +158,8 @@ struct pirb_ctx {
     u32 n_ranks = 0, rank = 0, max_local = 0, n_sub = 0, sub_q = 0;  // sub_q = local queries per sub-batch
     u32 rows_per_rank = 0;
     u64 sv_qstride = 0;                       // limbs per query in a selection-vector slot (compact layout)
+    u32 packed_nb = 0;                        // != 0: last-dimension entries travel as packed residues of this many bytes
+    u64 packed_off = 0;                       // ... at this limb offset inside a query's part of the slot
     u64 flag_limbs = 0, sv_slot_limbs = 0, part_slot_limbs = 0;
     u64* base = nullptr;
     size_t bytes = 0;
@@ -184,6 +186,7 @@ struct pirb_ctx {
   // batched scan on the tensor cores (kernels_tc.cu): byte-planar copy of the shard, built on first use
   struct Tc {
     int min_queries = 4;     // batches of at least this many queries take the tensor-core scan (0 = never)
+    u64 min_pt = 1024;       // ... on shards of at least this many plaintexts
     bool built = false;
     TcGeom g = {};
     u32 dimL = 0, n_rows = 0;
@@ -327,12 +330,15 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
 
 // Last-dimension scan of n_queries selection vectors against the shard into c->part ([q][split][row][2][k][N]):
 // the HBM-bound streaming kernel for single queries, the tensor-core contraction for batches.
+// sv_packed: sv_last points at packed last-dimension residues (exchange slots, PushArgs) — tensor-core scan only.
 int run_scan(pirb_ctx* c, const u64* sv_last, u64 sv_qstride, int n_queries, u32 dimL, u32 n_rows, u64 npt, bool allow_tc,
-             int* n_split_out, cudaStream_t st) {
+             int* n_split_out, cudaStream_t st, bool sv_packed = false) {
   const DevParams& P = c->P;
   const u64 ctL = c->ctL;
   int n_split;
-  const bool use_tc = allow_tc && c->tc.min_queries > 0 && n_queries >= c->tc.min_queries && tc_supported(P, dimL);
+  // small shards are launch-latency territory: the CUDA-core batched scan is as fast there
+  const bool use_tc = sv_packed || (allow_tc && c->tc.min_queries > 0 && n_queries >= c->tc.min_queries &&
+                                    npt >= c->tc.min_pt && tc_supported(P, dimL));
   if (use_tc) {
     // batch of queries: dense u8 contraction per coefficient slot on the tensor cores
     pirb_ctx::Tc& T = c->tc;
@@ -358,8 +364,9 @@ int run_scan(pirb_ctx* c, const u64* sv_last, u64 sv_qstride, int n_queries, u32
     n_split = 1;
     c->scan_split = 1;
     RC(c->part.ensure((size_t)n_queries * n_rows * ctL * sizeof(u64)));
-    LAUNCH(c, launch_tc_scan(P, T.g, reinterpret_cast<const u8*>(T.dbT.p), dimL, n_rows, sv_last, sv_qstride, (u32)n_queries,
-                             reinterpret_cast<u8*>(T.svT.p), T.err, c->sm_count, c->part.p, st));
+    LAUNCH(c, launch_tc_scan(P, T.g, reinterpret_cast<const u8*>(T.dbT.p), dimL, n_rows, sv_last, sv_qstride,
+                             sv_packed ? 1 : 0, (u32)n_queries, reinterpret_cast<u8*>(T.svT.p), T.err, c->sm_count,
+                             c->part.p, st));
   } else {
     scan_config(P, dimL, n_rows, n_queries, c->sm_count, &n_split);
     c->scan_split = n_split;
@@ -378,7 +385,8 @@ int run_scan(pirb_ctx* c, const u64* sv_last, u64 sv_qstride, int n_queries, u32
 // compact_rows != 0: the per-query selection vector holds only this shard's rows of the first dimension (compact_rows
 // slots, own row r at slot r - top_lo) followed by the other dimensions — the layout of the multi-GPU exchange slots.
 int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_out, int partial, cudaStream_t st,
-                 bool sv_is_ntt = false, u64 sv_item0 = 0, u64 sv_items = ~0ull, u32 compact_rows = 0) {
+                 bool sv_is_ntt = false, u64 sv_item0 = 0, u64 sv_items = ~0ull, u32 compact_rows = 0,
+                 u64 packed_last_off = 0) {
   if (sv_items == ~0ull) sv_items = c->dim_sum;
   const int d = c->d, k = c->k;
   const u64 ctL = c->ctL;
@@ -430,10 +438,10 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
     n_rows = (u32)((npt + dimL - 1) / dimL);
     u64 off = compact_rows ? compact_rows : c->dims[0];
     for (int e = 1; e < d - 1; ++e) off += c->dims[e];
-    sv_last = d_sv + off * ctL;
+    sv_last = packed_last_off ? d_sv + packed_last_off : d_sv + off * ctL;
   }
   int n_split;
-  RC(run_scan(c, sv_last, sv_qstride, n_queries, dimL, n_rows, npt, d >= 2, &n_split, st));
+  RC(run_scan(c, sv_last, sv_qstride, n_queries, dimL, n_rows, npt, d >= 2, &n_split, st, packed_last_off != 0));
   if (prof) cudaEventRecord(c->ev[3], st);
   if (d == 1) {
     if (partial) {
@@ -787,6 +795,7 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   }
   if (const char* e = getenv("PIRB_GRAPHS")) c->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("PIRB_TC_MIN")) c->tc.min_queries = atoi(e);  // 0 disables the tensor-core scan
+  if (const char* e = getenv("PIRB_TC_MIN_PT")) c->tc.min_pt = (u64)atoll(e);
   {
     int* herr = nullptr;
     if (cudaHostAlloc(&herr, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
@@ -1295,9 +1304,27 @@ static int dist_layout(pirb_ctx* c, u32 max_local, u32 sub_q) {
   D.sub_q = sub_q;
   D.n_sub = (max_local + sub_q - 1) / sub_q;
   D.rows_per_rank = (c->dims[0] + D.n_ranks - 1) / D.n_ranks;
-  u64 rest = 0;
-  for (int e = 1; e < c->d; ++e) rest += c->dims[e];
-  D.sv_qstride = ((u64)D.rows_per_rank + rest) * c->ctL;
+  u64 mid = 0;
+  for (int e = 1; e < c->d - 1; ++e) mid += c->dims[e];
+  const u32 last = c->dims[c->d - 1];
+  // Packed last dimension (5/8 or 6/8 of the NVLink bytes) whenever the consumers' scans run on the tensor cores.  The
+  // choice uses only quantities every rank agrees on.
+  const char* pk = getenv("PIRB_DIST_PACKED");
+  D.packed_nb = 0;
+  if (!(pk && pk[0] == '0') && c->tc.min_queries > 0 && tc_supported(c->P, last) &&
+      c->prm.num_pt / D.n_ranks >= c->tc.min_pt) {
+    TcGeom g;
+    tc_geometry(c->P, last, 1, &g);
+    D.packed_nb = g.nb;
+  }
+  const u64 head = ((u64)D.rows_per_rank + mid) * c->ctL;
+  if (D.packed_nb) {
+    D.packed_off = head;
+    D.sv_qstride = head + ((u64)last * c->ctL * D.packed_nb + 7) / 8;
+  } else {
+    D.packed_off = 0;
+    D.sv_qstride = head + (u64)last * c->ctL;
+  }
   D.flag_limbs = ((1 + 2ull * D.n_sub * D.n_ranks) + 15) / 16 * 16;
   const u64 slot_queries = (u64)D.n_sub * D.sub_q * D.n_ranks;
   D.sv_slot_limbs = slot_queries * D.sv_qstride;
@@ -1320,9 +1347,10 @@ int pirb_dist_create(pirb_ctx* c, uint32_t max_local_queries, uint32_t sub_batch
   CU(cudaSetDevice(c->device));
   pirb_ctx::Dist& D = c->dist;
   if (D.base) return fail(PIRB_INVALID_ARGUMENT, "exchange block already created");
-  if (!sub_batch) {  // default: up to four sub-batches per step, never more than there are ranks
-    const u32 n_sub = std::max<u32>(1, std::min<u32>(std::min<u32>(4, c->prm.shard_count), max_local_queries));
-    sub_batch = (max_local_queries + n_sub - 1) / n_sub;
+  if (!sub_batch) {
+    // default: as many sub-batches as keep each multiply at >= 8 queries (ranks x sub-batch): the exchange of one
+    // sub-batch hides behind the expansion of the next, so small sub-batches leave the shortest exposed tail
+    sub_batch = std::max<u32>(1, (8 + c->prm.shard_count - 1) / c->prm.shard_count);
   }
   RC(dist_layout(c, max_local_queries, std::min(sub_batch, max_local_queries)));
   CU(cudaMalloc(&D.base, D.bytes));
@@ -1463,6 +1491,9 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
     A.slot_off = dist_sv_off(D, slot);
     A.g_first = ((u64)sb * W + D.rank) * SB;
     A.dst_qstride = D.sv_qstride;
+    A.last_first = (u32)(c->dim_sum - c->dims[c->d - 1]);
+    A.packed_nb = D.packed_nb;
+    A.packed_off = D.packed_off;
     LAUNCH(c, launch_ntt_fwd_push(c->P, c->work.p + (u64)q0 * q_stride, q_stride, (u32)c->dim_sum, qn, A, D.xfer));
     LAUNCH(c, launch_signal(peers, W, dist_flag_off(D, 0, sb, D.rank), seq, D.xfer));
   }
@@ -1480,12 +1511,12 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
     if (qn == SB) {
       RC(run_multiply(c, D.base + dist_sv_off(D, slot) + g0 * D.sv_qstride, D.sv_qstride, (int)(W * SB),
                       D.base + dist_part_off(D, slot) + g0 * c->reply_cts * c->ctL, 1, D.cons, true, 0, ~0ull,
-                      D.rows_per_rank));
+                      D.rows_per_rank, D.packed_nb ? D.packed_off : 0));
     } else {  // ragged last sub-batch: the ranks' queries are not contiguous, one multiply per rank
       for (u32 r = 0; r < W; ++r)
         RC(run_multiply(c, D.base + dist_sv_off(D, slot) + (g0 + (u64)r * SB) * D.sv_qstride, D.sv_qstride, (int)qn,
                         D.base + dist_part_off(D, slot) + (g0 + (u64)r * SB) * c->reply_cts * c->ctL, 1, D.cons, true, 0,
-                        ~0ull, D.rows_per_rank));
+                        ~0ull, D.rows_per_rank, D.packed_nb ? D.packed_off : 0));
     }
     LAUNCH(c, launch_signal(peers, W, dist_flag_off(D, 1, sb, D.rank), seq, D.cons));
   }

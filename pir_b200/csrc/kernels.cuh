@@ -87,7 +87,13 @@ struct PushArgs {
   u32 rows_per_rank;   // ceil(d0 / n_ranks): rank r owns rows [r * rows_per_rank, ...) of the first dimension
   u64 slot_off;        // limb offset of the destination slot inside every rank's block
   u64 g_first;         // position of this launch's first query in the slot's query order
-  u64 dst_qstride;     // limbs per query in the slot: (rows_per_rank + dims[1] + ... + dims[d-1]) * ct_limbs
+  u64 dst_qstride;     // limbs per query in the slot
+  // last-dimension entries (they only feed the scan) may travel as packed residues instead of u64 limbs: per
+  // polynomial a plane of N low 32-bit words followed by a plane of N high parts (packed_nb - 4 bytes each) — the input
+  // format of the tensor-core scan's operand repacking, and 5/8 (6/8) of the NVLink bytes
+  u32 last_first;      // first entry of the last dimension
+  u32 packed_nb;       // 0: u64 limbs everywhere; 5 / 6: bytes per residue of the packed last-dimension entries
+  u64 packed_off;      // limb offset of the packed region inside a query's part of the slot
 };
 // forward NTT of the first n_entries selection ciphertexts of n_queries queries (in: coefficient form, in_qstride limbs
 // apart) with the outputs stored into the peers' slots in the compact layout [own rows of dim 0 | dims 1..]
@@ -115,8 +121,10 @@ cudaError_t launch_tc_pack_db(const DevParams& P, const u64* db, u64 num_pt, u32
                               u8* dbT, cudaStream_t st);
 // part[q][row][2][k][N] = sum_i1 sv[q][i1] (.) db[row*dimL + i1] mod q for a batch of queries (svT: scratch of
 // tc_sv_bytes; err_flag: device-visible int raised if the kernel's internal pipeline times out)
+// sv_packed = 0: sv is [q][i1][2][k][N] u64 (sv_qstride limbs between queries); sv_packed = 1: sv points at the packed
+// last-dimension region (PushArgs) of query 0, again sv_qstride limbs between queries
 cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u32 dimL, u32 n_rows, const u64* sv,
-                           u64 sv_qstride, u32 n_queries, u8* svT, int* err_flag, int sm_count, u64* part,
+                           u64 sv_qstride, int sv_packed, u32 n_queries, u8* svT, int* err_flag, int sm_count, u64* part,
                            cudaStream_t st);
 
 // StringEncoder packing on the device: raw item bytes -> plaintext coefficients [n_pt][N]

@@ -52,7 +52,22 @@ k_ntt_fwd_push(const __grid_constant__ DevParams P, const u64* __restrict__ in, 
     r_hi = A.n_ranks;
     ce = A.rows_per_rank + (e - A.d0);
   }
-  const u64 off = A.slot_off + (A.g_first + qi) * A.dst_qstride + ce * two_k * N + (u64)within * N;
+  const u64 qoff = A.slot_off + (A.g_first + qi) * A.dst_qstride;
+  if (A.packed_nb && e >= A.last_first) {
+    // last dimension, packed: low 32-bit plane + high plane per polynomial
+    const u64 boff = ((u64)(e - A.last_first) * two_k + within) * N * A.packed_nb;
+    for (int i = tid; i < N; i += NT) {
+      const u64 v = eng_store_fwd<ENG>(s[swz(i)], m);
+      for (u32 r = r_lo; r < r_hi; ++r) {
+        unsigned char* base = reinterpret_cast<unsigned char*>(A.peers[r] + qoff + A.packed_off) + boff;
+        reinterpret_cast<u32*>(base)[i] = (u32)v;
+        if (A.packed_nb == 5) (base + 4 * (size_t)N)[i] = (unsigned char)(v >> 32);
+        else reinterpret_cast<unsigned short*>(base + 4 * (size_t)N)[i] = (unsigned short)(v >> 32);
+      }
+    }
+    return;
+  }
+  const u64 off = qoff + ce * two_k * N + (u64)within * N;
   for (u32 r = r_lo; r < r_hi; ++r) {
     u64* dst = A.peers[r] + off;
 #pragma unroll

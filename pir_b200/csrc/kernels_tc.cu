@@ -130,24 +130,40 @@ k_tc_pack_db(const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows, u32 k
   }
 }
 
-// selection vectors u64 [q][i1][2][k][N] (NTT form, qstride limbs between queries) -> svT (see header).
+// selection vectors (NTT form, sv_qstride limbs between queries) -> svT (see header).  PACKED = false: u64 limbs
+// [q][i1][2][k][N]; PACKED = true: per polynomial a plane of N low 32-bit words and a plane of N high parts of nb - 4
+// bytes (what k_ntt_fwd_push stores into the exchange slots).
 // grid (q * 2 + p, c / 32), block (32, 32); the K padding of svT stays zero from allocation.
+template <bool PACKED>
 __global__ void __launch_bounds__(1024)
-k_tc_pack_sv(const u64* __restrict__ sv, u64 sv_qstride, u32 dimL, u32 kN, u32 nb, u32 n_rows_total, u32 Kp,
+k_tc_pack_sv(const u64* __restrict__ sv, u64 sv_qstride, u32 dimL, u32 N, u32 kN, u32 nb, u32 n_rows_total, u32 Kp,
              u8* __restrict__ svT) {
   __shared__ u64 t[32][33];
   const u32 qp = blockIdx.x, c0 = blockIdx.y * 32;
   const u32 q = qp >> 1, p = qp & 1;
   const u32 tx = threadIdx.x, ty = threadIdx.y;
-  const u64* src = sv + (u64)q * sv_qstride + (u64)p * kN + c0;
   for (u32 i0 = 0; i0 < dimL; i0 += 32) {
     const u32 i = i0 + ty;
-    t[ty][tx] = i < dimL ? src[(u64)i * 2 * kN + tx] : 0ull;
+    u64 v = 0;
+    if (i < dimL) {
+      if constexpr (PACKED) {
+        // polynomial (i, p, j) with j = c0 / N starts at ((i * 2k + p * k + j) * N) * nb bytes
+        const u32 j = c0 / N, n = c0 % N + tx;
+        const u8* base = reinterpret_cast<const u8*>(sv + (u64)q * sv_qstride) +
+                         ((u64)i * 2 * kN + (u64)p * kN + (u64)j * N) * nb;
+        const u64 lo = reinterpret_cast<const u32*>(base)[n];
+        const u64 hi = nb == 5 ? (u64)(base + 4 * (size_t)N)[n] : (u64)reinterpret_cast<const unsigned short*>(base + 4 * (size_t)N)[n];
+        v = lo | (hi << 32);
+      } else {
+        v = sv[(u64)q * sv_qstride + (u64)i * 2 * kN + (u64)p * kN + c0 + tx];
+      }
+    }
+    t[ty][tx] = v;
     __syncthreads();
-    const u64 v = t[tx][ty];
+    const u64 w = t[tx][ty];
     if (i0 + tx < dimL) {
       u8* o = svT + ((u64)(c0 + ty) * n_rows_total + (u64)qp * nb) * Kp + i0 + tx;
-      for (u32 b = 0; b < nb; ++b) o[(u64)b * Kp] = (u8)(v >> (8 * b));
+      for (u32 b = 0; b < nb; ++b) o[(u64)b * Kp] = (u8)(w >> (8 * b));
     }
     __syncthreads();
   }
@@ -442,7 +458,7 @@ u64 tc_sv_bytes(const DevParams& P, const TcGeom& g, u32 n_queries, u32* qt_out,
 }
 
 cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u32 dimL, u32 n_rows, const u64* sv,
-                           u64 sv_qstride, u32 n_queries, u8* svT, int* err_flag, int sm_count, u64* part,
+                           u64 sv_qstride, int sv_packed, u32 n_queries, u8* svT, int* err_flag, int sm_count, u64* part,
                            cudaStream_t st) {
   const u32 kN = (u32)P.k * P.N;
   u32 qt, n_qt;
@@ -457,8 +473,12 @@ cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u
     if (e != cudaSuccess) return e;
   }
   (void)sv_bytes;
-  k_tc_pack_sv<<<dim3(n_queries * 2, kN / 32), dim3(32, 32), 0, st>>>(sv, sv_qstride, dimL, kN, g.nb, sv_rows_total, g.Kp,
-                                                                      svT);
+  if (sv_packed)
+    k_tc_pack_sv<true><<<dim3(n_queries * 2, kN / 32), dim3(32, 32), 0, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb,
+                                                                              sv_rows_total, g.Kp, svT);
+  else
+    k_tc_pack_sv<false><<<dim3(n_queries * 2, kN / 32), dim3(32, 32), 0, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb,
+                                                                               sv_rows_total, g.Kp, svT);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
 

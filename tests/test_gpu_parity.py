@@ -650,8 +650,10 @@ def test_device_populate_and_shard_file_roundtrip(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------ NVLink exchange flow
-@pytest.mark.parametrize("dbsize,world,ql,sub", [(82, 2, 2, 1), (82, 3, 3, 2), (300, 4, 4, 0), (3, 4, 1, 0), (300, 2, 5, 2)])
-def test_peer_memory_exchange_flow_matches_oracle(dbsize, world, ql, sub):
+@pytest.mark.parametrize("dbsize,world,ql,sub,packed", [(82, 2, 2, 1, 0), (82, 3, 3, 2, 0), (300, 4, 4, 0, 0), (3, 4, 1, 0, 0),
+                                                        (300, 2, 5, 2, 0), (300, 2, 5, 2, 1), (82, 3, 3, 2, 1),
+                                                        (300, 4, 2, 0, 1)])
+def test_peer_memory_exchange_flow_matches_oracle(dbsize, world, ql, sub, packed, monkeypatch):
     """pirb_dist_*: the row-sharded flow whose exchange is done by the kernels over peer memory (selection-vector NTT
     storing into every rank's slot, per-sub-batch flags, partial replies added by peer loads).  All ranks live in this
     process and on this one GPU (ShardGroup), which exercises exactly the kernels, flags and slot arithmetic of the
@@ -663,6 +665,12 @@ def test_peer_memory_exchange_flow_matches_oracle(dbsize, world, ql, sub):
     kernel — one rank per GPU, the deployment, is far below that.)"""
     import torch
     from pir_b200 import sharded
+    if packed:
+        # packed = 1: the last-dimension entries travel as packed 5-byte residues and every rank's scan runs on the
+        # tensor cores (normally chosen for shards of >= 1024 plaintexts; forced here on the small test database)
+        monkeypatch.setenv("PIRB_TC_MIN_PT", "0")
+    else:
+        monkeypatch.setenv("PIRB_DIST_PACKED", "0")
     n = 4096
     ep = pb.GenerateEncryptionParams(n, 20)
     p = pb.CreatePIRParameters(dbsize, 0, 2, ep)
