@@ -445,8 +445,7 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
   if (prof) cudaEventRecord(c->ev[3], st);
   if (d == 1) {
     if (partial) {
-      for (int qi = 0; qi < n_queries; ++qi)
-        LAUNCH(c, launch_modadd_reduce(P, c->part.p + (u64)qi * n_split * ctL, ctL, n_split, d_out + qi * ctL, 1, st));
+      LAUNCH(c, launch_modadd_reduce(P, c->part.p, ctL, n_split, d_out, 1, st, n_queries, (u64)n_split * ctL, ctL));
     } else {
       LAUNCH(c, launch_ntt_inv(P, c->part.p, d_out, 2 * k, k, 0, n_split, (u64)n_rows * ctL, n_queries,
                                (u64)n_split * n_rows * ctL, ctL, st));
@@ -480,9 +479,8 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
                              n_entries, n_groups, w_out, ns, c->part.p, st));
     const u64 lvl_cts = (u64)n_groups * w_out;  // per query
     if (l == 0 && partial) {
-      for (int qi = 0; qi < n_queries; ++qi)
-        LAUNCH(c, launch_modadd_reduce(P, c->part.p + (u64)qi * ns * lvl_cts * ctL, lvl_cts * ctL, ns,
-                                       d_out + (u64)qi * lvl_cts * ctL, lvl_cts, st));
+      LAUNCH(c, launch_modadd_reduce(P, c->part.p, lvl_cts * ctL, ns, d_out, lvl_cts, st, n_queries, (u64)ns * lvl_cts * ctL,
+                                     lvl_cts * ctL));
     } else {
       u64* dst = d_out;
       if (l != 0) {
@@ -1182,6 +1180,7 @@ int pirb_multiply_partial_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_
   const int rc = run_graphed(c, std::make_tuple(3, n_queries, 0ull, (const void*)d_sv_ntt, (const void*)d_partial),
                              st, [&](cudaStream_t s_) -> int {
                                c->launches = 0;
+                               if (c->profiling) cudaEventRecord(c->ev[0], s_);
                                return run_multiply(c, const_cast<u64*>(U(d_sv_ntt)), c->dim_sum * c->ctL, (int)n_queries,
                                                    U(d_partial), 1, s_, true);
                              });
@@ -1633,9 +1632,8 @@ int pirb_scan_dev(pirb_ctx* c, const uint64_t* d_sv_ntt, uint32_t n_queries, uin
   if (d_rows && n_split == 1)
     CU(cudaMemcpyAsync(d_rows, c->part.p, (size_t)n_queries * n_rows * c->ctL * sizeof(u64), cudaMemcpyDeviceToDevice, st));
   if (d_rows && n_split != 1) {
-    for (u32 qi = 0; qi < n_queries; ++qi)
-      LAUNCH(c, launch_modadd_reduce(c->P, c->part.p + (u64)qi * n_split * n_rows * c->ctL, (u64)n_rows * c->ctL,
-                                     n_split, U(d_rows) + (u64)qi * n_rows * c->ctL, n_rows, st));
+    LAUNCH(c, launch_modadd_reduce(c->P, c->part.p, (u64)n_rows * c->ctL, n_split, U(d_rows), n_rows, st, (int)n_queries,
+                                   (u64)n_split * n_rows * c->ctL, (u64)n_rows * c->ctL));
   }
   return 0;
 }

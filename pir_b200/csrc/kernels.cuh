@@ -68,8 +68,9 @@ cudaError_t launch_dim_mac(const DevParams& P, const u64* pts, u64 pts_qstride, 
                            cudaStream_t st);
 
 // out[i] = sum_g in[g*stride + i] mod q_j(i)   for [n_cts][2][k][N] arrays (cross-GPU partial combine)
+// (n_batch independent reductions, in_bstride / out_bstride limbs apart)
 cudaError_t launch_modadd_reduce(const DevParams& P, const u64* in, u64 stride, int n_parts, u64* out, u64 n_cts,
-                                 cudaStream_t st);
+                                 cudaStream_t st, int n_batch = 1, u64 in_bstride = 0, u64 out_bstride = 0);
 // out[i] = sum over peers of *(peers[g] + i) mod q: same, reading each partial through its own (peer) pointer
 cudaError_t launch_modadd_reduce_ptrs(const DevParams& P, const u64* const* peers_dev, int n_parts, u64 offset_limbs,
                                       u64* out, u64 n_cts, cudaStream_t st);

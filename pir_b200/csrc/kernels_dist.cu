@@ -8,6 +8,8 @@
 //                    scope).  Stream order puts it behind the producer's stores.
 //   k_wait           before a consumer kernel: spin (acquire, system scope) until every rank's flag has reached the
 //                    sequence number; bounded by a timeout that raises an error word instead of hanging the GPU.
+#include <algorithm>
+#include <cstdlib>
 #include <set>
 #include <type_traits>
 #include <utility>
@@ -24,54 +26,72 @@ struct DCfg {
   static constexpr size_t SMEM = sizeof(u64) * N;
 };
 
-// grid (polynomial p of the selection vector: entry e = p / 2k, query qi of the sub-batch)
+// Persistent and deliberately NARROW: a polynomial's stores to up to n_ranks peers drain at NVLink speed (~770 GB/s
+// for the whole GPU, i.e. tens of microseconds per CTA), so a full-width grid would park two 512-thread CTAs on every SM
+// for most of the exchange and lock the concurrently running expansion out of registers.  A few dozen CTAs saturate
+// the links; each loops over work items (polynomial p of the selection vector: entry e = p / 2k, query qi).
 template <int LOGN, int ENG>
 __global__ void __launch_bounds__(DCfg<LOGN>::NT, LOGN <= 13 ? 2 : 1)
-k_ntt_fwd_push(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64 in_qstride, const PushArgs A) {
+k_ntt_fwd_push(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64 in_qstride, u32 n_polys,
+               u32 n_queries, const PushArgs A) {
   constexpr int N = DCfg<LOGN>::N, NT = DCfg<LOGN>::NT;
   extern __shared__ u64 s[];
   const int tid = threadIdx.x;
-  const u32 p = blockIdx.x, qi = blockIdx.y;
   const u32 two_k = 2 * P.k;
-  const u32 e = p / two_k, within = p % two_k;
-  const ModC& m = P.m[within % P.k];
-  const u64* src = in + (u64)qi * in_qstride + (u64)p * N;
+  for (u32 item = blockIdx.x; item < n_polys * n_queries; item += gridDim.x) {
+    const u32 p = item % n_polys, qi = item / n_polys;
+    const u32 e = p / two_k, within = p % two_k;
+    const ModC& m = P.m[within % P.k];
+    const u64* src = in + (u64)qi * in_qstride + (u64)p * N;
 #pragma unroll
-  for (int i = tid; i < N; i += NT) s[swz(i)] = eng_load<ENG>(src[i]);
-  __syncthreads();
-  eng_forward<LOGN, NT, ENG>(s, m, tid);
-  // destination(s): compact per-query layout [own rows of dimension 0 | dimensions 1..] in every rank's buffer
-  u32 r_lo, r_hi;
-  u64 ce;  // compact entry index at the destination
-  if (e < A.d0) {
-    r_lo = e / A.rows_per_rank;
-    r_hi = r_lo + 1;
-    ce = e - r_lo * A.rows_per_rank;
-  } else {
-    r_lo = 0;
-    r_hi = A.n_ranks;
-    ce = A.rows_per_rank + (e - A.d0);
-  }
-  const u64 qoff = A.slot_off + (A.g_first + qi) * A.dst_qstride;
-  if (A.packed_nb && e >= A.last_first) {
-    // last dimension, packed: low 32-bit plane + high plane per polynomial
-    const u64 boff = ((u64)(e - A.last_first) * two_k + within) * N * A.packed_nb;
-    for (int i = tid; i < N; i += NT) {
-      const u64 v = eng_store_fwd<ENG>(s[swz(i)], m);
-      for (u32 r = r_lo; r < r_hi; ++r) {
-        unsigned char* base = reinterpret_cast<unsigned char*>(A.peers[r] + qoff + A.packed_off) + boff;
-        reinterpret_cast<u32*>(base)[i] = (u32)v;
-        if (A.packed_nb == 5) (base + 4 * (size_t)N)[i] = (unsigned char)(v >> 32);
-        else reinterpret_cast<unsigned short*>(base + 4 * (size_t)N)[i] = (unsigned short)(v >> 32);
+    for (int i = tid; i < N; i += NT) s[swz(i)] = eng_load<ENG>(src[i]);
+    __syncthreads();
+    eng_forward<LOGN, NT, ENG>(s, m, tid);
+    // destination(s): compact per-query layout [own rows of dimension 0 | dimensions 1..] in every rank's buffer
+    u32 r_lo, r_hi;
+    u64 ce;  // compact entry index at the destination
+    if (e < A.d0) {
+      r_lo = e / A.rows_per_rank;
+      r_hi = r_lo + 1;
+      ce = e - r_lo * A.rows_per_rank;
+    } else {
+      r_lo = 0;
+      r_hi = A.n_ranks;
+      ce = A.rows_per_rank + (e - A.d0);
+    }
+    const u64 qoff = A.slot_off + (A.g_first + qi) * A.dst_qstride;
+    if (A.packed_nb && e >= A.last_first) {
+      // last dimension, packed: per polynomial a plane of low 32-bit words + a plane of high parts.  Four consecutive
+      // coefficients per thread: one 16-byte and one 4-byte (8-byte for 6-byte residues) store per peer.
+      const u64 boff = ((u64)(e - A.last_first) * two_k + within) * N * A.packed_nb;
+      for (int i4 = tid * 4; i4 < N; i4 += NT * 4) {
+        u64 v[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) v[x] = eng_store_fwd<ENG>(s[swz(i4 + x)], m);
+        const uint4 lo = make_uint4((u32)v[0], (u32)v[1], (u32)v[2], (u32)v[3]);
+        for (u32 r = r_lo; r < r_hi; ++r) {
+          unsigned char* base = reinterpret_cast<unsigned char*>(A.peers[r] + qoff + A.packed_off) + boff;
+          *reinterpret_cast<uint4*>(base + 4 * (size_t)i4) = lo;
+          unsigned char* hp = base + 4 * (size_t)N;
+          if (A.packed_nb == 5) {
+            *reinterpret_cast<u32*>(hp + i4) = (u32)(v[0] >> 32) | ((u32)(v[1] >> 32) << 8) | ((u32)(v[2] >> 32) << 16) |
+                                               ((u32)(v[3] >> 32) << 24);
+          } else {
+            *reinterpret_cast<uint2*>(hp + 2 * (size_t)i4) =
+                make_uint2((u32)(v[0] >> 32) | ((u32)(v[1] >> 32) << 16), (u32)(v[2] >> 32) | ((u32)(v[3] >> 32) << 16));
+          }
+        }
+      }
+    } else {
+      const u64 off = qoff + ce * two_k * N + (u64)within * N;
+      for (int i2 = tid * 2; i2 < N; i2 += NT * 2) {
+        ulonglong2 v;
+        v.x = eng_store_fwd<ENG>(s[swz(i2)], m);
+        v.y = eng_store_fwd<ENG>(s[swz(i2 + 1)], m);
+        for (u32 r = r_lo; r < r_hi; ++r) *reinterpret_cast<ulonglong2*>(A.peers[r] + off + i2) = v;
       }
     }
-    return;
-  }
-  const u64 off = qoff + ce * two_k * N + (u64)within * N;
-  for (u32 r = r_lo; r < r_hi; ++r) {
-    u64* dst = A.peers[r] + off;
-#pragma unroll
-    for (int i = tid; i < N; i += NT) dst[i] = eng_store_fwd<ENG>(s[swz(i)], m);
+    __syncthreads();  // the shared-memory polynomial is overwritten by the next item
   }
 }
 
@@ -96,7 +116,10 @@ cudaError_t launch_ntt_fwd_push(const DevParams& P, const u64* in, u64 in_qstrid
         configured.insert(key);
       }
     }
-    kern<<<dim3(n_entries * 2 * P.k, n_queries), DCfg<LN>::NT, DCfg<LN>::SMEM, st>>>(P, in, in_qstride, A);
+    const u32 n_polys = n_entries * 2 * P.k;
+    static const int width = getenv("PIRB_PUSH_CTAS") ? atoi(getenv("PIRB_PUSH_CTAS")) : 64;
+    const u32 grid = std::min<u64>((u64)n_polys * n_queries, (u64)std::max(1, width));
+    kern<<<grid, DCfg<LN>::NT, DCfg<LN>::SMEM, st>>>(P, in, in_qstride, n_polys, n_queries, A);
     return cudaGetLastError();
   };
 #define PIRB_CASE(LN)                                              \

@@ -956,9 +956,11 @@ cudaError_t launch_mul_inv_pow_x(const DevParams& P, const u64* in, u64* out, u3
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_modadd_reduce(const __grid_constant__ DevParams P, const u64* __restrict__ in, u64 stride, int n_parts,
-                u64* __restrict__ out, u64 total_limbs) {
+                u64* __restrict__ out, u64 total_limbs, u64 in_bstride, u64 out_bstride) {
   const u64 i = ((u64)blockIdx.x * 256 + threadIdx.x) * 2;
   if (i >= total_limbs) return;
+  in += blockIdx.y * in_bstride;
+  out += blockIdx.y * out_bstride;
   const u64 q = P.m[(i / P.N) % P.k].q;
   ulonglong2 v = ldg128(in + i);
   for (int g = 1; g < n_parts; ++g) {
@@ -969,10 +971,11 @@ k_modadd_reduce(const __grid_constant__ DevParams P, const u64* __restrict__ in,
   *reinterpret_cast<ulonglong2*>(out + i) = v;
 }
 cudaError_t launch_modadd_reduce(const DevParams& P, const u64* in, u64 stride, int n_parts, u64* out, u64 n_cts,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, int n_batch, u64 in_bstride, u64 out_bstride) {
   const u64 total = n_cts * 2 * P.k * P.N;
-  if (!total) return cudaSuccess;
-  k_modadd_reduce<<<(unsigned)((total / 2 + 255) / 256), 256, 0, st>>>(P, in, stride, n_parts, out, total);
+  if (!total || n_batch <= 0) return cudaSuccess;
+  k_modadd_reduce<<<dim3((unsigned)((total / 2 + 255) / 256), (unsigned)n_batch), 256, 0, st>>>(P, in, stride, n_parts, out,
+                                                                                              total, in_bstride, out_bstride);
   return cudaGetLastError();
 }
 

@@ -133,17 +133,19 @@ k_tc_pack_db(const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows, u32 k
 // selection vectors (NTT form, sv_qstride limbs between queries) -> svT (see header).  PACKED = false: u64 limbs
 // [q][i1][2][k][N]; PACKED = true: per polynomial a plane of N low 32-bit words and a plane of N high parts of nb - 4
 // bytes (what k_ntt_fwd_push stores into the exchange slots).
-// grid (q * 2 + p, c / 32), block (32, 32); the K padding of svT stays zero from allocation.
+// A block transposes a tile of 128 selection entries (one K chunk) x 32 coefficients through shared memory: loads are
+// coalesced along the coefficient axis, stores are 16 bytes of K per (coefficient, limb byte).
+// grid (q * 2 + p, c / 32, K chunk), block 256; the K padding of svT stays zero from allocation.
 template <bool PACKED>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 k_tc_pack_sv(const u64* __restrict__ sv, u64 sv_qstride, u32 dimL, u32 N, u32 kN, u32 nb, u32 n_rows_total, u32 Kp,
              u8* __restrict__ svT) {
-  __shared__ u64 t[32][33];
-  const u32 qp = blockIdx.x, c0 = blockIdx.y * 32;
+  __shared__ u64 t[128][33];
+  const u32 qp = blockIdx.x, c0 = blockIdx.y * 32, i0 = blockIdx.z * 128;
   const u32 q = qp >> 1, p = qp & 1;
-  const u32 tx = threadIdx.x, ty = threadIdx.y;
-  for (u32 i0 = 0; i0 < dimL; i0 += 32) {
-    const u32 i = i0 + ty;
+  const u32 tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
+  for (u32 ii = ty; ii < 128; ii += 8) {
+    const u32 i = i0 + ii;
     u64 v = 0;
     if (i < dimL) {
       if constexpr (PACKED) {
@@ -152,20 +154,31 @@ k_tc_pack_sv(const u64* __restrict__ sv, u64 sv_qstride, u32 dimL, u32 N, u32 kN
         const u8* base = reinterpret_cast<const u8*>(sv + (u64)q * sv_qstride) +
                          ((u64)i * 2 * kN + (u64)p * kN + (u64)j * N) * nb;
         const u64 lo = reinterpret_cast<const u32*>(base)[n];
-        const u64 hi = nb == 5 ? (u64)(base + 4 * (size_t)N)[n] : (u64)reinterpret_cast<const unsigned short*>(base + 4 * (size_t)N)[n];
+        const u64 hi = nb == 5 ? (u64)(base + 4 * (size_t)N)[n]
+                               : (u64)reinterpret_cast<const unsigned short*>(base + 4 * (size_t)N)[n];
         v = lo | (hi << 32);
       } else {
         v = sv[(u64)q * sv_qstride + (u64)i * 2 * kN + (u64)p * kN + c0 + tx];
       }
     }
-    t[ty][tx] = v;
-    __syncthreads();
-    const u64 w = t[tx][ty];
-    if (i0 + tx < dimL) {
-      u8* o = svT + ((u64)(c0 + ty) * n_rows_total + (u64)qp * nb) * Kp + i0 + tx;
-      for (u32 b = 0; b < nb; ++b) o[(u64)b * Kp] = (u8)(w >> (8 * b));
+    t[ii][tx] = v;
+  }
+  __syncthreads();
+  // thread (coefficient tx, group ty of 16 consecutive selection entries)
+  const u32 ib = i0 + ty * 16;
+  if (ib < Kp) {
+    u64 w[16];
+#pragma unroll
+    for (int x = 0; x < 16; ++x) w[x] = t[ty * 16 + x][tx];
+    u8* o = svT + ((u64)(c0 + tx) * n_rows_total + (u64)qp * nb) * Kp + ib;
+    for (u32 b = 0; b < nb; ++b) {
+      u32 r[4];
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4)
+        r[g4] = (u32)((w[g4 * 4] >> (8 * b)) & 0xFF) | ((u32)((w[g4 * 4 + 1] >> (8 * b)) & 0xFF) << 8) |
+                ((u32)((w[g4 * 4 + 2] >> (8 * b)) & 0xFF) << 16) | ((u32)((w[g4 * 4 + 3] >> (8 * b)) & 0xFF) << 24);
+      *reinterpret_cast<uint4*>(o + (u64)b * Kp) = make_uint4(r[0], r[1], r[2], r[3]);
     }
-    __syncthreads();
   }
 }
 
@@ -473,12 +486,11 @@ cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u
     if (e != cudaSuccess) return e;
   }
   (void)sv_bytes;
+  const dim3 pgrid(n_queries * 2, kN / 32, g.kch);
   if (sv_packed)
-    k_tc_pack_sv<true><<<dim3(n_queries * 2, kN / 32), dim3(32, 32), 0, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb,
-                                                                              sv_rows_total, g.Kp, svT);
+    k_tc_pack_sv<true><<<pgrid, 256, 0, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb, sv_rows_total, g.Kp, svT);
   else
-    k_tc_pack_sv<false><<<dim3(n_queries * 2, kN / 32), dim3(32, 32), 0, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb,
-                                                                               sv_rows_total, g.Kp, svT);
+    k_tc_pack_sv<false><<<pgrid, 256, 0, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb, sv_rows_total, g.Kp, svT);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
 

@@ -694,3 +694,99 @@ def test_peer_memory_exchange_flow_matches_oracle(dbsize, world, ql, sub, packed
             for i in range(ql):
                 want = orc.process_query(db_ntt, p.dimensions, elts, keys.reshape(-1), queries[r, i])
                 assert np.array_equal(got[i], want), (step, r, i)
+
+
+# ------------------------------------------------------------------------------------------------ engines, wide moduli
+@pytest.mark.parametrize("env", [{"PIRB_NTT_ENGINE": "0"}, {"PIRB_NTT_ENGINE": "1"}, {"PIRB_MAC_MODE": "0"},
+                                 {"PIRB_MAC_MODE": "1"}, {"PIRB_KS_CLUSTER": "0"}, {"PIRB_TC_MIN": "0"},
+                                 {"PIRB_TC_MIN_PT": "0"}, {"PIRB_GRAPHS": "0"},
+                                 {"PIRB_NTT_ENGINE": "0", "PIRB_MAC_MODE": "0", "PIRB_KS_CLUSTER": "0"}])
+def test_every_engine_variant_is_bit_identical(env, monkeypatch):
+    """The library picks the fastest exact arithmetic the moduli allow (FP64 / lazy integer / corrected integer NTT
+    engines, FP64 / 24-bit / 128-bit multiply-accumulate chains, cluster or three-launch key switch, tensor-core or
+    CUDA-core batched scan, graph replay or eager launches).  All of them are exact, so forcing any of them must give the
+    oracle's answer limb for limb: a batch of 5 queries on the reference's 2-dimensional test shape."""
+    for kk, v in env.items():
+        monkeypatch.setenv(kk, v)
+    n = 4096
+    ep = pb.GenerateEncryptionParams(n, 20)
+    p = pb.CreatePIRParameters(82, 0, 2, ep)
+    mods = list(ep.coeff_modulus)
+    k = len(mods) - 1
+    rng = np.random.default_rng(17)
+    coeffs = rng.integers(0, ep.plain_modulus, (p.num_pt, n), dtype=np.uint64)
+    db = pb.PIRDatabase(p)
+    db.load_coeff(coeffs)
+    server = pb.PIRServer.Create(db, p)
+    orc = ob.Oracle(n, mods, ep.plain_modulus)
+    db_ntt = np.stack([orc.plain_to_ntt(c) for c in coeffs])
+    elts = [(n >> i) + 1 for i in range(12)]
+    keys = np.stack([rng.integers(0, q, (len(elts), k, 2, n), dtype=np.uint64) for q in mods], axis=3)
+    gk = pb.GaloisKeys(elts, keys.reshape(-1))
+    queries = np.stack([rng.integers(0, q, (5, 1, 2, n), dtype=np.uint64) for q in mods[:k]], axis=3)
+    for rep in range(2):  # second call replays the captured graph where graphs are on
+        got = server.ProcessRequest(pb.Request([q for q in queries], gk)).reply
+        for i in range(5):
+            want = orc.process_query(db_ntt, p.dimensions, elts, keys.reshape(-1), queries[i])
+            assert np.array_equal(got[i], want), (env, rep, i)
+
+
+@pytest.mark.parametrize("dims", [[600], [300, 2]])
+def test_sixty_bit_moduli_keep_lazy_accumulation_chains_exact(dims):
+    """Moduli up to 2^61 are accepted (SEAL allows user moduli up to 60 bits); products are then below 2^120 and a
+    128-bit lazy accumulator wraps after 256 terms.  A dimension of 600 (scan) or 300 (upper dimension) must therefore
+    be split into exact chains: pirb_db_multiply against the oracle, N=2048, one 60-bit data modulus."""
+    n = 2048
+    mods = [0xfffffffffffc001, 0xffffffffffe8001]       # data modulus, special prime: 60-bit, = 1 mod 2N
+    t = int(pb.GenerateEncryptionParams(4096, 20).plain_modulus)
+    assert all((q - 1) % (2 * n) == 0 for q in mods)
+    num_pt = 600
+    ep = pb.EncryptionParameters(n, t, mods)
+    p = pb.PIRParameters(num_items=num_pt, num_pt=num_pt, dimensions=list(dims), bytes_per_item=0, items_per_plaintext=1,
+                         bits_per_coeff=0, encryption_parameters=ep)
+    rng = np.random.default_rng(23)
+    orc = ob.Oracle(n, mods, t)
+    db_ntt = rng.integers(0, mods[0], (num_pt, 1, n), dtype=np.uint64)
+    db = pb.PIRDatabase(p)
+    db.load_ntt(db_ntt)
+    sv = rng.integers(0, mods[0], (sum(dims), 2, 1, n), dtype=np.uint64)
+    want, sv_after = orc.db_multiply(db_ntt, dims, sv)
+    got_sv = sv.copy()
+    got = db.multiply(got_sv)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got_sv, sv_after)
+
+
+# ------------------------------------------------------------------------------------------------ parity at full size
+@pytest.mark.parametrize("workload,nq", [("cfg4", 1), ("cfg4", 8), ("cfg3", 1), ("cfg3", 4), ("cfg5b", 1)])
+def test_full_size_databases_sampled_parity(workload, nq):
+    """BASELINE configs[3] (2^22 x 256 B, 6.7 GiB), configs[2] (N=8192, 2^20 x 1 KiB, 13.5 GiB) and configs[4] d=2
+    (2^24 x 256 B, 27 GiB) at their real sizes on one GPU, synthetic NTT-form database.  The oracle cannot process
+    gigabytes in a test, so the chain is checked in pieces that together cover every kernel at full grid size
+    (sharded.sampled_parity): the full expansion + selection-vector NTT of a query; the scan of the whole database with
+    the first, a middle and the short last row recomputed by the oracle from the device's database; the upper dimension
+    recomputed by the oracle from ALL device rows.  nq > 1 answers a batch (tensor-core scan) and checks query 0 and
+    that every query of the batch equals its single-query answer."""
+    import torch
+    import bench
+    from pir_b200 import sharded
+    items, size, d, n, bits, _ = bench.WORKLOADS[workload]
+    p = pb.CreatePIRParameters(items, size, d, pb.GenerateEncryptionParams(n, bits))
+    ep = p.encryption_parameters
+    mods = list(ep.coeff_modulus)
+    free, _total = torch.cuda.mem_get_info()
+    need = p.num_pt * (len(mods) - 1) * n * 8 * (1.8 if nq > 1 else 1.1) + (8 << 30)
+    if free < need:
+        pytest.skip("not enough free device memory for %s" % workload)
+    srv = sharded.ShardServer(p, device=0)
+    srv.db.fill_random(5)
+    queries, elts, keys = bench.synth_inputs(n, mods, list(p.dimensions), nq, 31)
+    srv.set_keys(pb.GaloisKeys(elts, keys.reshape(-1)))
+    d_q = sharded.to_device(queries, "cuda:0")
+    replies = sharded.to_host(srv.answer(d_q))
+    orc = ob.Oracle(n, mods, ep.plain_modulus)
+    ok, desc = sharded.sampled_parity(srv, orc, p, elts, keys, queries[0], replies[0])
+    assert ok, desc
+    for i in range(1, nq):
+        single = sharded.to_host(srv.answer(d_q[i:i + 1]))[0]
+        assert np.array_equal(replies[i], single), i
