@@ -408,6 +408,11 @@ def run_ours(args):
         if ref_srv is not srv:
             del ref_srv
 
+    # ---------------- N=1: the C++ drop-in itself (pir::PIRServer::ProcessRequest of the shim), limbs and wire bytes ----
+    shim = None
+    if world == 1 and not args.no_shim:
+        shim = run_shim_bench(items, size, d, n, bits, ql, min(args.steps, 20))
+
     # ---------------- N=1: single-query latency on BASELINE configs[1] ----------------
     latency_cfg2 = None
     if world == 1 and args.workload != "cfg2" and not args.no_cfg2:
@@ -483,11 +488,27 @@ def run_ours(args):
         "parity_vs_oracle": parity,
         "parity": parity_detail,
         "latency_cfg2": latency_cfg2,
+        "e2e_cpp": (shim or {}).get("e2e_cpp"),
+        "e2e_wire": (shim or {}).get("e2e_wire"),
         "clocks": clocks,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_shim_bench(items, size, d, n, bits, nq, steps, n_gpus=1):
+    """build/shim_bench: the same workload through the C++ shim's PIRServer::ProcessRequest, in its own process."""
+    import subprocess
+    exe = os.path.join(ROOT, "build", "shim_bench")
+    if not os.path.exists(exe):
+        return {"e2e_cpp": {"unavailable": "build/shim_bench not built"}, "e2e_wire": None}
+    try:
+        out = subprocess.run([exe, str(items), str(size), str(d), str(n), str(bits), str(nq), str(steps), str(n_gpus)],
+                             capture_output=True, text=True, timeout=600)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"e2e_cpp": {"unavailable": "%s: %s" % (type(e).__name__, e)}, "e2e_wire": None}
 
 
 def cfg2_latency(pb, sharded, torch, dev, local_rank, flush_l2, steps=30):
@@ -544,6 +565,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cfg2", action="store_true")
+    ap.add_argument("--no-shim", action="store_true")
     ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "nccl"],
                     help="N>1: selection vectors and partial replies travel by in-kernel NVLink peer stores/loads "
                          "(default) or by NCCL all-gather")

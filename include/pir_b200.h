@@ -199,6 +199,12 @@ int pirb_last_scan_ms(pirb_ctx* ctx, float* out_ms);
 uint64_t pirb_last_launch_count(const pirb_ctx* ctx);
 uint64_t pirb_scan_bytes(const pirb_ctx* ctx, uint32_t n_queries);
 
+/* Page-locked host memory (portable across devices, mapped): buffers from here are read and written IN PLACE by the
+ * kernels of pirb_answer / pirb_dist_answer* — no staging copies — and keep the captured CUDA graphs of pirb_answer
+ * valid across calls (they are keyed on the buffer addresses).  For hosts that do not link the CUDA runtime. */
+int pirb_host_alloc(uint64_t bytes, void** out);
+void pirb_host_free(void* p);
+
 /* Host-side shape math of the reference, exported so bindings need not re-implement it:
  * PIRDatabase::calculate_dimensions (database.cpp:334-342), next_power_two / ceil_log2 / log2 (utils.h:29-37,
  * utils.cpp:16-44), PlainModulus::Batching and CoeffModulus::BFVDefault as used by GenerateEncryptionParams

@@ -92,6 +92,8 @@ SYMBOLS = {
     "pirb_last_scan_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pirb_last_launch_count": (C.c_uint64, [C.c_void_p]),
     "pirb_scan_bytes": (C.c_uint64, [C.c_void_p, C.c_uint32]),
+    "pirb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "pirb_host_free": (None, [C.c_void_p]),
     "pirb_calculate_dimensions": (None, [C.c_uint32, C.c_uint32, u32p]),
     "pirb_next_power_two": (C.c_uint64, [C.c_uint64]),
     "pirb_ceil_log2": (C.c_uint32, [C.c_uint32]),

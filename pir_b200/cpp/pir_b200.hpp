@@ -343,42 +343,101 @@ inline std::vector<uint64_t> integer_encode(int64_t value, size_t N, uint64_t t)
     if (v & 1) pt[i] = neg ? t - 1 : 1;
   return pt;
 }
+// page-locked staging that lives as long as the server: the kernels read / write it in place and the captured graph of
+// the answer path (keyed on the buffer addresses) is replayed from the second request on
+struct PinnedBuf {
+  uint64_t* p = nullptr;
+  size_t cap = 0;  // limbs
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf() { if (p) pirb_host_free(p); }
+  Status ensure(size_t limbs) {
+    if (limbs <= cap) return OkStatus();
+    if (p) { pirb_host_free(p); p = nullptr; cap = 0; }
+    void* q = nullptr;
+    Status st = FromRc(pirb_host_alloc(limbs * sizeof(uint64_t), &q));
+    if (!st.ok()) return st;
+    p = static_cast<uint64_t*>(q);
+    cap = limbs;
+    return OkStatus();
+  }
+};
+// 128-bit content fingerprint (four independent multiply-rotate lanes over 64-bit words + the length): identifies a
+// client's key material so that its device-resident copy is reused by later requests
+struct Fingerprint {
+  uint64_t a = 0, b = 0;
+  bool operator==(const Fingerprint& o) const { return a == o.a && b == o.b; }
+};
+inline Fingerprint fingerprint(const void* data, size_t n_bytes, uint64_t salt = 0) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint64_t h[4] = {0x9e3779b97f4a7c15ull ^ salt, 0xbf58476d1ce4e5b9ull, 0x94d049bb133111ebull, 0x2545f4914f6cdd1dull ^ n_bytes};
+  auto mix = [](uint64_t h_, uint64_t w) {
+    h_ ^= w;
+    h_ = (h_ << 27) | (h_ >> 37);
+    return h_ * 0xff51afd7ed558ccdull + 0xc4ceb9fe1a85ec53ull;
+  };
+  size_t i = 0;
+  for (; i + 32 <= n_bytes; i += 32) {
+    uint64_t w[4];
+    std::memcpy(w, p + i, 32);
+    h[0] = mix(h[0], w[0]);
+    h[1] = mix(h[1], w[1]);
+    h[2] = mix(h[2], w[2]);
+    h[3] = mix(h[3], w[3]);
+  }
+  for (int lane = 0; i < n_bytes; i += 8, lane = (lane + 1) & 3) {
+    uint64_t w = 0;
+    std::memcpy(&w, p + i, std::min<size_t>(8, n_bytes - i));
+    h[lane] = mix(h[lane], w);
+  }
+  Fingerprint f;
+  f.a = mix(mix(h[0], h[1]), h[2] ^ 0x1234567);
+  f.b = mix(mix(h[3], h[2]), h[0] ^ 0x7654321);
+  return f;
+}
 }  // namespace detail
 
 // ---------------------------------------------------------------------------------------------------------------
+// PIRDatabase (database.h:47-127).  One context per GPU: Create(params) / Create(params, device) hold the whole
+// database on one device; Create(params, {d0, d1, ...}) shards it by rows of the first dimension across the listed
+// devices of this process — populate() hands every shard the plaintexts it owns.
 class PIRDatabase {
  public:
-  static StatusOr<std::shared_ptr<PIRDatabase>> Create(std::shared_ptr<PIRParameters> params, int device = 0) {
-    pirb_params p{};
+  static StatusOr<std::shared_ptr<PIRDatabase>> Create(std::shared_ptr<PIRParameters> params,
+                                                       const std::vector<int>& devices) {
+    if (devices.empty()) return InvalidArgumentError("no device given");
     const auto& ep = params->encryption_parameters;
     if (ep.coeff_modulus.size() > PIRB_MAX_MODULI || params->dimensions.size() > PIRB_MAX_DIMS)
       return InvalidArgumentError("too many moduli or dimensions");
-    p.poly_modulus_degree = ep.poly_modulus_degree;
-    p.n_moduli = (uint32_t)ep.coeff_modulus.size();
-    std::copy(ep.coeff_modulus.begin(), ep.coeff_modulus.end(), p.coeff_modulus);
-    p.plain_modulus = ep.plain_modulus;
-    p.n_dims = (uint32_t)params->dimensions.size();
-    std::copy(params->dimensions.begin(), params->dimensions.end(), p.dims);
-    p.num_pt = params->num_pt;
-    p.device = device;
-    p.shard_index = 0;
-    p.shard_count = 1;
-    pirb_ctx* ctx = nullptr;
-    Status st = FromRc(pirb_ctx_create(&p, &ctx));
-    if (!st.ok()) return st;
-    return std::shared_ptr<PIRDatabase>(new PIRDatabase(params, ctx));
-  }
-  static StatusOr<std::shared_ptr<PIRDatabase>> Create(const std::vector<std::string>& rawdb,
-                                                       std::shared_ptr<PIRParameters> params, int device = 0) {
-    auto db = Create(params, device);
-    if (!db.ok()) return db.status();
-    Status st = (*db)->populate(rawdb);
-    if (!st.ok()) return st;
+    std::shared_ptr<PIRDatabase> db(new PIRDatabase(params));
+    for (size_t i = 0; i < devices.size(); ++i) {
+      pirb_params p{};
+      p.poly_modulus_degree = ep.poly_modulus_degree;
+      p.n_moduli = (uint32_t)ep.coeff_modulus.size();
+      std::copy(ep.coeff_modulus.begin(), ep.coeff_modulus.end(), p.coeff_modulus);
+      p.plain_modulus = ep.plain_modulus;
+      p.n_dims = (uint32_t)params->dimensions.size();
+      std::copy(params->dimensions.begin(), params->dimensions.end(), p.dims);
+      p.num_pt = params->num_pt;
+      p.device = devices[i];
+      p.shard_index = (uint32_t)i;
+      p.shard_count = (uint32_t)devices.size();
+      pirb_ctx* ctx = nullptr;
+      Status st = FromRc(pirb_ctx_create(&p, &ctx));
+      if (!st.ok()) return st;
+      db->ctx_.emplace_back(ctx);
+    }
     return db;
   }
-  static StatusOr<std::shared_ptr<PIRDatabase>> Create(const std::vector<int64_t>& rawdb,
-                                                       std::shared_ptr<PIRParameters> params, int device = 0) {
-    auto db = Create(params, device);
+  static StatusOr<std::shared_ptr<PIRDatabase>> Create(std::shared_ptr<PIRParameters> params, int device = 0) {
+    return Create(std::move(params), std::vector<int>{device});
+  }
+  template <typename Raw>
+  static StatusOr<std::shared_ptr<PIRDatabase>> Create(const std::vector<Raw>& rawdb,
+                                                       std::shared_ptr<PIRParameters> params,
+                                                       const std::vector<int>& devices = {0}) {
+    auto db = Create(params, devices);
     if (!db.ok()) return db.status();
     Status st = (*db)->populate(rawdb);
     if (!st.ok()) return st;
@@ -407,8 +466,10 @@ class PIRDatabase {
         std::copy(coeffs.begin(), coeffs.end(), buf.begin() + (i - start) * N);
         raw_it = end_it;
       }
-      Status st = FromRc(pirb_db_load_coeff(ctx_.get(), buf.data(), start, stop - start));
-      if (!st.ok()) return st;
+      for (auto& c : ctx_) {  // every shard keeps the plaintexts it owns
+        Status st = FromRc(pirb_db_load_coeff(c.get(), buf.data(), start, stop - start));
+        if (!st.ok()) return st;
+      }
     }
     return OkStatus();
   }
@@ -423,21 +484,36 @@ class PIRDatabase {
       auto pt = detail::integer_encode(rawdb[i], N, params_->encryption_parameters.plain_modulus);
       std::copy(pt.begin(), pt.end(), buf.begin() + i * N);
     }
-    return FromRc(pirb_db_load_coeff(ctx_.get(), buf.data(), 0, rawdb.size()));
+    for (auto& c : ctx_) {
+      Status st = FromRc(pirb_db_load_coeff(c.get(), buf.data(), 0, rawdb.size()));
+      if (!st.ok()) return st;
+    }
+    return OkStatus();
+  }
+  // synthetic NTT-form database (benchmarks): uniform limbs keyed by the global limb index, so the shards of a database
+  // are slices of the unsharded fill with the same seed
+  Status fill_random(uint64_t seed) {
+    for (auto& c : ctx_) {
+      Status st = FromRc(pirb_db_fill_random(c.get(), seed));
+      if (!st.ok()) return st;
+    }
+    return OkStatus();
   }
 
   // database.cpp:290-316 — the selection vector is transformed to NTT form in place
   StatusOr<std::vector<Ciphertext>> multiply(std::vector<Ciphertext>& selection_vector) const {
-    const size_t L = pirb_ct_limbs(ctx_.get());
+    if (ctx_.size() != 1) return InvalidArgumentError("multiply() needs an unsharded database; use PIRServer");
+    pirb_ctx* ctx = ctx_[0].get();
+    const size_t L = pirb_ct_limbs(ctx);
     std::vector<uint64_t> sv(selection_vector.size() * L);
     for (size_t i = 0; i < selection_vector.size(); ++i) {
       if (selection_vector[i].limbs.size() != L) return InvalidArgumentError("bad ciphertext size");
       std::copy(selection_vector[i].limbs.begin(), selection_vector[i].limbs.end(), sv.begin() + i * L);
     }
-    const size_t cap = pirb_reply_cts(ctx_.get());
+    const size_t cap = pirb_reply_cts(ctx);
     std::vector<uint64_t> out(cap * L);
     uint64_t cnt = 0;
-    Status st = FromRc(pirb_db_multiply(ctx_.get(), sv.data(), selection_vector.size(), out.data(), cap, &cnt));
+    Status st = FromRc(pirb_db_multiply(ctx, sv.data(), selection_vector.size(), out.data(), cap, &cnt));
     if (!st.ok()) return st;
     for (size_t i = 0; i < selection_vector.size(); ++i)
       if (std::memcmp(selection_vector[i].limbs.data(), sv.data() + i * L, L * 8) != 0) {
@@ -449,7 +525,11 @@ class PIRDatabase {
     return res;
   }
 
-  size_t size() const { return pirb_db_size(ctx_.get()); }
+  size_t size() const {  // database.h:94 — plaintexts held, over all shards
+    size_t n = 0;
+    for (auto& c : ctx_) n += pirb_db_size(c.get());
+    return n;
+  }
 
   // database.cpp:318-332 (the parameter-only forms need no device and are what the instance methods use)
   static std::vector<uint32_t> calculate_indices(const PIRParameters& p, uint32_t index) {
@@ -473,84 +553,99 @@ class PIRDatabase {
     return r;
   }
 
-  pirb_ctx* handle() const { return ctx_.get(); }
+  pirb_ctx* handle(size_t shard = 0) const { return ctx_[shard].get(); }
+  size_t shard_count() const { return ctx_.size(); }
   const std::shared_ptr<PIRParameters>& params() const { return params_; }
 
  private:
-  PIRDatabase(std::shared_ptr<PIRParameters> p, pirb_ctx* c) : params_(std::move(p)), ctx_(c) {}
+  explicit PIRDatabase(std::shared_ptr<PIRParameters> p) : params_(std::move(p)) {}
   std::shared_ptr<PIRParameters> params_;
-  std::unique_ptr<pirb_ctx, detail::CtxDeleter> ctx_;
+  std::vector<std::unique_ptr<pirb_ctx, detail::CtxDeleter>> ctx_;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// PIRServer (server.h:43-131).  Differences from the reference that a caller can observe are performance only:
+//   * a client's Galois keys are uploaded once and found again by a fingerprint of their bytes (the reference
+//     deserializes them on every request, server.cpp:46-48);
+//   * all queries of a request are answered by one batched device call (the reference loops, server.cpp:60-63);
+//   * over a sharded database the queries of a request are spread over the GPUs, every GPU multiplies all of them
+//     against its rows, and the exchange runs inside the kernels over NVLink peer memory (pirb_dist_*).
 class PIRServer {
  public:
-  // server.cpp:35-42
+  // server.cpp:35-42.  max_queries_per_gpu: queries one GPU expands per step of the sharded flow.
   static StatusOr<std::unique_ptr<PIRServer>> Create(std::shared_ptr<PIRDatabase> db,
-                                                     std::shared_ptr<PIRParameters> params) {
+                                                     std::shared_ptr<PIRParameters> params,
+                                                     uint32_t max_queries_per_gpu = 8) {
     if (params->num_pt != db->size()) return InvalidArgumentError("database size mismatch");
-    return std::unique_ptr<PIRServer>(new PIRServer(std::move(db), std::move(params)));
+    std::unique_ptr<PIRServer> s(new PIRServer(std::move(db), std::move(params)));
+    const size_t W = s->db_->shard_count();
+    if (W > 1) {
+      if (s->params_->dimensions.size() < 2)
+        return InvalidArgumentError("a sharded PIRServer needs a database of two or more dimensions");
+      s->max_local_ = std::max<uint32_t>(1, max_queries_per_gpu);
+      std::vector<void*> bases(W, nullptr);
+      for (size_t r = 0; r < W; ++r) {
+        Status st = FromRc(pirb_dist_create(s->db_->handle(r), s->max_local_, 0, nullptr, &bases[r]));
+        if (!st.ok()) return st;
+      }
+      for (size_t r = 0; r < W; ++r) {
+        Status st = FromRc(pirb_dist_attach(s->db_->handle(r), bases.data(), (uint32_t)W, (uint32_t)r));
+        if (!st.ok()) return st;
+      }
+    }
+    return s;
   }
 
   // server.cpp:44-65: all queries of the request in one batched device call
   StatusOr<Response> ProcessRequest(const Request& request) const {
-    pirb_ctx* ctx = db_->handle();
-    std::unique_ptr<pirb_keys, detail::KeysDeleter> keys;
-    Status st = LoadKeys(request.galois_keys, keys);
-    if (!st.ok()) return st;
-    Response response;
-    if (request.query.empty()) return response;
-    const size_t L = pirb_ct_limbs(ctx), n_ct = request.query[0].size(), R = pirb_reply_cts(ctx);
-    std::vector<uint64_t> q(request.query.size() * n_ct * L), r(request.query.size() * R * L);
-    for (size_t i = 0; i < request.query.size(); ++i) {
-      if (request.query[i].size() != n_ct || n_ct != pirb_query_cts(ctx))
-        return InvalidArgumentError("Number of ciphertexts doesn't match number of items for oblivious expansion.");
-      for (size_t c = 0; c < n_ct; ++c) {
-        if (request.query[i][c].limbs.size() != L) return InvalidArgumentError("bad ciphertext size");
-        std::copy(request.query[i][c].limbs.begin(), request.query[i][c].limbs.end(), q.begin() + (i * n_ct + c) * L);
-      }
+    const detail::Fingerprint fp = KeyFingerprint(request.galois_keys);
+    auto keys = FindKeys(fp);
+    if (!keys) {
+      auto loaded = UploadKeys(request.galois_keys, fp);
+      if (!loaded.ok()) return loaded.status();
+      keys = *loaded;
     }
-    st = FromRc(pirb_answer(ctx, keys.get(), q.data(), (uint32_t)request.query.size(), n_ct, r.data()));
-    if (!st.ok()) return st;
-    response.reply.resize(request.query.size());
-    for (size_t i = 0; i < request.query.size(); ++i) {
-      response.reply[i].resize(R);
-      for (size_t c = 0; c < R; ++c)
-        response.reply[i][c].limbs.assign(r.begin() + (i * R + c) * L, r.begin() + (i * R + c + 1) * L);
-    }
-    return response;
+    return Answer(request.query, *keys);
   }
 
   // server.cpp:44-65 on the wire: serialized pir.Request in, serialized pir.Response out.  Deserialization failures
   // are InvalidArgument (serialization.h:113-115); relin_keys are parsed for validity and otherwise unused
-  // (server.cpp:53-58).  Reply ciphertexts carry the parms_id of the query's first ciphertext.
+  // (server.cpp:53-58).  Reply ciphertexts carry the parms_id of the query's first ciphertext.  The serialized key
+  // bytes are fingerprinted BEFORE they are parsed: a returning client's keys are neither deserialized nor (for
+  // seed-compressed keys) re-expanded.
   StatusOr<std::string> ProcessRequest(const std::string& serialized_request, bool strict_parms_id = false) const {
     wire::RequestMsg msg;
     if (!wire::Parse(serialized_request, &msg)) return InvalidArgumentError("malformed Request message");
     const EncryptionParameters& ep = params_->encryption_parameters;
     const wire::SealParams sp = ToSealParams(ep);
-    auto gk = DeserializeGaloisKeys(ep, msg.galois_keys);
-    if (!gk.ok()) return gk.status();
+    const detail::Fingerprint fp = detail::fingerprint(msg.galois_keys.data(), msg.galois_keys.size(), /*salt=*/1);
+    auto keys = FindKeys(fp);
+    if (!keys) {
+      auto gk = DeserializeGaloisKeys(ep, msg.galois_keys);
+      if (!gk.ok()) return gk.status();
+      auto loaded = UploadKeys(*gk, fp);
+      if (!loaded.ok()) return loaded.status();
+      keys = *loaded;
+    }
     std::string err;
     if (!msg.relin_keys.empty()) {
       wire::KSwitchKeysData rk;
       if (!wire::LoadKSwitchKeys(msg.relin_keys, sp, &rk, &err, /*keep_data=*/false)) return InvalidArgumentError(err);
     }
-    Request req;
-    req.galois_keys = std::move(*gk);
+    std::vector<std::vector<Ciphertext>> query;
     wire::parms_id_type pid = wire::data_parms_id(sp), got;
     bool first = true;
     for (const auto& q : msg.query) {
-      req.query.emplace_back();
+      query.emplace_back();
       for (const auto& blob : q.ct) {
         auto ct = DeserializeCiphertext(ep, blob, &got);
         if (!ct.ok()) return ct.status();
         if (strict_parms_id && got != wire::data_parms_id(sp)) return InvalidArgumentError("ciphertext data is invalid");
         if (first) { pid = got; first = false; }
-        req.query.back().push_back(std::move(*ct));
+        query.back().push_back(std::move(*ct));
       }
     }
-    auto resp = ProcessRequest(req);
+    auto resp = Answer(query, *keys);
     if (!resp.ok()) return resp.status();
     wire::ResponseMsg out;
     for (const auto& r : resp->reply) {
@@ -562,10 +657,9 @@ class PIRServer {
 
   // server.cpp:67-76
   Status substitute_power_x_inplace(Ciphertext& ct, uint32_t power, const GaloisKeys& gal_keys) const {
-    std::unique_ptr<pirb_keys, detail::KeysDeleter> keys;
-    Status st = LoadKeys(gal_keys, keys);
-    if (!st.ok()) return st;
-    return FromRc(pirb_substitute(db_->handle(), keys.get(), ct.data(), power));
+    auto keys = KeysFor(gal_keys);
+    if (!keys.ok()) return keys.status();
+    return FromRc(pirb_substitute(db_->handle(), (*keys)->per_shard[0].get(), ct.data(), power));
   }
   // server.cpp:78-103
   void multiply_inverse_power_of_x(const Ciphertext& encrypted, uint32_t k, Ciphertext& destination) const {
@@ -586,25 +680,121 @@ class PIRServer {
     return Expand(in.data(), cts.size(), total_items, 0, gal_keys);
   }
 
+  void set_key_cache_capacity(size_t n) { key_cache_capacity_ = std::max<size_t>(1, n); }
+  size_t key_cache_hits() const { return key_hits_; }
+
  private:
+  struct KeySet {  // one client's Galois keys, resident on every shard's device
+    std::vector<std::unique_ptr<pirb_keys, detail::KeysDeleter>> per_shard;
+  };
   PIRServer(std::shared_ptr<PIRDatabase> db, std::shared_ptr<PIRParameters> params)
       : db_(std::move(db)), params_(std::move(params)) {}
-  Status LoadKeys(const GaloisKeys& gk, std::unique_ptr<pirb_keys, detail::KeysDeleter>& out) const {
-    pirb_keys* k = nullptr;
+
+  static detail::Fingerprint KeyFingerprint(const GaloisKeys& gk) {
+    detail::Fingerprint a = detail::fingerprint(gk.limbs.data(), gk.limbs.size() * sizeof(uint64_t));
+    detail::Fingerprint b = detail::fingerprint(gk.elts.data(), gk.elts.size() * sizeof(uint32_t), a.a);
+    return detail::Fingerprint{a.a ^ b.b, a.b ^ b.a};
+  }
+  std::shared_ptr<KeySet> FindKeys(const detail::Fingerprint& fp) const {
+    for (auto it = key_cache_.begin(); it != key_cache_.end(); ++it)
+      if (it->first == fp) {
+        auto hit = *it;
+        key_cache_.erase(it);
+        key_cache_.insert(key_cache_.begin(), hit);  // most recently used first
+        ++key_hits_;
+        return hit.second;
+      }
+    return nullptr;
+  }
+  StatusOr<std::shared_ptr<KeySet>> UploadKeys(const GaloisKeys& gk, const detail::Fingerprint& fp) const {
     if (gk.limbs.size() != gk.elts.size() * pirb_key_limbs(db_->handle()))
       return InvalidArgumentError("Galois key data has the wrong size");
-    Status st = FromRc(pirb_keys_load(db_->handle(), gk.elts.data(), (uint32_t)gk.elts.size(), gk.limbs.data(), &k));
-    out.reset(k);
-    return st;
+    auto ks = std::make_shared<KeySet>();
+    for (size_t r = 0; r < db_->shard_count(); ++r) {
+      pirb_keys* k = nullptr;
+      Status st = FromRc(pirb_keys_load(db_->handle(r), gk.elts.data(), (uint32_t)gk.elts.size(), gk.limbs.data(), &k));
+      ks->per_shard.emplace_back(k);
+      if (!st.ok()) return st;
+    }
+    key_cache_.insert(key_cache_.begin(), std::make_pair(fp, ks));
+    while (key_cache_.size() > key_cache_capacity_) key_cache_.pop_back();
+    return ks;
+  }
+  StatusOr<std::shared_ptr<KeySet>> KeysFor(const GaloisKeys& gk) const {
+    const detail::Fingerprint fp = KeyFingerprint(gk);
+    if (auto hit = FindKeys(fp)) return hit;
+    return UploadKeys(gk, fp);
+  }
+
+  // processQuery for every query of a request (server.cpp:60-63, 173-195)
+  StatusOr<Response> Answer(const std::vector<std::vector<Ciphertext>>& query, const KeySet& keys) const {
+    pirb_ctx* ctx = db_->handle();
+    Response response;
+    if (query.empty()) return response;
+    const size_t L = pirb_ct_limbs(ctx), n_ct = query[0].size(), R = pirb_reply_cts(ctx), Q = query.size();
+    for (size_t i = 0; i < Q; ++i) {
+      if (query[i].size() != n_ct || n_ct != pirb_query_cts(ctx))
+        return InvalidArgumentError("Number of ciphertexts doesn't match number of items for oblivious expansion.");
+      for (size_t c = 0; c < n_ct; ++c)
+        if (query[i][c].limbs.size() != L) return InvalidArgumentError("bad ciphertext size");
+    }
+    const size_t W = db_->shard_count();
+    // sharded: every GPU takes the same number of queries per step (the last step is padded with zero queries)
+    const size_t ql = W > 1 ? std::min<size_t>(max_local_, (Q + W - 1) / W) : Q;
+    const size_t per_step = W > 1 ? W * ql : Q;
+    const size_t n_steps = (Q + per_step - 1) / per_step;
+    Status st = q_pin_.ensure(per_step * n_ct * L);
+    if (!st.ok()) return st;
+    st = r_pin_.ensure(per_step * R * L);
+    if (!st.ok()) return st;
+    response.reply.resize(Q);
+    for (size_t step = 0; step < n_steps; ++step) {
+      const size_t q0 = step * per_step, qn = std::min(per_step, Q - q0);
+      for (size_t i = 0; i < per_step; ++i)
+        for (size_t c = 0; c < n_ct; ++c) {
+          uint64_t* dst = q_pin_.p + (i * n_ct + c) * L;
+          if (i < qn) std::memcpy(dst, query[q0 + i][c].limbs.data(), L * sizeof(uint64_t));
+          else std::memset(dst, 0, L * sizeof(uint64_t));
+        }
+      if (W == 1) {
+        st = FromRc(pirb_answer(ctx, keys.per_shard[0].get(), q_pin_.p, (uint32_t)qn, n_ct, r_pin_.p));
+        if (!st.ok()) return st;
+      } else {
+        // one host thread drives all ranks: nothing that may synchronise a device (allocations, first launches) may
+        // happen between one rank's launches and the next's, so every rank is prepared before the first step
+        for (size_t r = 0; r < W; ++r) {
+          st = FromRc(pirb_dist_prepare(db_->handle(r), keys.per_shard[r].get(), (uint32_t)ql));
+          if (!st.ok()) return st;
+        }
+        for (size_t r = 0; r < W; ++r) {
+          st = FromRc(pirb_dist_answer_dev(db_->handle(r), keys.per_shard[r].get(), q_pin_.p + r * ql * n_ct * L,
+                                           (uint32_t)ql, n_ct, r_pin_.p + r * ql * R * L, nullptr));
+          if (!st.ok()) return st;
+        }
+        for (size_t r = 0; r < W; ++r) {
+          st = FromRc(pirb_sync(db_->handle(r)));
+          if (!st.ok()) return st;
+        }
+        for (size_t r = 0; r < W; ++r) {
+          st = FromRc(pirb_dist_status(db_->handle(r)));
+          if (!st.ok()) return st;
+        }
+      }
+      for (size_t i = 0; i < qn; ++i) {
+        response.reply[q0 + i].resize(R);
+        for (size_t c = 0; c < R; ++c)
+          response.reply[q0 + i][c].limbs.assign(r_pin_.p + (i * R + c) * L, r_pin_.p + (i * R + c + 1) * L);
+      }
+    }
+    return response;
   }
   StatusOr<std::vector<Ciphertext>> Expand(const uint64_t* cts, size_t n_ct, size_t total, int single,
                                            const GaloisKeys& gal_keys) const {
-    std::unique_ptr<pirb_keys, detail::KeysDeleter> keys;
-    Status st = LoadKeys(gal_keys, keys);
-    if (!st.ok()) return st;
+    auto keys = KeysFor(gal_keys);
+    if (!keys.ok()) return keys.status();
     const size_t L = pirb_ct_limbs(db_->handle());
     std::vector<uint64_t> out(std::max<size_t>(1, total) * L);
-    st = FromRc(pirb_expand(db_->handle(), keys.get(), cts, n_ct, total, single, out.data()));
+    Status st = FromRc(pirb_expand(db_->handle(), (*keys)->per_shard[0].get(), cts, n_ct, total, single, out.data()));
     if (!st.ok()) return st;
     std::vector<Ciphertext> res(total);
     for (size_t i = 0; i < total; ++i) res[i].limbs.assign(out.begin() + i * L, out.begin() + (i + 1) * L);
@@ -612,6 +802,11 @@ class PIRServer {
   }
   std::shared_ptr<PIRDatabase> db_;
   std::shared_ptr<PIRParameters> params_;
+  uint32_t max_local_ = 8;
+  // ProcessRequest is const like the reference's, but reuses staging and cached keys: one host thread at a time
+  mutable detail::PinnedBuf q_pin_, r_pin_;
+  mutable std::vector<std::pair<detail::Fingerprint, std::shared_ptr<KeySet>>> key_cache_;
+  mutable size_t key_cache_capacity_ = 4, key_hits_ = 0;
 };
 
 }  // namespace pir

@@ -1685,6 +1685,16 @@ uint64_t pirb_scan_bytes(const pirb_ctx* c, uint32_t n_queries) {
   return (c->pt_count * c->ptL + (u64)n_queries * dimL * c->ctL + (u64)n_queries * n_rows * c->ctL) * sizeof(u64);
 }
 
+int pirb_host_alloc(uint64_t bytes, void** out) {
+  if (!out) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  CU(cudaHostAlloc(out, std::max<uint64_t>(bytes, 16), cudaHostAllocPortable | cudaHostAllocMapped));
+  return 0;
+}
+void pirb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 void pirb_calculate_dimensions(uint32_t db_size, uint32_t nd, uint32_t* out) {
   auto v = hm::calculate_dimensions(db_size, nd);
   for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];

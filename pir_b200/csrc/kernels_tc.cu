@@ -133,50 +133,63 @@ k_tc_pack_db(const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows, u32 k
 // selection vectors (NTT form, sv_qstride limbs between queries) -> svT (see header).  PACKED = false: u64 limbs
 // [q][i1][2][k][N]; PACKED = true: per polynomial a plane of N low 32-bit words and a plane of N high parts of nb - 4
 // bytes (what k_ntt_fwd_push stores into the exchange slots).
-// A block transposes a tile of 128 selection entries (one K chunk) x 32 coefficients through shared memory: loads are
-// coalesced along the coefficient axis, stores are 16 bytes of K per (coefficient, limb byte).
-// grid (q * 2 + p, c / 32, K chunk), block 256; the K padding of svT stays zero from allocation.
+// A block transposes a tile of 128 selection entries (one K chunk) x 64 coefficients through shared memory: every
+// row of the tile is read as 512 contiguous bytes (all loads of a thread in flight before the first shared-memory
+// store) and every (coefficient, limb byte) row of svT is written as the 128 contiguous bytes of the chunk.
+// grid (q * 2 + p, c / 64, K chunk), block 512, 128 * 66 * 8 bytes of dynamic shared memory; the K padding of svT
+// beyond Kp's last chunk stays zero from allocation.
+constexpr int PACK_C = 64, PACK_PITCH = PACK_C + 2;
 template <bool PACKED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512, 2)
 k_tc_pack_sv(const u64* __restrict__ sv, u64 sv_qstride, u32 dimL, u32 N, u32 kN, u32 nb, u32 n_rows_total, u32 Kp,
              u8* __restrict__ svT) {
-  __shared__ u64 t[128][33];
-  const u32 qp = blockIdx.x, c0 = blockIdx.y * 32, i0 = blockIdx.z * 128;
+  extern __shared__ __align__(16) u64 t[];  // [128][PACK_PITCH]
+  const u32 qp = blockIdx.x, c0 = blockIdx.y * PACK_C, i0 = blockIdx.z * 128;
   const u32 q = qp >> 1, p = qp & 1;
-  const u32 tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
-  for (u32 ii = ty; ii < 128; ii += 8) {
-    const u32 i = i0 + ii;
-    u64 v = 0;
+  const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;  // 16 warps; a warp reads one row: 32 lanes x 2 coefficients
+  ulonglong2 v[8];
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    const u32 i = i0 + w + 16 * x;
+    v[x] = make_ulonglong2(0, 0);
     if (i < dimL) {
       if constexpr (PACKED) {
         // polynomial (i, p, j) with j = c0 / N starts at ((i * 2k + p * k + j) * N) * nb bytes
-        const u32 j = c0 / N, n = c0 % N + tx;
+        const u32 j = c0 / N, n = c0 % N + 2 * lane;
         const u8* base = reinterpret_cast<const u8*>(sv + (u64)q * sv_qstride) +
                          ((u64)i * 2 * kN + (u64)p * kN + (u64)j * N) * nb;
-        const u64 lo = reinterpret_cast<const u32*>(base)[n];
-        const u64 hi = nb == 5 ? (u64)(base + 4 * (size_t)N)[n]
-                               : (u64)reinterpret_cast<const unsigned short*>(base + 4 * (size_t)N)[n];
-        v = lo | (hi << 32);
+        const uint2 lo = __ldg(reinterpret_cast<const uint2*>(base + 4 * (size_t)n));
+        if (nb == 5) {
+          const unsigned short hi = __ldg(reinterpret_cast<const unsigned short*>(base + 4 * (size_t)N + n));
+          v[x].x = (u64)lo.x | ((u64)(hi & 0xFF) << 32);
+          v[x].y = (u64)lo.y | ((u64)(hi >> 8) << 32);
+        } else {
+          const u32 hi = __ldg(reinterpret_cast<const u32*>(base + 4 * (size_t)N + 2 * (size_t)n));
+          v[x].x = (u64)lo.x | ((u64)(hi & 0xFFFF) << 32);
+          v[x].y = (u64)lo.y | ((u64)(hi >> 16) << 32);
+        }
       } else {
-        v = sv[(u64)q * sv_qstride + (u64)i * 2 * kN + (u64)p * kN + c0 + tx];
+        v[x] = __ldg(reinterpret_cast<const ulonglong2*>(sv + (u64)q * sv_qstride + (u64)i * 2 * kN + (u64)p * kN + c0) + lane);
       }
     }
-    t[ii][tx] = v;
   }
-  __syncthreads();
-  // thread (coefficient tx, group ty of 16 consecutive selection entries)
-  const u32 ib = i0 + ty * 16;
-  if (ib < Kp) {
-    u64 w[16];
 #pragma unroll
-    for (int x = 0; x < 16; ++x) w[x] = t[ty * 16 + x][tx];
-    u8* o = svT + ((u64)(c0 + tx) * n_rows_total + (u64)qp * nb) * Kp + ib;
+  for (int x = 0; x < 8; ++x) *reinterpret_cast<ulonglong2*>(t + (size_t)(w + 16 * x) * PACK_PITCH + 2 * lane) = v[x];
+  __syncthreads();
+  // thread (coefficient cc, group g of 16 consecutive selection entries)
+  const u32 cc = threadIdx.x & (PACK_C - 1), g = threadIdx.x / PACK_C;  // 8 groups
+  const u32 ib = i0 + g * 16;
+  if (ib < Kp) {
+    u64 r64[16];
+#pragma unroll
+    for (int x = 0; x < 16; ++x) r64[x] = t[(size_t)(g * 16 + x) * PACK_PITCH + cc];
+    u8* o = svT + ((u64)(c0 + cc) * n_rows_total + (u64)qp * nb) * Kp + ib;
     for (u32 b = 0; b < nb; ++b) {
       u32 r[4];
 #pragma unroll
       for (int g4 = 0; g4 < 4; ++g4)
-        r[g4] = (u32)((w[g4 * 4] >> (8 * b)) & 0xFF) | ((u32)((w[g4 * 4 + 1] >> (8 * b)) & 0xFF) << 8) |
-                ((u32)((w[g4 * 4 + 2] >> (8 * b)) & 0xFF) << 16) | ((u32)((w[g4 * 4 + 3] >> (8 * b)) & 0xFF) << 24);
+        r[g4] = (u32)((r64[g4 * 4] >> (8 * b)) & 0xFF) | ((u32)((r64[g4 * 4 + 1] >> (8 * b)) & 0xFF) << 8) |
+                ((u32)((r64[g4 * 4 + 2] >> (8 * b)) & 0xFF) << 16) | ((u32)((r64[g4 * 4 + 3] >> (8 * b)) & 0xFF) << 24);
       *reinterpret_cast<uint4*>(o + (u64)b * Kp) = make_uint4(r[0], r[1], r[2], r[3]);
     }
   }
@@ -192,11 +205,13 @@ struct TcScanArgs {
   u32 n_cols;                             // N of the MMA = qt * 2 * NB
   u32 sv_rows_total;                      // rows of svT per coefficient = n_qt * n_cols
   u32 stages, b_bufs;                     // A ring depth, B buffers (1 or 2)
+  u32 n_acc;                              // TMEM accumulator buffers = epilogue groups (2..4)
   u64* part;                              // [q][row][2][k][N]
   int* err;
 };
 
-constexpr int TC_THREADS = 384;
+constexpr int TC_MAX_ACC = 4;                            // accumulator buffers / epilogue groups
+constexpr int TC_THREADS = 128 + 128 * TC_MAX_ACC;       // 4 control warps + 4 warps per epilogue group
 constexpr u32 TC_A_STAGE_BYTES = 128 * 128;
 
 template <int NB>
@@ -211,14 +226,14 @@ k_tc_scan(const __grid_constant__ DevParams P, const __grid_constant__ CUtensorM
   u8* sA = smem;
   u8* sB = sA + (size_t)A.stages * TC_A_STAGE_BYTES;
   u64* sE = reinterpret_cast<u64*>(sB + (size_t)A.b_bufs * b_buf_bytes);  // [2 groups][16 qp][128 lanes][EW]
-  u64* bars = sE + 2 * 16 * 128 * EW;
+  u64* bars = sE + (size_t)TC_MAX_ACC * 16 * 128 * EW;
   u64* a_full = bars;
   u64* a_empty = a_full + A.stages;
   u64* b_full = a_empty + A.stages;
   u64* b_empty = b_full + 2;
   u64* t_full = b_empty + 2;
-  u64* t_empty = t_full + 2;
-  u32* tmem_slot = reinterpret_cast<u32*>(t_empty + 2);
+  u64* t_empty = t_full + TC_MAX_ACC;
+  u32* tmem_slot = reinterpret_cast<u32*>(t_empty + TC_MAX_ACC);
   volatile int* err = A.err;
 
   if (threadIdx.x == 0) {
@@ -226,18 +241,20 @@ k_tc_scan(const __grid_constant__ DevParams P, const __grid_constant__ CUtensorM
     for (u32 s = 0; s < 2; ++s) {
       mbar_init(b_full + s, 1);
       mbar_init(b_empty + s, 1);
+    }
+    for (u32 s = 0; s < TC_MAX_ACC; ++s) {
       mbar_init(t_full + s, 1);
       mbar_init(t_empty + s, 4);  // one arrival per epilogue warp of the group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const u32 tmem_cols = 2 * A.n_cols <= 256 ? 256 : 512;
+  const u32 acc_stride = A.n_acc * A.n_cols <= 256 ? 256 / A.n_acc : 512 / A.n_acc;  // columns per accumulator buffer
+  const u32 tmem_cols = A.n_acc * acc_stride;  // 256 or 512 for n_acc in {2, 4}
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const u32 tmem_base = *tmem_slot;
-  const u32 acc_stride = tmem_cols / 2;  // column offset of accumulator buffer 1
 
   const u32 n_items = A.kN;
   if (warp == 0) {
@@ -283,7 +300,7 @@ k_tc_scan(const __grid_constant__ DevParams P, const __grid_constant__ CUtensorM
           if (!ok) break;
           const u32 sB_addr = smem_u32(sB + (size_t)bb * b_buf_bytes);
           for (u32 mt = 0; mt < A.ntiles && ok; ++mt) {
-            const u32 ab = tcount & 1, tph = (tcount >> 1) & 1;
+            const u32 ab = tcount % A.n_acc, tph = (tcount / A.n_acc) & 1;
             ok = mbar_wait_b(t_empty + ab, tph ^ 1, err);
             if (!ok) break;
             tc_fence_after();
@@ -308,7 +325,7 @@ k_tc_scan(const __grid_constant__ DevParams P, const __grid_constant__ CUtensorM
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && ((warp - 4) >> 2) < A.n_acc) {
     // ------------------------------------------------ epilogue ----------------------------------------------------
     const u32 g = (warp - 4) >> 2;           // group <-> accumulator buffer
     const u32 wq = warp & 3;                 // TMEM lane quarter this warp may read
@@ -322,8 +339,8 @@ k_tc_scan(const __grid_constant__ DevParams P, const __grid_constant__ CUtensorM
       const ModC& mod = P.m[c / P.N];
       for (u32 qt = 0; qt < A.n_qt && ok; ++qt)
         for (u32 mt = 0; mt < A.ntiles && ok; ++mt, ++tcount) {
-          if ((tcount & 1) != g) continue;
-          const u32 tph = (tcount >> 1) & 1;
+          if (tcount % A.n_acc != g) continue;
+          const u32 tph = (tcount / A.n_acc) & 1;
           ok = mbar_wait_b(t_full + g, tph, err);
           if (!ok) break;
           tc_fence_after();
@@ -445,7 +462,7 @@ bool tc_supported(const DevParams& P, u32 dimL) {
   TcGeom g;
   tc_geometry(P, dimL, 1, &g);
   // s32 accumulators: dimL * 255^2 < 2^31; operand limbs: 5 or 6 bytes; the tile arithmetic below needs N % 32 == 0
-  return (g.nb == 5 || g.nb == 6) && dimL <= 32768 && encode_fn() != nullptr && (P.N % 32) == 0;
+  return (g.nb == 5 || g.nb == 6) && dimL <= 32768 && encode_fn() != nullptr && (P.N % 64) == 0;
 }
 
 cudaError_t launch_tc_pack_db(const DevParams& P, const u64* db, u64 num_pt, u32 dimL, u32 n_rows, const TcGeom& g,
@@ -486,11 +503,24 @@ cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u
     if (e != cudaSuccess) return e;
   }
   (void)sv_bytes;
-  const dim3 pgrid(n_queries * 2, kN / 32, g.kch);
+  const dim3 pgrid(n_queries * 2, kN / PACK_C, g.kch);
+  const size_t psmem = (size_t)128 * PACK_PITCH * sizeof(u64);
+  {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+      cudaError_t e1 = cudaFuncSetAttribute(k_tc_pack_sv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+      cudaError_t e2 = cudaFuncSetAttribute(k_tc_pack_sv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+      if (e1 != cudaSuccess) return e1;
+      if (e2 != cudaSuccess) return e2;
+      configured[dev & 63] = true;
+    }
+  }
   if (sv_packed)
-    k_tc_pack_sv<true><<<pgrid, 256, 0, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb, sv_rows_total, g.Kp, svT);
+    k_tc_pack_sv<true><<<pgrid, 512, psmem, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb, sv_rows_total, g.Kp, svT);
   else
-    k_tc_pack_sv<false><<<pgrid, 256, 0, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb, sv_rows_total, g.Kp, svT);
+    k_tc_pack_sv<false><<<pgrid, 512, psmem, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb, sv_rows_total, g.Kp, svT);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
 
@@ -513,7 +543,8 @@ cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u
   A.part = part;
   A.err = err_flag;
   const size_t b_buf = (size_t)g.kch * n_cols * 128;
-  const size_t e_bytes = (size_t)2 * 16 * 128 * 8 * (g.nb <= 5 ? 1 : 2);
+  const size_t e_bytes = (size_t)TC_MAX_ACC * 16 * 128 * 8 * (g.nb <= 5 ? 1 : 2);
+  A.n_acc = 4 * n_cols <= 512 ? 4 : 2;  // 4 accumulator buffers while they fit the 512 TMEM columns
   const size_t fixed = e_bytes + 1024;  // barriers, TMEM slot, alignment slack
   const size_t budget = 227 * 1024;
   A.b_bufs = (2 * b_buf + fixed + 4 * TC_A_STAGE_BYTES <= budget) ? 2 : 1;

@@ -17,7 +17,7 @@
     }                                                               \
   } while (0)
 
-static int run_case(size_t dbsize, size_t elem_size, size_t d, size_t desired_index) {
+static int run_case(size_t dbsize, size_t elem_size, size_t d, size_t desired_index, size_t shards = 1) {
   auto ep = pir::GenerateEncryptionParams(4096, 20);
   auto params_or = pir::CreatePIRParameters(dbsize, elem_size, d, ep);
   CHECK(params_or.ok(), "CreatePIRParameters");
@@ -26,10 +26,13 @@ static int run_case(size_t dbsize, size_t elem_size, size_t d, size_t desired_in
   std::vector<std::string> db(dbsize, std::string(params->bytes_per_item, 0));
   for (auto& s : db)
     for (auto& ch : s) ch = (char)(rng() & 0xff);
-  auto db_or = pir::PIRDatabase::Create(db, params);
+  // shards > 1: the database is split by rows over `shards` contexts of this process (all on GPU 0 here; one per GPU
+  // in a deployment) and the server runs the peer-memory exchange flow (pirb_dist_*) behind the same ProcessRequest
+  auto db_or = pir::PIRDatabase::Create(db, params, std::vector<int>(shards, 0));
   CHECK(db_or.ok(), db_or.status().message().c_str());
-  auto server_or = pir::PIRServer::Create(*db_or, params);
-  CHECK(server_or.ok(), "PIRServer::Create");
+  CHECK((*db_or)->shard_count() == shards, "shard count");
+  auto server_or = pir::PIRServer::Create(*db_or, params, /*max_queries_per_gpu=*/2);
+  CHECK(server_or.ok(), server_or.status().message().c_str());
   auto& server = *server_or;
 
   // ---- client side (oracle harness) ----
@@ -89,6 +92,24 @@ static int run_case(size_t dbsize, size_t elem_size, size_t d, size_t desired_in
   for (size_t i = 0; i < reply.size(); ++i)
     CHECK(std::memcmp(reply[i].data(), want.data() + i * octx.ct_limbs(), octx.ct_limbs() * 8) == 0,
           "GPU reply differs from the oracle");
+
+  // ---- a batch of five copies of the query (more than ranks x queries per GPU when sharded: two steps, the last one
+  // padded), keys found again in the server's cache ----
+  {
+    pir::Request req5 = req;
+    req5.query.assign(5, req.query[0]);
+    const size_t hits_before = server->key_cache_hits();
+    auto r5 = server->ProcessRequest(req5);
+    CHECK(r5.ok(), r5.status().message().c_str());
+    CHECK(server->key_cache_hits() == hits_before + 1, "Galois keys of a returning client must come from the cache");
+    CHECK(r5->reply.size() == 5, "one reply per query");
+    for (size_t qi = 0; qi < 5; ++qi) {
+      CHECK(r5->reply[qi].size() == reply.size(), "reply count in batch");
+      for (size_t i = 0; i < reply.size(); ++i)
+        CHECK(std::memcmp(r5->reply[qi][i].data(), want.data() + i * octx.ct_limbs(), octx.ct_limbs() * 8) == 0,
+              "batched reply differs from the oracle");
+    }
+  }
 
   // ---- the same request over the reference's wire format (serialization.h:81-138, payload.proto) ----
   // Keys travel seed-compressed as the reference client sends them (client.cpp:47-54): replace every key's uniform
@@ -202,8 +223,8 @@ static int run_case(size_t dbsize, size_t elem_size, size_t d, size_t desired_in
   auto got = enc.decode(pts[0], params->bytes_per_item, (*db_or)->calculate_item_offset((uint32_t)desired_index));
   CHECK(got.ok(), "decode");
   CHECK(*got == db[desired_index], "retrieved element differs");
-  std::printf("ok: %zu items x %u B, d=%zu, index %zu: reply (%zu cts) bit-exact vs oracle, element recovered\n", dbsize,
-              params->bytes_per_item, d, desired_index, reply.size());
+  std::printf("ok: %zu items x %u B, d=%zu, index %zu, %zu shard(s): reply (%zu cts) bit-exact vs oracle, element recovered\n",
+              dbsize, params->bytes_per_item, d, desired_index, shards, reply.size());
   return 0;
 }
 
@@ -219,6 +240,8 @@ int main() {
   if (run_case(10, 0, 1, 7)) return 1;         // server_test.cpp TestProcessRequest shape
   if (run_case(82, 0, 2, 42)) return 1;        // server_test.cpp TestProcessRequest_2Dim shape (dims [10,9])
   if (run_case(1200, 64, 1, 777)) return 1;    // correctness_test.cpp:110 shape
+  if (run_case(82, 0, 2, 42, 2)) return 1;     // the 2-dimensional shape, rows sharded over two contexts
+  if (run_case(300, 0, 2, 123, 3)) return 1;   // dims [18,17] over three contexts
   std::printf("SHIM_TEST_OK\n");
   return 0;
 }
