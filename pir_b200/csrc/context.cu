@@ -158,8 +158,13 @@ struct pirb_ctx {
     u32 n_ranks = 0, rank = 0, max_local = 0, n_sub = 0, sub_q = 0;  // sub_q = local queries per sub-batch
     u32 rows_per_rank = 0;
     u64 sv_qstride = 0;                       // limbs per query in a selection-vector slot (compact layout)
-    u32 packed_nb = 0;                        // != 0: last-dimension entries travel as packed residues of this many bytes
-    u64 packed_off = 0;                       // ... at this limb offset inside a query's part of the slot
+    // tensor-core mode: the last-dimension entries travel repacked into the scan's operand layout (svT region of the
+    // slot, [coefficient][slot rows][Kp] bytes) instead of as u64 limbs in the per-query part
+    bool tc_mode = false;
+    TcGeom g = {};
+    u32 slot_rows = 0;                        // svT rows per coefficient in a slot: queries of a slot * 2 * nb
+    u64 svt_off = 0;                          // limb offset of the svT region inside a slot
+    DevBuf stage;                             // local repacking of the rank's own queries before the push
     u64 flag_limbs = 0, sv_slot_limbs = 0, part_slot_limbs = 0;
     u64* base = nullptr;
     size_t bytes = 0;
@@ -196,7 +201,7 @@ struct pirb_ctx {
   } tc;
   pirb_ctx() {
     for (DevBuf* b : {&db, &stage, &work, &dig, &acc, &xch, &part, &bufA[0], &bufA[1], &pts, &qbuf, &rbuf, &svbuf, &xptrs,
-                      &dbg, &dist.peer_table, &dist.self_table, &tc.dbT, &tc.svT})
+                      &dbg, &dist.peer_table, &dist.self_table, &dist.stage, &tc.dbT, &tc.svT})
       b->epoch = &alloc_epoch;
   }
 };
@@ -330,15 +335,21 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
 
 // Last-dimension scan of n_queries selection vectors against the shard into c->part ([q][split][row][2][k][N]):
 // the HBM-bound streaming kernel for single queries, the tensor-core contraction for batches.
-// sv_packed: sv_last points at packed last-dimension residues (exchange slots, PushArgs) — tensor-core scan only.
+// svt != nullptr: the last-dimension selection entries arrive already repacked into the tensor-core scan's operand
+// layout (rows [row0, ...) of an svT array with rows_total rows per coefficient: the exchange slots of the multi-GPU
+// flow) — tensor-core scan only, no repacking here.
+struct SvtRef {
+  const u8* p;
+  u32 rows_total, row0;
+};
 int run_scan(pirb_ctx* c, const u64* sv_last, u64 sv_qstride, int n_queries, u32 dimL, u32 n_rows, u64 npt, bool allow_tc,
-             int* n_split_out, cudaStream_t st, bool sv_packed = false) {
+             int* n_split_out, cudaStream_t st, const SvtRef* svt = nullptr) {
   const DevParams& P = c->P;
   const u64 ctL = c->ctL;
   int n_split;
   // small shards are launch-latency territory: the CUDA-core batched scan is as fast there
-  const bool use_tc = sv_packed || (allow_tc && c->tc.min_queries > 0 && n_queries >= c->tc.min_queries &&
-                                    npt >= c->tc.min_pt && tc_supported(P, dimL));
+  const bool use_tc = svt || (allow_tc && c->tc.min_queries > 0 && n_queries >= c->tc.min_queries &&
+                              npt >= c->tc.min_pt && tc_supported(P, dimL));
   if (use_tc) {
     // batch of queries: dense u8 contraction per coefficient slot on the tensor cores
     pirb_ctx::Tc& T = c->tc;
@@ -355,18 +366,22 @@ int run_scan(pirb_ctx* c, const u64* sv_last, u64 sv_qstride, int n_queries, u32
         T.npt = npt;
       }
     }
-    u32 qt, n_qt;
-    const u64 sv_bytes = tc_sv_bytes(P, T.g, (u32)n_queries, &qt, &n_qt);
-    if (sv_bytes > T.svT.bytes) {
-      RC(T.svT.ensure(sv_bytes));
-      CU(cudaMemsetAsync(T.svT.p, 0, sv_bytes, st));  // the K padding is never written afterwards
-    }
     n_split = 1;
     c->scan_split = 1;
     RC(c->part.ensure((size_t)n_queries * n_rows * ctL * sizeof(u64)));
-    LAUNCH(c, launch_tc_scan(P, T.g, reinterpret_cast<const u8*>(T.dbT.p), dimL, n_rows, sv_last, sv_qstride,
-                             sv_packed ? 1 : 0, (u32)n_queries, reinterpret_cast<u8*>(T.svT.p), T.err, c->sm_count,
-                             c->part.p, st));
+    if (svt) {
+      LAUNCH(c, launch_tc_scan_packed(P, T.g, reinterpret_cast<const u8*>(T.dbT.p), dimL, n_rows, svt->p, svt->rows_total,
+                                      svt->row0, (u32)n_queries, T.err, c->sm_count, c->part.p, st));
+    } else {
+      u32 qt, n_qt;
+      const u64 sv_bytes = tc_sv_bytes(P, T.g, (u32)n_queries, &qt, &n_qt);
+      if (sv_bytes > T.svT.bytes) {
+        RC(T.svT.ensure(sv_bytes));
+        CU(cudaMemsetAsync(T.svT.p, 0, sv_bytes, st));  // the K padding is never written afterwards
+      }
+      LAUNCH(c, launch_tc_scan(P, T.g, reinterpret_cast<const u8*>(T.dbT.p), dimL, n_rows, sv_last, sv_qstride,
+                               (u32)n_queries, reinterpret_cast<u8*>(T.svT.p), T.err, c->sm_count, c->part.p, st));
+    }
   } else {
     scan_config(P, dimL, n_rows, n_queries, c->sm_count, &n_split);
     c->scan_split = n_split;
@@ -386,7 +401,7 @@ int run_scan(pirb_ctx* c, const u64* sv_last, u64 sv_qstride, int n_queries, u32
 // slots, own row r at slot r - top_lo) followed by the other dimensions — the layout of the multi-GPU exchange slots.
 int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_out, int partial, cudaStream_t st,
                  bool sv_is_ntt = false, u64 sv_item0 = 0, u64 sv_items = ~0ull, u32 compact_rows = 0,
-                 u64 packed_last_off = 0) {
+                 const SvtRef* svt = nullptr) {
   if (sv_items == ~0ull) sv_items = c->dim_sum;
   const int d = c->d, k = c->k;
   const u64 ctL = c->ctL;
@@ -438,10 +453,10 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
     n_rows = (u32)((npt + dimL - 1) / dimL);
     u64 off = compact_rows ? compact_rows : c->dims[0];
     for (int e = 1; e < d - 1; ++e) off += c->dims[e];
-    sv_last = packed_last_off ? d_sv + packed_last_off : d_sv + off * ctL;
+    sv_last = d_sv + off * ctL;  // (not present in the exchange slots when svt is given)
   }
   int n_split;
-  RC(run_scan(c, sv_last, sv_qstride, n_queries, dimL, n_rows, npt, d >= 2, &n_split, st, packed_last_off != 0));
+  RC(run_scan(c, sv_last, sv_qstride, n_queries, dimL, n_rows, npt, d >= 2, &n_split, st, svt));
   if (prof) cudaEventRecord(c->ev[3], st);
   if (d == 1) {
     if (partial) {
@@ -1306,27 +1321,24 @@ static int dist_layout(pirb_ctx* c, u32 max_local, u32 sub_q) {
   u64 mid = 0;
   for (int e = 1; e < c->d - 1; ++e) mid += c->dims[e];
   const u32 last = c->dims[c->d - 1];
-  // Packed last dimension (5/8 or 6/8 of the NVLink bytes) whenever the consumers' scans run on the tensor cores.  The
-  // choice uses only quantities every rank agrees on.
-  const char* pk = getenv("PIRB_DIST_PACKED");
-  D.packed_nb = 0;
-  if (!(pk && pk[0] == '0') && c->tc.min_queries > 0 && tc_supported(c->P, last) &&
-      c->prm.num_pt / D.n_ranks >= c->tc.min_pt) {
-    TcGeom g;
-    tc_geometry(c->P, last, 1, &g);
-    D.packed_nb = g.nb;
-  }
+  // Tensor-core mode whenever the consumers' scans run on the tensor cores; the choice uses only quantities every rank
+  // agrees on.
+  const char* pk = getenv("PIRB_DIST_TC");
+  D.tc_mode = !(pk && pk[0] == '0') && c->tc.min_queries > 0 && tc_supported(c->P, last) &&
+              c->prm.num_pt / D.n_ranks >= c->tc.min_pt;
+  const u64 slot_queries = (u64)D.n_sub * D.sub_q * D.n_ranks;
   const u64 head = ((u64)D.rows_per_rank + mid) * c->ctL;
-  if (D.packed_nb) {
-    D.packed_off = head;
-    D.sv_qstride = head + ((u64)last * c->ctL * D.packed_nb + 7) / 8;
+  if (D.tc_mode) {
+    tc_geometry(c->P, last, 1, &D.g);
+    D.sv_qstride = head;
+    D.slot_rows = (u32)(slot_queries * 2 * D.g.nb);
+    D.svt_off = slot_queries * head;
+    D.sv_slot_limbs = (D.svt_off + ((u64)c->k * c->N * D.slot_rows * D.g.Kp + 7) / 8 + 15) / 16 * 16;
   } else {
-    D.packed_off = 0;
     D.sv_qstride = head + (u64)last * c->ctL;
+    D.sv_slot_limbs = slot_queries * D.sv_qstride;
   }
   D.flag_limbs = ((1 + 2ull * D.n_sub * D.n_ranks) + 15) / 16 * 16;
-  const u64 slot_queries = (u64)D.n_sub * D.sub_q * D.n_ranks;
-  D.sv_slot_limbs = slot_queries * D.sv_qstride;
   D.part_slot_limbs = slot_queries * c->reply_cts * c->ctL;
   D.bytes = (D.flag_limbs + 2 * D.sv_slot_limbs + 2 * D.part_slot_limbs) * sizeof(u64);
   return 0;
@@ -1490,10 +1502,27 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
     A.slot_off = dist_sv_off(D, slot);
     A.g_first = ((u64)sb * W + D.rank) * SB;
     A.dst_qstride = D.sv_qstride;
-    A.last_first = (u32)(c->dim_sum - c->dims[c->d - 1]);
-    A.packed_nb = D.packed_nb;
-    A.packed_off = D.packed_off;
-    LAUNCH(c, launch_ntt_fwd_push(c->P, c->work.p + (u64)q0 * q_stride, q_stride, (u32)c->dim_sum, qn, A, D.xfer));
+    const u32 last = c->dims[c->d - 1], last_first = (u32)(c->dim_sum - last);
+    const u64* sub_work = c->work.p + (u64)q0 * q_stride;
+    if (!D.tc_mode) {
+      LAUNCH(c, launch_ntt_fwd_push(c->P, sub_work, q_stride, (u32)c->dim_sum, qn, A, D.xfer));
+    } else {
+      // first / middle dimensions: u64 limbs to the owning rank / to everybody, straight from the NTT kernel
+      LAUNCH(c, launch_ntt_fwd_push(c->P, sub_work, q_stride, last_first, qn, A, D.xfer));
+      // last dimension: NTT in place, repack ONCE here into the tensor-core scan's operand layout, then copy every
+      // coefficient's rows into every rank's svT region — no rank repacks another rank's queries
+      u64* last_sv = c->work.p + (u64)q0 * q_stride + (u64)last_first * c->ctL;
+      LAUNCH(c, launch_ntt_fwd(c->P, last_sv, last_sv, (int)(last * 2 * c->k), c->k, 0, (int)qn, q_stride, q_stride, D.xfer));
+      const u32 stage_rows = SB * 2 * D.g.nb;
+      RC(D.stage.ensure((size_t)c->k * c->N * stage_rows * D.g.Kp));
+      LAUNCH(c, launch_tc_pack_sv(c->P, D.g, last_sv, q_stride, last, qn, reinterpret_cast<u8*>(D.stage.p), stage_rows, 0,
+                                  D.xfer));
+      const u64 row0 = (((u64)sb * W + D.rank) * SB) * 2 * D.g.nb;
+      LAUNCH(c, launch_push_rows(peers, W, reinterpret_cast<const u8*>(D.stage.p), (u64)stage_rows * D.g.Kp,
+                                 qn * 2 * D.g.nb * D.g.Kp,
+                                 (u32)c->k * c->N, (dist_sv_off(D, slot) + D.svt_off) * sizeof(u64) + row0 * D.g.Kp,
+                                 (u64)D.slot_rows * D.g.Kp, D.xfer));
+    }
     LAUNCH(c, launch_signal(peers, W, dist_flag_off(D, 0, sb, D.rank), seq, D.xfer));
   }
   if (prof) cudaEventRecord(D.prof[1], D.prod);
@@ -1507,15 +1536,19 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
     LAUNCH(c, launch_wait(D.base + dist_flag_off(D, 0, sb, 0), W, seq, D.timeout_ns, err, D.cons));
     if (prof && sb == 0) cudaEventRecord(D.prof[3], D.cons);
     const u64 g0 = (u64)sb * W * SB;
+    const u8* svt_base = reinterpret_cast<const u8*>(D.base + dist_sv_off(D, slot) + D.svt_off);
     if (qn == SB) {
+      SvtRef ref{svt_base, D.slot_rows, (u32)(g0 * 2 * D.g.nb)};
       RC(run_multiply(c, D.base + dist_sv_off(D, slot) + g0 * D.sv_qstride, D.sv_qstride, (int)(W * SB),
                       D.base + dist_part_off(D, slot) + g0 * c->reply_cts * c->ctL, 1, D.cons, true, 0, ~0ull,
-                      D.rows_per_rank, D.packed_nb ? D.packed_off : 0));
+                      D.rows_per_rank, D.tc_mode ? &ref : nullptr));
     } else {  // ragged last sub-batch: the ranks' queries are not contiguous, one multiply per rank
-      for (u32 r = 0; r < W; ++r)
+      for (u32 r = 0; r < W; ++r) {
+        SvtRef ref{svt_base, D.slot_rows, (u32)((g0 + (u64)r * SB) * 2 * D.g.nb)};
         RC(run_multiply(c, D.base + dist_sv_off(D, slot) + (g0 + (u64)r * SB) * D.sv_qstride, D.sv_qstride, (int)qn,
                         D.base + dist_part_off(D, slot) + (g0 + (u64)r * SB) * c->reply_cts * c->ctL, 1, D.cons, true, 0,
-                        ~0ull, D.rows_per_rank, D.packed_nb ? D.packed_off : 0));
+                        ~0ull, D.rows_per_rank, D.tc_mode ? &ref : nullptr));
+      }
     }
     LAUNCH(c, launch_signal(peers, W, dist_flag_off(D, 1, sb, D.rank), seq, D.cons));
   }

@@ -89,17 +89,18 @@ struct PushArgs {
   u64 slot_off;        // limb offset of the destination slot inside every rank's block
   u64 g_first;         // position of this launch's first query in the slot's query order
   u64 dst_qstride;     // limbs per query in the slot
-  // last-dimension entries (they only feed the scan) may travel as packed residues instead of u64 limbs: per
-  // polynomial a plane of N low 32-bit words followed by a plane of N high parts (packed_nb - 4 bytes each) — the input
-  // format of the tensor-core scan's operand repacking, and 5/8 (6/8) of the NVLink bytes
-  u32 last_first;      // first entry of the last dimension
-  u32 packed_nb;       // 0: u64 limbs everywhere; 5 / 6: bytes per residue of the packed last-dimension entries
-  u64 packed_off;      // limb offset of the packed region inside a query's part of the slot
 };
 // forward NTT of the first n_entries selection ciphertexts of n_queries queries (in: coefficient form, in_qstride limbs
 // apart) with the outputs stored into the peers' slots in the compact layout [own rows of dim 0 | dims 1..]
 cudaError_t launch_ntt_fwd_push(const DevParams& P, const u64* in, u64 in_qstride, u32 n_entries, u32 n_queries,
                                 const PushArgs& A, cudaStream_t st);
+// The last-dimension entries only feed the scan.  When that runs on the tensor cores they travel already repacked into
+// its operand layout (svT, kernels_tc.cu): the producing rank packs its own queries once into a staging buffer
+// [coefficient][rows][Kp] (src_stride bytes per coefficient) and this kernel copies every coefficient's segment (seg_bytes) into every
+// peer's svT region at dst_off + coefficient * dst_stride (bytes from the peer's block base).  Narrow grid, 16-byte
+// loads and stores: the copy drains at NVLink speed.
+cudaError_t launch_push_rows(u64* const* peers_dev, u32 n_ranks, const u8* stage, u64 src_stride, u32 seg_bytes, u32 n_segs,
+                             u64 dst_off, u64 dst_stride, cudaStream_t st);
 // flag[off] = value in every rank's block (release, system scope), ordered after the stream's earlier kernels
 cudaError_t launch_signal(u64* const* peers_dev, u32 n_ranks, u64 flag_off_limbs, u64 value, cudaStream_t st);
 // spin until flags[0..n_ranks) >= value (acquire, system scope); after timeout_ns sets *err and returns
@@ -122,11 +123,18 @@ cudaError_t launch_tc_pack_db(const DevParams& P, const u64* db, u64 num_pt, u32
                               u8* dbT, cudaStream_t st);
 // part[q][row][2][k][N] = sum_i1 sv[q][i1] (.) db[row*dimL + i1] mod q for a batch of queries (svT: scratch of
 // tc_sv_bytes; err_flag: device-visible int raised if the kernel's internal pipeline times out)
-// sv_packed = 0: sv is [q][i1][2][k][N] u64 (sv_qstride limbs between queries); sv_packed = 1: sv points at the packed
-// last-dimension region (PushArgs) of query 0, again sv_qstride limbs between queries
+// pack + scan for selection vectors held as u64 limbs [q][i1][2][k][N] (sv_qstride limbs between queries); svT: scratch
+// of tc_sv_bytes
 cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u32 dimL, u32 n_rows, const u64* sv,
-                           u64 sv_qstride, int sv_packed, u32 n_queries, u8* svT, int* err_flag, int sm_count, u64* part,
+                           u64 sv_qstride, u32 n_queries, u8* svT, int* err_flag, int sm_count, u64* part,
                            cudaStream_t st);
+// the two halves: repack n_queries selection vectors into rows [row0, row0 + n_queries*2*nb) of an svT array with
+// rows_total rows per coefficient; scan against an svT array whose rows [row0, ...) hold the n_queries queries
+cudaError_t launch_tc_pack_sv(const DevParams& P, const TcGeom& g, const u64* sv, u64 sv_qstride, u32 dimL, u32 n_queries,
+                              u8* svT, u32 rows_total, u32 row0, cudaStream_t st);
+cudaError_t launch_tc_scan_packed(const DevParams& P, const TcGeom& g, const u8* dbT, u32 dimL, u32 n_rows, const u8* svT,
+                                  u32 rows_total, u32 row0, u32 n_queries, int* err_flag, int sm_count, u64* part,
+                                  cudaStream_t st);
 
 // StringEncoder packing on the device: raw item bytes -> plaintext coefficients [n_pt][N]
 cudaError_t launch_pack_items(const u8* bytes, u64* coeffs, u32 N, u32 bits, u64 bytes_per_pt, u64 total_bytes,

@@ -60,29 +60,7 @@ k_ntt_fwd_push(const __grid_constant__ DevParams P, const u64* __restrict__ in, 
       ce = A.rows_per_rank + (e - A.d0);
     }
     const u64 qoff = A.slot_off + (A.g_first + qi) * A.dst_qstride;
-    if (A.packed_nb && e >= A.last_first) {
-      // last dimension, packed: per polynomial a plane of low 32-bit words + a plane of high parts.  Four consecutive
-      // coefficients per thread: one 16-byte and one 4-byte (8-byte for 6-byte residues) store per peer.
-      const u64 boff = ((u64)(e - A.last_first) * two_k + within) * N * A.packed_nb;
-      for (int i4 = tid * 4; i4 < N; i4 += NT * 4) {
-        u64 v[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) v[x] = eng_store_fwd<ENG>(s[swz(i4 + x)], m);
-        const uint4 lo = make_uint4((u32)v[0], (u32)v[1], (u32)v[2], (u32)v[3]);
-        for (u32 r = r_lo; r < r_hi; ++r) {
-          unsigned char* base = reinterpret_cast<unsigned char*>(A.peers[r] + qoff + A.packed_off) + boff;
-          *reinterpret_cast<uint4*>(base + 4 * (size_t)i4) = lo;
-          unsigned char* hp = base + 4 * (size_t)N;
-          if (A.packed_nb == 5) {
-            *reinterpret_cast<u32*>(hp + i4) = (u32)(v[0] >> 32) | ((u32)(v[1] >> 32) << 8) | ((u32)(v[2] >> 32) << 16) |
-                                               ((u32)(v[3] >> 32) << 24);
-          } else {
-            *reinterpret_cast<uint2*>(hp + 2 * (size_t)i4) =
-                make_uint2((u32)(v[0] >> 32) | ((u32)(v[1] >> 32) << 16), (u32)(v[2] >> 32) | ((u32)(v[3] >> 32) << 16));
-          }
-        }
-      }
-    } else {
+    {
       const u64 off = qoff + ce * two_k * N + (u64)within * N;
       for (int i2 = tid * 2; i2 < N; i2 += NT * 2) {
         ulonglong2 v;
@@ -137,6 +115,30 @@ cudaError_t launch_ntt_fwd_push(const DevParams& P, const u64* in, u64 in_qstrid
     default: return cudaErrorInvalidValue;
   }
 #undef PIRB_CASE
+}
+
+// ---------------------------------------------------------------------------------------------
+// one warp per (segment, peer): segment c of the staging buffer -> peer r's svT region
+__global__ void __launch_bounds__(256)
+k_push_rows(u64* const* __restrict__ peers, u32 n_ranks, const u8* __restrict__ stage, u64 src_stride, u32 seg_bytes,
+            u32 n_segs, u64 dst_off, u64 dst_stride) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const u32 vecs = seg_bytes / 16;
+  for (u64 item = warp; item < (u64)n_segs * n_ranks; item += n_warps) {
+    const u32 c = (u32)(item / n_ranks), r = (u32)(item % n_ranks);
+    const uint4* src = reinterpret_cast<const uint4*>(stage + (u64)c * src_stride);
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<u8*>(peers[r]) + dst_off + (u64)c * dst_stride);
+    for (u32 v = lane; v < vecs; v += 32) dst[v] = __ldg(src + v);
+  }
+}
+cudaError_t launch_push_rows(u64* const* peers_dev, u32 n_ranks, const u8* stage, u64 src_stride, u32 seg_bytes, u32 n_segs,
+                             u64 dst_off, u64 dst_stride, cudaStream_t st) {
+  if (!n_segs || !seg_bytes) return cudaSuccess;
+  if (seg_bytes % 16 || src_stride % 16 || dst_off % 16 || dst_stride % 16) return cudaErrorInvalidValue;
+  static const int width = getenv("PIRB_PUSH_CTAS") ? atoi(getenv("PIRB_PUSH_CTAS")) : 64;
+  k_push_rows<<<std::max(1, width), 256, 0, st>>>(peers_dev, n_ranks, stage, src_stride, seg_bytes, n_segs, dst_off, dst_stride);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -130,18 +130,16 @@ k_tc_pack_db(const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows, u32 k
   }
 }
 
-// selection vectors (NTT form, sv_qstride limbs between queries) -> svT (see header).  PACKED = false: u64 limbs
-// [q][i1][2][k][N]; PACKED = true: per polynomial a plane of N low 32-bit words and a plane of N high parts of nb - 4
-// bytes (what k_ntt_fwd_push stores into the exchange slots).
+// selection vectors u64 [q][i1][2][k][N] (NTT form, sv_qstride limbs between queries) -> rows [row0 + qp*nb, ...) of an
+// svT array with n_rows_total rows per coefficient (see header).
 // A block transposes a tile of 128 selection entries (one K chunk) x 64 coefficients through shared memory: every
 // row of the tile is read as 512 contiguous bytes (all loads of a thread in flight before the first shared-memory
 // store) and every (coefficient, limb byte) row of svT is written as the 128 contiguous bytes of the chunk.
 // grid (q * 2 + p, c / 64, K chunk), block 512, 128 * 66 * 8 bytes of dynamic shared memory; the K padding of svT
 // beyond Kp's last chunk stays zero from allocation.
 constexpr int PACK_C = 64, PACK_PITCH = PACK_C + 2;
-template <bool PACKED>
 __global__ void __launch_bounds__(512, 2)
-k_tc_pack_sv(const u64* __restrict__ sv, u64 sv_qstride, u32 dimL, u32 N, u32 kN, u32 nb, u32 n_rows_total, u32 Kp,
+k_tc_pack_sv(const u64* __restrict__ sv, u64 sv_qstride, u32 dimL, u32 kN, u32 nb, u32 n_rows_total, u32 row0, u32 Kp,
              u8* __restrict__ svT) {
   extern __shared__ __align__(16) u64 t[];  // [128][PACK_PITCH]
   const u32 qp = blockIdx.x, c0 = blockIdx.y * PACK_C, i0 = blockIdx.z * 128;
@@ -152,26 +150,8 @@ k_tc_pack_sv(const u64* __restrict__ sv, u64 sv_qstride, u32 dimL, u32 N, u32 kN
   for (int x = 0; x < 8; ++x) {
     const u32 i = i0 + w + 16 * x;
     v[x] = make_ulonglong2(0, 0);
-    if (i < dimL) {
-      if constexpr (PACKED) {
-        // polynomial (i, p, j) with j = c0 / N starts at ((i * 2k + p * k + j) * N) * nb bytes
-        const u32 j = c0 / N, n = c0 % N + 2 * lane;
-        const u8* base = reinterpret_cast<const u8*>(sv + (u64)q * sv_qstride) +
-                         ((u64)i * 2 * kN + (u64)p * kN + (u64)j * N) * nb;
-        const uint2 lo = __ldg(reinterpret_cast<const uint2*>(base + 4 * (size_t)n));
-        if (nb == 5) {
-          const unsigned short hi = __ldg(reinterpret_cast<const unsigned short*>(base + 4 * (size_t)N + n));
-          v[x].x = (u64)lo.x | ((u64)(hi & 0xFF) << 32);
-          v[x].y = (u64)lo.y | ((u64)(hi >> 8) << 32);
-        } else {
-          const u32 hi = __ldg(reinterpret_cast<const u32*>(base + 4 * (size_t)N + 2 * (size_t)n));
-          v[x].x = (u64)lo.x | ((u64)(hi & 0xFFFF) << 32);
-          v[x].y = (u64)lo.y | ((u64)(hi >> 16) << 32);
-        }
-      } else {
-        v[x] = __ldg(reinterpret_cast<const ulonglong2*>(sv + (u64)q * sv_qstride + (u64)i * 2 * kN + (u64)p * kN + c0) + lane);
-      }
-    }
+    if (i < dimL)
+      v[x] = __ldg(reinterpret_cast<const ulonglong2*>(sv + (u64)q * sv_qstride + (u64)i * 2 * kN + (u64)p * kN + c0) + lane);
   }
 #pragma unroll
   for (int x = 0; x < 8; ++x) *reinterpret_cast<ulonglong2*>(t + (size_t)(w + 16 * x) * PACK_PITCH + 2 * lane) = v[x];
@@ -183,7 +163,7 @@ k_tc_pack_sv(const u64* __restrict__ sv, u64 sv_qstride, u32 dimL, u32 N, u32 kN
     u64 r64[16];
 #pragma unroll
     for (int x = 0; x < 16; ++x) r64[x] = t[(size_t)(g * 16 + x) * PACK_PITCH + cc];
-    u8* o = svT + ((u64)(c0 + cc) * n_rows_total + (u64)qp * nb) * Kp + ib;
+    u8* o = svT + ((u64)(c0 + cc) * n_rows_total + row0 + (u64)qp * nb) * Kp + ib;
     for (u32 b = 0; b < nb; ++b) {
       u32 r[4];
 #pragma unroll
@@ -203,7 +183,8 @@ struct TcScanArgs {
   u32 n_queries;                          // real queries (outputs of padded ones are dropped)
   u32 n_qt, qt;                           // query tiles per coefficient, queries per tile (multiple of 8)
   u32 n_cols;                             // N of the MMA = qt * 2 * NB
-  u32 sv_rows_total;                      // rows of svT per coefficient = n_qt * n_cols
+  u32 sv_rows_total;                      // rows of svT per coefficient
+  u32 sv_row0;                            // first row of this call's queries inside a coefficient's rows
   u32 stages, b_bufs;                     // A ring depth, B buffers (1 or 2)
   u32 n_acc;                              // TMEM accumulator buffers = epilogue groups (2..4)
   u64* part;                              // [q][row][2][k][N]
@@ -271,7 +252,7 @@ k_tc_scan(const __grid_constant__ DevParams P, const __grid_constant__ CUtensorM
           mbar_expect_tx(b_full + bb, b_buf_bytes);
           for (u32 kc = 0; kc < A.kch; ++kc)
             tma_load_2d(sB + (size_t)bb * b_buf_bytes + (size_t)kc * b_chunk_bytes, &mapB, (int)(kc * 128),
-                        (int)(c * A.sv_rows_total + qt * A.n_cols), b_full + bb);
+                        (int)(c * A.sv_rows_total + A.sv_row0 + qt * A.n_cols), b_full + bb);
           ++bcount;
           for (u32 mt = 0; mt < A.ntiles && ok; ++mt)
             for (u32 kc = 0; kc < A.kch; ++kc) {
@@ -487,14 +468,31 @@ u64 tc_sv_bytes(const DevParams& P, const TcGeom& g, u32 n_queries, u32* qt_out,
   return (u64)P.k * P.N * n_qt * qt * 2 * g.nb * g.Kp;
 }
 
+cudaError_t launch_tc_pack_sv(const DevParams& P, const TcGeom& g, const u64* sv, u64 sv_qstride, u32 dimL, u32 n_queries,
+                              u8* svT, u32 rows_total, u32 row0, cudaStream_t st) {
+  if (!n_queries) return cudaSuccess;
+  const u32 kN = (u32)P.k * P.N;
+  const dim3 pgrid(n_queries * 2, kN / PACK_C, g.kch);
+  const size_t psmem = (size_t)128 * PACK_PITCH * sizeof(u64);
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e1 = cudaFuncSetAttribute(k_tc_pack_sv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+    if (e1 != cudaSuccess) return e1;
+    configured[dev & 63] = true;
+  }
+  k_tc_pack_sv<<<pgrid, 512, psmem, st>>>(sv, sv_qstride, dimL, kN, g.nb, rows_total, row0, g.Kp, svT);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u32 dimL, u32 n_rows, const u64* sv,
-                           u64 sv_qstride, int sv_packed, u32 n_queries, u8* svT, int* err_flag, int sm_count, u64* part,
+                           u64 sv_qstride, u32 n_queries, u8* svT, int* err_flag, int sm_count, u64* part,
                            cudaStream_t st) {
   const u32 kN = (u32)P.k * P.N;
   u32 qt, n_qt;
-  const u64 sv_bytes = tc_sv_bytes(P, g, n_queries, &qt, &n_qt);
-  const u32 n_cols = qt * 2 * g.nb;
-  const u32 sv_rows_total = n_qt * n_cols;
+  tc_sv_bytes(P, g, n_queries, &qt, &n_qt);
+  const u32 sv_rows_total = n_qt * qt * 2 * g.nb;
   // rows of padded queries must be zero; real ones are rewritten entirely (the K padding is never written)
   const u64 real_rows = (u64)n_queries * 2 * g.nb;
   if (real_rows < sv_rows_total) {
@@ -502,27 +500,19 @@ cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u
                                       (size_t)(sv_rows_total - real_rows) * g.Kp, kN, st);
     if (e != cudaSuccess) return e;
   }
-  (void)sv_bytes;
-  const dim3 pgrid(n_queries * 2, kN / PACK_C, g.kch);
-  const size_t psmem = (size_t)128 * PACK_PITCH * sizeof(u64);
-  {
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-      cudaError_t e1 = cudaFuncSetAttribute(k_tc_pack_sv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-      cudaError_t e2 = cudaFuncSetAttribute(k_tc_pack_sv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-      if (e1 != cudaSuccess) return e1;
-      if (e2 != cudaSuccess) return e2;
-      configured[dev & 63] = true;
-    }
-  }
-  if (sv_packed)
-    k_tc_pack_sv<true><<<pgrid, 512, psmem, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb, sv_rows_total, g.Kp, svT);
-  else
-    k_tc_pack_sv<false><<<pgrid, 512, psmem, st>>>(sv, sv_qstride, dimL, P.N, kN, g.nb, sv_rows_total, g.Kp, svT);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_tc_pack_sv(P, g, sv, sv_qstride, dimL, n_queries, svT, sv_rows_total, 0, st);
   if (e != cudaSuccess) return e;
+  return launch_tc_scan_packed(P, g, dbT, dimL, n_rows, svT, sv_rows_total, 0, n_queries, err_flag, sm_count, part, st);
+}
+
+cudaError_t launch_tc_scan_packed(const DevParams& P, const TcGeom& g, const u8* dbT, u32 dimL, u32 n_rows, const u8* svT,
+                                  u32 sv_rows_total, u32 row0, u32 n_queries, int* err_flag, int sm_count, u64* part,
+                                  cudaStream_t st) {
+  (void)dimL;
+  const u32 kN = (u32)P.k * P.N;
+  u32 qt, n_qt;
+  tc_sv_bytes(P, g, n_queries, &qt, &n_qt);
+  const u32 n_cols = qt * 2 * g.nb;
 
   CUtensorMap mapA, mapB;
   if (!make_map(&mapA, dbT, (u64)kN * g.ntiles * 128, g.Kp, 128)) return cudaErrorInvalidValue;
@@ -540,6 +530,7 @@ cudaError_t launch_tc_scan(const DevParams& P, const TcGeom& g, const u8* dbT, u
   A.qt = qt;
   A.n_cols = n_cols;
   A.sv_rows_total = sv_rows_total;
+  A.sv_row0 = row0;
   A.part = part;
   A.err = err_flag;
   const size_t b_buf = (size_t)g.kch * n_cols * 128;

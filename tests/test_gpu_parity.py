@@ -666,11 +666,11 @@ def test_peer_memory_exchange_flow_matches_oracle(dbsize, world, ql, sub, packed
     import torch
     from pir_b200 import sharded
     if packed:
-        # packed = 1: the last-dimension entries travel as packed 5-byte residues and every rank's scan runs on the
+        # packed = 1: the last-dimension entries travel repacked into the tensor-core operand layout and every scan runs on the
         # tensor cores (normally chosen for shards of >= 1024 plaintexts; forced here on the small test database)
         monkeypatch.setenv("PIRB_TC_MIN_PT", "0")
     else:
-        monkeypatch.setenv("PIRB_DIST_PACKED", "0")
+        monkeypatch.setenv("PIRB_DIST_TC", "0")
     n = 4096
     ep = pb.GenerateEncryptionParams(n, 20)
     p = pb.CreatePIRParameters(dbsize, 0, 2, ep)
