@@ -179,7 +179,8 @@ int pirb_dist_answer(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* queri
 int pirb_dist_status(pirb_ctx* ctx);
 /* device times of the last profiled step: 0 expansion, 1 exchange tail after the expansion, 2 start -> first sub-batch
  * of every rank has arrived, 3 multiplies, 4 partial-reply reduce + inverse NTT, 5 whole step */
-int pirb_dist_stage_ms(pirb_ctx* ctx, float* out_ms /*[6]*/);
+int pirb_dist_stage_ms(pirb_ctx* ctx, float* out_ms /*[10]: the six above, then the transfer stream's phases for the last
+                                                      sub-batch: selection-vector NTT, first-dimension push, repack, row push */);
 
 /* Scan only (the HBM-bound kernel): d_sv_ntt[n_queries][dims[d-1]][2][k][N] NTT form -> rows in NTT form.
  * Used by the bench to time the scan in isolation.  d_rows may be NULL (internal scratch). */

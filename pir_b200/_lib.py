@@ -16,7 +16,8 @@ PIRB_MAX_MODULI = 9
 PIRB_MAX_DIMS = 8
 PIRB_N_STAGES = 6
 STAGE_NAMES = ("expand", "sv_ntt", "scan", "row_intt", "upper_dims", "total")
-DIST_STAGE_NAMES = ("expand", "exchange_tail", "first_subbatch_arrived", "multiply", "reduce", "total")
+DIST_STAGE_NAMES = ("expand", "exchange_tail", "first_subbatch_arrived", "multiply", "reduce", "total",
+                    "x_ntt", "x_head_push", "x_repack", "x_row_push")
 
 
 class pirb_params(C.Structure):

@@ -179,6 +179,7 @@ struct pirb_ctx {
     std::vector<cudaEvent_t> ev_exp;          // per sub-batch: expansion finished (prod -> xfer)
     bool done_valid[2] = {false, false}, xfer_valid = false;
     cudaEvent_t prof[6] = {};                 // step start, expansion end, exchange end, multiply start/end, step end
+    cudaEvent_t xprof[5] = {};                // transfer stream, last sub-batch: start, NTT, head push, repack, row push
     bool prof_valid = false;
     u64 timeout_ns = 20ull * 1000 * 1000 * 1000;
     u64 launches = 0;
@@ -855,6 +856,8 @@ void pirb_ctx_destroy(pirb_ctx* c) {
     for (cudaEvent_t e_ : D.ev_exp) cudaEventDestroy(e_);
     for (cudaEvent_t e_ : D.prof)
       if (e_) cudaEventDestroy(e_);
+    for (cudaEvent_t e_ : D.xprof)
+      if (e_) cudaEventDestroy(e_);
   }
   if (c->xbuf) cudaFree(c->xbuf);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1358,6 +1361,7 @@ int pirb_dist_create(pirb_ctx* c, uint32_t max_local_queries, uint32_t sub_batch
   CU(cudaSetDevice(c->device));
   pirb_ctx::Dist& D = c->dist;
   if (D.base) return fail(PIRB_INVALID_ARGUMENT, "exchange block already created");
+  if (!sub_batch && getenv("PIRB_DIST_SUB")) sub_batch = (u32)atoi(getenv("PIRB_DIST_SUB"));
   if (!sub_batch) {
     // default: as many sub-batches as keep each multiply at >= 8 queries (ranks x sub-batch): the exchange of one
     // sub-batch hides behind the expansion of the next, so small sub-batches leave the shortest exposed tail
@@ -1376,6 +1380,7 @@ int pirb_dist_create(pirb_ctx* c, uint32_t max_local_queries, uint32_t sub_batch
   D.ev_exp.resize(D.n_sub);
   for (auto& e : D.ev_exp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : D.prof) CU(cudaEventCreate(&e));
+  for (auto& e : D.xprof) CU(cudaEventCreate(&e));
   if (const char* e = getenv("PIRB_DIST_TIMEOUT_MS")) D.timeout_ns = (u64)atoll(e) * 1000000ull;
   if (ipc_handle_out) {
     cudaIpcMemHandle_t h;
@@ -1504,24 +1509,32 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
     A.dst_qstride = D.sv_qstride;
     const u32 last = c->dims[c->d - 1], last_first = (u32)(c->dim_sum - last);
     const u64* sub_work = c->work.p + (u64)q0 * q_stride;
+    const bool xp = prof && sb + 1 == n_sub;
+    if (xp) cudaEventRecord(D.xprof[0], D.xfer);
     if (!D.tc_mode) {
       LAUNCH(c, launch_ntt_fwd_push(c->P, sub_work, q_stride, (u32)c->dim_sum, qn, A, D.xfer));
     } else {
-      // first / middle dimensions: u64 limbs to the owning rank / to everybody, straight from the NTT kernel
-      LAUNCH(c, launch_ntt_fwd_push(c->P, sub_work, q_stride, last_first, qn, A, D.xfer));
-      // last dimension: NTT in place, repack ONCE here into the tensor-core scan's operand layout, then copy every
-      // coefficient's rows into every rank's svT region — no rank repacks another rank's queries
-      u64* last_sv = c->work.p + (u64)q0 * q_stride + (u64)last_first * c->ctL;
-      LAUNCH(c, launch_ntt_fwd(c->P, last_sv, last_sv, (int)(last * 2 * c->k), c->k, 0, (int)qn, q_stride, q_stride, D.xfer));
+      // one full-width NTT of the whole selection vector in place (database.cpp:190,222), then copy kernels narrow
+      // enough to leave the SMs to the expansion: first / middle dimensions as u64 limbs to the owning rank / to everybody
+      u64* sv_all = c->work.p + (u64)q0 * q_stride;
+      u64* last_sv = sv_all + (u64)last_first * c->ctL;
+      LAUNCH(c, launch_ntt_fwd(c->P, sv_all, sv_all, (int)(c->dim_sum * 2 * c->k), c->k, 0, (int)qn, q_stride, q_stride, D.xfer));
+      if (xp) cudaEventRecord(D.xprof[1], D.xfer);
+      LAUNCH(c, launch_push_head(c->P, sv_all, q_stride, last_first, qn, A, D.xfer));
+      // last dimension: repacked ONCE here into the tensor-core scan's operand layout, then every coefficient's rows are
+      // copied into every rank's svT region — no rank repacks another rank's queries
+      if (xp) cudaEventRecord(D.xprof[2], D.xfer);
       const u32 stage_rows = SB * 2 * D.g.nb;
       RC(D.stage.ensure((size_t)c->k * c->N * stage_rows * D.g.Kp));
       LAUNCH(c, launch_tc_pack_sv(c->P, D.g, last_sv, q_stride, last, qn, reinterpret_cast<u8*>(D.stage.p), stage_rows, 0,
                                   D.xfer));
+      if (xp) cudaEventRecord(D.xprof[3], D.xfer);
       const u64 row0 = (((u64)sb * W + D.rank) * SB) * 2 * D.g.nb;
       LAUNCH(c, launch_push_rows(peers, W, reinterpret_cast<const u8*>(D.stage.p), (u64)stage_rows * D.g.Kp,
                                  qn * 2 * D.g.nb * D.g.Kp,
                                  (u32)c->k * c->N, (dist_sv_off(D, slot) + D.svt_off) * sizeof(u64) + row0 * D.g.Kp,
                                  (u64)D.slot_rows * D.g.Kp, D.xfer));
+      if (xp) cudaEventRecord(D.xprof[4], D.xfer);
     }
     LAUNCH(c, launch_signal(peers, W, dist_flag_off(D, 0, sb, D.rank), seq, D.xfer));
   }
@@ -1646,6 +1659,10 @@ int pirb_dist_stage_ms(pirb_ctx* c, float* out) {
   CU(cudaEventElapsedTime(out + 3, D.prof[3], D.prof[4]));
   CU(cudaEventElapsedTime(out + 4, D.prof[4], D.prof[5]));
   CU(cudaEventElapsedTime(out + 5, D.prof[0], D.prof[5]));
+  for (int i = 0; i < 4; ++i) {
+    out[6 + i] = 0.f;
+    if (D.tc_mode && cudaEventElapsedTime(out + 6 + i, D.xprof[i], D.xprof[i + 1]) != cudaSuccess) cudaGetLastError();
+  }
   return 0;
 }
 

@@ -94,6 +94,9 @@ struct PushArgs {
 // apart) with the outputs stored into the peers' slots in the compact layout [own rows of dim 0 | dims 1..]
 cudaError_t launch_ntt_fwd_push(const DevParams& P, const u64* in, u64 in_qstride, u32 n_entries, u32 n_queries,
                                 const PushArgs& A, cudaStream_t st);
+// copy-only variant for selection vectors that are already in NTT form (n_entries leading entries of n_queries queries)
+cudaError_t launch_push_head(const DevParams& P, const u64* in, u64 in_qstride, u32 n_entries, u32 n_queries,
+                             const PushArgs& A, cudaStream_t st);
 // The last-dimension entries only feed the scan.  When that runs on the tensor cores they travel already repacked into
 // its operand layout (svT, kernels_tc.cu): the producing rank packs its own queries once into a staging buffer
 // [coefficient][rows][Kp] (src_stride bytes per coefficient) and this kernel copies every coefficient's segment (seg_bytes) into every

@@ -118,20 +118,82 @@ cudaError_t launch_ntt_fwd_push(const DevParams& P, const u64* in, u64 in_qstrid
 }
 
 // ---------------------------------------------------------------------------------------------
-// one warp per (segment, peer): segment c of the staging buffer -> peer r's svT region
+// flat copy of the staging buffer's segments into every peer: a thread keeps 8 independent 16-byte loads in flight and
+// stores each vector to all ranks (one load, n_ranks stores; consecutive threads -> consecutive bytes at every peer)
 __global__ void __launch_bounds__(256)
 k_push_rows(u64* const* __restrict__ peers, u32 n_ranks, const u8* __restrict__ stage, u64 src_stride, u32 seg_bytes,
             u32 n_segs, u64 dst_off, u64 dst_stride) {
-  const u32 lane = threadIdx.x & 31;
-  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const u32 vecs = seg_bytes / 16;
-  for (u64 item = warp; item < (u64)n_segs * n_ranks; item += n_warps) {
-    const u32 c = (u32)(item / n_ranks), r = (u32)(item % n_ranks);
-    const uint4* src = reinterpret_cast<const uint4*>(stage + (u64)c * src_stride);
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<u8*>(peers[r]) + dst_off + (u64)c * dst_stride);
-    for (u32 v = lane; v < vecs; v += 32) dst[v] = __ldg(src + v);
+  const u64 total = (u64)n_segs * vecs;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 base = (u64)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += 8 * stride) {
+    uint4 v[8];
+    u32 cs[8], os[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const u64 idx = base + x * stride;
+      cs[x] = (u32)(idx / vecs);
+      os[x] = (u32)(idx % vecs);
+      if (idx < total) v[x] = __ldg(reinterpret_cast<const uint4*>(stage + (u64)cs[x] * src_stride) + os[x]);
+    }
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      if (base + x * stride >= total) break;
+      for (u32 r = 0; r < n_ranks; ++r)
+        reinterpret_cast<uint4*>(reinterpret_cast<u8*>(peers[r]) + dst_off + (u64)cs[x] * dst_stride)[os[x]] = v[x];
+    }
   }
 }
+// first / middle dimensions of already transformed selection vectors (u64 limbs, in_qstride limbs between queries):
+// entry e < d0 goes to the rank that owns row e, entries of the middle dimensions to every rank, into the compact
+// per-query layout of the slot.  Same flat copy scheme as k_push_rows.
+__global__ void __launch_bounds__(256)
+k_push_head(const u64* __restrict__ in, u64 in_qstride, u32 n_entries, u32 n_queries, u32 ct_vecs, const PushArgs A) {
+  const u64 per_q = (u64)n_entries * ct_vecs;  // 16-byte vectors per query
+  const u64 total = per_q * n_queries;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 base = (u64)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += 8 * stride) {
+    uint4 v[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const u64 idx = base + x * stride;
+      if (idx < total) {
+        const u32 qi = (u32)(idx / per_q);
+        v[x] = __ldg(reinterpret_cast<const uint4*>(in + (u64)qi * in_qstride) + (idx % per_q));
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const u64 idx = base + x * stride;
+      if (idx >= total) break;
+      const u32 qi = (u32)(idx / per_q);
+      const u64 w = idx % per_q;
+      const u32 e = (u32)(w / ct_vecs);
+      const u64 within = w % ct_vecs;
+      u32 r_lo, r_hi;
+      u64 ce;
+      if (e < A.d0) {
+        r_lo = e / A.rows_per_rank;
+        r_hi = r_lo + 1;
+        ce = e - r_lo * A.rows_per_rank;
+      } else {
+        r_lo = 0;
+        r_hi = A.n_ranks;
+        ce = A.rows_per_rank + (e - A.d0);
+      }
+      const u64 off = A.slot_off + (A.g_first + qi) * A.dst_qstride;  // limbs
+      for (u32 r = r_lo; r < r_hi; ++r) (reinterpret_cast<uint4*>(A.peers[r] + off) + ce * ct_vecs)[within] = v[x];
+    }
+  }
+}
+cudaError_t launch_push_head(const DevParams& P, const u64* in, u64 in_qstride, u32 n_entries, u32 n_queries,
+                             const PushArgs& A, cudaStream_t st) {
+  if (!n_entries || !n_queries) return cudaSuccess;
+  static const int width = getenv("PIRB_PUSH_CTAS") ? atoi(getenv("PIRB_PUSH_CTAS")) : 64;
+  k_push_head<<<std::max(1, width), 256, 0, st>>>(in, in_qstride, n_entries, n_queries, (u32)P.k * P.N, A);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_push_rows(u64* const* peers_dev, u32 n_ranks, const u8* stage, u64 src_stride, u32 seg_bytes, u32 n_segs,
                              u64 dst_off, u64 dst_stride, cudaStream_t st) {
   if (!n_segs || !seg_bytes) return cudaSuccess;

@@ -338,7 +338,7 @@ class ShardServer:
         _check(_lib.lib().pirb_dist_status(self.ctx.h))
 
     def dist_stage_ms(self):
-        out = (C.c_float * 6)()
+        out = (C.c_float * 10)()
         _check(_lib.lib().pirb_dist_stage_ms(self.ctx.h, out))
         return dict(zip(_lib.DIST_STAGE_NAMES, [float(x) for x in out]))
 
