@@ -162,7 +162,8 @@ struct pirb_ctx {
     // slot, [coefficient][slot rows][Kp] bytes) instead of as u64 limbs in the per-query part
     bool tc_mode = false;
     TcGeom g = {};
-    u32 slot_rows = 0;                        // svT rows per coefficient in a slot: queries of a slot * 2 * nb
+    u32 sub_rows = 0;                         // svT rows per coefficient of ONE sub-batch: n_ranks * sub_q * 2 * nb
+    u64 sub_bytes = 0;                        // bytes of one sub-batch's svT region [coefficient][sub_rows][Kp]
     u64 svt_off = 0;                          // limb offset of the svT region inside a slot
     DevBuf stage;                             // local repacking of the rank's own queries before the push
     u64 flag_limbs = 0, sv_slot_limbs = 0, part_slot_limbs = 0;
@@ -1334,9 +1335,13 @@ static int dist_layout(pirb_ctx* c, u32 max_local, u32 sub_q) {
   if (D.tc_mode) {
     tc_geometry(c->P, last, 1, &D.g);
     D.sv_qstride = head;
-    D.slot_rows = (u32)(slot_queries * 2 * D.g.nb);
+    // one svT region per sub-batch, [coefficient][rows of the sub-batch's n_ranks * sub_q queries][Kp]: what one push
+    // writes at a peer (and one scan reads) stays within a few hundred MB — peer-memory TLB reach matters for the
+    // push throughput — and the scan's B tiles are dense
+    D.sub_rows = (u32)(D.n_ranks * D.sub_q * 2 * D.g.nb);
+    D.sub_bytes = (u64)c->k * c->N * D.sub_rows * D.g.Kp;
     D.svt_off = slot_queries * head;
-    D.sv_slot_limbs = (D.svt_off + ((u64)c->k * c->N * D.slot_rows * D.g.Kp + 7) / 8 + 15) / 16 * 16;
+    D.sv_slot_limbs = (D.svt_off + (D.n_sub * D.sub_bytes + 7) / 8 + 15) / 16 * 16;
   } else {
     D.sv_qstride = head + (u64)last * c->ctL;
     D.sv_slot_limbs = slot_queries * D.sv_qstride;
@@ -1372,8 +1377,10 @@ int pirb_dist_create(pirb_ctx* c, uint32_t max_local_queries, uint32_t sub_batch
   CU(cudaMemset(D.base, 0, D.flag_limbs * sizeof(u64)));
   int lo = 0, hi = 0;
   CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
-  CU(cudaStreamCreateWithPriority(&D.prod, cudaStreamNonBlocking, hi));
+  // transfer > expansion > multiply: the peers wait for what the transfer stream sends, and its narrow kernels must get
+  // an SM slot as soon as any expansion CTA retires instead of queueing behind the whole level
   CU(cudaStreamCreateWithPriority(&D.xfer, cudaStreamNonBlocking, hi));
+  CU(cudaStreamCreateWithPriority(&D.prod, cudaStreamNonBlocking, std::min(lo, hi + 1)));
   CU(cudaStreamCreateWithPriority(&D.cons, cudaStreamNonBlocking, lo));
   for (cudaEvent_t* e : {&D.ev_in, &D.ev_prod, &D.ev_xfer, &D.ev_done[0], &D.ev_done[1]})
     CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
@@ -1529,11 +1536,11 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
       LAUNCH(c, launch_tc_pack_sv(c->P, D.g, last_sv, q_stride, last, qn, reinterpret_cast<u8*>(D.stage.p), stage_rows, 0,
                                   D.xfer));
       if (xp) cudaEventRecord(D.xprof[3], D.xfer);
-      const u64 row0 = (((u64)sb * W + D.rank) * SB) * 2 * D.g.nb;
+      const u64 row0 = (u64)D.rank * SB * 2 * D.g.nb;  // this rank's rows inside the sub-batch's region
       LAUNCH(c, launch_push_rows(peers, W, reinterpret_cast<const u8*>(D.stage.p), (u64)stage_rows * D.g.Kp,
-                                 qn * 2 * D.g.nb * D.g.Kp,
-                                 (u32)c->k * c->N, (dist_sv_off(D, slot) + D.svt_off) * sizeof(u64) + row0 * D.g.Kp,
-                                 (u64)D.slot_rows * D.g.Kp, D.xfer));
+                                 qn * 2 * D.g.nb * D.g.Kp, (u32)c->k * c->N,
+                                 (dist_sv_off(D, slot) + D.svt_off) * sizeof(u64) + sb * D.sub_bytes + row0 * D.g.Kp,
+                                 (u64)D.sub_rows * D.g.Kp, D.xfer));
       if (xp) cudaEventRecord(D.xprof[4], D.xfer);
     }
     LAUNCH(c, launch_signal(peers, W, dist_flag_off(D, 0, sb, D.rank), seq, D.xfer));
@@ -1549,15 +1556,15 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
     LAUNCH(c, launch_wait(D.base + dist_flag_off(D, 0, sb, 0), W, seq, D.timeout_ns, err, D.cons));
     if (prof && sb == 0) cudaEventRecord(D.prof[3], D.cons);
     const u64 g0 = (u64)sb * W * SB;
-    const u8* svt_base = reinterpret_cast<const u8*>(D.base + dist_sv_off(D, slot) + D.svt_off);
+    const u8* svt_base = reinterpret_cast<const u8*>(D.base + dist_sv_off(D, slot) + D.svt_off) + sb * D.sub_bytes;
     if (qn == SB) {
-      SvtRef ref{svt_base, D.slot_rows, (u32)(g0 * 2 * D.g.nb)};
+      SvtRef ref{svt_base, D.sub_rows, 0};
       RC(run_multiply(c, D.base + dist_sv_off(D, slot) + g0 * D.sv_qstride, D.sv_qstride, (int)(W * SB),
                       D.base + dist_part_off(D, slot) + g0 * c->reply_cts * c->ctL, 1, D.cons, true, 0, ~0ull,
                       D.rows_per_rank, D.tc_mode ? &ref : nullptr));
     } else {  // ragged last sub-batch: the ranks' queries are not contiguous, one multiply per rank
       for (u32 r = 0; r < W; ++r) {
-        SvtRef ref{svt_base, D.slot_rows, (u32)((g0 + (u64)r * SB) * 2 * D.g.nb)};
+        SvtRef ref{svt_base, D.sub_rows, (u32)(r * SB * 2 * D.g.nb)};
         RC(run_multiply(c, D.base + dist_sv_off(D, slot) + (g0 + (u64)r * SB) * D.sv_qstride, D.sv_qstride, (int)qn,
                         D.base + dist_part_off(D, slot) + (g0 + (u64)r * SB) * c->reply_cts * c->ctL, 1, D.cons, true, 0,
                         ~0ull, D.rows_per_rank, D.tc_mode ? &ref : nullptr));

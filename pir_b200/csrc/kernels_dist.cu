@@ -118,71 +118,64 @@ cudaError_t launch_ntt_fwd_push(const DevParams& P, const u64* in, u64 in_qstrid
 }
 
 // ---------------------------------------------------------------------------------------------
-// flat copy of the staging buffer's segments into every peer: a thread keeps 8 independent 16-byte loads in flight and
-// stores each vector to all ranks (one load, n_ranks stores; consecutive threads -> consecutive bytes at every peer)
+// copy of the staging buffer's segments into every peer: one warp per segment chunk of 256 vectors, a lane keeps 8
+// independent 16-byte loads in flight and stores each vector to all ranks (one load, n_ranks stores; consecutive lanes
+// -> consecutive bytes at every peer).  No per-vector index arithmetic.
 __global__ void __launch_bounds__(256)
 k_push_rows(u64* const* __restrict__ peers, u32 n_ranks, const u8* __restrict__ stage, u64 src_stride, u32 seg_bytes,
             u32 n_segs, u64 dst_off, u64 dst_stride) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const u32 vecs = seg_bytes / 16;
-  const u64 total = (u64)n_segs * vecs;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 base = (u64)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += 8 * stride) {
+  const u32 chunks = (vecs + 255) / 256;
+  for (u32 item = warp; item < n_segs * chunks; item += n_warps) {
+    const u32 c = item / chunks, v0 = (item % chunks) * 256;
+    const uint4* src = reinterpret_cast<const uint4*>(stage + (u64)c * src_stride) + v0;
     uint4 v[8];
-    u32 cs[8], os[8];
 #pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      const u64 idx = base + x * stride;
-      cs[x] = (u32)(idx / vecs);
-      os[x] = (u32)(idx % vecs);
-      if (idx < total) v[x] = __ldg(reinterpret_cast<const uint4*>(stage + (u64)cs[x] * src_stride) + os[x]);
-    }
+    for (int x = 0; x < 8; ++x)
+      if (v0 + lane + 32 * x < vecs) v[x] = __ldg(src + lane + 32 * x);
+    for (u32 r = 0; r < n_ranks; ++r) {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<u8*>(peers[r]) + dst_off + (u64)c * dst_stride) + v0;
 #pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      if (base + x * stride >= total) break;
-      for (u32 r = 0; r < n_ranks; ++r)
-        reinterpret_cast<uint4*>(reinterpret_cast<u8*>(peers[r]) + dst_off + (u64)cs[x] * dst_stride)[os[x]] = v[x];
+      for (int x = 0; x < 8; ++x)
+        if (v0 + lane + 32 * x < vecs) dst[lane + 32 * x] = v[x];
     }
   }
 }
 // first / middle dimensions of already transformed selection vectors (u64 limbs, in_qstride limbs between queries):
 // entry e < d0 goes to the rank that owns row e, entries of the middle dimensions to every rank, into the compact
-// per-query layout of the slot.  Same flat copy scheme as k_push_rows.
+// per-query layout of the slot.  One block per (query, entry, chunk of 2048 vectors); same load batching.
 __global__ void __launch_bounds__(256)
 k_push_head(const u64* __restrict__ in, u64 in_qstride, u32 n_entries, u32 n_queries, u32 ct_vecs, const PushArgs A) {
-  const u64 per_q = (u64)n_entries * ct_vecs;  // 16-byte vectors per query
-  const u64 total = per_q * n_queries;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 base = (u64)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += 8 * stride) {
+  const u32 chunks = (ct_vecs + 2047) / 2048;
+  const u32 n_items = n_queries * n_entries * chunks;
+  for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const u32 ch = item % chunks, qe = item / chunks;
+    const u32 e = qe % n_entries, qi = qe / n_entries;
+    const u32 v0 = ch * 2048 + threadIdx.x;
+    const uint4* src = reinterpret_cast<const uint4*>(in + (u64)qi * in_qstride) + (u64)e * ct_vecs;
     uint4 v[8];
 #pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      const u64 idx = base + x * stride;
-      if (idx < total) {
-        const u32 qi = (u32)(idx / per_q);
-        v[x] = __ldg(reinterpret_cast<const uint4*>(in + (u64)qi * in_qstride) + (idx % per_q));
-      }
+    for (int x = 0; x < 8; ++x)
+      if (v0 + 256 * x < ct_vecs) v[x] = __ldg(src + v0 + 256 * x);
+    u32 r_lo, r_hi;
+    u64 ce;
+    if (e < A.d0) {
+      r_lo = e / A.rows_per_rank;
+      r_hi = r_lo + 1;
+      ce = e - r_lo * A.rows_per_rank;
+    } else {
+      r_lo = 0;
+      r_hi = A.n_ranks;
+      ce = A.rows_per_rank + (e - A.d0);
     }
+    const u64 off = A.slot_off + (A.g_first + qi) * A.dst_qstride;  // limbs
+    for (u32 r = r_lo; r < r_hi; ++r) {
+      uint4* dst = reinterpret_cast<uint4*>(A.peers[r] + off) + ce * ct_vecs;
 #pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      const u64 idx = base + x * stride;
-      if (idx >= total) break;
-      const u32 qi = (u32)(idx / per_q);
-      const u64 w = idx % per_q;
-      const u32 e = (u32)(w / ct_vecs);
-      const u64 within = w % ct_vecs;
-      u32 r_lo, r_hi;
-      u64 ce;
-      if (e < A.d0) {
-        r_lo = e / A.rows_per_rank;
-        r_hi = r_lo + 1;
-        ce = e - r_lo * A.rows_per_rank;
-      } else {
-        r_lo = 0;
-        r_hi = A.n_ranks;
-        ce = A.rows_per_rank + (e - A.d0);
-      }
-      const u64 off = A.slot_off + (A.g_first + qi) * A.dst_qstride;  // limbs
-      for (u32 r = r_lo; r < r_hi; ++r) (reinterpret_cast<uint4*>(A.peers[r] + off) + ce * ct_vecs)[within] = v[x];
+      for (int x = 0; x < 8; ++x)
+        if (v0 + 256 * x < ct_vecs) dst[v0 + 256 * x] = v[x];
     }
   }
 }
