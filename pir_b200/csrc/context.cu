@@ -1368,9 +1368,11 @@ int pirb_dist_create(pirb_ctx* c, uint32_t max_local_queries, uint32_t sub_batch
   if (D.base) return fail(PIRB_INVALID_ARGUMENT, "exchange block already created");
   if (!sub_batch && getenv("PIRB_DIST_SUB")) sub_batch = (u32)atoi(getenv("PIRB_DIST_SUB"));
   if (!sub_batch) {
-    // default: as many sub-batches as keep each multiply at >= 8 queries (ranks x sub-batch): the exchange of one
-    // sub-batch hides behind the expansion of the next, so small sub-batches leave the shortest exposed tail
-    sub_batch = std::max<u32>(1, (8 + c->prm.shard_count - 1) / c->prm.shard_count);
+    // default: sub-batches of two local queries, more while ranks x sub-batch < 8 (each multiply should see >= 8
+    // queries): the exchange of one sub-batch hides behind the expansion of the next, so small sub-batches leave a
+    // short exposed tail, while larger ones push longer contiguous rows (measured on 8 B200s: 2 beats 1 and 4)
+    sub_batch = std::max<u32>(2, (8 + c->prm.shard_count - 1) / c->prm.shard_count);
+    sub_batch = std::min<u32>(sub_batch, max_local_queries);
   }
   RC(dist_layout(c, max_local_queries, std::min(sub_batch, max_local_queries)));
   CU(cudaMalloc(&D.base, D.bytes));
