@@ -5,6 +5,7 @@
 //   k_mul_inv_pow_x   negacyclic shift (server.cpp:78-103)
 //   k_modadd_reduce   mod-q sum of per-GPU partial replies
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -636,23 +637,37 @@ static void scan_pick(const DevParams& P, u32 n_rows, int* R, int* U, int* mode)
 }
 
 void scan_config(const DevParams& P, u32 dimL, u32 n_rows, int n_queries, int sm_count, int* n_split) {
-  // enough CTAs for several resident per SM; split the i1 loop when the row count alone cannot provide them
+  // The grid is (slices x row tiles x queries) CTAs, each optionally working on 1/n_split of the last dimension.  Small
+  // and medium databases give only one to three waves of CTAs, so the last, partly filled wave is a large share of the
+  // kernel (2.27 waves = 32 % tail on BASELINE config 2 and on a 1/8 shard of config 4).  Choose the split whose CTA
+  // count fills whole waves best, charging the extra partial-result traffic (every split writes its own row results,
+  // which the inverse NTT's load side sums) and keeping at least 8 database tiles per CTA.
   int R, U, mode;
   scan_pick(P, n_rows, &R, &U, &mode);
   const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
-  const u64 base = (u64)slices * ((n_rows + R - 1) / R) * n_queries;
-  const u64 want = (u64)sm_count * env_int("PIRB_SCAN_CTAS_PER_SM", 8);
-  int s = 1;
-  if (base < want) s = (int)((want + base - 1) / base);
-  const int max_split = (int)((dimL + 7) / 8);  // keep at least 8 database tiles per CTA
-  if (s > max_split) s = max_split;
+  const u64 row_tiles = (n_rows + R - 1) / R;
+  const u64 base = (u64)slices * row_tiles * n_queries;
+  const u64 slots = (u64)sm_count * env_int("PIRB_SCAN_CTAS_PER_SM", 4);  // resident CTAs (124 registers x 128 threads)
   // exact lazy accumulation chains have a maximum length (pirb_device.cuh)
   const u32 max_terms = mode >= MAC_FP64 ? P.mac_max_terms : (mode == MAC_INT24 ? PIRB_SMALL_MAX_TERMS : P.wide_max_terms);
-  const int min_split = (int)((dimL + max_terms - 1) / max_terms);
-  if (s < min_split) s = min_split;
-  s = env_int("PIRB_SCAN_SPLIT", s);
-  if (s < 1) s = 1;
-  *n_split = s;
+  const int min_split = std::max(1, (int)((dimL + max_terms - 1) / max_terms));
+  const int max_split = std::max(min_split, (int)(dimL / 8));
+  const double db_bytes = (double)row_tiles * R * dimL + 2.0 * dimL;  // in plaintext-sized units (x pt bytes)
+  int best = min_split;
+  double best_score = -1.0;
+  // six or more waves without splitting: the tail is already small (measured: 76 % of the copy bandwidth on the 6.7 GiB
+  // database), keep one pass per row
+  for (int sp = min_split; sp <= max_split && sp <= 64 && base < 6 * slots; ++sp) {
+    const double ctas = (double)base * sp;
+    const double waves = std::ceil(ctas / (double)slots);
+    const double fill = ctas / ((double)slots * waves);               // 1.0 = every wave full
+    const double extra = 2.0 * 2.0 * (double)n_rows * (sp - 1);       // partial rows written + read again (2 pt each)
+    const double score = fill / (1.0 + extra / db_bytes) * (waves >= 2.0 || ctas <= (double)slots ? 1.0 : 0.9);
+    if (score > best_score + 1e-9) { best_score = score; best = sp; }
+  }
+  int sp = env_int("PIRB_SCAN_SPLIT", best);
+  if (sp < min_split) sp = min_split;
+  *n_split = sp;
 }
 
 cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL, u32 n_rows, const u64* sv,
