@@ -318,6 +318,7 @@ int run_expand(pirb_ctx* c, const pirb_keys* keys, ExpandPlan* pl, const u64* d_
     L.n_trees = pl->lvl_ntrees[j];
     L.j = j;
     L.ginv = inv_mod_2n(g, c->N);
+    L.g = g;
     L.q_stride = q_stride;
     L.n_queries = q_count;
     L.xch = c->xch.p;
@@ -1010,6 +1011,7 @@ int pirb_substitute(pirb_ctx* c, const pirb_keys* keys, uint64_t* ct, uint32_t p
   L.n_trees = 1;
   L.j = 0;
   L.ginv = inv_mod_2n(power, c->N);
+  L.g = power;
   L.q_stride = 0;
   L.n_queries = 1;
   L.dbg = nullptr;

@@ -15,6 +15,7 @@ struct LevelArgs {
   int n_trees;
   int j;         // tree level; 2^j nodes per tree
   u32 ginv;      // inverse of the Galois element (N>>j)+1 modulo 2N
+  u32 g;         // the Galois element itself
   u64 q_stride;  // limbs between consecutive queries' workspaces
   int n_queries;
   u64* xch;      // cluster kernel: [node][2][N] scratch through which the special-prime accumulators reach the

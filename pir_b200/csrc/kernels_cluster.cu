@@ -356,11 +356,15 @@ k_ks_level_cluster2(const __grid_constant__ DevParams P, u64* __restrict__ work,
     const u64* c1 = src + (u64)(k + J) * N;
     const u64 qJ = P.m[J].q;
     const bool need_reduce = qJ > mI.q;
+    // the automorphism as a SCATTER into shared memory: coalesced global reads of a[i], destination slot i*g mod N
+    // with the sign of floor(i*g / N)'s parity (sigma_g(a)[i*g mod N] = +-a[i]; the same map galois_gather inverts)
 #pragma unroll
     for (int i = tid; i < N; i += NT) {
-      u64 v = galois_gather(c1, i, L.ginv, N, qJ);
+      u64 v = c1[i];
+      const u32 t = ((u32)i * L.g) & (2 * N - 1);
+      if (t & N) v = negmod(v, qJ);
       if (need_reduce) v = barrett64(v, mI.q, mI.ratio_hi);
-      D[swz(i)] = eng_load<ENG_FP64>(v);
+      D[swz(t & (N - 1))] = eng_load<ENG_FP64>(v);
     }
   }
   __syncthreads();
