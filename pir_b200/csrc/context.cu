@@ -1541,10 +1541,20 @@ static int dist_step(pirb_ctx* c, const pirb_keys* keys, const u64* d_queries, u
                                   D.xfer));
       if (xp) cudaEventRecord(D.xprof[3], D.xfer);
       const u64 row0 = (u64)D.rank * SB * 2 * D.g.nb;  // this rank's rows inside the sub-batch's region
-      LAUNCH(c, launch_push_rows(peers, W, reinterpret_cast<const u8*>(D.stage.p), (u64)stage_rows * D.g.Kp,
-                                 qn * 2 * D.g.nb * D.g.Kp, (u32)c->k * c->N,
-                                 (dist_sv_off(D, slot) + D.svt_off) * sizeof(u64) + sb * D.sub_bytes + row0 * D.g.Kp,
-                                 (u64)D.sub_rows * D.g.Kp, D.xfer));
+      const u64 dst_off = (dist_sv_off(D, slot) + D.svt_off) * sizeof(u64) + sb * D.sub_bytes + row0 * D.g.Kp;
+      static const bool dma = getenv("PIRB_PUSH_DMA") && getenv("PIRB_PUSH_DMA")[0] == '1';
+      if (dma) {
+        // the same row push by the copy engines (one strided 2-D copy per rank): no SM is occupied by the transfer
+        if (!dry)
+          for (u32 r = 0; r < W; ++r) {
+            u8* dstp = reinterpret_cast<u8*>(solo ? D.base : D.peer_base[r]) + dst_off;
+            CU(cudaMemcpy2DAsync(dstp, (size_t)D.sub_rows * D.g.Kp, D.stage.p, (size_t)stage_rows * D.g.Kp,
+                                 (size_t)qn * 2 * D.g.nb * D.g.Kp, (size_t)c->k * c->N, cudaMemcpyDeviceToDevice, D.xfer));
+          }
+      } else {
+        LAUNCH(c, launch_push_rows(peers, W, reinterpret_cast<const u8*>(D.stage.p), (u64)stage_rows * D.g.Kp,
+                                   qn * 2 * D.g.nb * D.g.Kp, (u32)c->k * c->N, dst_off, (u64)D.sub_rows * D.g.Kp, D.xfer));
+      }
       if (xp) cudaEventRecord(D.xprof[4], D.xfer);
     }
     LAUNCH(c, launch_signal(peers, W, dist_flag_off(D, 0, sb, D.rank), seq, D.xfer));

@@ -34,8 +34,8 @@ __device__ __forceinline__ ulonglong2 ldg128_stream(const u64* p) {
 constexpr int SCAN_NT = 128;
 constexpr int SCAN_LIMBS = 2 * SCAN_NT;
 
-template <int R, int U, int MODE, int MINB = 1>
-__global__ void __launch_bounds__(SCAN_NT, MINB)
+template <int R, int U, int MODE>
+__global__ void __launch_bounds__(SCAN_NT)
 k_scan(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
        const u64* __restrict__ sv, u64 sv_qstride, int n_split, u64* __restrict__ part) {
   const u32 kN = (u32)P.k * P.N;
@@ -85,108 +85,6 @@ k_scan(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_
         acc[r][1][1].mac(a1y, by);
       }
     }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    if (row0 + r >= n_rows) break;
-    u64* o = part + (((u64)qi * n_split + split) * n_rows + row0 + r) * ctL + limb;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      ulonglong2 v;
-      v.x = acc[r][c][0].reduce(m, hb);
-      v.y = acc[r][c][1].reduce(m, hb);
-      *reinterpret_cast<ulonglong2*>(o + (u64)c * kN) = v;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// scan, shared-selection variant: G groups of 128 threads in one CTA work on different rows (R rows each) of the same
-// 256-limb slice and share the selection-vector tiles through a double-buffered shared-memory stage, so the L2->SM
-// traffic for the selection vector per database byte drops from 2/R to 2/(R*G) without more registers per thread.
-//   grid (slice, row tile of R*G rows, qi*n_split + split); G*128 threads
-// ---------------------------------------------------------------------------------------------
-template <int R, int G, int U, int MODE>
-__global__ void __launch_bounds__(SCAN_NT * G)
-k_scan_share(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
-             const u64* __restrict__ sv, u64 sv_qstride, int n_split, u64* __restrict__ part) {
-  __shared__ __align__(16) u64 stage[2][U][2][SCAN_LIMBS];  // [buffer][i1][poly][limb]
-  constexpr int NTH = SCAN_NT * G;
-  constexpr int VEC = U * 2 * SCAN_LIMBS / 2;  // 128-bit vectors per stage buffer
-  constexpr int VPT = (VEC + NTH - 1) / NTH;   // vectors each thread moves per chunk
-  const u32 kN = (u32)P.k * P.N;
-  const int g = threadIdx.x / SCAN_NT, t = threadIdx.x % SCAN_NT;
-  const u32 limb0 = blockIdx.x * SCAN_LIMBS;
-  const u32 limb = limb0 + t * 2;
-  const u32 row0 = (blockIdx.y * G + g) * R;
-  const u32 split = blockIdx.z % n_split, qi = blockIdx.z / n_split;
-  const ModC& m = P.m[limb / P.N];
-  const u32 per = (dimL + n_split - 1) / n_split;
-  const u32 i_lo = split * per;
-  const u32 i_hi = min(dimL, i_lo + per);
-  Acc<MODE> acc[R][2][2];
-  const int hb = P.half_bits;
-  const u64 ctL = 2ull * kN;
-  const u64* svq = sv + qi * sv_qstride + limb0;
-  const u64* dbr[R];
-  u32 cnt[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const u64 first = (u64)(row0 + r) * dimL;
-    dbr[r] = db + first * kN + limb;
-    cnt[r] = (row0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
-  }
-  // cooperative fetch of one chunk (U consecutive i1) of selection tiles: vector v -> (u, poly, pair of limbs)
-  auto fetch = [&](u32 i_base, ulonglong2 (&regs)[VPT]) {
-#pragma unroll
-    for (int x = 0; x < VPT; ++x) {
-      const int v = threadIdx.x + x * NTH;
-      const int u = v / SCAN_LIMBS, rem = v % SCAN_LIMBS;  // SCAN_LIMBS vectors per i1 (2 polys x 128 vectors)
-      const int poly = rem / (SCAN_LIMBS / 2), l2 = rem % (SCAN_LIMBS / 2);
-      const u32 i = i_base + u;
-      regs[x] = (v < VEC && i < i_hi) ? ldg128(svq + i * ctL + (u64)poly * kN + l2 * 2) : make_ulonglong2(0, 0);
-    }
-  };
-  auto stash = [&](int buf, const ulonglong2 (&regs)[VPT]) {
-#pragma unroll
-    for (int x = 0; x < VPT; ++x) {
-      const int v = threadIdx.x + x * NTH;
-      if (v < VEC) reinterpret_cast<ulonglong2*>(&stage[buf][0][0][0])[v] = regs[x];
-    }
-  };
-  ulonglong2 nxt[VPT];
-  fetch(i_lo, nxt);
-  stash(0, nxt);
-  __syncthreads();
-  int buf = 0;
-#pragma unroll 1
-  for (u32 i1 = i_lo; i1 < i_hi; i1 += U) {
-    fetch(i1 + U, nxt);  // next chunk's selection tiles travel while this chunk is multiplied
-    ulonglong2 d[U][R];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const u32 i = i1 + u;
-        d[u][r] = (i < i_hi && i < cnt[r]) ? ldg128_stream(dbr[r] + (u64)i * kN) : make_ulonglong2(0, 0);
-      }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(&stage[buf][u][0][t * 2]);
-      const ulonglong2 s1 = *reinterpret_cast<const ulonglong2*>(&stage[buf][u][1][t * 2]);
-      const Opnd<MODE> a0x(s0.x, hb), a0y(s0.y, hb), a1x(s1.x, hb), a1y(s1.y, hb);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const Opnd<MODE> bx(d[u][r].x, hb), by(d[u][r].y, hb);
-        acc[r][0][0].mac(a0x, bx);
-        acc[r][0][1].mac(a0y, by);
-        acc[r][1][0].mac(a1x, bx);
-        acc[r][1][1].mac(a1y, by);
-      }
-    }
-    stash(buf ^ 1, nxt);
-    __syncthreads();
-    buf ^= 1;
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -420,216 +318,11 @@ k_scan_batch2(const __grid_constant__ DevParams P, const u64* __restrict__ db, u
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// scan, register-pipelined LDG variant: the loads of step i+PD-1 are issued before the multiply-accumulates of
-// step i, so every warp keeps PD-1 steps of database/selection tiles in flight while it computes.
-// ---------------------------------------------------------------------------------------------
-template <int R, int PD, int MODE>
-__global__ void __launch_bounds__(SCAN_NT)
-k_scan_pipe(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
-            const u64* __restrict__ sv, u64 sv_qstride, int n_split, u64* __restrict__ part) {
-  const u32 kN = (u32)P.k * P.N;
-  const u32 limb = blockIdx.x * SCAN_LIMBS + threadIdx.x * 2;
-  const u32 row0 = blockIdx.y * R;
-  const u32 split = blockIdx.z % n_split, qi = blockIdx.z / n_split;
-  const ModC& m = P.m[limb / P.N];
-  const u32 per = (dimL + n_split - 1) / n_split;
-  const u32 i_lo = split * per;
-  const u32 i_hi = min(dimL, i_lo + per);
-  Acc<MODE> acc[R][2][2];
-  const int hb = P.half_bits;
-  const u64 ctL = 2ull * kN;
-  const u64* svq = sv + qi * sv_qstride + limb;
-  const u64* dbr[R];
-  u32 cnt[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const u64 first = (u64)(row0 + r) * dimL;
-    dbr[r] = db + first * kN + limb;
-    cnt[r] = (row0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
-  }
-  ulonglong2 s0[PD], s1[PD], d[PD][R];
-  auto load = [&](int slot, u32 i) {
-    const bool in = i < i_hi;
-    s0[slot] = in ? ldg128(svq + i * ctL) : make_ulonglong2(0, 0);
-    s1[slot] = in ? ldg128(svq + i * ctL + kN) : make_ulonglong2(0, 0);
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      d[slot][r] = (in && i < cnt[r]) ? ldg128_stream(dbr[r] + (u64)i * kN) : make_ulonglong2(0, 0);
-  };
-#pragma unroll
-  for (int p = 0; p < PD - 1; ++p) load(p, i_lo + p);
-#pragma unroll 1
-  for (u32 i = i_lo; i < i_hi; i += PD) {
-#pragma unroll
-    for (int p = 0; p < PD; ++p) {
-      load((p + PD - 1) % PD, i + p + PD - 1);
-      const Opnd<MODE> a0x(s0[p].x, hb), a0y(s0[p].y, hb), a1x(s1[p].x, hb), a1y(s1[p].y, hb);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const Opnd<MODE> bx(d[p][r].x, hb), by(d[p][r].y, hb);
-        acc[r][0][0].mac(a0x, bx);
-        acc[r][0][1].mac(a0y, by);
-        acc[r][1][0].mac(a1x, bx);
-        acc[r][1][1].mac(a1y, by);
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    if (row0 + r >= n_rows) break;
-    u64* o = part + (((u64)qi * n_split + split) * n_rows + row0 + r) * ctL + limb;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      ulonglong2 v;
-      v.x = acc[r][c][0].reduce(m, hb);
-      v.y = acc[r][c][1].reduce(m, hb);
-      *reinterpret_cast<ulonglong2*>(o + (u64)c * kN) = v;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// scan, TMA variant: the same arithmetic, but database and selection-vector tiles are moved global->shared by the
-// bulk-copy engine (cp.async.bulk, completion on an mbarrier) through a STAGES-deep ring, issued by one producer
-// lane; four consumer warps read the tiles from shared memory and keep the accumulators in registers.  Bytes in
-// flight per SM are set by the ring depth instead of by registers.
-//   grid (slice of 256 limbs, row tile of R rows, qi*n_split + split); 160 threads = 1 producer warp + 128 consumers
-// ---------------------------------------------------------------------------------------------
-constexpr int TMA_L = 256;              // limbs per tile (2 KiB)
-constexpr int TMA_CONSUMERS = 128;
-constexpr int TMA_NT = TMA_CONSUMERS + 32;
-
-// G consumer groups of 128 threads share the selection-vector tiles of a stage; group g owns rows g*RG .. g*RG+RG-1
-// of the CTA's R = G*RG rows, so L2->SM traffic per database byte is (R + 2) / R.
-template <int RG, int G, int STAGES, int MODE>
-__global__ void __launch_bounds__(32 + TMA_CONSUMERS * G)
-k_scan_tma(const __grid_constant__ DevParams P, const u64* __restrict__ db, u64 num_pt, u32 dimL, u32 n_rows,
-           const u64* __restrict__ sv, u64 sv_qstride, int n_split, u64* __restrict__ part) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int R = RG * G;
-  constexpr u32 TILE_BYTES = TMA_L * sizeof(u64);
-  constexpr u32 STAGE_BYTES = (R + 2) * TILE_BYTES;
-  u64* tiles = reinterpret_cast<u64*>(smem_raw);
-  u64* full = reinterpret_cast<u64*>(smem_raw + (size_t)STAGES * STAGE_BYTES);
-  u64* empty = full + STAGES;
-
-  const u32 kN = (u32)P.k * P.N;
-  const u64 ctL = 2ull * kN;
-  const u32 limb0 = blockIdx.x * TMA_L;
-  const u32 row0 = blockIdx.y * R;
-  const u32 split = blockIdx.z % n_split, qi = blockIdx.z / n_split;
-  const u32 per = (dimL + n_split - 1) / n_split;
-  const u32 i_lo = split * per;
-  const u32 i_hi = min(dimL, i_lo + per);
-  const int warp = threadIdx.x >> 5;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(empty + s, G * TMA_CONSUMERS / 32);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == 0) {
-    // ---------------- producer ----------------
-    if (threadIdx.x == 0) {
-      u32 cnt[R];  // valid plaintexts per row (short last row; rows past the end)
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const u64 first = (u64)(row0 + r) * dimL;
-        cnt[r] = (row0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
-      }
-      u64 pol_stream, pol_keep;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-      const u64* svq = sv + qi * sv_qstride + limb0;
-      u32 stage = 0, phase = 0;
-      for (u32 i = i_lo; i < i_hi; ++i) {
-        mbar_wait(empty + stage, phase ^ 1);
-        u64* dst = tiles + (size_t)stage * (R + 2) * TMA_L;
-        u32 nvalid = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) nvalid += (i < cnt[r]);
-        mbar_expect_tx(full + stage, (2 + nvalid) * TILE_BYTES);
-        bulk_g2s(dst, svq + i * ctL, TILE_BYTES, full + stage, pol_keep);
-        bulk_g2s(dst + TMA_L, svq + i * ctL + kN, TILE_BYTES, full + stage, pol_keep);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (i < cnt[r])
-            bulk_g2s(dst + (2 + r) * TMA_L, db + ((u64)(row0 + r) * dimL + i) * kN + limb0, TILE_BYTES, full + stage,
-                     pol_stream);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-    return;
-  }
-  // ---------------- consumers ----------------
-  const int ct = threadIdx.x - 32;
-  const int g = ct / TMA_CONSUMERS, t = ct % TMA_CONSUMERS;
-  const u32 grow0 = row0 + g * RG;
-  u32 cnt[RG];
-#pragma unroll
-  for (int r = 0; r < RG; ++r) {
-    const u64 first = (u64)(grow0 + r) * dimL;
-    cnt[r] = (grow0 + r < n_rows && first < num_pt) ? (u32)min((u64)dimL, num_pt - first) : 0;
-  }
-  const ModC& m = P.m[limb0 / P.N];
-  Acc<MODE> acc[RG][2][2];
-  const int hb = P.half_bits;
-  u32 stage = 0, phase = 0;
-#pragma unroll 1
-  for (u32 i = i_lo; i < i_hi; ++i) {
-    mbar_wait(full + stage, phase);
-    const u64* src = tiles + (size_t)stage * (R + 2) * TMA_L + 2 * t;
-    const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(src);
-    const ulonglong2 s1 = *reinterpret_cast<const ulonglong2*>(src + TMA_L);
-    ulonglong2 d[RG];
-#pragma unroll
-    for (int r = 0; r < RG; ++r)
-      d[r] = (i < cnt[r]) ? *reinterpret_cast<const ulonglong2*>(src + (2 + g * RG + r) * TMA_L) : make_ulonglong2(0, 0);
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(empty + stage);  // tile values are in registers: free the slot
-    const Opnd<MODE> a0x(s0.x, hb), a0y(s0.y, hb), a1x(s1.x, hb), a1y(s1.y, hb);
-#pragma unroll
-    for (int r = 0; r < RG; ++r) {
-      const Opnd<MODE> bx(d[r].x, hb), by(d[r].y, hb);
-      acc[r][0][0].mac(a0x, bx);
-      acc[r][0][1].mac(a0y, by);
-      acc[r][1][0].mac(a1x, bx);
-      acc[r][1][1].mac(a1y, by);
-    }
-    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-  }
-#pragma unroll
-  for (int r = 0; r < RG; ++r) {
-    if (grow0 + r >= n_rows) break;
-    u64* o = part + (((u64)qi * n_split + split) * n_rows + grow0 + r) * ctL + limb0 + 2 * t;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      ulonglong2 v;
-      v.x = acc[r][c][0].reduce(m, hb);
-      v.y = acc[r][c][1].reduce(m, hb);
-      *reinterpret_cast<ulonglong2*>(o + (u64)c * kN) = v;
-    }
-  }
-}
-
-
 // tuning knobs (overridable through the environment for sweeps): rows per CTA, unroll, generic MAC
-static int scan_mode() { return env_int("PIRB_SCAN_MODE", 0); }  // 0 = LDG kernel (default), 1 = TMA bulk-copy ring
-static int scan_groups(int R) {  // consumer groups per CTA of the TMA kernel
-  int g = R >= 8 ? 4 : (R >= 4 ? 2 : 1);
-  g = env_int("PIRB_SCAN_G", g);
-  return (g >= 1 && R % g == 0) ? g : 1;
-}
 static void scan_pick(const DevParams& P, u32 n_rows, int* R, int* U, int* mode) {
-  // measured on B200 (tools/bench_scan.py, profiles/): 2 rows x unroll 2 with the FP64 MAC is the fastest LDG shape
+  // measured on B200 (profiles/): 2 rows x unroll 2 with the FP64 MAC is the fastest shape
   int r = n_rows >= 2 ? 2 : 1;
   int u = r == 2 ? 2 : 4;
-  if (scan_mode() == 1) u = 8;  // U = ring depth for the TMA kernel
   r = env_int("PIRB_SCAN_R", r);
   u = env_int("PIRB_SCAN_U", u);
   *R = r; *U = u;
@@ -684,38 +377,29 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
   const u32 slices = (u32)P.k * P.N / SCAN_LIMBS;
   dim3 grid(slices, (n_rows + R - 1) / R, n_queries * n_split);
   if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidConfiguration;
-  if (n_queries >= env_int("PIRB_SCAN_BATCH_MIN", 4) && scan_mode() == 0) {
-    // batch of queries: share every database tile between QB queries
-    if (mode == MAC_FP64 && env_int("PIRB_SCAN_BATCH_V", 2) == 2) {
-      const int R2 = env_int("PIRB_B2_R", n_rows >= 2 ? 2 : 1);
-      const int QB2 = env_int("PIRB_B2_QB", 2);
-      const int U2 = env_int("PIRB_B2_U", 2);  // measured: 2 rows x 2 queries, 4 row groups, 2 columns per barrier
-      int RG2 = env_int("PIRB_B2_RG", 4);
+  if (n_queries >= env_int("PIRB_SCAN_BATCH_MIN", 4)) {
+    // batch of queries on CUDA cores (shards too small for the tensor-core scan, or moduli it does not cover): share
+    // every database tile between QB queries
+    if (mode == MAC_FP64) {
+      const int R2 = n_rows >= 2 ? 2 : 1;
+      int RG2 = 4;
       while (RG2 > 1 && (u32)(R2 * RG2) > n_rows + R2 - 1) RG2 >>= 1;  // do not idle whole row groups on small shards
       const u32 tiles = (n_rows + R2 * RG2 - 1) / (R2 * RG2);
-      dim3 g2((n_queries + QB2 - 1) / QB2, tiles * n_split, (u32)P.k * P.N / BATCH_NT);
+      dim3 g2((n_queries + 1) / 2, tiles * n_split, (u32)P.k * P.N / BATCH_NT);
       if (g2.y > 65535 || g2.z > 65535) return cudaErrorInvalidConfiguration;
-      const size_t smem2 = (size_t)2 * U2 * QB2 * 2 * BATCH_NT * sizeof(double2);
-#define B2_CASE(RR, QQ, GG, UU)                                                                                    \
-  if (R2 == RR && QB2 == QQ && RG2 == GG && U2 == UU) {                                                            \
-    auto kern = k_scan_batch2<RR, QQ, GG, UU>;                                                                     \
-    if (smem2 > 48 * 1024) {                                                                                       \
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);         \
-      if (e != cudaSuccess) return e;                                                                              \
-    }                                                                                                              \
-    kern<<<g2, BATCH_NT * GG, smem2, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_queries, n_split, part); \
+      const size_t smem2 = (size_t)2 * 2 * 2 * 2 * BATCH_NT * sizeof(double2);
+#define B2_CASE(RR, GG)                                                                                            \
+  if (R2 == RR && RG2 == GG) {                                                                                     \
+    k_scan_batch2<RR, 2, GG, 2><<<g2, BATCH_NT * GG, smem2, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride,     \
+                                                                  n_queries, n_split, part);                      \
     return cudaGetLastError();                                                                                     \
   }
-      // default shape and its fallbacks for few rows, plus the shapes of the committed sweep
-      // (profiles/r1_scan_batch2_sweep.jsonl) that came closest
-      B2_CASE(2, 2, 4, 2) B2_CASE(2, 2, 2, 2) B2_CASE(2, 2, 1, 2)
-      B2_CASE(1, 2, 4, 2) B2_CASE(1, 2, 2, 2) B2_CASE(1, 2, 1, 2)
-      B2_CASE(2, 2, 4, 4) B2_CASE(2, 4, 4, 1) B2_CASE(4, 1, 4, 4)
+      // measured best shape (2 rows x 2 queries per thread, 4 row groups, 2 columns per barrier) and its fallbacks
+      B2_CASE(2, 4) B2_CASE(2, 2) B2_CASE(2, 1) B2_CASE(1, 4) B2_CASE(1, 2) B2_CASE(1, 1)
 #undef B2_CASE
-      // unlisted shape: fall through to the first-generation kernel
     }
-    const int QB = env_int("PIRB_SCAN_QB", n_queries >= 4 ? 4 : 2);
-    const int RB = env_int("PIRB_SCAN_RB", n_rows >= 2 ? 2 : 1);
+    const int QB = n_queries >= 4 ? 4 : 2;
+    const int RB = n_rows >= 2 ? 2 : 1;
     dim3 bgrid((n_queries + QB - 1) / QB, ((n_rows + RB - 1) / RB) * n_split, (u32)P.k * P.N / BATCH_NT);
     if (bgrid.y > 65535 || bgrid.z > 65535) return cudaErrorInvalidConfiguration;
 #define BATCH_CASE(RR, QQ)                                                                                         \
@@ -728,70 +412,6 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
     BATCH_CASE(1, 2) BATCH_CASE(1, 4) BATCH_CASE(2, 2) BATCH_CASE(2, 4)
 #undef BATCH_CASE
   }
-  if (scan_mode() == 3) {
-    const int G = env_int("PIRB_SCAN_G", 2);
-    dim3 sgrid(slices, (n_rows + R * G - 1) / (R * G), n_queries * n_split);
-#define SHARE_CASE(RR, GG, UU)                                                                                     \
-  if (R == RR && G == GG && U == UU) {                                                                             \
-    if (mode == MAC_FP64) k_scan_share<RR, GG, UU, MAC_FP64><<<sgrid, SCAN_NT * GG, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
-    else if (mode == MAC_INT24) k_scan_share<RR, GG, UU, MAC_INT24><<<sgrid, SCAN_NT * GG, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
-    else k_scan_share<RR, GG, UU, MAC_WIDE><<<sgrid, SCAN_NT * GG, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
-    return cudaGetLastError();                                                                                     \
-  }
-    SHARE_CASE(2, 2, 2) SHARE_CASE(2, 4, 2) SHARE_CASE(2, 2, 1) SHARE_CASE(2, 4, 1) SHARE_CASE(1, 4, 2) SHARE_CASE(1, 8, 2)
-    SHARE_CASE(2, 8, 2)
-#undef SHARE_CASE
-    return cudaErrorInvalidValue;
-  }
-  if (scan_mode() == 2) {
-#define PIPE_CASE(RR, PP)                                                                                          \
-  if (R == RR && U == PP) {                                                                                        \
-    if (mode == MAC_FP64) k_scan_pipe<RR, PP, MAC_FP64><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
-    else if (mode == MAC_INT24) k_scan_pipe<RR, PP, MAC_INT24><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
-    else k_scan_pipe<RR, PP, MAC_WIDE><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
-    return cudaGetLastError();                                                                                     \
-  }
-    PIPE_CASE(1, 2) PIPE_CASE(1, 3) PIPE_CASE(1, 4)
-    PIPE_CASE(2, 2) PIPE_CASE(2, 3) PIPE_CASE(2, 4)
-    PIPE_CASE(4, 2) PIPE_CASE(4, 3)
-#undef PIPE_CASE
-    return cudaErrorInvalidValue;
-  }
-  if (scan_mode() == 1) {
-    const int G = scan_groups(R);
-    const int RG = R / G;
-#define TMA_LAUNCH(RGG, GG, SS, MM)                                                                                \
-  if (mode == MM) {                                                                                                \
-    cudaError_t e = cudaFuncSetAttribute(k_scan_tma<RGG, GG, SS, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                                \
-    k_scan_tma<RGG, GG, SS, MM><<<grid, 32 + TMA_CONSUMERS * GG, smem, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
-    return cudaGetLastError();                                                                                     \
-  }
-#define TMA_CASE(RGG, GG, SS)                                                                                      \
-  if (RG == RGG && G == GG && U == SS) {                                                                           \
-    const size_t smem = (size_t)SS * (RGG * GG + 2) * TMA_L * sizeof(u64) + 2 * SS * sizeof(u64);                    \
-    TMA_LAUNCH(RGG, GG, SS, MAC_WIDE) TMA_LAUNCH(RGG, GG, SS, MAC_INT24) TMA_LAUNCH(RGG, GG, SS, MAC_FP64)          \
-    return cudaErrorInvalidValue;                                                                                  \
-  }
-    TMA_CASE(1, 1, 8)
-    TMA_CASE(2, 1, 8)
-    TMA_CASE(4, 1, 8)
-    TMA_CASE(1, 2, 8) TMA_CASE(2, 2, 6) TMA_CASE(2, 2, 8)
-    TMA_CASE(1, 4, 8) TMA_CASE(2, 4, 4) TMA_CASE(2, 4, 6) TMA_CASE(2, 4, 8)
-    TMA_CASE(4, 2, 6)
-#undef TMA_CASE
-#undef TMA_LAUNCH
-    return cudaErrorInvalidValue;
-  }
-  {
-    const int minb = env_int("PIRB_SCAN_MINB", 1);
-    if (R == 2 && U == 2 && mode == MAC_FP64 && minb > 1) {
-      if (minb == 5) k_scan<2, 2, MAC_FP64, 5><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part);
-      else if (minb == 6) k_scan<2, 2, MAC_FP64, 6><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part);
-      else k_scan<2, 2, MAC_FP64, 8><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part);
-      return cudaGetLastError();
-    }
-  }
 #define SCAN_CASE(RR, UU)                                                                                          \
   if (R == RR && U == UU) {                                                                                        \
     if (mode == MAC_FP64) k_scan<RR, UU, MAC_FP64><<<grid, SCAN_NT, 0, st>>>(P, db, num_pt, dimL, n_rows, sv, sv_qstride, n_split, part); \
@@ -801,8 +421,6 @@ cudaError_t launch_scan(const DevParams& P, const u64* db, u64 num_pt, u32 dimL,
   }
   SCAN_CASE(1, 1) SCAN_CASE(1, 2) SCAN_CASE(1, 4)
   SCAN_CASE(2, 1) SCAN_CASE(2, 2) SCAN_CASE(2, 4)
-  SCAN_CASE(4, 1) SCAN_CASE(4, 2)
-  SCAN_CASE(8, 1)
 #undef SCAN_CASE
   return cudaErrorInvalidValue;
 }

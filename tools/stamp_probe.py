@@ -7,9 +7,11 @@ import bench
 from pir_b200 import sharded, _lib
 import pir_b200 as pb
 level = int(os.environ.setdefault("PIRB_DEBUG_STAMPS", "0"))
-params = bench.make_params("cfg2")
+items, size, d, n, bits, _ = bench.WORKLOADS["cfg2"]
+params = pb.CreatePIRParameters(items, size, d, pb.GenerateEncryptionParams(n, bits))
+_ep = params.encryption_parameters
 srv = sharded.ShardServer(params, device=0); srv.db.fill_random(1)
-q, elts, keys = bench.synth_inputs(params, 1, 5)
+q, elts, keys = bench.synth_inputs(_ep.poly_modulus_degree, _ep.coeff_modulus, list(params.dimensions), 1, 5)
 srv.set_keys(pb.GaloisKeys(elts, keys.reshape(-1)))
 dq = sharded.to_device(q, srv.device)
 for _ in range(3): srv.answer(dq)
