@@ -418,10 +418,12 @@ k_ks_level_cluster2(const __grid_constant__ DevParams P, u64* __restrict__ work,
           a1[e] = __dadd_rn(a1[e], f64_modmul(y, kd1, __dmul_rn(kd1, qinv), qd));
         }
       }
+      // sums of k products of magnitude <= 0.54 q each: the inverse transform's butterflies only need |v| < 2^48 and add
+      // at most 0.54 q per stage, so the accumulators go in as they are (no canonicalisation pass)
 #pragma unroll
       for (int e = 0; e < CH; ++e) {
-        smem[si[e]] = (u64)__double_as_longlong(f64_canon(a0[e], qd, qinv));
-        (smem + N)[si[e]] = (u64)__double_as_longlong(f64_canon(a1[e], qd, qinv));
+        smem[si[e]] = (u64)__double_as_longlong(a0[e]);
+        (smem + N)[si[e]] = (u64)__double_as_longlong(a1[e]);
       }
     }
   }
@@ -455,8 +457,12 @@ k_ks_level_cluster2(const __grid_constant__ DevParams P, u64* __restrict__ work,
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       u64* A = smem + (size_t)c * N;
+      // N^-1 psi^-i scaling; the signed representative (|t| <= 0.54 q) is all the mod-down below needs
 #pragma unroll
-      for (int i = tid; i < N; i += NT) A[swz(i)] = eng_finish_inv_native<ENG_FP64>(A[swz(i)], i, mI);
+      for (int i = tid; i < N; i += NT) {
+        const double2 f2 = __ldg(mI.fin + i);
+        A[swz(i)] = (u64)__double_as_longlong(f64_modmul(__longlong_as_double((long long)A[swz(i)]), f2.x, f2.y, qd));
+      }
     }
     // stage c0's polynomial of this modulus in the free table buffer: the Galois gather of phase 4 becomes a
     // shared-memory permutation
@@ -491,26 +497,26 @@ k_ks_level_cluster2(const __grid_constant__ DevParams P, u64* __restrict__ work,
           gv[e] = (c == 0) ? galois_gather(SB, i, L.ginv, N, q) : 0;
           pv[e] = (mode == 1) ? 0 : (c == 0 ? SB[i] : sp1[i]);
         }
+        // Everything stays an integer-valued double until the two outputs are canonicalised.  With l = (acc_P + P/2)
+        // mod P in [0, P):  md = (a - l + (P/2 mod q)) * P^-1 mod q  — any representative of l mod q serves, since the
+        // exact product only needs |y| < 2^48 — then E = p + (sigma_g(c0) +) md and O = +-(p - (sigma_g(c0) +) md).
 #pragma unroll
         for (int e = 0; e < CH; ++e) {
           const int i = i0 + e * NT;
           double l = __dadd_rn(__longlong_as_double((long long)la[e]), P.half_P_d);
           l = l >= Pqd ? __dadd_rn(l, -Pqd) : l;
-          const double r = f64_submod(f64_canon(l, qd, qinv), P.half_P_mod_d[j], qd);
-          const double dd = f64_submod(__longlong_as_double((long long)av[e]), r, qd);
+          const double dd = __dadd_rn(__dadd_rn(__longlong_as_double((long long)av[e]), -l), P.half_P_mod_d[j]);
           double md = f64_modmul(dd, P.inv_P_d[j], P.inv_P_di[j], qd);
-          md = md < 0.0 ? __dadd_rn(md, qd) : md;
-          u64 c0 = f64_to_u64_exact(md);
-          if (c == 0) c0 = addmod(gv[e], c0, q);
+          if (c == 0) md = __dadd_rn(md, u64_to_f64_exact(gv[e]));
           if (mode == 1) {
-            dstE[(u64)(c * k + j) * N + i] = c0;
+            dstE[(u64)(c * k + j) * N + i] = f64_to_u64_exact(f64_canon(md, qd, qinv));
           } else {
-            const u64 p = pv[e];
-            dstE[(u64)(c * k + j) * N + i] = addmod(p, c0, q);
+            const double pd = u64_to_f64_exact(pv[e]);
+            dstE[(u64)(c * k + j) * N + i] = f64_to_u64_exact(f64_canon(__dadd_rn(pd, md), qd, qinv));
             const u32 rr = i + s1;
-            u64 d = submod(p, c0, q);
-            if (rr & N) d = negmod(d, q);
-            (dstE + ((u64)ctL << L.j))[(u64)(c * k + j) * N + (rr & (N - 1))] = d;
+            double d = __dadd_rn(pd, -md);
+            if (rr & N) d = -d;
+            (dstE + ((u64)ctL << L.j))[(u64)(c * k + j) * N + (rr & (N - 1))] = f64_to_u64_exact(f64_canon(d, qd, qinv));
           }
         }
       }
