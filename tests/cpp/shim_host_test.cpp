@@ -136,8 +136,38 @@ static int index_tests() {
   return 0;
 }
 
+// the fingerprint that finds a returning client's Galois keys again (PIRServer's key cache): deterministic, sensitive to
+// every byte, to the length and to the salt that separates raw-limb keys from serialized ones
+static int fingerprint_tests() {
+  std::vector<uint64_t> a(5000), b;
+  for (size_t i = 0; i < a.size(); ++i) a[i] = i * 0x9e3779b97f4a7c15ull + 12345;
+  const auto f0 = pir::detail::fingerprint(a.data(), a.size() * 8);
+  CHECK(f0 == pir::detail::fingerprint(a.data(), a.size() * 8), "deterministic");
+  for (size_t pos : {size_t(0), size_t(1), size_t(31), size_t(32), size_t(4999 * 8 + 7), size_t(2500 * 8 + 3)}) {
+    b = a;
+    reinterpret_cast<unsigned char*>(b.data())[pos] ^= 1;
+    CHECK(!(pir::detail::fingerprint(b.data(), b.size() * 8) == f0), "one flipped bit changes the fingerprint");
+  }
+  CHECK(!(pir::detail::fingerprint(a.data(), a.size() * 8 - 1) == f0), "length enters the fingerprint");
+  CHECK(!(pir::detail::fingerprint(a.data(), a.size() * 8 - 8) == f0), "length enters the fingerprint (whole word)");
+  CHECK(!(pir::detail::fingerprint(a.data(), a.size() * 8, 1) == f0), "salt enters the fingerprint");
+  // tails shorter than a word and shorter than a 32-byte block
+  for (size_t n : {size_t(0), size_t(1), size_t(7), size_t(8), size_t(9), size_t(33), size_t(63)}) {
+    const auto f1 = pir::detail::fingerprint(a.data(), n);
+    b = a;
+    if (n) {
+      reinterpret_cast<unsigned char*>(b.data())[n - 1] ^= 0x80;
+      CHECK(!(pir::detail::fingerprint(b.data(), n) == f1), "last byte of a short input counts");
+    }
+    reinterpret_cast<unsigned char*>(b.data())[n] ^= 0x80;  // the byte after the end must not matter
+    if (n) reinterpret_cast<unsigned char*>(b.data())[n - 1] ^= 0x80;
+    CHECK(pir::detail::fingerprint(b.data(), n) == f1, "bytes beyond the length are not read");
+  }
+  return 0;
+}
+
 int main() {
-  if (parameters_tests() || string_encoder_tests() || index_tests()) return 1;
+  if (parameters_tests() || string_encoder_tests() || index_tests() || fingerprint_tests()) return 1;
   // without a device the factories must fail loudly, never fall back (server.cpp:35-42 shape)
   auto p = *pir::CreatePIRParameters(10, 0, 1);
   auto db = pir::PIRDatabase::Create(p);
