@@ -614,45 +614,69 @@ class PIRServer {
   // bytes are fingerprinted BEFORE they are parsed: a returning client's keys are neither deserialized nor (for
   // seed-compressed keys) re-expanded.
   StatusOr<std::string> ProcessRequest(const std::string& serialized_request, bool strict_parms_id = false) const {
-    wire::RequestMsg msg;
-    if (!wire::Parse(serialized_request, &msg)) return InvalidArgumentError("malformed Request message");
+    wire::RequestView msg;  // views into the caller's bytes: the ~5 MB of key material are not copied
+    if (!wire::ParseView(serialized_request, &msg)) return InvalidArgumentError("malformed Request message");
     const EncryptionParameters& ep = params_->encryption_parameters;
     const wire::SealParams sp = ToSealParams(ep);
     const detail::Fingerprint fp = detail::fingerprint(msg.galois_keys.data(), msg.galois_keys.size(), /*salt=*/1);
     auto keys = FindKeys(fp);
     if (!keys) {
-      auto gk = DeserializeGaloisKeys(ep, msg.galois_keys);
+      auto gk = DeserializeGaloisKeys(ep, std::string(msg.galois_keys));
       if (!gk.ok()) return gk.status();
       auto loaded = UploadKeys(*gk, fp);
       if (!loaded.ok()) return loaded.status();
       keys = *loaded;
     }
     std::string err;
-    if (!msg.relin_keys.empty()) {
-      wire::KSwitchKeysData rk;
-      if (!wire::LoadKSwitchKeys(msg.relin_keys, sp, &rk, &err, /*keep_data=*/false)) return InvalidArgumentError(err);
-    }
-    std::vector<std::vector<Ciphertext>> query;
-    wire::parms_id_type pid = wire::data_parms_id(sp), got;
-    bool first = true;
-    for (const auto& q : msg.query) {
-      query.emplace_back();
-      for (const auto& blob : q.ct) {
-        auto ct = DeserializeCiphertext(ep, blob, &got);
-        if (!ct.ok()) return ct.status();
-        if (strict_parms_id && got != wire::data_parms_id(sp)) return InvalidArgumentError("ciphertext data is invalid");
-        if (first) { pid = got; first = false; }
-        query.back().push_back(std::move(*ct));
+    if (!msg.relin_keys.empty()) {  // parsed for validity only (server.cpp:53-58); once per distinct key blob
+      const detail::Fingerprint rfp = detail::fingerprint(msg.relin_keys.data(), msg.relin_keys.size(), /*salt=*/2);
+      if (!(rfp == last_relin_ok_)) {
+        wire::KSwitchKeysData rk;
+        if (!wire::LoadKSwitchKeys(std::string(msg.relin_keys), sp, &rk, &err, /*keep_data=*/false))
+          return InvalidArgumentError(err);
+        last_relin_ok_ = rfp;
       }
     }
-    auto resp = Answer(query, *keys);
-    if (!resp.ok()) return resp.status();
-    wire::ResponseMsg out;
-    for (const auto& r : resp->reply) {
-      out.reply.emplace_back();
-      for (const auto& ct : r) out.reply.back().ct.push_back(SerializeCiphertext(ep, ct, &pid));
-    }
-    return wire::Serialize(out);
+    pirb_ctx* ctx = db_->handle();
+    const size_t Q = msg.query.size(), k = ep.coeff_modulus.size() - 1, N = ep.poly_modulus_degree;
+    const size_t L = pirb_ct_limbs(ctx), R = pirb_reply_cts(ctx);
+    if (Q == 0) return wire::Serialize(wire::ResponseMsg());
+    const size_t n_ct = msg.query[0].size();
+    for (const auto& q : msg.query)
+      if (q.size() != n_ct || n_ct != pirb_query_cts(ctx))
+        return InvalidArgumentError("Number of ciphertexts doesn't match number of items for oblivious expansion.");
+    // ciphertexts are deserialized straight into the page-locked staging buffer and the response is serialized straight
+    // out of it: one pass each way, no intermediate Ciphertext objects
+    const wire::parms_id_type data_pid = wire::data_parms_id(sp);
+    wire::parms_id_type pid = data_pid;
+    bool first = true;
+    const size_t blob = wire::CiphertextBlobSize(2, N, k);
+    const size_t inner = R * (1 + wire::varint_size(blob) + blob);
+    std::string out;
+    out.reserve(Q * (1 + wire::varint_size(inner) + inner));
+    Status st = AnswerSteps(
+        Q, n_ct, *keys,
+        [&](size_t qi, uint64_t* dst) -> Status {
+          for (size_t c = 0; c < n_ct; ++c) {
+            wire::CiphertextData meta;
+            if (!wire::LoadCiphertextTo(msg.query[qi][c], (uint32_t)N, ep.coeff_modulus.data(), k, dst + c * L, &meta, &err))
+              return InvalidArgumentError(err);
+            if (strict_parms_id && meta.parms_id != data_pid) return InvalidArgumentError("ciphertext data is invalid");
+            if (first) { pid = meta.parms_id; first = false; }
+          }
+          return OkStatus();
+        },
+        [&](size_t, const uint64_t* src) {
+          wire::put_tag(out, 1, 2);
+          wire::put_varint(out, inner);
+          for (size_t c = 0; c < R; ++c) {
+            wire::put_tag(out, 1, 2);
+            wire::put_varint(out, blob);
+            wire::AppendCiphertextBlob(out, src + c * L, 2, N, k, pid, false);
+          }
+        });
+    if (!st.ok()) return st;
+    return out;
   }
 
   // server.cpp:67-76
@@ -738,6 +762,26 @@ class PIRServer {
       for (size_t c = 0; c < n_ct; ++c)
         if (query[i][c].limbs.size() != L) return InvalidArgumentError("bad ciphertext size");
     }
+    response.reply.resize(Q);
+    Status st = AnswerSteps(
+        Q, n_ct, keys,
+        [&](size_t qi, uint64_t* dst) -> Status {
+          for (size_t c = 0; c < n_ct; ++c) std::memcpy(dst + c * L, query[qi][c].limbs.data(), L * sizeof(uint64_t));
+          return OkStatus();
+        },
+        [&](size_t qi, const uint64_t* src) {
+          response.reply[qi].resize(R);
+          for (size_t c = 0; c < R; ++c) response.reply[qi][c].limbs.assign(src + c * L, src + (c + 1) * L);
+        });
+    if (!st.ok()) return st;
+    return response;
+  }
+  // The step engine behind both forms of ProcessRequest: fill(qi, dst) writes query qi's n_ct ciphertexts into the
+  // page-locked staging buffer, drain(qi, src) consumes its reply ciphertexts from there, in query order.
+  template <typename Fill, typename Drain>
+  Status AnswerSteps(size_t Q, size_t n_ct, const KeySet& keys, Fill&& fill, Drain&& drain) const {
+    pirb_ctx* ctx = db_->handle();
+    const size_t L = pirb_ct_limbs(ctx), R = pirb_reply_cts(ctx);
     const size_t W = db_->shard_count();
     // sharded: every GPU takes the same number of queries per step (the last step is padded with zero queries)
     const size_t ql = W > 1 ? std::min<size_t>(max_local_, (Q + W - 1) / W) : Q;
@@ -747,15 +791,17 @@ class PIRServer {
     if (!st.ok()) return st;
     st = r_pin_.ensure(per_step * R * L);
     if (!st.ok()) return st;
-    response.reply.resize(Q);
     for (size_t step = 0; step < n_steps; ++step) {
       const size_t q0 = step * per_step, qn = std::min(per_step, Q - q0);
-      for (size_t i = 0; i < per_step; ++i)
-        for (size_t c = 0; c < n_ct; ++c) {
-          uint64_t* dst = q_pin_.p + (i * n_ct + c) * L;
-          if (i < qn) std::memcpy(dst, query[q0 + i][c].limbs.data(), L * sizeof(uint64_t));
-          else std::memset(dst, 0, L * sizeof(uint64_t));
+      for (size_t i = 0; i < per_step; ++i) {
+        uint64_t* dst = q_pin_.p + i * n_ct * L;
+        if (i < qn) {
+          st = fill(q0 + i, dst);
+          if (!st.ok()) return st;
+        } else {
+          std::memset(dst, 0, n_ct * L * sizeof(uint64_t));
         }
+      }
       if (W == 1) {
         st = FromRc(pirb_answer(ctx, keys.per_shard[0].get(), q_pin_.p, (uint32_t)qn, n_ct, r_pin_.p));
         if (!st.ok()) return st;
@@ -780,13 +826,9 @@ class PIRServer {
           if (!st.ok()) return st;
         }
       }
-      for (size_t i = 0; i < qn; ++i) {
-        response.reply[q0 + i].resize(R);
-        for (size_t c = 0; c < R; ++c)
-          response.reply[q0 + i][c].limbs.assign(r_pin_.p + (i * R + c) * L, r_pin_.p + (i * R + c + 1) * L);
-      }
+      for (size_t i = 0; i < qn; ++i) drain(q0 + i, r_pin_.p + i * R * L);
     }
-    return response;
+    return OkStatus();
   }
   StatusOr<std::vector<Ciphertext>> Expand(const uint64_t* cts, size_t n_ct, size_t total, int single,
                                            const GaloisKeys& gal_keys) const {
@@ -807,6 +849,7 @@ class PIRServer {
   mutable detail::PinnedBuf q_pin_, r_pin_;
   mutable std::vector<std::pair<detail::Fingerprint, std::shared_ptr<KeySet>>> key_cache_;
   mutable size_t key_cache_capacity_ = 4, key_hits_ = 0;
+  mutable detail::Fingerprint last_relin_ok_;
 };
 
 }  // namespace pir

@@ -168,6 +168,51 @@ inline bool Parse(std::string_view in, RequestMsg* m) {
   }
   return true;
 }
+// The same message as views into the caller's buffer: nothing is copied (a request carries ~5 MB of key material that
+// a server with a key cache usually does not even need to look at beyond fingerprinting it).
+struct RequestView {
+  std::vector<std::vector<std::string_view>> query;
+  std::string_view galois_keys, relin_keys;
+};
+inline bool ParseView(std::string_view in, RequestView* m) {
+  Reader r(in);
+  *m = RequestView();
+  while (!r.done()) {
+    uint32_t f, wt;
+    if (!r.tag(&f, &wt)) return false;
+    std::string_view b;
+    if (f >= 1 && f <= 3 && wt == 2) {
+      if (!r.bytes(&b)) return false;
+      if (f == 1) {
+        m->query.emplace_back();
+        Reader rq(b);
+        while (!rq.done()) {
+          uint32_t f2, wt2;
+          if (!rq.tag(&f2, &wt2)) return false;
+          if (f2 == 1 && wt2 == 2) {
+            std::string_view ct;
+            if (!rq.bytes(&ct)) return false;
+            m->query.back().push_back(ct);
+          } else if (!rq.skip(wt2)) {
+            return false;
+          }
+        }
+      } else if (f == 2) {
+        m->galois_keys = b;
+      } else {
+        m->relin_keys = b;
+      }
+    } else if (!r.skip(wt)) {
+      return false;
+    }
+  }
+  return true;
+}
+inline size_t varint_size(uint64_t v) {
+  size_t n = 1;
+  while (v >= 0x80) { v >>= 7; ++n; }
+  return n;
+}
 inline std::string Serialize(const ResponseMsg& m) {
   std::string out;
   for (const auto& q : m.reply) put_len_field(out, 1, Serialize(q));
@@ -557,8 +602,10 @@ inline std::string SaveCiphertext(const CiphertextData& ct, const seed_type* see
 
 // Ciphertext::load (header + load_members + the is_valid_for checks that matter for the raw-limb path).
 // `moduli` are the moduli of the level this object must live at (n_moduli of them).
+// ext != nullptr: the limbs go straight into the caller's buffer of ext_polys * n_moduli * N words (a page-locked
+// staging buffer, say) instead of ct->limbs; objects of another size are rejected.
 inline bool LoadCiphertextFrom(detail::In& in, uint32_t N, const uint64_t* moduli, size_t n_moduli,
-                               CiphertextData* ct, std::string* err) {
+                               CiphertextData* ct, std::string* err, uint64_t* ext = nullptr, uint64_t ext_polys = 0) {
   detail::In b{nullptr, nullptr};
   if (!detail::get_header(in, &b, err)) return false;
   uint8_t ntt;
@@ -579,18 +626,25 @@ inline bool LoadCiphertextFrom(detail::In& in, uint32_t N, const uint64_t* modul
   if (!a.get(&count)) { *err = "truncated ciphertext data"; return false; }
   const uint64_t full = ct->size * N * n_moduli, seeded = (uint64_t)N * n_moduli;
   if (count != full && !(count == seeded && ct->size == 2)) { *err = "ciphertext data is invalid"; return false; }
-  ct->limbs.assign(full, 0);
-  if (!a.raw(ct->limbs.data(), count * 8)) { *err = "truncated ciphertext data"; return false; }
+  uint64_t* limbs;
+  if (ext) {
+    if (ct->size != ext_polys) { *err = "ciphertext data is invalid"; return false; }
+    limbs = ext;
+  } else {
+    ct->limbs.assign(full, 0);
+    limbs = ct->limbs.data();
+  }
+  if (!a.raw(limbs, count * 8)) { *err = "truncated ciphertext data"; return false; }
   ct->was_seeded = count != full;
   if (ct->was_seeded) {  // Ciphertext::expand_seed: second polynomial = sample_poly_uniform(BlakePRNG(seed))
     seed_type seed;
     if (!b.raw(seed.data(), sizeof(seed_type))) { *err = "truncated ciphertext seed"; return false; }
     BlakePRNG prng(seed);
-    sample_poly_uniform(prng, N, moduli, n_moduli, ct->limbs.data() + seeded);
+    sample_poly_uniform(prng, N, moduli, n_moduli, limbs + seeded);
   }
   for (uint64_t p = 0; p < ct->size; ++p)  // is_data_valid_for: every limb below its modulus
     for (size_t j = 0; j < n_moduli; ++j) {
-      const uint64_t* v = ct->limbs.data() + (p * n_moduli + j) * N;
+      const uint64_t* v = limbs + (p * n_moduli + j) * N;
       for (uint32_t i = 0; i < N; ++i)
         if (v[i] >= moduli[j]) { *err = "ciphertext data is invalid"; return false; }
     }
@@ -600,6 +654,31 @@ inline bool LoadCiphertext(std::string_view bytes, uint32_t N, const uint64_t* m
                            CiphertextData* ct, std::string* err) {
   detail::In in{bytes.data(), bytes.data() + bytes.size()};
   return LoadCiphertextFrom(in, N, moduli, n_moduli, ct, err);
+}
+// a two-polynomial ciphertext deserialized straight into dst[2][n_moduli][N]; meta receives everything but the limbs
+inline bool LoadCiphertextTo(std::string_view bytes, uint32_t N, const uint64_t* moduli, size_t n_moduli, uint64_t* dst,
+                             CiphertextData* meta, std::string* err) {
+  detail::In in{bytes.data(), bytes.data() + bytes.size()};
+  return LoadCiphertextFrom(in, N, moduli, n_moduli, meta, err, dst, 2);
+}
+// exactly the bytes SaveCiphertext produces for an unseeded ciphertext of `polys` polynomials, appended to `out` from
+// raw limbs without an intermediate object
+inline size_t CiphertextBlobSize(uint64_t polys, uint64_t N, uint64_t n_moduli) {
+  return SEAL_HEADER_BYTES + 32 + 1 + 3 * 8 + 8 + SEAL_HEADER_BYTES + 8 + polys * n_moduli * N * 8;
+}
+inline void AppendCiphertextBlob(std::string& out, const uint64_t* limbs, uint64_t polys, uint64_t N, uint64_t n_moduli,
+                                 const parms_id_type& parms_id, bool is_ntt_form) {
+  const uint64_t count = polys * n_moduli * N;
+  detail::put_header(out, (uint64_t)CiphertextBlobSize(polys, N, n_moduli));
+  out.append((const char*)parms_id.data(), 32);
+  detail::put<uint8_t>(out, is_ntt_form ? 1 : 0);
+  detail::put<uint64_t>(out, polys);
+  detail::put<uint64_t>(out, N);
+  detail::put<uint64_t>(out, n_moduli);
+  detail::put<double>(out, 1.0);
+  detail::put_header(out, (uint64_t)(SEAL_HEADER_BYTES + 8 + count * 8));
+  detail::put<uint64_t>(out, count);
+  out.append((const char*)limbs, count * 8);
 }
 
 // KSwitchKeys (GaloisKeys / RelinKeys): parms_id, keys_.size(), then per slot its length and that many PublicKey

@@ -156,6 +156,72 @@ int main() {
   uint64_t value = 0;
   for (size_t i = 0; i < 63; ++i) value += dec[i] << i;
   CHECK(value == 10 * index, "decrypted reply must be the selected database entry");
+
+  // ---- the copy-free variants the device server uses must be byte-for-byte the object-based ones ----
+  {
+    w::RequestView view;
+    CHECK(w::ParseView(wire_request, &view), "ParseView");
+    CHECK(view.query.size() == got.query.size() && view.query[0].size() == got.query[0].ct.size(), "view: query shape");
+    CHECK(view.query[0][0] == std::string_view(got.query[0].ct[0]), "view: ciphertext bytes");
+    CHECK(view.galois_keys == std::string_view(got.galois_keys), "view: galois keys");
+    CHECK(view.relin_keys == std::string_view(got.relin_keys), "view: relin keys");
+    CHECK(view.galois_keys.data() >= wire_request.data() &&
+              view.galois_keys.data() + view.galois_keys.size() <= wire_request.data() + wire_request.size(),
+          "view must point into the request buffer");
+    w::RequestView bad;
+    CHECK(!w::ParseView(std::string_view(wire_request).substr(0, wire_request.size() - 5), &bad),
+          "truncated request must not parse as a view");
+
+    // LoadCiphertextTo: limbs land in the caller's buffer, metadata in `meta`, same validation
+    std::vector<uint64_t> direct(octx.ct_limbs(), ~0ull);
+    w::CiphertextData meta;
+    CHECK(w::LoadCiphertextTo(view.query[0][0], N, mods.data(), k, direct.data(), &meta, &err), err.c_str());
+    CHECK(direct == qct.limbs && meta.limbs.empty() && meta.parms_id == qct.parms_id && !meta.is_ntt_form && meta.size == 2,
+          "LoadCiphertextTo: limbs / metadata");
+    // a seed-compressed query ciphertext expands into the same buffer exactly as LoadCiphertext expands it
+    w::seed_type s{};
+    for (auto& x : s) x = seeder();
+    const std::string seeded_blob = w::SaveCiphertext(qct, &s);
+    w::CiphertextData via_obj;
+    CHECK(w::LoadCiphertext(seeded_blob, N, mods.data(), k, &via_obj, &err) && via_obj.was_seeded, err.c_str());
+    std::fill(direct.begin(), direct.end(), ~0ull);
+    CHECK(w::LoadCiphertextTo(seeded_blob, N, mods.data(), k, direct.data(), &meta, &err) && meta.was_seeded, err.c_str());
+    CHECK(direct == via_obj.limbs, "seeded ciphertext: in-place expansion differs");
+    // wrong size (3 polynomials) and out-of-range limbs are refused, as by the object path
+    w::CiphertextData three = qct;
+    three.size = 3;
+    three.limbs.resize(3 * k * N, 1);
+    CHECK(!w::LoadCiphertextTo(w::SaveCiphertext(three), N, mods.data(), k, direct.data(), &meta, &err),
+          "a 3-polynomial object must not load into a 2-polynomial slot");
+    w::CiphertextData big = qct;
+    big.limbs[5] = mods[0];
+    CHECK(!w::LoadCiphertextTo(w::SaveCiphertext(big), N, mods.data(), k, direct.data(), &meta, &err),
+          "limb >= modulus must be refused");
+
+    // AppendCiphertextBlob == SaveCiphertext, and the hand-framed response == Serialize(ResponseMsg)
+    std::string blob;
+    w::AppendCiphertextBlob(blob, reply.data(), 2, N, k, rct.parms_id, false);
+    const std::string want = w::SaveCiphertext(rct);
+    CHECK(blob == want && blob.size() == w::CiphertextBlobSize(2, N, k), "AppendCiphertextBlob bytes");
+    // Response{ reply: [ Ciphertexts{ ct: [blob, blob] }, Ciphertexts{ ct: [blob] } ] } framed by hand
+    w::ResponseMsg multi;
+    multi.reply.resize(2);
+    multi.reply[0].ct = {want, want};
+    multi.reply[1].ct = {want};
+    std::string framed;
+    const size_t bsz = w::CiphertextBlobSize(2, N, k);
+    for (size_t n_ct : {size_t(2), size_t(1)}) {
+      const size_t inner = n_ct * (1 + w::varint_size(bsz) + bsz);
+      w::put_varint(framed, (1u << 3) | 2);
+      w::put_varint(framed, inner);
+      for (size_t c = 0; c < n_ct; ++c) {
+        w::put_varint(framed, (1u << 3) | 2);
+        w::put_varint(framed, bsz);
+        w::AppendCiphertextBlob(framed, reply.data(), 2, N, k, rct.parms_id, false);
+      }
+    }
+    CHECK(framed == w::Serialize(multi), "hand-framed response differs from Serialize(ResponseMsg)");
+  }
   // ---- the reference's own serialization tests, restated (pir/cpp/serialization_test.cpp) ----
   {
     // TestResponseSerialization (:62-78): encode 987654321, encrypt, save into a Response, reload, decrypt
