@@ -72,6 +72,16 @@ def lib():
         L.orc_gen_galois_keys.argtypes = [C.c_void_p, C.c_uint64, u64p, i8p, u32p, C.c_uint32, u64p]
         L.orc_encrypt.argtypes = [C.c_void_p, C.c_uint64, u64p, u64p, C.c_uint64, u64p]
         L.orc_decrypt.argtypes = [C.c_void_p, u64p, u64p, u64p]
+        L.orc_rns_bases.restype = C.c_uint32
+        L.orc_rns_bases.argtypes = [C.c_void_p, u64p, C.c_uint32]
+        L.orc_bfv_multiply.argtypes = [C.c_void_p, u64p, C.c_uint32, u64p, C.c_uint32, u64p]
+        L.orc_relinearize.argtypes = [C.c_void_p, u64p, u64p]
+        L.orc_gen_relin_key.argtypes = [C.c_void_p, C.c_uint64, u64p, i8p, u64p]
+        L.orc_decrypt_polys.argtypes = [C.c_void_p, u64p, u64p, C.c_uint32, u64p]
+        L.orc_db_multiply_ct.argtypes = [C.c_void_p, u64p, C.c_uint64, u32p, C.c_uint32, u64p, C.c_uint64, u64p, u64p,
+                                         C.c_uint32, u32p]
+        L.orc_process_query_ct.argtypes = [C.c_void_p, u64p, C.c_uint64, u32p, C.c_uint32, u32p, C.c_uint32, u64p, u64p,
+                                           u64p, C.c_uint64, u64p, C.c_uint32, u32p]
         _lib = L
     return _lib
 
@@ -274,6 +284,75 @@ class Oracle:
         if rc:
             raise OracleStatus(rc)
         return out[:cnt.value]
+
+    # ciphertext-multiplication mode (database.cpp:202-211; oracle/bfv_mul_oracle.hpp) ---------
+    def rns_bases(self):
+        """(m_sk, [primes of B]) — the auxiliary BEHZ bases SEAL's RNSTool picks for the first data level."""
+        buf = np.zeros(16, dtype=np.uint64)
+        nb = int(lib().orc_rns_bases(self.h, _p64(buf), 16))
+        return int(buf[0]), [int(x) for x in buf[1:1 + nb]]
+
+    def bfv_multiply(self, a, b):
+        """a [s1][k][N] x b [s2][k][N] (coefficient form) -> [s1+s2-1][k][N]  (Evaluator::multiply)."""
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        s1, s2 = a.size // self.pt_limbs, b.size // self.pt_limbs
+        out = np.zeros((s1 + s2 - 1, self.k, self.N), dtype=np.uint64)
+        lib().orc_bfv_multiply(self.h, _p64(a), s1, _p64(b), s2, _p64(out))
+        return out
+
+    def relinearize(self, ct3, relin_key):
+        """[3][k][N] -> [2][k][N]  (Evaluator::relinearize_inplace with one relinearization key)."""
+        a = np.ascontiguousarray(ct3, dtype=np.uint64).copy().reshape(3, self.k, self.N)
+        lib().orc_relinearize(self.h, _p64(a), _p64(relin_key))
+        return a[:2].copy()
+
+    def relin_key(self, keys, seed):
+        out = np.zeros(self.key_limbs, dtype=np.uint64)
+        lib().orc_gen_relin_key(self.h, seed, _p64(keys["sk_ntt"]), keys["sk_coeff"].ctypes.data_as(i8p), _p64(out))
+        return out
+
+    def decrypt_polys(self, keys, ct, with_budget=False):
+        a = np.ascontiguousarray(ct, dtype=np.uint64)
+        polys = a.size // self.pt_limbs
+        pt = np.zeros(self.N, dtype=np.uint64)
+        budget = lib().orc_decrypt_polys(self.h, _p64(keys["sk_ntt"]), _p64(a), polys, _p64(pt))
+        return (pt, budget) if with_budget else pt
+
+    def db_multiply_ct(self, db_ntt, dims, sv, relin_key=None):
+        """PIRDatabase::multiply with use_ciphertext_multiplication: one ciphertext [polys][k][N] (polys = 2 with a
+        relinearization key, else one more per upper dimension).  The selection vector is not modified."""
+        db = np.ascontiguousarray(db_ntt, dtype=np.uint64)
+        num_pt = db.size // self.pt_limbs
+        svc = np.ascontiguousarray(sv, dtype=np.uint64)
+        n_sv = svc.size // self.ct_limbs
+        d = np.array(dims, dtype=np.uint32)
+        cap = len(dims) + 1
+        out = np.zeros((cap, self.k, self.N), dtype=np.uint64)
+        polys = C.c_uint32(0)
+        rk = _p64(relin_key) if relin_key is not None else None
+        rc = lib().orc_db_multiply_ct(self.h, _p64(db), num_pt, _p32(d), len(d), _p64(svc), n_sv, rk, _p64(out), cap,
+                                      C.byref(polys))
+        if rc:
+            raise OracleStatus(rc)
+        return out[:polys.value].copy()
+
+    def process_query_ct(self, db_ntt, dims, elts, keys, query, relin_key=None):
+        db = np.ascontiguousarray(db_ntt, dtype=np.uint64)
+        num_pt = db.size // self.pt_limbs
+        q = np.ascontiguousarray(query, dtype=np.uint64)
+        n_ct = q.size // self.ct_limbs
+        d = np.array(dims, dtype=np.uint32)
+        e = np.array(elts, dtype=np.uint32)
+        cap = len(dims) + 1
+        out = np.zeros((cap, self.k, self.N), dtype=np.uint64)
+        polys = C.c_uint32(0)
+        rk = _p64(relin_key) if relin_key is not None else None
+        rc = lib().orc_process_query_ct(self.h, _p64(db), num_pt, _p32(d), len(d), _p32(e), len(e), _p64(keys), rk,
+                                        _p64(q), n_ct, _p64(out), cap, C.byref(polys))
+        if rc:
+            raise OracleStatus(rc)
+        return out[:polys.value].copy()
 
     def scan_row(self, db_ntt, sv_ntt):
         db = np.ascontiguousarray(db_ntt, dtype=np.uint64)

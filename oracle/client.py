@@ -1,7 +1,7 @@
 """Harness-only restatement of the reference CLIENT side and parameter math (TEST INFRASTRUCTURE ONLY).
 
 Follows pir/cpp/parameters.cpp:56-107 (CreatePIRParameters), pir/cpp/client.cpp:92-144 (createQueryFor),
-pir/cpp/client.cpp:219-255 (ProcessReplyCiphertextDecomp), pir/cpp/database.cpp:318-332 (index math),
+pir/cpp/client.cpp:196-255 (ProcessReplyCiphertextMult / ProcessReplyCiphertextDecomp), pir/cpp/database.cpp:318-332 (index math),
 and SEAL's Plaintext hex-polynomial strings / IntegerEncoder (used by the reference's tests).
 """
 from dataclasses import dataclass, field
@@ -24,6 +24,7 @@ class PIRParameters:
     poly_modulus_degree: int
     plain_modulus: int
     coeff_modulus: List[int] = field(default_factory=list)  # data moduli + special prime (last)
+    use_ciphertext_multiplication: bool = False
 
     @property
     def dim_sum(self):
@@ -31,11 +32,13 @@ class PIRParameters:
 
 
 def create_pir_parameters(dbsize, bytes_per_item=0, dimensions=1, N=4096, plain_bits=20, bits_per_coeff=0,
-                          plain_modulus=None, coeff_modulus=None):
+                          plain_modulus=None, coeff_modulus=None, use_ciphertext_multiplication=False):
     """parameters.cpp:56-107."""
     t = plain_modulus if plain_modulus is not None else ob.plain_modulus_batching(N, plain_bits)
     moduli = coeff_modulus if coeff_modulus is not None else ob.bfv_default(N)
-    enc_bits = ob.log2(t)  # StringEncoder ctor, string_encoder.cpp:85
+    # StringEncoder ctor, string_encoder.cpp:85: pir::log2 takes a uint32_t, so a wider plain modulus (the reference
+    # tests one of 42 bits, correctness_test.cpp:100) is truncated to its low 32 bits first
+    enc_bits = ob.log2(t & 0xFFFFFFFF)
     bpc = 0
     if bits_per_coeff > 0:
         if bits_per_coeff > enc_bits:
@@ -55,7 +58,8 @@ def create_pir_parameters(dbsize, bytes_per_item=0, dimensions=1, N=4096, plain_
         items_per_pt = 1
         num_pt = dbsize
     dims = ob.calculate_dimensions(num_pt, dimensions)
-    return PIRParameters(dbsize, num_pt, dims, bpi, items_per_pt, bpc, N, t, list(moduli))
+    return PIRParameters(dbsize, num_pt, dims, bpi, items_per_pt, bpc, N, t, list(moduli),
+                         bool(use_ciphertext_multiplication))
 
 
 def calculate_indices(params: PIRParameters, index: int):
@@ -134,7 +138,15 @@ class HarnessClient:
         self.keys = self.orc.keygen(seed)
         self.elts = ob.generate_galois_elts(params.poly_modulus_degree)
         self.galois = self.orc.galois_keys(self.keys, self.elts, seed + 1000)
+        self._relin = None
         self._seed = seed * 7919 + 17
+
+    @property
+    def relin(self):
+        """client.cpp:49: keygen_->relin_keys() — one key (for s^2), same layout as one Galois key."""
+        if self._relin is None:
+            self._relin = self.orc.relin_key(self.keys, self._seed * 31 + 5)
+        return self._relin
 
     def _next_seed(self):
         self._seed += 1
@@ -200,13 +212,22 @@ class HarnessClient:
                    for i in range(len(cts) // exp_ratio)]
         return (pts[0], min_budget) if with_budget else pts[0]
 
+    def process_reply_ct(self, reply, with_budget=False):
+        """client.cpp:196-217 (ProcessReplyCiphertextMult): the reply is ONE ciphertext ([polys][k][N])."""
+        r = np.asarray(reply)
+        if r.ndim == 4:
+            if r.shape[0] != 1:
+                raise ValueError("Number of ciphertexts in reply must be 1 when using CT multiplication")
+            r = r[0]
+        return self.orc.decrypt_polys(self.keys, r, with_budget)
+
     def process_response_strings(self, indexes, replies):
         """client.cpp:161-184."""
         p = self.params
-        bits = p.bits_per_coeff if p.bits_per_coeff > 0 else self.orc.ptb
+        bits = p.bits_per_coeff if p.bits_per_coeff > 0 else ob.log2(p.plain_modulus & 0xFFFFFFFF)
         out = []
         for idx, reply in zip(indexes, replies):
-            pt = self.process_reply(reply)
+            pt = self.process_reply_ct(reply) if p.use_ciphertext_multiplication else self.process_reply(reply)
             out.append(ob.string_decode(pt, bits, p.bytes_per_item, calculate_item_offset(p, idx)))
         return out
 
@@ -214,7 +235,7 @@ class HarnessClient:
 def encode_string_db(params: PIRParameters, items: List[bytes]):
     """PIRDatabase::populate(vector<string>) packing step (database.cpp:84-110) -> [num_pt][N] coefficients."""
     N = params.poly_modulus_degree
-    bits = params.bits_per_coeff if params.bits_per_coeff > 0 else ob.log2(params.plain_modulus)
+    bits = params.bits_per_coeff if params.bits_per_coeff > 0 else ob.log2(params.plain_modulus & 0xFFFFFFFF)
     if len(items) != params.num_items:
         raise ValueError("Database size %d does not match params value %d" % (len(items), params.num_items))
     out = np.zeros((params.num_pt, N), dtype=np.uint64)

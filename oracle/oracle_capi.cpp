@@ -1,5 +1,7 @@
 // oracle/oracle_capi.cpp — C ABI over the CPU oracle (TEST INFRASTRUCTURE ONLY; see pir_oracle.hpp).
 // Loaded with ctypes by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+#include <memory>
+
 #include "pir_oracle.hpp"
 
 using namespace orc;
@@ -7,7 +9,12 @@ using namespace orc;
 struct OrcHandle {
   Context ctx;
   Crypto crypto;
+  std::unique_ptr<RnsTool> rns_;  // built on first use (ciphertext-multiplication mode only)
   OrcHandle(size_t N, const std::vector<u64>& mods, u64 t) : ctx(N, mods, t), crypto(ctx) {}
+  const RnsTool& rns() {
+    if (!rns_) rns_.reset(new RnsTool(ctx));
+    return *rns_;
+  }
 };
 
 static GaloisKeys make_keys(const OrcHandle* h, const uint32_t* elts, size_t n_elts, const u64* limbs) {
@@ -174,6 +181,68 @@ void orc_encrypt(void* hh, uint64_t seed, const uint64_t* pk_ntt, const uint64_t
   Rng rng(seed);
   h->crypto.encrypt(pk, pt, n_coeff, rng, ct);
 }
+// ---- ciphertext-multiplication mode (bfv_mul_oracle.hpp) -----------------------------
+// primes: m_sk, then the nB primes of B.  Returns nB.
+uint32_t orc_rns_bases(void* hh, uint64_t* primes, uint32_t cap) {
+  OrcHandle* h = (OrcHandle*)hh;
+  const RnsTool& R = h->rns();
+  if (cap >= R.nB + 1) {
+    primes[0] = R.m_sk;
+    for (size_t i = 0; i < R.nB; ++i) primes[1 + i] = R.bsk[i].mod.q;
+  }
+  return (uint32_t)R.nB;
+}
+// out: s1 + s2 - 1 polynomials [.][k][N]
+void orc_bfv_multiply(void* hh, const uint64_t* a, uint32_t s1, const uint64_t* b, uint32_t s2, uint64_t* out) {
+  OrcHandle* h = (OrcHandle*)hh;
+  std::vector<u64> v = bfv_multiply(h->ctx, h->rns(), a, s1, b, s2);
+  std::memcpy(out, v.data(), v.size() * sizeof(u64));
+}
+// ct: [3][k][N]; the first two polynomials are updated
+void orc_relinearize(void* hh, uint64_t* ct, const uint64_t* relin_key) { relinearize_inplace(((OrcHandle*)hh)->ctx, ct, relin_key); }
+void orc_gen_relin_key(void* hh, uint64_t seed, const uint64_t* sk_ntt, const int8_t* sk_coeff, uint64_t* out) {
+  OrcHandle* h = (OrcHandle*)hh;
+  const Context& c = h->ctx;
+  SecretKey sk;
+  sk.ntt.assign(sk_ntt, sk_ntt + (c.k + 1) * c.N);
+  sk.coeff.assign(sk_coeff, sk_coeff + c.N);
+  Rng rng(seed);
+  gen_relin_key(c, sk, rng, out);
+}
+int orc_decrypt_polys(void* hh, const uint64_t* sk_ntt, const uint64_t* ct, uint32_t polys, uint64_t* pt) {
+  OrcHandle* h = (OrcHandle*)hh;
+  SecretKey sk;
+  sk.ntt.assign(sk_ntt, sk_ntt + (h->ctx.k + 1) * h->ctx.N);
+  return decrypt_any(h->crypto, sk, ct, polys, pt);
+}
+// relin_key may be null.  out: one ciphertext of *out_polys polynomials (at most out_cap_polys).
+int orc_db_multiply_ct(void* hh, const uint64_t* db, uint64_t num_pt, const uint32_t* dims, uint32_t nd, const uint64_t* sv,
+                       uint64_t n_sv, const uint64_t* relin_key, uint64_t* out, uint32_t out_cap_polys, uint32_t* out_polys) {
+  OrcHandle* h = (OrcHandle*)hh;
+  std::vector<u64> v;
+  size_t polys = 0;
+  int rc = db_multiply_ct(h->ctx, h->rns(), db, num_pt, dims, nd, sv, n_sv, relin_key, v, &polys);
+  if (rc) return rc;
+  if (polys > out_cap_polys) return 13;
+  std::memcpy(out, v.data(), v.size() * sizeof(u64));
+  *out_polys = (uint32_t)polys;
+  return 0;
+}
+int orc_process_query_ct(void* hh, const uint64_t* db, uint64_t num_pt, const uint32_t* dims, uint32_t nd,
+                         const uint32_t* elts, uint32_t n_elts, const uint64_t* keys, const uint64_t* relin_key,
+                         const uint64_t* query, uint64_t n_ct, uint64_t* out, uint32_t out_cap_polys, uint32_t* out_polys) {
+  OrcHandle* h = (OrcHandle*)hh;
+  GaloisKeys gk = make_keys(h, elts, n_elts, keys);
+  std::vector<u64> v;
+  size_t polys = 0;
+  int rc = process_query_ct(h->ctx, h->rns(), db, num_pt, dims, nd, gk, relin_key, query, n_ct, v, &polys);
+  if (rc) return rc;
+  if (polys > out_cap_polys) return 13;
+  std::memcpy(out, v.data(), v.size() * sizeof(u64));
+  *out_polys = (uint32_t)polys;
+  return 0;
+}
+
 int orc_decrypt(void* hh, const uint64_t* sk_ntt, const uint64_t* ct, uint64_t* pt) {
   OrcHandle* h = (OrcHandle*)hh;
   SecretKey sk;

@@ -958,3 +958,5 @@ struct Crypto {
 };
 
 }  // namespace orc
+
+#include "bfv_mul_oracle.hpp"  // ciphertext-multiplication mode (database.cpp:202-211)

@@ -390,6 +390,108 @@ def test_end_to_end_correctness(n, bits, elem, bpc, dbsize, d, indices):
     assert got == [items[i] for i in indices]
 
 
+# ------------------------------------------------------------------ ciphertext-multiplication mode (database.cpp:202-211)
+def test_behz_auxiliary_bases():
+    # [SEAL RNSTool::initialize]: m_sk, gamma, then |q| primes for B from get_primes(N, 61, .): descending from 2^61,
+    # all = 1 mod 2N; m_tilde = 2^32.  4096: |q| = 2 data primes, 8192: 4.
+    for n, k in ((4096, 2), (8192, 4)):
+        o = ob.Oracle.default(n, 20)
+        m_sk, B = o.rns_bases()
+        assert len(B) == k
+        aux = [m_sk] + B
+        assert all(ob.is_prime(p) and p % (2 * n) == 1 and p.bit_length() == 61 for p in aux)
+        assert aux[0] > aux[1] and all(B[i] > B[i + 1] for i in range(k - 1))
+        assert m_sk == max(p for p in range((1 << 61) - 2 * n + 1, (1 << 61) - 200 * n, -2 * n) if ob.is_prime(p))
+
+
+def test_bfv_multiply_and_relinearize():
+    """Evaluator::multiply + relinearize_inplace at the decrypt level: the product of two plaintext polynomials
+    mod (x^N + 1, t), through a size-3 ciphertext, through relinearization, and through a size-4 one."""
+    p = oc.create_pir_parameters(10, 0, 1, 8192, 20, use_ciphertext_multiplication=True)
+    cl = oc.HarnessClient(p, seed=21)
+    n, t = 8192, p.plain_modulus
+    rng = np.random.default_rng(5)
+    a = np.zeros(n, dtype=np.uint64); b = np.zeros(n, dtype=np.uint64)
+    ia, ib = rng.choice(n, 40, replace=False), rng.choice(n, 3, replace=False)
+    a[ia] = rng.integers(1, t, 40); b[ib] = rng.integers(1, t, 3)
+    want = np.zeros(n, dtype=object)
+    for i in ia:
+        for j in ib:
+            d, v = int(i + j), int(a[i]) * int(b[j])
+            if d >= n:
+                d, v = d - n, -v
+            want[d] = (want[d] + v) % t
+    ca, cb = cl.encrypt(a), cl.encrypt(b)
+    prod = cl.orc.bfv_multiply(ca, cb)
+    assert prod.shape == (3, cl.orc.k, n)
+    got, budget3 = cl.orc.decrypt_polys(cl.keys, prod, True)
+    assert [int(x) for x in got] == [int(x) for x in want] and budget3 > 60
+    assert np.array_equal(cl.orc.bfv_multiply(cb, ca), prod)  # symmetric in its operands
+    rel = cl.orc.relinearize(prod, cl.relin)
+    got, budget2 = cl.decrypt(rel, True)
+    assert [int(x) for x in got] == [int(x) for x in want] and budget2 >= budget3 - 2
+    one = np.zeros(n, dtype=np.uint64); one[0] = 1
+    prod4 = cl.orc.bfv_multiply(prod, cl.encrypt(one))
+    assert prod4.shape == (4, cl.orc.k, n)
+    assert [int(x) for x in cl.orc.decrypt_polys(cl.keys, prod4)] == [int(x) for x in want]
+
+
+@pytest.mark.parametrize("n,bits,dbsize,d,idx", [(4096, 16, 10, 1, 7), (4096, 16, 16, 2, 11), (4096, 16, 16, 2, 0),
+                                                  (4096, 16, 16, 2, 15), (4096, 16, 82, 2, 42), (8192, 20, 27, 3, 2),
+                                                  (8192, 20, 117, 3, 17)])
+def test_multiply_multi_dim_strings_ct_multiply(n, bits, dbsize, d, idx):
+    # database_test.cpp:343-388, CTMultiply arm: relinearization keys given, ONE reply ciphertext of size 2
+    p = oc.create_pir_parameters(dbsize, 0, d, n, bits, use_ciphertext_multiplication=True)
+    cl = oc.HarnessClient(p, seed=11)
+    rng = np.random.default_rng(42)
+    items = [rng.integers(0, 256, p.bytes_per_item, dtype=np.uint8).tobytes() for _ in range(dbsize)]
+    db = oc.db_to_ntt(cl.orc, oc.encode_string_db(p, items))
+    sv = _selection_vector(cl, p.dimensions, oc.calculate_indices(p, idx))
+    out = cl.orc.db_multiply_ct(db, p.dimensions, sv, cl.relin)
+    assert out.shape == (2, cl.orc.k, n)
+    res, budget = cl.process_reply_ct(out, with_budget=True)
+    assert budget > 0
+    assert ob.string_decode(res, cl.orc.ptb, p.bytes_per_item) == items[idx]
+    if d == 2:  # server.cpp:185-190 without relinearization keys: the reply keeps its third polynomial
+        out3 = cl.orc.db_multiply_ct(db, p.dimensions, sv, None)
+        assert out3.shape == (3, cl.orc.k, n)
+        assert ob.string_decode(cl.process_reply_ct(out3), cl.orc.ptb, p.bytes_per_item) == items[idx]
+        with pytest.raises(ob.OracleStatus) as e:  # database.cpp:297-300
+            cl.orc.db_multiply_ct(db, p.dimensions, sv[:-1], cl.relin)
+        assert e.value.code == 3
+
+
+def test_process_request_2dim_ct_multiply():
+    # server_test.cpp:209-260 with GetParam() == true: reply is one ciphertext of size 2 ("Were relin keys used?")
+    p = oc.create_pir_parameters(82, 7680, 2, 4096, 20, use_ciphertext_multiplication=True)
+    cl = oc.HarnessClient(p, seed=89)
+    vals = _int_db(p)
+    db = oc.db_to_ntt(cl.orc, oc.encode_int_db(p, vals))
+    m_inv = pow(ob.next_power_two(19), -1, p.plain_modulus)
+    pt = np.zeros(N, dtype=np.uint64); pt[4] = m_inv; pt[16] = m_inv
+    reply = cl.orc.process_query_ct(db, p.dimensions, cl.elts, cl.galois, cl.encrypt(pt)[None], cl.relin)
+    assert reply.shape == (2, cl.orc.k, N)
+    assert oc.integer_decode(cl.process_reply_ct(reply), p.plain_modulus) == vals[42]
+
+
+@pytest.mark.parametrize("n,bits,elem,bpc,dbsize,d,indices",
+                         [(4096, 24, 0, 0, 10, 1, [0]), (4096, 16, 0, 10, 9, 2, [1, 5]),
+                          (4096, 16, 0, 6, 500, 2, [9, 125]), (8192, 42, 0, 0, 87, 2, [5, 33, 86]),
+                          (4096, 16, 64, 10, 1200, 1, [0, 80, 81, 123, 777, 1199]),
+                          (4096, 16, 289, 10, 1200, 1, [0, 47, 777, 1199])])
+def test_end_to_end_correctness_ct_multiply(n, bits, elem, bpc, dbsize, d, indices):
+    # correctness_test.cpp:94-105: the six use_ciphertext_multiplication == true cases
+    p = oc.create_pir_parameters(dbsize, elem, d, n, bits, bpc, use_ciphertext_multiplication=True)
+    cl = oc.HarnessClient(p, seed=5)
+    rng = np.random.default_rng(42)
+    items = [rng.integers(0, 256, p.bytes_per_item, dtype=np.uint8).tobytes() for _ in range(dbsize)]
+    db = oc.db_to_ntt(cl.orc, oc.encode_string_db(p, items))
+    replies = [cl.orc.process_query_ct(db, p.dimensions, cl.elts, cl.galois, cl.create_query(i), cl.relin)
+               for i in indices]
+    assert all(r.shape[0] == 2 for r in replies)
+    assert cl.process_response_strings(indices, replies) == [items[i] for i in indices]
+
+
 # ------------------------------------------------------------------ the oracle frozen against itself
 def test_oracle_outputs_match_the_committed_digests():
     """tests/golden/oracle_digests.json: SHA-256 of the oracle's substitution / shift / expansion / reply for inputs
