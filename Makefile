@@ -5,12 +5,12 @@ NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall 
 SRC := pir_b200/csrc
 OBJ := build/obj
 LIB := pir_b200/lib/libpirb200.so
-OBJS := $(OBJ)/kernels_ntt.o $(OBJ)/kernels_stream.o $(OBJ)/kernels_cluster.o $(OBJ)/kernels_dist.o $(OBJ)/kernels_tc.o $(OBJ)/context.o
+OBJS := $(OBJ)/kernels_ntt.o $(OBJ)/kernels_stream.o $(OBJ)/kernels_cluster.o $(OBJ)/kernels_dist.o $(OBJ)/kernels_tc.o $(OBJ)/kernels_ctmul.o $(OBJ)/context.o
 HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/pir_b200.h
 
 WIRE := pir_b200/lib/libpirb_wire.so
 
-all: $(LIB) $(WIRE) oracle build/shim_test build/shim_host_test build/wire_test build/device_math_host_test build/shim_bench
+all: $(LIB) $(WIRE) oracle build/shim_test build/shim_host_test build/wire_test build/device_math_host_test build/ctmul_host_test build/shim_bench
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -27,7 +27,7 @@ $(WIRE): pir_b200/cpp/wire_capi.cpp pir_b200/cpp/wire.hpp
 	g++ -O2 -std=c++17 -Wall -Wextra -shared -fPIC -o $@ pir_b200/cpp/wire_capi.cpp
 
 # C++ end-to-end test of the pir:: shim (host code in the reference's language over the C ABI)
-build/shim_test: tests/cpp/shim_test.cpp pir_b200/cpp/pir_b200.hpp pir_b200/cpp/wire.hpp oracle/pir_oracle.hpp include/pir_b200.h $(LIB)
+build/shim_test: tests/cpp/shim_test.cpp pir_b200/cpp/pir_b200.hpp pir_b200/cpp/wire.hpp oracle/pir_oracle.hpp oracle/bfv_mul_oracle.hpp include/pir_b200.h $(LIB)
 	@mkdir -p build
 	g++ -O2 -std=c++17 -march=x86-64-v3 -o $@ tests/cpp/shim_test.cpp -Lpir_b200/lib -lpirb200 -Wl,-rpath,'$$ORIGIN/../pir_b200/lib'
 
@@ -42,7 +42,7 @@ build/shim_host_test: tests/cpp/shim_host_test.cpp pir_b200/cpp/pir_b200.hpp pir
 	g++ -O2 -std=c++17 -Wall -Wextra -o $@ tests/cpp/shim_host_test.cpp -Lpir_b200/lib -lpirb200 -Wl,-rpath,'$$ORIGIN/../pir_b200/lib'
 
 # CPU-only end-to-end test of the wire layer against the oracle (no CUDA anywhere in it)
-build/wire_test: tests/cpp/wire_test.cpp pir_b200/cpp/wire.hpp oracle/pir_oracle.hpp
+build/wire_test: tests/cpp/wire_test.cpp pir_b200/cpp/wire.hpp oracle/pir_oracle.hpp oracle/bfv_mul_oracle.hpp
 	@mkdir -p build
 	g++ -O2 -std=c++17 -march=x86-64-v3 -Wall -o $@ tests/cpp/wire_test.cpp
 
@@ -50,6 +50,12 @@ build/wire_test: tests/cpp/wire_test.cpp pir_b200/cpp/wire.hpp oracle/pir_oracle
 build/device_math_host_test: tests/cpp/device_math_host_test.cpp $(HDRS) oracle/pir_oracle.hpp
 	@mkdir -p build
 	g++ -O2 -std=c++17 -march=x86-64-v3 -ffp-contract=off -I/usr/local/cuda/include -Wno-attributes -o $@ tests/cpp/device_math_host_test.cpp
+
+# the ciphertext-multiplication kernels' bodies (pirb_behz.cuh) and host setup compiled for the HOST: constants,
+# per-coefficient functions and a whole upper dimension, launch by launch, against the oracle
+build/ctmul_host_test: tests/cpp/ctmul_host_test.cpp $(HDRS) oracle/pir_oracle.hpp oracle/bfv_mul_oracle.hpp
+	@mkdir -p build
+	g++ -O2 -std=c++17 -march=x86-64-v3 -I/usr/local/cuda/include -Wno-attributes -o $@ tests/cpp/ctmul_host_test.cpp
 
 oracle:
 	$(MAKE) -C oracle

@@ -52,6 +52,9 @@ typedef struct {
   int32_t device;                             /* CUDA device ordinal */
   uint32_t shard_index;                       /* row shard of dims[0] owned by this context ... */
   uint32_t shard_count;                       /* ... out of shard_count (1 = whole database) */
+  uint32_t use_ciphertext_multiplication;     /* PIRParameters.use_ciphertext_multiplication (payload.proto:69): upper
+                                               * dimensions by Evaluator::multiply instead of the re-encoder
+                                               * (database.cpp:202-211); one GPU, entry points pirb_*_ct below */
 } pirb_params;
 
 const char* pirb_last_error(void);
@@ -111,6 +114,26 @@ int pirb_db_multiply(pirb_ctx* ctx, uint64_t* sv, uint64_t n_sv, uint64_t* out, 
  * (cudaHostAlloc / cudaHostRegister) are read and written in place by the kernels, pageable ones are staged. */
 int pirb_answer(pirb_ctx* ctx, const pirb_keys* keys, const uint64_t* queries, uint32_t n_queries, uint64_t n_ct,
                 uint64_t* replies);
+
+/* ---- Ciphertext-multiplication mode (PIRParameters.use_ciphertext_multiplication; contexts created with the flag).
+ * The upper dimensions multiply the lower result with the selection ciphertext by Evaluator::multiply and, when the
+ * request carries relinearization keys, Evaluator::relinearize_inplace (database.cpp:202-211, server.cpp:185-190)
+ * [SEAL 3.5.6: BEHZ RNS multiplication, switch_key_inplace].  The reply of a query is ONE ciphertext
+ * (client.cpp:196-217) of pirb_reply_polys polynomials: 2 with relinearization keys (or d = 1), else d + 1.
+ * The entry points above that multiply (pirb_db_multiply, pirb_answer*, pirb_dist_*) fail with 3 on such a context. */
+/* seal::RelinKeys as KeyGenerator::relin_keys() makes them (client.cpp:49): one key-switching key (for s^2),
+ * limbs [k][2][k+1][N] in NTT form — the layout of one Galois key.  Freed with pirb_keys_destroy. */
+int pirb_relin_keys_load(pirb_ctx* ctx, const uint64_t* limbs, pirb_keys** out);
+uint32_t pirb_reply_polys(const pirb_ctx* ctx, int with_relin_keys);
+/* PIRDatabase::multiply(selection_vector, relin_keys) (database.cpp:290-316).  sv[n_sv][2][k][N] in coefficient form
+ * is NOT modified (database.cpp:188 only transforms it on the re-encoder path).  relin may be NULL.
+ * out[polys][k][N]; *out_polys = polys (0 for an empty database).  3 if n_sv != dim_sum. */
+int pirb_db_multiply_ct(pirb_ctx* ctx, const uint64_t* sv, uint64_t n_sv, const pirb_keys* relin, uint64_t* out,
+                        uint64_t out_cap_limbs, uint32_t* out_polys);
+/* PIRServer::processQuery with optional<RelinKeys> for every query of a request (server.cpp:60-63, 173-195).
+ * queries[n_queries][n_ct][2][k][N] -> replies[n_queries][polys][k][N].  Host buffers. */
+int pirb_answer_ct(pirb_ctx* ctx, const pirb_keys* galois_keys, const pirb_keys* relin, const uint64_t* queries,
+                   uint32_t n_queries, uint64_t n_ct, uint64_t* replies);
 
 /* Device-resident variants (pointers are CUDA device pointers on ctx's device; stream = cudaStream_t or NULL
  * for the context's own stream).  pirb_answer_dev writes final replies (shard_count == 1).  With shards, each rank

@@ -113,10 +113,9 @@ def CreatePIRParameters(dbsize, bytes_per_item=0, dimensions=1, seal_params=None
     """parameters.cpp:56-107"""
     if seal_params is None:
         seal_params = GenerateEncryptionParams()
-    if use_ciphertext_multiplication:
-        raise PIRStatusError(INVALID_ARGUMENT, "ciphertext-multiplication mode is outside this library's path")
     enc = StringEncoder(seal_params)
-    p = PIRParameters(num_items=dbsize, encryption_parameters=seal_params)
+    p = PIRParameters(num_items=dbsize, encryption_parameters=seal_params,
+                      use_ciphertext_multiplication=bool(use_ciphertext_multiplication))  # parameters.cpp:71
     if bits_per_coeff > 0:
         if bits_per_coeff > enc.bits_per_coeff:
             raise PIRStatusError(INVALID_ARGUMENT, "Bits per coefficient greater than max")
@@ -144,7 +143,8 @@ class StringEncoder:
 
     def __init__(self, seal_params: EncryptionParameters):
         self.poly_modulus_degree = seal_params.poly_modulus_degree
-        self.bits_per_coeff = log2(seal_params.plain_modulus)  # string_encoder.cpp:85
+        # string_encoder.cpp:85: pir::log2 takes a uint32_t, a wider plain modulus is truncated to its low 32 bits
+        self.bits_per_coeff = log2(seal_params.plain_modulus & 0xFFFFFFFF)
 
     def set_bits_per_coeff(self, b):
         self.bits_per_coeff = b
@@ -199,7 +199,9 @@ class Request:
     """payload.proto:28-36"""
     query: List[np.ndarray] = field(default_factory=list)
     galois_keys: Optional[GaloisKeys] = None
-    relin_keys: Optional[object] = None  # parsed but unused on the re-encoder path (server.cpp:53-58)
+    # seal::RelinKeys as raw limbs [k][2][k+1][N] (one key, NTT form).  Used in ciphertext-multiplication mode
+    # (server.cpp:185-190); parsed but unused on the re-encoder path (server.cpp:53-58)
+    relin_keys: Optional[object] = None
 
 
 @dataclass
@@ -230,6 +232,8 @@ class _Context:
         pp.device = device
         pp.shard_index = shard_index
         pp.shard_count = shard_count
+        pp.use_ciphertext_multiplication = 1 if params.use_ciphertext_multiplication else 0
+        self.ct_mode = bool(params.use_ciphertext_multiplication)
         h = C.c_void_p()
         _check(_lib.lib().pirb_ctx_create(C.byref(pp), C.byref(h)))
         self.h = h
@@ -263,6 +267,28 @@ class _KeyHandle:
         if gk.data.size != len(gk.elts) * ctx.key_limbs:
             raise PIRStatusError(INVALID_ARGUMENT, "Galois key data has the wrong size")
         _check(_lib.lib().pirb_keys_load(ctx.h, elts, len(gk.elts), _ptr(gk.data), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.lib().pirb_keys_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _RelinHandle:
+    """seal::RelinKeys (one key-switching key for s^2) resident in HBM."""
+
+    def __init__(self, ctx: _Context, limbs):
+        self.h = C.c_void_p()
+        a = _u64(limbs)
+        if a.size != ctx.key_limbs:
+            raise PIRStatusError(INVALID_ARGUMENT, "relinearization key data has the wrong size")
+        _check(_lib.lib().pirb_relin_keys_load(ctx.h, _ptr(a), C.byref(self.h)))
 
     def close(self):
         if getattr(self, "h", None):
@@ -395,6 +421,20 @@ class PIRDatabase:
         if sv.dtype != np.uint64 or not sv.flags["C_CONTIGUOUS"]:
             raise PIRStatusError(INVALID_ARGUMENT, "selection vector must be a C-contiguous uint64 array")
         n_sv = sv.size // self.ctx.ct_limbs
+        if self.ctx.ct_mode:
+            # database.cpp:202-211: Evaluator::multiply (+ relinearize_inplace when keys are given); the selection
+            # vector stays in coefficient form; ONE result ciphertext [polys][k][N]
+            rh = _RelinHandle(self.ctx, relin_keys) if relin_keys is not None else None
+            try:
+                polys = int(_lib.lib().pirb_reply_polys(self.ctx.h, 1 if rh else 0))
+                out = np.zeros((polys, self.ctx.k, self.ctx.N), dtype=np.uint64)
+                got = C.c_uint32(0)
+                _check(_lib.lib().pirb_db_multiply_ct(self.ctx.h, _ptr(sv), n_sv, rh.h if rh else None, _ptr(out), out.size,
+                                                      C.byref(got)))
+            finally:
+                if rh:
+                    rh.close()
+            return out[None] if got.value else out[:0][None]
         out = np.zeros((self.ctx.reply_cts, 2, self.ctx.k, self.ctx.N), dtype=np.uint64)
         cnt = C.c_uint64(0)
         _check(_lib.lib().pirb_db_multiply(self.ctx.h, _ptr(sv), n_sv, _ptr(out), out.shape[0], C.byref(cnt)))
@@ -440,6 +480,7 @@ class PIRServer:
         self.params = params
         self.ctx = db.ctx  # device state is shared with the database it serves
         self._key_cache = (None, None)
+        self._relin_cache = (None, None)
 
     @classmethod
     def Create(cls, db: PIRDatabase, params: PIRParameters):
@@ -474,6 +515,22 @@ class PIRServer:
             q = _u64(request.query[0])  # no copy when already contiguous uint64
         else:
             q = _u64(np.stack([np.asarray(x).reshape(n_ct, 2, self.ctx.k, self.ctx.N) for x in request.query]))
+        if getattr(self.ctx, "ct_mode", False):
+            # server.cpp:185-190: relinearization keys, when the request carries them, are applied after every
+            # ciphertext multiplication; each reply is ONE ciphertext of `polys` polynomials (client.cpp:196-217)
+            rk = request.relin_keys
+            if rk is not None and self._relin_cache[0] is not rk:
+                old = self._relin_cache[1]
+                self._relin_cache = (rk, _RelinHandle(self.ctx, rk))
+                if old is not None:
+                    old.close()
+            rh = self._relin_cache[1] if rk is not None else None
+            polys = int(_lib.lib().pirb_reply_polys(self.ctx.h, 1 if rh else 0))
+            res = np.empty((n_q, 1, polys, self.ctx.k, self.ctx.N), dtype=np.uint64)
+            _check(_lib.lib().pirb_answer_ct(self.ctx.h, keys.h, rh.h if rh else None, C.c_void_p(q.ctypes.data), n_q, n_ct,
+                                             C.c_void_p(res.ctypes.data)))
+            resp.reply = [res[i] for i in range(n_q)]
+            return resp
         shape = (n_q, self.ctx.reply_cts, 2, self.ctx.k, self.ctx.N)
         if out is None:
             out = np.empty(shape, dtype=np.uint64)

@@ -176,10 +176,9 @@ inline StatusOr<std::shared_ptr<PIRParameters>> CreatePIRParameters(
     size_t bits_per_coeff = 0) {
   if (seal_params.coeff_modulus.size() < 2 || !seal_params.plain_modulus)
     return InvalidArgumentError("Error setting encryption parameters: invalid parameters");
-  if (use_ciphertext_multiplication)
-    return InvalidArgumentError("ciphertext-multiplication mode is outside this library's path");
   StringEncoder encoder(seal_params);
   auto p = std::make_shared<PIRParameters>();
+  p->use_ciphertext_multiplication = use_ciphertext_multiplication;  // parameters.cpp:71
   p->num_items = dbsize;
   p->encryption_parameters = seal_params;
   if (bits_per_coeff > 0) {
@@ -206,7 +205,8 @@ inline StatusOr<std::shared_ptr<PIRParameters>> CreatePIRParameters(
 
 // ---------------------------------------------------------------------------------------------------------------
 struct Ciphertext {
-  std::vector<uint64_t> limbs;  // [2][k][N]
+  std::vector<uint64_t> limbs;  // [2][k][N]  ([size][k][N]: replies of the ciphertext-multiplication mode without
+                                // relinearization keys keep more than two polynomials, server.cpp:185-190)
   bool is_ntt_form = false;
   uint64_t* data() { return limbs.data(); }
   const uint64_t* data() const { return limbs.data(); }
@@ -215,9 +215,13 @@ struct GaloisKeys {
   std::vector<uint32_t> elts;
   std::vector<uint64_t> limbs;  // [n][k][2][k+1][N], NTT form
 };
+struct RelinKeys {
+  std::vector<uint64_t> limbs;  // [k][2][k+1][N], NTT form: the one key KeyGenerator::relin_keys() makes (client.cpp:49)
+};
 struct Request {
   std::vector<std::vector<Ciphertext>> query;
   GaloisKeys galois_keys;
+  std::optional<RelinKeys> relin_keys;  // used in ciphertext-multiplication mode only (server.cpp:53-58, 185-190)
 };
 struct Response {
   std::vector<std::vector<Ciphertext>> reply;
@@ -423,6 +427,7 @@ class PIRDatabase {
       p.device = devices[i];
       p.shard_index = (uint32_t)i;
       p.shard_count = (uint32_t)devices.size();
+      p.use_ciphertext_multiplication = params->use_ciphertext_multiplication ? 1 : 0;
       pirb_ctx* ctx = nullptr;
       Status st = FromRc(pirb_ctx_create(&p, &ctx));
       if (!st.ok()) return st;
@@ -500,8 +505,10 @@ class PIRDatabase {
     return OkStatus();
   }
 
-  // database.cpp:290-316 — the selection vector is transformed to NTT form in place
-  StatusOr<std::vector<Ciphertext>> multiply(std::vector<Ciphertext>& selection_vector) const {
+  // database.cpp:290-316 — on the re-encoder path the selection vector is transformed to NTT form in place; in
+  // ciphertext-multiplication mode it is left alone and relin_keys (may be null) are applied after every multiplication
+  StatusOr<std::vector<Ciphertext>> multiply(std::vector<Ciphertext>& selection_vector,
+                                             const RelinKeys* relin_keys = nullptr) const {
     if (ctx_.size() != 1) return InvalidArgumentError("multiply() needs an unsharded database; use PIRServer");
     pirb_ctx* ctx = ctx_[0].get();
     const size_t L = pirb_ct_limbs(ctx);
@@ -509,6 +516,25 @@ class PIRDatabase {
     for (size_t i = 0; i < selection_vector.size(); ++i) {
       if (selection_vector[i].limbs.size() != L) return InvalidArgumentError("bad ciphertext size");
       std::copy(selection_vector[i].limbs.begin(), selection_vector[i].limbs.end(), sv.begin() + i * L);
+    }
+    if (params_->use_ciphertext_multiplication) {
+      std::unique_ptr<pirb_keys, detail::KeysDeleter> rk;
+      if (relin_keys) {
+        if (relin_keys->limbs.size() != pirb_key_limbs(ctx)) return InvalidArgumentError("bad relinearization key size");
+        pirb_keys* h = nullptr;
+        Status st = FromRc(pirb_relin_keys_load(ctx, relin_keys->limbs.data(), &h));
+        if (!st.ok()) return st;
+        rk.reset(h);
+      }
+      const size_t polys = pirb_reply_polys(ctx, rk ? 1 : 0), ptL = pirb_pt_limbs(ctx);
+      std::vector<Ciphertext> res(1);
+      res[0].limbs.assign(polys * ptL, 0);
+      uint32_t got = 0;
+      Status st = FromRc(pirb_db_multiply_ct(ctx, sv.data(), selection_vector.size(), rk.get(), res[0].limbs.data(),
+                                             res[0].limbs.size(), &got));
+      if (!st.ok()) return st;
+      if (!got) res.clear();
+      return res;
     }
     const size_t cap = pirb_reply_cts(ctx);
     std::vector<uint64_t> out(cap * L);
@@ -605,6 +631,8 @@ class PIRServer {
       if (!loaded.ok()) return loaded.status();
       keys = *loaded;
     }
+    if (params_->use_ciphertext_multiplication)
+      return AnswerCt(request.query, *keys, request.relin_keys ? &*request.relin_keys : nullptr);
     return Answer(request.query, *keys);
   }
 
@@ -641,6 +669,43 @@ class PIRServer {
     const size_t Q = msg.query.size(), k = ep.coeff_modulus.size() - 1, N = ep.poly_modulus_degree;
     const size_t L = pirb_ct_limbs(ctx), R = pirb_reply_cts(ctx);
     if (Q == 0) return wire::Serialize(wire::ResponseMsg());
+    if (params_->use_ciphertext_multiplication) {
+      // server.cpp:53-58, 185-190: here the relinearization keys ARE used; the reply is one ciphertext per query
+      Request req;
+      wire::parms_id_type pid0 = wire::data_parms_id(sp);
+      for (size_t qi = 0; qi < Q; ++qi) {
+        req.query.emplace_back();
+        for (const auto& blob : msg.query[qi]) {
+          wire::parms_id_type pid;
+          auto ct = DeserializeCiphertext(ep, std::string(blob), &pid);
+          if (!ct.ok()) return ct.status();
+          if (strict_parms_id && pid != pid0) return InvalidArgumentError("ciphertext data is invalid");
+          if (qi == 0 && req.query[0].empty()) pid0 = pid;
+          req.query.back().push_back(std::move(*ct));
+        }
+      }
+      std::optional<RelinKeys> relin;
+      if (!msg.relin_keys.empty()) {
+        auto rk = DeserializeGaloisKeys(ep, std::string(msg.relin_keys));  // same KSwitchKeys object, one slot
+        if (!rk.ok()) return rk.status();
+        if (rk->elts.size() != 1) return InvalidArgumentError("relinearization keys must hold exactly one key");
+        relin.emplace();
+        relin->limbs = std::move(rk->limbs);
+      }
+      auto resp = AnswerCt(req.query, *keys, relin ? &*relin : nullptr);
+      if (!resp.ok()) return resp.status();
+      std::string out;
+      for (const auto& reply : resp->reply) {
+        const size_t polys = reply[0].limbs.size() / (k * N);
+        const size_t blob = wire::CiphertextBlobSize(polys, N, k);
+        wire::put_tag(out, 1, 2);
+        wire::put_varint(out, 1 + wire::varint_size(blob) + blob);
+        wire::put_tag(out, 1, 2);
+        wire::put_varint(out, blob);
+        wire::AppendCiphertextBlob(out, reply[0].limbs.data(), polys, N, k, pid0, false);
+      }
+      return out;
+    }
     const size_t n_ct = msg.query[0].size();
     for (const auto& q : msg.query)
       if (q.size() != n_ct || n_ct != pirb_query_cts(ctx))
@@ -774,6 +839,43 @@ class PIRServer {
           for (size_t c = 0; c < R; ++c) response.reply[qi][c].limbs.assign(src + c * L, src + (c + 1) * L);
         });
     if (!st.ok()) return st;
+    return response;
+  }
+  // processQuery in ciphertext-multiplication mode (server.cpp:173-195 with database.cpp:202-211): one reply ciphertext
+  // per query, of 2 polynomials when relinearization keys are given, else one more per upper dimension
+  StatusOr<Response> AnswerCt(const std::vector<std::vector<Ciphertext>>& query, const KeySet& keys,
+                              const RelinKeys* relin) const {
+    if (db_->shard_count() != 1) return InvalidArgumentError("ciphertext-multiplication mode runs on one GPU");
+    pirb_ctx* ctx = db_->handle();
+    Response response;
+    if (query.empty()) return response;
+    const size_t L = pirb_ct_limbs(ctx), ptL = pirb_pt_limbs(ctx), n_ct = query[0].size(), Q = query.size();
+    std::vector<uint64_t> q(Q * n_ct * L);
+    for (size_t i = 0; i < Q; ++i) {
+      if (query[i].size() != n_ct || n_ct != pirb_query_cts(ctx))
+        return InvalidArgumentError("Number of ciphertexts doesn't match number of items for oblivious expansion.");
+      for (size_t c = 0; c < n_ct; ++c) {
+        if (query[i][c].limbs.size() != L) return InvalidArgumentError("bad ciphertext size");
+        std::memcpy(q.data() + (i * n_ct + c) * L, query[i][c].limbs.data(), L * sizeof(uint64_t));
+      }
+    }
+    std::unique_ptr<pirb_keys, detail::KeysDeleter> rk;
+    if (relin) {
+      if (relin->limbs.size() != pirb_key_limbs(ctx)) return InvalidArgumentError("bad relinearization key size");
+      pirb_keys* h = nullptr;
+      Status st = FromRc(pirb_relin_keys_load(ctx, relin->limbs.data(), &h));
+      if (!st.ok()) return st;
+      rk.reset(h);
+    }
+    const size_t polys = pirb_reply_polys(ctx, rk ? 1 : 0);
+    std::vector<uint64_t> r(Q * polys * ptL);
+    Status st = FromRc(pirb_answer_ct(ctx, keys.per_shard[0].get(), rk.get(), q.data(), (uint32_t)Q, n_ct, r.data()));
+    if (!st.ok()) return st;
+    response.reply.resize(Q);
+    for (size_t i = 0; i < Q; ++i) {
+      response.reply[i].resize(1);
+      response.reply[i][0].limbs.assign(r.begin() + i * polys * ptL, r.begin() + (i + 1) * polys * ptL);
+    }
     return response;
   }
   // The step engine behind both forms of ProcessRequest: fill(qi, dst) writes query qi's n_ct ciphertexts into the

@@ -116,6 +116,21 @@ int pirw_ct_load(const uint8_t* in, size_t in_len, uint32_t N, const uint64_t* m
   *was_seeded = ct.was_seeded;
   return 0;
 }
+// Same for a ciphertext of up to cap_polys polynomials (ciphertext-multiplication replies without relinearization
+// keep a third polynomial, server.cpp:185-190); *size_out receives the count.
+int pirw_ct_load_any(const uint8_t* in, size_t in_len, uint32_t N, const uint64_t* moduli, uint32_t n_moduli,
+                     uint64_t* limbs_out, uint32_t cap_polys, uint32_t* size_out, uint64_t* parms_id4, int* is_ntt,
+                     int* was_seeded) {
+  CiphertextData ct;
+  if (!LoadCiphertext(std::string_view((const char*)in, in_len), N, moduli, n_moduli, &ct, &g_err)) return 3;
+  if (ct.size > cap_polys) { g_err = "ciphertext larger than expected"; return 3; }
+  std::memcpy(limbs_out, ct.limbs.data(), ct.limbs.size() * 8);
+  std::memcpy(parms_id4, ct.parms_id.data(), 32);
+  *size_out = (uint32_t)ct.size;
+  *is_ntt = ct.is_ntt_form;
+  *was_seeded = ct.was_seeded;
+  return 0;
+}
 // Galois keys in the C-ABI layout: elts[n], limbs [n][k][2][k+1][N].  seeds (optional) [n][k][8]: write every key
 // seed-compressed, its second polynomial REPLACED by the expansion of its seed (as SEAL's keygen produces them).
 int pirw_galois_keys_save(uint32_t N, const uint64_t* moduli, uint32_t n_moduli, uint64_t t, const uint32_t* elts,

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/pir_b200.h"
+#include "behz_host.h"
 #include "host_math.h"
 #include "kernels.cuh"
 
@@ -201,6 +202,18 @@ struct pirb_ctx {
     DevBuf dbT, svT;
     int* err = nullptr;      // mapped host memory: raised by the kernel if its pipeline times out
   } tc;
+  // ciphertext-multiplication mode (PIRParameters.use_ciphertext_multiplication, database.cpp:202-211)
+  struct CtMul {
+    bool on = false;
+    BehzC B;                     // SEAL RNSTool constants of the first data level
+    DevParams PB;                // NTT tables of the auxiliary base Bsk for kernels_ntt.cu (integer engine): m[i] = bsk_i
+    int nbsk = 0;                // |Bsk| = |B| + 1
+    std::vector<DevBuf> tables;
+    // selection entries of the scanned / of the current upper dimension (NTT form, bases q and Bsk), lower results in
+    // both bases, tensor products, scaled products, relinearization scratch, level results
+    DevBuf svq, sq, sb, aq, ab, dq, db, prod, dig, acc, x, low[2];
+    u64 work_bytes = 4ull << 30;  // products of a level are formed for as many queries at a time as fit this budget
+  } ct;
   pirb_ctx() {
     for (DevBuf* b : {&db, &stage, &work, &dig, &acc, &xch, &part, &bufA[0], &bufA[1], &pts, &qbuf, &rbuf, &svbuf, &xptrs,
                       &dbg, &dist.peer_table, &dist.self_table, &dist.stage, &tc.dbT, &tc.svT})
@@ -405,6 +418,9 @@ int run_scan(pirb_ctx* c, const u64* sv_last, u64 sv_qstride, int n_queries, u32
 int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_out, int partial, cudaStream_t st,
                  bool sv_is_ntt = false, u64 sv_item0 = 0, u64 sv_items = ~0ull, u32 compact_rows = 0,
                  const SvtRef* svt = nullptr) {
+  if (c->ct.on)
+    return fail(PIRB_INVALID_ARGUMENT,
+                "context is in ciphertext-multiplication mode: use pirb_answer_ct / pirb_db_multiply_ct");
   if (sv_items == ~0ull) sv_items = c->dim_sum;
   const int d = c->d, k = c->k;
   const u64 ctL = c->ctL;
@@ -513,6 +529,139 @@ int run_multiply(pirb_ctx* c, u64* d_sv, u64 sv_qstride, int n_queries, u64* d_o
     cur ^= 1;
   }
   if (prof) cudaEventRecord(c->ev[5], st);
+  return 0;
+}
+
+// One upper dimension in ciphertext-multiplication mode (database.cpp:196-211, 240-247), for every query of the batch:
+//   out[g] = sum_{i} relinearize( multiply( A[g*dim + i], S[i] ) )
+// A: [Q][n_entries][s1][k][N] lower results, S: [Q] x (s_bstride apart) [dim][2][k][N] selection entries, both in
+// coefficient form; key: relinearization key or nullptr; out: [Q][n_groups][so][k][N], so = 2 with a key, else s1 + 1.
+int ct_level(pirb_ctx* c, const u64* key, const u64* A, u64 a_bstride, int s1, const u64* S, u64 s_bstride, u32 dim,
+             u32 n_entries, int n_queries, u64* out, u64 out_bstride, cudaStream_t st) {
+  pirb_ctx::CtMul& M = c->ct;
+  const DevParams& P = c->P;
+  const BehzC& B = M.B;
+  const int k = c->k, nb = M.nbsk, sp = s1 + 1;
+  const u64 N = c->N;
+  const u64 ctL = c->ctL;
+  // selection entries of this dimension in both bases, NTT form
+  const u64 sq_stride = (u64)dim * ctL, sb_stride = (u64)dim * 2 * nb * N;
+  RC(M.sq.ensure((size_t)n_queries * sq_stride * sizeof(u64)));
+  RC(M.sb.ensure((size_t)n_queries * sb_stride * sizeof(u64)));
+  LAUNCH(c, launch_ntt_fwd(P, S, M.sq.p, (int)(dim * 2 * k), k, 0, n_queries, s_bstride, sq_stride, st));
+  LAUNCH(c, launch_behz_extend(B, S, s_bstride, dim * 2, M.sb.p, sb_stride, n_queries, st));
+  LAUNCH(c, launch_ntt_fwd(M.PB, M.sb.p, M.sb.p, (int)(dim * 2 * nb), nb, 0, n_queries, sb_stride, sb_stride, st));
+  // per-query strides of the product workspaces
+  const u64 aq_s = (u64)n_entries * s1 * k * N, ab_s = (u64)n_entries * s1 * nb * N;
+  const u64 dq_s = (u64)n_entries * sp * k * N, db_s = (u64)n_entries * sp * nb * N;
+  const u64 dig_s = (u64)n_entries * k * (k + 1) * N, acc_s = (u64)n_entries * 2 * (k + 1) * N, x_s = (u64)n_entries * ctL;
+  u64 per_q = aq_s + ab_s + 2 * dq_s + db_s;
+  if (key) per_q += dig_s + acc_s + x_s;
+  const int qc = (int)std::max<u64>(1, std::min<u64>((u64)n_queries, M.work_bytes / (per_q * sizeof(u64))));
+  RC(M.aq.ensure((size_t)qc * aq_s * sizeof(u64)));
+  RC(M.ab.ensure((size_t)qc * ab_s * sizeof(u64)));
+  RC(M.dq.ensure((size_t)qc * dq_s * sizeof(u64)));
+  RC(M.db.ensure((size_t)qc * db_s * sizeof(u64)));
+  RC(M.prod.ensure((size_t)qc * dq_s * sizeof(u64)));
+  if (key) {
+    if (sp != 3) return fail(PIRB_INTERNAL, "not enough relinearization keys");  // SEAL: relinearize_internal throws
+    RC(M.dig.ensure((size_t)qc * dig_s * sizeof(u64)));
+    RC(M.acc.ensure((size_t)qc * acc_s * sizeof(u64)));
+    RC(M.x.ensure((size_t)qc * x_s * sizeof(u64)));
+  }
+  for (int q0 = 0; q0 < n_queries; q0 += qc) {
+    const int nq = std::min(qc, n_queries - q0);
+    const u64* A0 = A + (u64)q0 * a_bstride;
+    // bfv_multiply (1)-(3): both operands to base q u Bsk, NTT form
+    LAUNCH(c, launch_ntt_fwd(P, A0, M.aq.p, (int)(n_entries * s1 * k), k, 0, nq, a_bstride, aq_s, st));
+    LAUNCH(c, launch_behz_extend(B, A0, a_bstride, n_entries * s1, M.ab.p, ab_s, nq, st));
+    LAUNCH(c, launch_ntt_fwd(M.PB, M.ab.p, M.ab.p, (int)(n_entries * s1 * nb), nb, 0, nq, ab_s, ab_s, st));
+    // (4) tensor product, (5) back to coefficient form
+    LAUNCH(c, launch_behz_tensor(B, 0, M.aq.p, aq_s, M.sq.p + (u64)q0 * sq_stride, sq_stride, M.dq.p, dq_s, n_entries, dim, s1,
+                                 nq, st));
+    LAUNCH(c, launch_behz_tensor(B, 1, M.ab.p, ab_s, M.sb.p + (u64)q0 * sb_stride, sb_stride, M.db.p, db_s, n_entries, dim, s1,
+                                 nq, st));
+    LAUNCH(c, launch_ntt_inv(P, M.dq.p, M.dq.p, (int)(n_entries * sp * k), k, 0, 1, 0, nq, dq_s, dq_s, st));
+    LAUNCH(c, launch_ntt_inv(M.PB, M.db.p, M.db.p, (int)(n_entries * sp * nb), nb, 0, 1, 0, nq, db_s, db_s, st));
+    // (6)-(8) scale by t/Q, round, back to base q
+    LAUNCH(c, launch_behz_floor(B, M.dq.p, dq_s, M.db.p, db_s, M.prod.p, dq_s, n_entries * sp, nq, st));
+    u64* dst = out + (u64)q0 * out_bstride;
+    if (key) {  // relinearize_inplace: switch_key_inplace on the third polynomial
+      LAUNCH(c, launch_relin_digits(B, M.prod.p, dq_s, M.dig.p, dig_s, n_entries, nq, st));
+      LAUNCH(c, launch_ntt_fwd(P, M.dig.p, M.dig.p, (int)(n_entries * k * (k + 1)), k + 1, 0, nq, dig_s, dig_s, st));
+      LAUNCH(c, launch_relin_mac(B, M.dig.p, dig_s, key, M.acc.p, acc_s, n_entries, nq, st));
+      LAUNCH(c, launch_ntt_inv(P, M.acc.p, M.acc.p, (int)(n_entries * 2 * (k + 1)), k + 1, 0, 1, 0, nq, acc_s, acc_s, st));
+      LAUNCH(c, launch_relin_finish(B, M.prod.p, dq_s, M.acc.p, acc_s, M.x.p, x_s, n_entries, nq, st));
+      LAUNCH(c, launch_ct_reduce(B, M.x.p, x_s, dst, out_bstride, n_entries, dim, 2, nq, st));
+    } else {
+      LAUNCH(c, launch_ct_reduce(B, M.prod.p, dq_s, dst, out_bstride, n_entries, dim, (u32)sp, nq, st));
+    }
+  }
+  return 0;
+}
+
+// DatabaseMultiplier::multiply with ct_reencoder_ == nullptr (database.cpp:170-258) on the device.
+// d_sv: [n_queries] x (sv_qstride limbs apart) x [dim_sum][2][k][N], coefficient form, NOT modified (database.cpp:188
+// transforms the selection vector only on the re-encoder path).  The plaintexts are held in NTT form as always: the
+// reference keeps them in coefficient form in this mode and multiply_plain transforms both operands per call
+// [SEAL multiply_plain_normal] — the product is the same canonical polynomial.
+// d_out: [n_queries][polys][k][N] coefficient form, polys = 2 with a relinearization key (or d = 1), else d + 1.
+int run_multiply_ct(pirb_ctx* c, const pirb_keys* relin, const u64* d_sv, u64 sv_qstride, int n_queries, u64* d_out,
+                    cudaStream_t st) {
+  const int d = c->d, k = c->k;
+  const u64 ctL = c->ctL, ptL = c->ptL;
+  const DevParams& P = c->P;
+  pirb_ctx::CtMul& M = c->ct;
+  const u64* key = nullptr;
+  if (relin) {
+    key = relin->find(0);
+    if (!key) return fail(PIRB_INVALID_ARGUMENT, "not a relinearization key handle (pirb_relin_keys_load)");
+  }
+  const u32 out_polys = (d == 1 || key) ? 2u : (u32)d + 1;
+  const u64 npt = c->loaded_prefix();
+  if (npt != c->loaded) return fail(PIRB_INVALID_ARGUMENT, "database has unloaded gaps");
+  if (npt == 0) {
+    if (!c->dry) CU(cudaMemsetAsync(d_out, 0, (size_t)n_queries * out_polys * ptL * sizeof(u64), st));
+    return 0;
+  }
+  // ---- last dimension: scan against the database, on an NTT-form COPY of its selection entries ----
+  const u32 dimL = c->dims[d - 1];
+  const u32 n_rows = d == 1 ? 1u : (u32)((npt + dimL - 1) / dimL);
+  const u64 off = c->dim_sum - dimL;
+  const u64 svq_stride = (u64)dimL * ctL;
+  RC(M.svq.ensure((size_t)n_queries * svq_stride * sizeof(u64)));
+  LAUNCH(c, launch_ntt_fwd(P, d_sv + off * ctL, M.svq.p, (int)(dimL * 2 * k), k, 0, n_queries, sv_qstride, svq_stride, st));
+  int n_split;
+  RC(run_scan(c, M.svq.p, svq_stride, n_queries, dimL, n_rows, npt, d >= 2, &n_split, st));
+  if (d == 1) {
+    LAUNCH(c, launch_ntt_inv(P, c->part.p, d_out, 2 * k, k, 0, n_split, (u64)n_rows * ctL, n_queries,
+                             (u64)n_split * n_rows * ctL, ctL, st));
+    return 0;
+  }
+  RC(M.low[0].ensure((size_t)n_queries * n_rows * ctL * sizeof(u64)));
+  LAUNCH(c, launch_ntt_inv(P, c->part.p, M.low[0].p, (int)(n_rows * 2 * k), k, 0, n_split, (u64)n_rows * ctL, n_queries,
+                           (u64)n_split * n_rows * ctL, (u64)n_rows * ctL, st));
+  // ---- upper dimensions: Evaluator::multiply (+ relinearize_inplace) per entry, summed per group ----
+  u32 n_entries = n_rows;
+  int s1 = 2, cur = 0;
+  for (int l = d - 2; l >= 0; --l) {
+    const u32 dim = c->dims[l];
+    const u32 n_groups = (n_entries + dim - 1) / dim;
+    u64 sv_off = 0;
+    for (int e = 0; e < l; ++e) sv_off += c->dims[e];
+    const int so = key ? 2 : s1 + 1;
+    const u64 out_bstride = (u64)n_groups * so * ptL;
+    u64* dst = d_out;
+    if (l != 0) {
+      RC(M.low[cur ^ 1].ensure((size_t)n_queries * out_bstride * sizeof(u64)));
+      dst = M.low[cur ^ 1].p;
+    }
+    RC(ct_level(c, key, M.low[cur].p, (u64)n_entries * s1 * ptL, s1, d_sv + sv_off * ctL, sv_qstride, dim, n_entries,
+                n_queries, dst, out_bstride, st));
+    n_entries = n_groups;
+    s1 = so;
+    cur ^= 1;
+  }
   return 0;
 }
 
@@ -655,7 +804,12 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
       if (prm->coeff_modulus[j] == q) return fail(PIRB_INVALID_ARGUMENT, "coefficient moduli must be distinct");
   }
   const u64 t = prm->plain_modulus;
-  if (t < 2 || t >> 32) return fail(PIRB_INVALID_ARGUMENT, "plain modulus out of range");
+  const bool ct_mode = prm->use_ciphertext_multiplication != 0;
+  // the re-encoder splits residues into chunks of log2(t) bits through 32-bit arithmetic (ct_reencoder.cpp:45); the
+  // ciphertext-multiplication mode has no such limit (the reference tests a 42-bit t, correctness_test.cpp:100)
+  if (t < 2 || (!ct_mode && (t >> 32))) return fail(PIRB_INVALID_ARGUMENT, "plain modulus out of range");
+  if (ct_mode && prm->shard_count != 1)
+    return fail(PIRB_INVALID_ARGUMENT, "ciphertext-multiplication mode runs on one GPU (shard_count must be 1)");
   for (u32 i = 0; i + 1 < prm->n_moduli; ++i)
     if (t >= prm->coeff_modulus[i]) return fail(PIRB_INVALID_ARGUMENT, "plain modulus must be below every data modulus");
   for (u32 i = 0; i < prm->n_dims; ++i)
@@ -690,7 +844,7 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   P.N = N;
   P.t = t;
   P.thr = (t + 1) >> 1;
-  P.ptb = hm::trunc_log2((uint32_t)t);
+  P.ptb = hm::trunc_log2((uint32_t)t);  // pir::log2 takes a uint32_t (utils.h:43): a wider t is truncated first
   if (P.ptb == 0) return fail(PIRB_INVALID_ARGUMENT, "plain modulus too small");
   const u64 Pq = prm->coeff_modulus[c->k];
   P.half_P = Pq >> 1;
@@ -747,7 +901,7 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   }
   // re-encode chunk table (ct_reencoder.cpp:29-71: double log2, ceil)
   u32 e = 0;
-  for (int poly = 0; poly < 2; ++poly)
+  for (int poly = 0; poly < 2 && !ct_mode; ++poly)  // (no re-encoder in ciphertext-multiplication mode, database.cpp:302-305)
     for (int j = 0; j < c->k; ++j) {
       const u32 le = (u32)std::ceil(std::log2((double)prm->coeff_modulus[j]) / P.ptb);
       for (u32 i = 0; i < le; ++i, ++e) {
@@ -792,7 +946,47 @@ int pirb_ctx_create(const pirb_params* prm, pirb_ctx** out) {
   P.wide_max_terms = 1u << std::min(30, 128 - 2 * max_bits);
   if (P.mac_mode == 0) P.mac_max_terms = P.wide_max_terms;
   c->two_er = e;
-  for (int i = 1; i < c->d; ++i) c->reply_cts *= e;
+  for (int i = 1; i < c->d && !ct_mode; ++i) c->reply_cts *= e;  // ciphertext-multiplication mode: always one ciphertext
+
+  if (ct_mode) {
+    // SEAL RNSTool of the first data level + NTT tables of the auxiliary base Bsk (61-bit primes: integer engine)
+    pirb_ctx::CtMul& M = c->ct;
+    std::vector<u64> bsk;
+    std::vector<u64> qv(prm->coeff_modulus, prm->coeff_modulus + c->k);
+    if (c->k > PIRB_MAX_DATA || !hm::build_behz(qv.data(), c->k, Pq, N, logn, t, &M.B, &bsk))
+      return fail(PIRB_INVALID_ARGUMENT, "cannot set up the auxiliary bases for ciphertext multiplication");
+    M.nbsk = (int)bsk.size();
+    if (M.nbsk > PIRB_MAX_MODULI) return fail(PIRB_INVALID_ARGUMENT, "too many auxiliary primes for this parameter set");
+    memset(&M.PB, 0, sizeof(M.PB));
+    M.PB.logn = logn;
+    M.PB.k = M.nbsk;
+    M.PB.N = N;
+    M.PB.ntt_engine = 0;
+    M.PB.lazy_ntt = 0;
+    M.tables.resize(bsk.size());
+    for (size_t i = 0; i < bsk.size(); ++i) {
+      const hm::Tables T = hm::build_tables(bsk[i], logn);
+      RC(M.tables[i].ensure(4ull * N * sizeof(u64)));
+      u64* base = M.tables[i].p;
+      CU(cudaMemcpy(base, T.rp.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(base + N, T.rps.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(base + 2ull * N, T.irp.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(base + 3ull * N, T.irps.data(), N * sizeof(u64), cudaMemcpyHostToDevice));
+      ModC& m = M.PB.m[i];
+      m.q = bsk[i];
+      hm::barrett_ratio(bsk[i], &m.ratio_hi, &m.ratio_lo);
+      m.inv_n = T.inv_n;
+      m.inv_n_s = T.inv_n_s;
+      m.rp = base;
+      m.rps = base + N;
+      m.irp = base + 2ull * N;
+      m.irps = base + 3ull * N;
+      m.qd = (double)bsk[i];
+      m.qinv = 1.0 / (double)bsk[i];
+    }
+    if (const char* e2 = getenv("PIRB_CT_WORK_MB")) M.work_bytes = std::max<u64>(1, (u64)atoll(e2)) << 20;
+    M.on = true;
+  }
 
   // row shard of the first dimension
   const u32 d0 = c->dims[0];
@@ -1131,6 +1325,73 @@ int pirb_answer(pirb_ctx* c, const pirb_keys* keys, const uint64_t* queries, uin
   if (!r_direct) RC(c->rbuf.ensure(std::max<size_t>(rbytes, 256)));
   RC(answer_buffers(c, keys, n_queries, n_ct, 0, st, q_direct ? U(queries) : nullptr, r_direct ? U(replies) : nullptr));
   if (!r_direct) CU(cudaMemcpyAsync(replies, c->rbuf.p, rbytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- ciphertext-multiplication mode (PIRParameters.use_ciphertext_multiplication; database.cpp:202-211) ----
+int pirb_relin_keys_load(pirb_ctx* c, const uint64_t* limbs, pirb_keys** out) {
+  if (!c || !out || !limbs) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  std::unique_ptr<pirb_keys> kz(new pirb_keys());
+  kz->elts.assign(1, 0u);  // not a Galois element: marks the handle as the relinearization key (RelinKeys::get_index(2) == 0)
+  kz->key_limbs = pirb_key_limbs(c);
+  kz->device = c->device;
+  RC(kz->d.ensure(kz->key_limbs * sizeof(u64)));
+  CU(cudaMemcpy(kz->d.p, limbs, kz->key_limbs * sizeof(u64), cudaMemcpyHostToDevice));
+  *out = kz.release();
+  return 0;
+}
+
+uint32_t pirb_reply_polys(const pirb_ctx* c, int with_relin_keys) {
+  if (!c || !c->ct.on) return 2;
+  return (c->d == 1 || with_relin_keys) ? 2u : (uint32_t)c->d + 1;
+}
+
+int pirb_db_multiply_ct(pirb_ctx* c, const uint64_t* sv, uint64_t n_sv, const pirb_keys* relin, uint64_t* out,
+                        uint64_t out_cap_limbs, uint32_t* out_polys) {
+  if (!c || !sv || !out) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (!c->ct.on) return fail(PIRB_INVALID_ARGUMENT, "context was not created with use_ciphertext_multiplication");
+  if (n_sv != c->dim_sum)  // database.cpp:297-300
+    return fail(PIRB_INVALID_ARGUMENT, "Selection vector size does not match dimensions");
+  const u32 polys = pirb_reply_polys(c, relin != nullptr);
+  if (out_cap_limbs < (u64)polys * c->ptL) return fail(PIRB_INVALID_ARGUMENT, "output buffer too small");
+  cudaStream_t st = c->stream;
+  RC(c->svbuf.ensure(n_sv * c->ctL * sizeof(u64)));
+  RC(c->rbuf.ensure((size_t)polys * c->ptL * sizeof(u64)));
+  CU(cudaMemcpyAsync(c->svbuf.p, sv, n_sv * c->ctL * sizeof(u64), cudaMemcpyHostToDevice, st));
+  c->launches = 0;
+  RC(run_multiply_ct(c, relin, c->svbuf.p, n_sv * c->ctL, 1, c->rbuf.p, st));
+  CU(cudaMemcpyAsync(out, c->rbuf.p, (size_t)polys * c->ptL * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (out_polys) *out_polys = c->loaded ? polys : 0;  // empty database: the reference returns no ciphertext at all
+  return 0;
+}
+
+int pirb_answer_ct(pirb_ctx* c, const pirb_keys* keys, const pirb_keys* relin, const uint64_t* queries, uint32_t n_queries,
+                   uint64_t n_ct, uint64_t* replies) {
+  if (!c || !queries || !replies) return fail(PIRB_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (!c->ct.on) return fail(PIRB_INVALID_ARGUMENT, "context was not created with use_ciphertext_multiplication");
+  if (!n_queries) return 0;
+  if (n_ct != c->dim_sum / c->N + 1)  // server.cpp:154-158
+    return fail(PIRB_INVALID_ARGUMENT, "Number of ciphertexts doesn't match number of items for oblivious expansion.");
+  if (c->loaded != c->pt_count) return fail(PIRB_INVALID_ARGUMENT, "database size mismatch");  // server.cpp:37-39
+  cudaStream_t st = c->stream;
+  const u32 polys = pirb_reply_polys(c, relin != nullptr);
+  const size_t qbytes = (size_t)n_queries * n_ct * c->ctL * sizeof(u64);
+  const size_t rbytes = (size_t)n_queries * polys * c->ptL * sizeof(u64);
+  RC(c->qbuf.ensure(qbytes));
+  RC(c->rbuf.ensure(rbytes));
+  CU(cudaMemcpyAsync(c->qbuf.p, queries, qbytes, cudaMemcpyHostToDevice, st));
+  int rc;
+  ExpandPlan* pl = get_plan(c, c->dim_sum, 0, &rc);
+  if (!pl) return rc;
+  c->launches = 0;
+  RC(run_expand(c, keys, pl, c->qbuf.p, (int)n_queries, st));
+  RC(run_multiply_ct(c, relin, c->work.p, 2 * pl->cap * c->ctL, (int)n_queries, c->rbuf.p, st));
+  CU(cudaMemcpyAsync(replies, c->rbuf.p, rbytes, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return 0;
 }

@@ -140,6 +140,30 @@ cudaError_t launch_tc_scan_packed(const DevParams& P, const TcGeom& g, const u8*
                                   u32 rows_total, u32 row0, u32 n_queries, int* err_flag, int sm_count, u64* part,
                                   cudaStream_t st);
 
+// ---- ciphertext-multiplication mode (kernels_ctmul.cu; database.cpp:202-211) ----
+// Evaluator::multiply [SEAL 3.5.6 bfv_multiply, BEHZ] split at its NTTs; n_batch independent problems, *_bstride apart.
+// (1)-(2) base q -> Bsk: in [n_polys][k][N] -> out [n_polys][nB+1][N], coefficient form
+cudaError_t launch_behz_extend(const BehzC& B, const u64* in, u64 in_bstride, u32 n_polys, u64* out, u64 out_bstride,
+                               int n_batch, cudaStream_t st);
+// (4) D[e][s1+1] = A[e][s1] (x) S[e % dim][2] in base q (base = 0) or Bsk (base = 1), NTT form
+cudaError_t launch_behz_tensor(const BehzC& B, int base, const u64* A, u64 a_bstride, const u64* S, u64 s_bstride, u64* D,
+                               u64 d_bstride, u32 n_entries, u32 dim, int s1, int n_batch, cudaStream_t st);
+// (6)-(8) scale by t/Q and round: Dq [n_polys][k][N], Db [n_polys][nB+1][N] -> out [n_polys][k][N], coefficient form
+cudaError_t launch_behz_floor(const BehzC& B, const u64* Dq, u64 dq_bstride, const u64* Db, u64 db_bstride, u64* out,
+                              u64 out_bstride, u32 n_polys, int n_batch, cudaStream_t st);
+// Evaluator::relinearize_inplace of n_entries size-3 products prod [e][3][k][N]:
+// digits [e][J][I][N] (then forward NTT, cycle k+1) -> mac with the key -> acc [e][2][k+1][N] (then inverse NTT)
+// -> finish: X [e][2][k][N]
+cudaError_t launch_relin_digits(const BehzC& B, const u64* prod, u64 p_bstride, u64* dig, u64 dig_bstride, u32 n_entries,
+                                int n_batch, cudaStream_t st);
+cudaError_t launch_relin_mac(const BehzC& B, const u64* dig, u64 dig_bstride, const u64* key, u64* acc, u64 acc_bstride,
+                             u32 n_entries, int n_batch, cudaStream_t st);
+cudaError_t launch_relin_finish(const BehzC& B, const u64* prod, u64 p_bstride, const u64* acc, u64 acc_bstride, u64* X,
+                                u64 x_bstride, u32 n_entries, int n_batch, cudaStream_t st);
+// out [g][polys][k][N] = sum over the entries of group g (dim per group, the last one may be short) of X [e][polys][k][N]
+cudaError_t launch_ct_reduce(const BehzC& B, const u64* X, u64 x_bstride, u64* out, u64 out_bstride, u32 n_entries, u32 dim,
+                             u32 polys, int n_batch, cudaStream_t st);
+
 // StringEncoder packing on the device: raw item bytes -> plaintext coefficients [n_pt][N]
 cudaError_t launch_pack_items(const u8* bytes, u64* coeffs, u32 N, u32 bits, u64 bytes_per_pt, u64 total_bytes,
                               u64 n_pt, cudaStream_t st);

@@ -11,6 +11,8 @@ typedef uint8_t u8;
 #define PIRB_MAX_MODULI 9    // key-level moduli (k data + 1 special); BFVDefault(16384) has 9
 #define PIRB_MAX_REENC 64    // 2 * ExpansionRatio upper bound
 #define PIRB_MAX_DIMS 8
+#define PIRB_MAX_DATA 8      // data-level moduli
+#define PIRB_MAX_BSK 10      // auxiliary BEHZ base Bsk = B u {m_sk}: |B| <= |q| + 1
 
 // Per-modulus constants.  Tables live in device memory.
 struct ModC {
@@ -62,3 +64,37 @@ struct DevParams {
   u8 re_shift[PIRB_MAX_REENC];      //                  -> right shift
 };
 
+
+// ---- ciphertext-multiplication mode (database.cpp:202-211): SEAL 3.5.6 RNSTool constants for the first data level ----
+struct ModLite {
+  u64 q;
+  u64 ratio_hi, ratio_lo;  // floor(2^128 / q)
+};
+// Bases: q = data moduli, B = nB auxiliary 61-bit primes, Bsk = B u {m_sk} (m_sk last), m_tilde = 2^32.
+// Passed by value to the kernels of kernels_ctmul.cu (constant bank).
+struct BehzC {
+  int k, nB;
+  u32 N;
+  int logn;
+  ModLite q[PIRB_MAX_DATA];
+  ModLite bsk[PIRB_MAX_BSK];
+  u64 t_mod_q[PIRB_MAX_DATA], t_mod_bsk[PIRB_MAX_BSK];
+  u64 mtilde_mod_q[PIRB_MAX_DATA];                 // 2^32 mod q_j
+  u64 inv_qhat_mod_q[PIRB_MAX_DATA];               // (Q/q_j)^-1 mod q_j
+  u64 qhat_mod_bsk[PIRB_MAX_BSK][PIRB_MAX_DATA];   // (Q/q_j) mod bsk_i
+  u64 qhat_mod_mtilde[PIRB_MAX_DATA];              // (Q/q_j) mod 2^32
+  u64 neg_inv_q_mod_mtilde;                        // -Q^-1 mod 2^32
+  u64 q_mod_bsk[PIRB_MAX_BSK];                     // Q mod bsk_i
+  u64 inv_mtilde_mod_bsk[PIRB_MAX_BSK];            // 2^-32 mod bsk_i
+  u64 inv_q_mod_bsk[PIRB_MAX_BSK];                 // Q^-1 mod bsk_i
+  u64 inv_bhat_mod_b[PIRB_MAX_BSK];                // (B/b_j)^-1 mod b_j
+  u64 bhat_mod_q[PIRB_MAX_DATA][PIRB_MAX_BSK];     // (B/b_j) mod q_i
+  u64 bhat_mod_msk[PIRB_MAX_BSK];                  // (B/b_j) mod m_sk
+  u64 inv_b_mod_msk;                               // B^-1 mod m_sk
+  u64 b_mod_q[PIRB_MAX_DATA];                      // B mod q_i
+  // relinearization (switch_key_inplace): the special prime and its mod-down constants
+  ModLite P;
+  u64 half_P;
+  u64 half_P_mod_q[PIRB_MAX_DATA], inv_P_mod_q[PIRB_MAX_DATA];
+};
+static_assert(sizeof(BehzC) <= 4000, "BehzC must fit the kernel parameter space");

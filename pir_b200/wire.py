@@ -72,21 +72,32 @@ def data_parms_id(ep: EncryptionParameters) -> np.ndarray:
 
 
 def save_ciphertext(ct: np.ndarray, ep: EncryptionParameters, parms_id: Optional[np.ndarray] = None) -> bytes:
-    """SEALSerialize<Ciphertext> of a data-level ciphertext [2][k][N]."""
+    """SEALSerialize<Ciphertext> of a data-level ciphertext [polys][k][N] (2 polynomials everywhere except replies of
+    the ciphertext-multiplication mode without relinearization keys)."""
     k, n = len(ep.coeff_modulus) - 1, ep.poly_modulus_degree
-    a = np.ascontiguousarray(ct, dtype=np.uint64).reshape(2, k, n)
+    a = np.ascontiguousarray(ct, dtype=np.uint64).reshape(-1, k, n)
     pid = np.ascontiguousarray(parms_id if parms_id is not None else data_parms_id(ep), dtype=np.uint64)
     out, ln = _u8p(), C.c_size_t()
-    if lib().pirw_ct_save(a.ctypes.data_as(_u64p), 2, n, k, pid.ctypes.data_as(_u64p), 0, None, C.byref(out),
+    if lib().pirw_ct_save(a.ctypes.data_as(_u64p), a.shape[0], n, k, pid.ctypes.data_as(_u64p), 0, None, C.byref(out),
                           C.byref(ln)):
         _fail("ciphertext")
     return _take(out, ln)
 
 
-def load_ciphertext(blob: bytes, ep: EncryptionParameters):
-    """SEALDeserialize<Ciphertext>: -> ([2][k][N] limbs, parms_id).  InvalidArgument on malformed input."""
+def load_ciphertext(blob: bytes, ep: EncryptionParameters, max_polys: int = 2):
+    """SEALDeserialize<Ciphertext>: -> ([2][k][N] limbs, parms_id).  InvalidArgument on malformed input.
+    max_polys > 2: accept larger ciphertexts (-> [polys][k][N])."""
     k, n = len(ep.coeff_modulus) - 1, ep.poly_modulus_degree
     m = _mods(ep)
+    if max_polys > 2:
+        out = np.zeros((max_polys, k, n), dtype=np.uint64)
+        pid = np.zeros(4, dtype=np.uint64)
+        ntt, seeded, size = C.c_int(), C.c_int(), C.c_uint32()
+        if lib().pirw_ct_load_any(_buf(blob), C.c_size_t(len(blob)), n, m.ctypes.data_as(_u64p), k,
+                                  out.ctypes.data_as(_u64p), max_polys, C.byref(size), pid.ctypes.data_as(_u64p),
+                                  C.byref(ntt), C.byref(seeded)):
+            _fail("ciphertext")
+        return out[:size.value].copy(), pid
     out = np.zeros((2, k, n), dtype=np.uint64)
     pid = np.zeros(4, dtype=np.uint64)
     ntt, seeded = C.c_int(), C.c_int()
@@ -198,12 +209,19 @@ def parse_request(data: bytes, params: PIRParameters) -> Request:
     try:
         gk = load_galois_keys(msg.keys(2), ep)
         rk = msg.keys(3)
-        if rk:
+        relin = None
+        if rk and params.use_ciphertext_multiplication:
+            # server.cpp:53-58, 185-190: RelinKeys is a KSwitchKeys object whose slot 0 holds the one key
+            rkeys = load_galois_keys(rk, ep)
+            if len(rkeys.elts) != 1:
+                raise PIRStatusError(INVALID_ARGUMENT, "relinearization keys must hold exactly one key")
+            relin = rkeys.data
+        elif rk:
             m = _mods(ep)
             if lib().pirw_kswitch_keys_check(_buf(rk), C.c_size_t(len(rk)), ep.poly_modulus_degree,
                                              m.ctypes.data_as(_u64p), len(m), C.c_uint64(ep.plain_modulus)):
                 _fail("relin keys")
-        req = Request(galois_keys=gk)
+        req = Request(galois_keys=gk, relin_keys=relin)
         req.parms_id = None
         for group in msg.groups():
             cts = []
@@ -255,8 +273,9 @@ def parse_response(data: bytes, params: PIRParameters) -> Response:
     msg = _Msg(2, data)
     try:
         resp = Response()
+        cap = len(params.dimensions) + 1 if params.use_ciphertext_multiplication else 2
         for group in msg.groups():
-            resp.reply.append(np.stack([load_ciphertext(b, ep)[0] for b in group]))
+            resp.reply.append(np.stack([load_ciphertext(b, ep, cap)[0] for b in group]))
         return resp
     finally:
         msg.close()

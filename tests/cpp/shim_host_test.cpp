@@ -31,12 +31,13 @@ static int parameters_tests() {
     CHECK(p.ok() && (*p)->num_pt == 1001 && (*p)->items_per_plaintext == 19 && (*p)->dimensions == (U32{11, 10, 10}),
           "CreateMultiDim");
   }
-  {  // CreateAllParams (:81-99) — CT multiplication is outside this library's path and must be refused, the rest holds
-    auto refused = pir::CreatePIRParameters(77412, 777, 2, pir::GenerateEncryptionParams(8192), true, 12);
-    CHECK(!refused.ok() && refused.status().code() == PIRB_INVALID_ARGUMENT, "use_ciphertext_multiplication refused");
-    auto p = pir::CreatePIRParameters(77412, 777, 2, pir::GenerateEncryptionParams(8192), false, 12);
+  {  // CreateAllParams (:81-99)
+    auto p = pir::CreatePIRParameters(77412, 777, 2, pir::GenerateEncryptionParams(8192), true, 12);
     CHECK(p.ok() && (*p)->num_pt == 5161 && (*p)->bytes_per_item == 777 && (*p)->items_per_plaintext == 15 &&
-              (*p)->dimensions == (U32{72, 72}) && (*p)->bits_per_coeff == 12, "CreateAllParams");
+              (*p)->dimensions == (U32{72, 72}) && (*p)->bits_per_coeff == 12 && (*p)->use_ciphertext_multiplication,
+          "CreateAllParams");
+    auto plain = pir::CreatePIRParameters(77412, 777, 2, pir::GenerateEncryptionParams(8192), false, 12);
+    CHECK(plain.ok() && !(*plain)->use_ciphertext_multiplication, "flag off by default");
     auto too_many_bits = pir::CreatePIRParameters(100, 0, 1, pir::GenerateEncryptionParams(4096), false, 25);
     CHECK(!too_many_bits.ok() && too_many_bits.status().code() == PIRB_INVALID_ARGUMENT, "bits_per_coeff above max");
     auto too_big = pir::CreatePIRParameters(100, 99999, 1);

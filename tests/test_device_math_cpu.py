@@ -12,3 +12,11 @@ def test_device_arithmetic_on_the_host():
     out = subprocess.run([os.path.join(ROOT, "build", "device_math_host_test")], capture_output=True, text=True,
                          timeout=600)
     assert out.returncode == 0 and "DEVICE_MATH_HOST_TEST_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_ciphertext_multiplication_kernels_on_the_host():
+    """tests/cpp/ctmul_host_test.cpp: the ciphertext-multiplication mode's host setup (auxiliary bases, base-conversion
+    constants) and kernel bodies (pirb_behz.cuh), a whole upper dimension emulated launch by launch, against the oracle."""
+    subprocess.check_call(["make", "-C", ROOT, "build/ctmul_host_test"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([os.path.join(ROOT, "build", "ctmul_host_test")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "CTMUL_HOST_TEST_OK" in out.stdout, out.stdout + out.stderr

@@ -16,15 +16,16 @@ pytestmark = pytest.mark.gpu
 N = 4096
 
 
-def _params(dbsize, elem=0, d=1, n=4096, bits=20, bpc=0):
+def _params(dbsize, elem=0, d=1, n=4096, bits=20, bpc=0, ct_mult=False):
     ep = pb.GenerateEncryptionParams(n, bits)
-    return pb.CreatePIRParameters(dbsize, elem, d, ep, False, bpc)
+    return pb.CreatePIRParameters(dbsize, elem, d, ep, ct_mult, bpc)
 
 
 def _harness(p, seed=1):
     ep = p.encryption_parameters
     hp = oc.PIRParameters(p.num_items, p.num_pt, list(p.dimensions), p.bytes_per_item, p.items_per_plaintext,
-                          p.bits_per_coeff, ep.poly_modulus_degree, ep.plain_modulus, list(ep.coeff_modulus))
+                          p.bits_per_coeff, ep.poly_modulus_degree, ep.plain_modulus, list(ep.coeff_modulus),
+                          bool(p.use_ciphertext_multiplication))
     return oc.HarnessClient(hp, seed=seed)
 
 
@@ -790,3 +791,102 @@ def test_full_size_databases_sampled_parity(workload, nq):
     for i in range(1, nq):
         single = sharded.to_host(srv.answer(d_q[i:i + 1]))[0]
         assert np.array_equal(replies[i], single), i
+
+
+# ------------------------------------------------------------------------------------------------ ciphertext-multiplication mode
+def _selection_vector(cl, dims, indices):
+    cts = []
+    for d, dim in enumerate(dims):
+        for i in range(dim):
+            pt = np.zeros(cl.orc.N, dtype=np.uint64)
+            if i == indices[d]:
+                pt[0] = 1
+            cts.append(cl.encrypt(pt))
+    return np.stack(cts)
+
+
+@pytest.mark.parametrize("n,bits,dbsize,d,idx", [(4096, 16, 10, 1, 7), (4096, 16, 16, 2, 11), (4096, 16, 82, 2, 42),
+                                                  (8192, 20, 27, 3, 2), (8192, 20, 117, 3, 17)])
+def test_ct_multiply_mode_db_multiply_matches_oracle(n, bits, dbsize, d, idx):
+    """database_test.cpp:343-388, CTMultiply arm (use_ciphertext_multiplication, relinearization keys given): the single
+    result ciphertext bit-exact against the oracle's Evaluator::multiply + relinearize_inplace restatement, decrypting
+    to the selected item; without keys (server.cpp:185-190) the result keeps one more polynomial per upper dimension."""
+    p = _params(dbsize, 0, d, n, bits, ct_mult=True)
+    cl = _harness(p, seed=11)
+    items = _random_items(p)
+    db = pb.PIRDatabase.Create(items, p)
+    db_ntt = oc.db_to_ntt(cl.orc, oc.encode_string_db(cl.params, items))
+    assert np.array_equal(db.read_ntt(0, p.num_pt), db_ntt)
+    sv = _selection_vector(cl, p.dimensions, oc.calculate_indices(cl.params, idx))
+    before = sv.copy()
+    got = db.multiply(sv, cl.relin)
+    assert np.array_equal(sv, before)  # database.cpp:188: left in coefficient form in this mode
+    want = cl.orc.db_multiply_ct(db_ntt, p.dimensions, sv, cl.relin)
+    assert got.shape == (1, 2, cl.orc.k, n) and np.array_equal(got[0], want)
+    res = cl.process_reply_ct(got)
+    assert ob.string_decode(res, cl.orc.ptb, p.bytes_per_item) == items[idx]
+    # no relinearization keys: d + 1 polynomials (d = 1: the plain two)
+    got_nr = db.multiply(sv)
+    want_nr = cl.orc.db_multiply_ct(db_ntt, p.dimensions, sv, None)
+    assert got_nr.shape == (1, 2 if d == 1 else d + 1, cl.orc.k, n) and np.array_equal(got_nr[0], want_nr)
+    with pytest.raises(pb.PIRStatusError) as e:  # database.cpp:297-300
+        db.multiply(np.ascontiguousarray(sv[:-1]), cl.relin)
+    assert e.value.code == pb.INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("n,bits,elem,bpc,dbsize,d,indices",
+                         [(4096, 24, 0, 0, 10, 1, [0]), (4096, 16, 0, 10, 9, 2, [1, 5]),
+                          (4096, 16, 0, 6, 500, 2, [9, 125]), (8192, 42, 0, 0, 87, 2, [5, 33, 86]),
+                          (4096, 16, 64, 10, 1200, 1, [0, 80, 81, 123, 777, 1199])])
+def test_ct_multiply_mode_end_to_end_matches_oracle(n, bits, elem, bpc, dbsize, d, indices):
+    """correctness_test.cpp:94-105 (use_ciphertext_multiplication == true): client -> PIRServer::ProcessRequest ->
+    client, every reply bit-exact against the oracle, the whole batch of queries in one device call."""
+    p = _params(dbsize, elem, d, n, bits, bpc, ct_mult=True)
+    cl = _harness(p, seed=5)
+    items = _random_items(p)
+    db = pb.PIRDatabase.Create(items, p)
+    server = pb.PIRServer.Create(db, p)
+    db_ntt = oc.db_to_ntt(cl.orc, oc.encode_string_db(cl.params, items))
+    queries = [cl.create_query(i) for i in indices]
+    gk, raw = _gk(cl)
+    resp = server.ProcessRequest(pb.Request(query=queries, galois_keys=gk, relin_keys=cl.relin))
+    assert len(resp.reply) == len(indices)
+    for q, r in zip(queries, resp.reply):
+        want = cl.orc.process_query_ct(db_ntt, p.dimensions, cl.elts, raw, q, cl.relin)
+        assert r.shape == (1, 2, cl.orc.k, n) and np.array_equal(r[0], want)
+    assert cl.process_response_strings(indices, resp.reply) == [items[i] for i in indices]
+    if d == 2 and n == 4096:  # a request without relinearization keys: size-3 replies
+        resp3 = server.ProcessRequest(pb.Request(query=queries[:1], galois_keys=gk))
+        want3 = cl.orc.process_query_ct(db_ntt, p.dimensions, cl.elts, raw, queries[0], None)
+        assert resp3.reply[0].shape == (1, 3, cl.orc.k, n) and np.array_equal(resp3.reply[0][0], want3)
+        assert cl.process_response_strings(indices[:1], resp3.reply) == [items[indices[0]]]
+
+
+def test_ct_multiply_mode_process_request_2dim_and_wire():
+    """server_test.cpp:209-260 with GetParam() == true (reply is one ciphertext of size 2: "Were relin keys used?"),
+    then the same request in its serialized form (relin_keys field used, server.cpp:53-58)."""
+    from pir_b200 import wire
+    p = _params(82, 7680, 2, ct_mult=True)
+    cl = _harness(p, seed=89)
+    rng = np.random.default_rng(42)
+    vals = [int(v) for v in rng.integers(0, 1 << 48, 82, dtype=np.int64)]
+    db = pb.PIRDatabase.Create(vals, p)
+    server = pb.PIRServer.Create(db, p)
+    m_inv = pow(ob.next_power_two(19), -1, p.encryption_parameters.plain_modulus)
+    pt = np.zeros(N, dtype=np.uint64); pt[4] = m_inv; pt[16] = m_inv
+    q = cl.encrypt(pt)[None]
+    gk, raw = _gk(cl)
+    resp = server.ProcessRequest(pb.Request(query=[q], galois_keys=gk, relin_keys=cl.relin))
+    assert resp.reply[0].shape == (1, 2, cl.orc.k, N)
+    assert oc.integer_decode(cl.process_reply_ct(resp.reply[0]), p.encryption_parameters.plain_modulus) == vals[42]
+    relin_blob = wire.save_galois_keys(pb.GaloisKeys([1], cl.relin), p.encryption_parameters)  # slot 0 of a KSwitchKeys
+    blob = wire.serialize_request([q], gk, p, relin_keys=relin_blob)
+    back = wire.parse_response(server.ProcessRequestBytes(blob), p)
+    assert np.array_equal(back.reply[0], resp.reply[0])
+    # the entry points of the re-encoder path refuse a context of this mode
+    import ctypes as C
+    from pir_b200 import _lib
+    out = np.zeros((1, 2, cl.orc.k, N), dtype=np.uint64)
+    rc = _lib.lib().pirb_answer(server.ctx.h, server._keys(gk).h, C.c_void_p(q.ctypes.data), 1, 1,
+                                C.c_void_p(out.ctypes.data))
+    assert rc == pb.INVALID_ARGUMENT and "ciphertext-multiplication" in _lib.last_error()
