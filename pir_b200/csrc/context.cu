@@ -557,7 +557,8 @@ int ct_level(pirb_ctx* c, const u64* key, const u64* A, u64 a_bstride, int s1, c
   const u64 dig_s = (u64)n_entries * k * (k + 1) * N, acc_s = (u64)n_entries * 2 * (k + 1) * N, x_s = (u64)n_entries * ctL;
   u64 per_q = aq_s + ab_s + 2 * dq_s + db_s;
   if (key) per_q += dig_s + acc_s + x_s;
-  const int qc = (int)std::max<u64>(1, std::min<u64>((u64)n_queries, M.work_bytes / (per_q * sizeof(u64))));
+  int qc = (int)std::max<u64>(1, std::min<u64>((u64)n_queries, M.work_bytes / (per_q * sizeof(u64))));
+  qc = (n_queries + (n_queries + qc - 1) / qc - 1) / ((n_queries + qc - 1) / qc);  // equal chunks
   RC(M.aq.ensure((size_t)qc * aq_s * sizeof(u64)));
   RC(M.ab.ensure((size_t)qc * ab_s * sizeof(u64)));
   RC(M.dq.ensure((size_t)qc * dq_s * sizeof(u64)));

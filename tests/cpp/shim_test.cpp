@@ -228,6 +228,144 @@ static int run_case(size_t dbsize, size_t elem_size, size_t d, size_t desired_in
   return 0;
 }
 
+// correctness_test.cpp:94-105 / server_test.cpp:209-260 with use_ciphertext_multiplication: relinearization keys in the
+// request, ONE reply ciphertext of size 2 per query (client.cpp:196-217), bit-exact against the oracle's restatement of
+// Evaluator::multiply + relinearize_inplace; the serialized form of the same request; a request without the keys.
+static int run_ct_case(size_t dbsize, size_t d, size_t desired_index, int plain_bits, size_t bits_per_coeff) {
+  auto ep = pir::GenerateEncryptionParams(4096, plain_bits);
+  auto params_or = pir::CreatePIRParameters(dbsize, 0, d, ep, /*use_ciphertext_multiplication=*/true, bits_per_coeff);
+  CHECK(params_or.ok() && (*params_or)->use_ciphertext_multiplication, "CreatePIRParameters (CT mode)");
+  auto params = *params_or;
+  std::mt19937_64 rng(43);
+  std::vector<std::string> db(dbsize, std::string(params->bytes_per_item, 0));
+  for (auto& s : db)
+    for (auto& ch : s) ch = (char)(rng() & 0xff);
+  auto db_or = pir::PIRDatabase::Create(db, params);
+  CHECK(db_or.ok(), db_or.status().message().c_str());
+  auto server_or = pir::PIRServer::Create(*db_or, params);
+  CHECK(server_or.ok(), server_or.status().message().c_str());
+  auto& server = *server_or;
+  {  // this mode runs on one GPU
+    auto two = pir::PIRDatabase::Create(params, std::vector<int>{0, 0});
+    CHECK(!two.ok() && two.status().code() == PIRB_INVALID_ARGUMENT, "sharded CT-mode database must be refused");
+  }
+  orc::Context octx(ep.poly_modulus_degree, ep.coeff_modulus, ep.plain_modulus);
+  orc::Crypto crypto(octx);
+  orc::RnsTool rns(octx);
+  orc::Rng r1(9);
+  orc::SecretKey sk = orc::gen_secret_key(octx, r1);
+  orc::PublicKey pk = orc::gen_public_key(octx, sk, r1);
+  const size_t N = octx.N, key_limbs = octx.k * 2 * (octx.k + 1) * N;
+  pir::GaloisKeys gk;
+  gk.elts = pir::generate_galois_elts(N);
+  gk.limbs.resize(gk.elts.size() * key_limbs);
+  for (size_t i = 0; i < gk.elts.size(); ++i) orc::gen_galois_key(octx, sk, gk.elts[i], r1, gk.limbs.data() + i * key_limbs);
+  pir::RelinKeys relin;
+  relin.limbs.resize(key_limbs);
+  orc::gen_relin_key(octx, sk, r1, relin.limbs.data());
+
+  auto indices = (*db_or)->calculate_indices((uint32_t)desired_index);
+  size_t dim_sum = 0;
+  for (auto v : params->dimensions) dim_sum += v;
+  const uint64_t m_inv = orc::invmod(pirb_next_power_two(dim_sum) % ep.plain_modulus, orc::Modulus(ep.plain_modulus));
+  std::vector<uint64_t> pt(N, 0);
+  size_t offset = 0;
+  for (size_t i = 0; i < indices.size(); ++i) {
+    pt[offset + indices[i]] = m_inv;
+    offset += params->dimensions[i];
+  }
+  pir::Request req;
+  req.galois_keys = gk;
+  req.relin_keys = relin;
+  req.query.assign(2, std::vector<pir::Ciphertext>(1));  // the same index twice, two fresh encryptions
+  for (auto& q : req.query) {
+    q[0].limbs.resize(octx.ct_limbs());
+    crypto.encrypt(pk, pt.data(), N, r1, q[0].data());
+  }
+  auto resp_or = server->ProcessRequest(req);
+  CHECK(resp_or.ok(), resp_or.status().message().c_str());
+  CHECK(resp_or->reply.size() == 2, "one reply per query");
+
+  // the oracle on the same inputs
+  std::vector<uint64_t> coeffs, db_ntt(params->num_pt * octx.pt_limbs());
+  pir::StringEncoder enc(ep);
+  if (bits_per_coeff) enc.set_bits_per_coeff(bits_per_coeff);
+  for (size_t i = 0; i < params->num_pt; ++i) {
+    CHECK(enc.encode(db[i], coeffs).ok(), "encode");
+    orc::plain_to_ntt(octx, coeffs.data(), coeffs.size(), db_ntt.data() + i * octx.pt_limbs());
+  }
+  orc::GaloisKeys ogk;
+  ogk.elts = gk.elts;
+  ogk.data.assign(gk.limbs.begin(), gk.limbs.end());
+  for (size_t qi = 0; qi < 2; ++qi) {
+    std::vector<uint64_t> want;
+    size_t polys = 0;
+    CHECK(orc::process_query_ct(octx, rns, db_ntt.data(), params->num_pt, params->dimensions.data(), d, ogk,
+                                relin.limbs.data(), req.query[qi][0].data(), 1, want, &polys) == 0, "oracle");
+    const auto& reply = resp_or->reply[qi];
+    CHECK(reply.size() == 1 && polys == 2 && reply[0].limbs == want, "CT-mode reply differs from the oracle");
+    std::vector<uint64_t> dec(N);
+    crypto.decrypt(sk, reply[0].data(), dec.data());
+    auto got = enc.decode(dec, params->bytes_per_item, (*db_or)->calculate_item_offset((uint32_t)desired_index));
+    CHECK(got.ok() && *got == db[desired_index], "retrieved element differs (CT mode)");
+  }
+  // the serialized form: relin_keys travel as a KSwitchKeys object with one slot (serialization.cpp:66-72)
+  {
+    pir::wire::RequestMsg m;
+    for (auto& q : req.query) {
+      m.query.emplace_back();
+      m.query.back().ct.push_back(pir::SerializeCiphertext(ep, q[0]));
+    }
+    m.galois_keys = pir::SerializeGaloisKeys(ep, gk);
+    pir::GaloisKeys as_slot0;
+    as_slot0.elts = {pir::wire::galois_elt_of_index(0)};
+    as_slot0.limbs = relin.limbs;
+    const auto sp = pir::ToSealParams(ep);
+    pir::wire::KSwitchKeysData R;
+    R.parms_id = pir::wire::key_parms_id(sp);
+    R.keys.resize(1);
+    R.keys[0].resize(octx.k);
+    const size_t per_digit = 2 * (octx.k + 1) * N;
+    for (size_t j = 0; j < octx.k; ++j) {
+      auto& c = R.keys[0][j];
+      c.parms_id = R.parms_id;
+      c.is_ntt_form = true;
+      c.size = 2;
+      c.poly_modulus_degree = N;
+      c.coeff_modulus_size = octx.k + 1;
+      c.limbs.assign(relin.limbs.begin() + j * per_digit, relin.limbs.begin() + (j + 1) * per_digit);
+    }
+    m.relin_keys = pir::wire::SaveKSwitchKeys(R);
+    auto wire_resp = server->ProcessRequest(pir::wire::Serialize(m));
+    CHECK(wire_resp.ok(), wire_resp.status().message().c_str());
+    pir::wire::ResponseMsg back;
+    CHECK(pir::wire::Parse(*wire_resp, &back) && back.reply.size() == 2 && back.reply[0].ct.size() == 1, "wire response");
+    for (size_t qi = 0; qi < 2; ++qi) {
+      auto ct = pir::DeserializeCiphertext(ep, back.reply[qi].ct[0]);
+      CHECK(ct.ok() && ct->limbs == resp_or->reply[qi][0].limbs, "wire reply differs from the limb-level reply");
+    }
+  }
+  if (d >= 2) {  // server.cpp:185-190 without keys: the reply keeps d + 1 polynomials
+    pir::Request no_relin = req;
+    no_relin.relin_keys.reset();
+    no_relin.query.resize(1);
+    auto r3 = server->ProcessRequest(no_relin);
+    CHECK(r3.ok(), r3.status().message().c_str());
+    std::vector<uint64_t> want;
+    size_t polys = 0;
+    CHECK(orc::process_query_ct(octx, rns, db_ntt.data(), params->num_pt, params->dimensions.data(), d, ogk, nullptr,
+                                req.query[0][0].data(), 1, want, &polys) == 0, "oracle (no relin)");
+    CHECK(polys == d + 1 && r3->reply[0][0].limbs == want, "size-(d+1) reply differs from the oracle");
+    std::vector<uint64_t> dec(N);
+    orc::decrypt_any(crypto, sk, want.data(), polys, dec.data());
+    auto got = enc.decode(dec, params->bytes_per_item, (*db_or)->calculate_item_offset((uint32_t)desired_index));
+    CHECK(got.ok() && *got == db[desired_index], "retrieved element differs (CT mode, no relinearization)");
+  }
+  std::printf("ok: CT-multiplication mode, %zu items, d=%zu, index %zu: replies bit-exact vs oracle, element recovered\n", dbsize, d,
+              desired_index);
+  return 0;
+}
+
 int main() {
   // error behaviour of the factories (server.cpp:37-39)
   {
@@ -242,6 +380,9 @@ int main() {
   if (run_case(1200, 64, 1, 777)) return 1;    // correctness_test.cpp:110 shape
   if (run_case(82, 0, 2, 42, 2)) return 1;     // the 2-dimensional shape, rows sharded over two contexts
   if (run_case(300, 0, 2, 123, 3)) return 1;   // dims [18,17] over three contexts
+  // the reference's own CT-multiplication shapes: larger ones run out of noise budget at these parameters
+  if (run_ct_case(10, 1, 7, 24, 0)) return 1;   // correctness_test.cpp:94 (d = 1)
+  if (run_ct_case(9, 2, 5, 16, 10)) return 1;   // correctness_test.cpp:95 (d = 2, 16-bit t, 10 bits per coefficient)
   std::printf("SHIM_TEST_OK\n");
   return 0;
 }

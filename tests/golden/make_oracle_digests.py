@@ -56,6 +56,10 @@ class OracleBackend:
     def answer(self, query):
         return self.orc.process_query(self.db, self.p.dimensions, self.elts, self.keys, query)
 
+    def answer_ct(self, query, relin):
+        """the same query in ciphertext-multiplication mode (database.cpp:202-211): ONE ciphertext [polys][k][N]"""
+        return self.orc.process_query_ct(self.db, self.p.dimensions, self.elts, self.keys, query, relin)
+
 
 def case_inputs(name, items, size, d, n, bits):
     """Pure integer inputs: SHAKE-derived ring elements (no noise sampling, no floating point)."""
@@ -71,17 +75,22 @@ def case_inputs(name, items, size, d, n, bits):
 
 
 def run_case(name, items, size, d, n, bits, index, make_backend=None):
-    """Digests of one case.  make_backend(p, db, elts, keys_flat) -> object with substitute / shift / expand / answer;
-    default: the oracle.  The GPU parity suite passes the CUDA path and must reproduce the same digests."""
+    """Digests of one case.  make_backend(p, db, elts, keys_flat) -> object with substitute / shift / expand / answer /
+    answer_ct; default: the oracle.  The GPU parity suite passes the CUDA path and must reproduce the same digests."""
     p, orc, elts, keys, query, db = case_inputs(name, items, size, d, n, bits)
     flat = keys.reshape(-1)
     be = make_backend(p, db, elts, flat) if make_backend else OracleBackend(orc, p, db, elts, flat)
     reply = be.answer(query)
+    relin = limbs(name + "/relin", (orc.k, 2), [int(q) for q in orc.moduli], n).reshape(-1)   # [k][2][k+1][N]
+    ct_relin, ct_plain = be.answer_ct(query, relin), be.answer_ct(query, None)
     return {"inputs": digest(np.concatenate([flat, query.reshape(-1), db.reshape(-1)])),
             "substitute": digest(be.substitute(query[0], elts[0])),
             "multiply_inverse_power_of_x": digest(be.shift(query[0], 5 + index)),
             "selection_vector": digest(be.expand(query, p.dim_sum)),
-            "reply": digest(reply), "reply_cts": int(reply.shape[0])}
+            "reply": digest(reply), "reply_cts": int(reply.shape[0]),
+            # ciphertext-multiplication mode on the same inputs, with and without a relinearization key
+            "ct_mult_reply_relin": digest(ct_relin), "ct_mult_reply": digest(ct_plain),
+            "ct_mult_polys": [int(ct_relin.shape[0]), int(ct_plain.shape[0])]}
 
 
 def main():

@@ -505,6 +505,16 @@ class _CudaBackend:
         self.db.load_ntt(db_limbs)
         self.server = pb.PIRServer.Create(self.db, self.p)
         self.gk = pb.GaloisKeys(elts, keys_flat)
+        self.db_limbs, self.ct_server = db_limbs, None
+
+    def answer_ct(self, query, relin):
+        if self.ct_server is None:  # the same database behind a context of the ciphertext-multiplication mode
+            import dataclasses
+            pc = dataclasses.replace(self.p, use_ciphertext_multiplication=True)
+            dbc = pb.PIRDatabase.Create(pc)
+            dbc.load_ntt(self.db_limbs)
+            self.ct_server = pb.PIRServer.Create(dbc, pc)
+        return self.ct_server.ProcessRequest(pb.Request([query], self.gk, relin_keys=relin)).reply[0][0]
 
     def substitute(self, ct, power):
         got = ct.copy()
@@ -523,7 +533,8 @@ class _CudaBackend:
 
 def test_cuda_path_reproduces_the_committed_golden_digests():
     """tests/golden/oracle_digests.json freezes the oracle's substitution / shift / expansion / reply for SHAKE-derived
-    inputs; the CUDA path must produce byte-identical objects (same SHA-256) for N=4096 d=1/d=2, t 24-bit and N=8192."""
+    inputs; the CUDA path must produce byte-identical objects (same SHA-256) for N=4096 d=1/d=2, t 24-bit and N=8192 —
+    including the replies of the ciphertext-multiplication mode with and without a relinearization key."""
     mod, want = _load_digest_module()
     for name, *args in mod.CASES:
         got = mod.run_case(name, *args, make_backend=_CudaBackend)
