@@ -191,8 +191,15 @@ static int run_level(const orc::Context& c, const orc::RnsTool& R, const BehzC& 
   return 0;
 }
 
-static int run_params(uint32_t N, int plain_bits, std::mt19937_64& rng, bool full) {
-  const std::vector<orc::u64> mods = orc::bfv_default_coeff_modulus(N);
+// custom_bits != 0: three primes of that many bits (two data moduli + the special prime) instead of BFVDefault
+static int run_params(uint32_t N, int plain_bits, std::mt19937_64& rng, bool full, int custom_bits = 0) {
+  std::vector<orc::u64> mods;
+  if (custom_bits) {
+    for (orc::u64 v = ((orc::u64)1 << custom_bits) - 2 * N + 1; mods.size() < 3; v -= 2 * N)
+      if (orc::is_prime_u64(v)) mods.push_back(v);
+  } else {
+    mods = orc::bfv_default_coeff_modulus(N);
+  }
   const u64 t = orc::plain_modulus_batching(N, plain_bits);
   orc::Context c(N, mods, t);
   orc::RnsTool R(c);
@@ -237,6 +244,7 @@ int main() {
   std::mt19937_64 rng(2024);
   if (run_params(4096, 16, rng, true)) return 1;
   if (run_params(8192, 20, rng, false)) return 1;
+  if (run_params(4096, 20, rng, false, 60)) return 1;  // 60-bit coefficient moduli next to the 61-bit auxiliary primes
   std::printf("CTMUL_HOST_TEST_OK\n");
   return 0;
 }

@@ -619,6 +619,38 @@ def test_custom_moduli_exercise_every_engine(n, bits, label):
     assert got.shape == want.shape and np.array_equal(got, want), label
 
 
+@pytest.mark.parametrize("n,bits", [(4096, 60), (4096, 47), (16384, 44)])
+def test_ct_multiply_mode_with_custom_moduli(n, bits):
+    """The ciphertext-multiplication mode next to the other arithmetic engines (integer NTTs for the data moduli too,
+    N = 16384 with three data moduli): expansion + multiply + relinearization on random ring elements, limb for limb."""
+    k = 2 if n != 16384 else 3
+    mods = _find_ntt_primes(bits, n, k + 1)
+    ep = pb.EncryptionParameters(n, ob.plain_modulus_batching(n, 20), mods)
+    p = pb.CreatePIRParameters(11, 0, 2, ep, True)
+    orc = ob.Oracle(n, mods, ep.plain_modulus)
+    rng = np.random.default_rng(bits + 1)
+    coeffs = rng.integers(0, ep.plain_modulus, (p.num_pt, n), dtype=np.uint64)
+    db = pb.PIRDatabase.Create(p)
+    db.load_coeff(coeffs)
+    want_db = np.stack([orc.plain_to_ntt(c) for c in coeffs])
+    server = pb.PIRServer.Create(db, p)
+    elts = pb.generate_galois_elts(n)[:pb.ceil_log2(sum(p.dimensions))]
+
+    def key_limbs(count):
+        return np.ascontiguousarray(np.stack([np.stack([np.stack([np.stack(
+            [rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(k + 1)]) for _ in range(2)]) for _ in range(k)])
+            for _ in range(count)]))
+    keys, relin = key_limbs(len(elts)), key_limbs(1).reshape(-1)
+    gk = pb.GaloisKeys(elts, keys.reshape(-1))
+    qs = [np.stack([rng.integers(0, mods[j], n, dtype=np.uint64) for _ in range(2) for j in range(k)]).reshape(1, 2, k, n)
+          for _ in range(2)]
+    for rk in (relin, None):
+        resp = server.ProcessRequest(pb.Request(qs, gk, relin_keys=rk))
+        for q, r in zip(qs, resp.reply):
+            want = orc.process_query_ct(want_db, p.dimensions, elts, keys.reshape(-1), q, rk)
+            assert r.shape[1:] == want.shape and np.array_equal(r[0], want), (n, bits, rk is None)
+
+
 def test_multiply_with_unused_selection_entries_and_empty_database():
     """database.cpp:183: the scan stops when the database runs out.  dims given by the caller need not be tight:
     [4,4] over 5 plaintexts leaves rows 2,3 empty and row 1 short; only the touched selection entries become NTT form."""
