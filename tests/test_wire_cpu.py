@@ -606,3 +606,50 @@ def test_process_request_bytes_composition_with_the_oracle_as_engine():
     assert len(resp.reply) == 2
     got = cl.process_response_strings(idxs, resp.reply)
     assert got == [items[i] for i in idxs]
+
+
+def test_process_request_bytes_in_ciphertext_multiplication_mode():
+    """The same composition with use_ciphertext_multiplication: the request's relin_keys field (a KSwitchKeys object
+    with one slot, serialization.cpp:66-72) is deserialized into raw limbs and USED (server.cpp:53-58, 185-190); every
+    reply is ONE ciphertext — 2 polynomials with keys, 3 without (d = 2) — and survives the wire round trip.  The
+    oracle plays ProcessRequest; the GPU suite covers the real one."""
+    import pir_b200 as pbm
+    from oracle import client as oc
+    from pir_b200 import wire
+    ep = pbm.GenerateEncryptionParams(4096, 16)
+    p = pbm.CreatePIRParameters(9, 0, 2, ep, True, 10)      # correctness_test.cpp:95
+    assert p.use_ciphertext_multiplication
+    hp = oc.PIRParameters(p.num_items, p.num_pt, list(p.dimensions), p.bytes_per_item, p.items_per_plaintext,
+                          p.bits_per_coeff, ep.poly_modulus_degree, ep.plain_modulus, list(ep.coeff_modulus), True)
+    cl = oc.HarnessClient(hp, seed=6)
+    rng = np.random.default_rng(10)
+    items = [rng.integers(0, 256, p.bytes_per_item, dtype=np.uint8).tobytes() for _ in range(p.num_items)]
+    db_ntt = oc.db_to_ntt(cl.orc, oc.encode_string_db(hp, items))
+    seen = []
+
+    class OracleServer:
+        params = p
+
+        def ProcessRequest(self, request):
+            gk = request.galois_keys
+            seen.append(request.relin_keys)
+            return pbm.Response([cl.orc.process_query_ct(db_ntt, p.dimensions, gk.elts, gk.data, q,
+                                                         request.relin_keys)[None] for q in request.query])
+
+    idxs = [1, 5]
+    queries = [cl.create_query(i) for i in idxs]
+    gk = pbm.GaloisKeys(cl.elts, cl.galois)
+    relin_blob = wire.save_galois_keys(pbm.GaloisKeys([1], cl.relin), ep)   # Galois element 1 <-> slot 0
+    for blob, polys in ((wire.serialize_request(queries, gk, p, relin_keys=relin_blob), 2),
+                        (wire.serialize_request(queries, gk, p), 3)):
+        resp = wire.parse_response(pbm.PIRServer.ProcessRequestBytes(OracleServer(), blob), p)
+        assert [r.shape for r in resp.reply] == [(1, polys, cl.orc.k, 4096)] * 2
+        assert cl.process_response_strings(idxs, resp.reply) == [items[i] for i in idxs]
+    assert np.array_equal(seen[0], cl.relin) and seen[1] is None
+    # outside this mode the field is only checked for well-formedness and dropped
+    p_plain = pbm.CreatePIRParameters(9, 0, 2, ep, False, 10)
+    req = wire.parse_request(wire.serialize_request(queries, gk, p_plain, relin_keys=relin_blob), p_plain)
+    assert req.relin_keys is None
+    with pytest.raises(pbm.PIRStatusError) as e:
+        wire.parse_request(wire.serialize_request(queries, gk, p, relin_keys=relin_blob[:-9]), p)
+    assert e.value.code == pbm.INVALID_ARGUMENT
