@@ -20,32 +20,46 @@ inline unsigned ct_blocks(u64 total) { return (unsigned)((total + CT_NT - 1) / C
 // The kernel bodies (index arithmetic + the per-coefficient functions) live in pirb_behz.cuh as k_*_body(B, idx, batch, ...)
 // so that the host test can run them thread by thread; a kernel is its body at idx = global thread index, batch = blockIdx.y.
 __global__ void __launch_bounds__(CT_NT)
-k_behz_extend(const __grid_constant__ BehzC B, const u64* __restrict__ in, u64 in_bstride, u32 n_polys, u64* __restrict__ out, u64 out_bstride) {
+k_behz_extend(const __grid_constant__ BehzC B, const u64* __restrict__ in, u64 in_bstride, u32 n_polys,
+              u64* __restrict__ out, u64 out_bstride) {
   k_behz_extend_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, in, in_bstride, n_polys, out, out_bstride);
 }
 __global__ void __launch_bounds__(CT_NT)
-k_behz_tensor(const __grid_constant__ BehzC B, int base, const u64* __restrict__ A, u64 a_bstride, const u64* __restrict__ S, u64 s_bstride, u64* __restrict__ D, u64 d_bstride, u32 n_entries, u32 dim, int s1) {
-  k_behz_tensor_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, base, A, a_bstride, S, s_bstride, D, d_bstride, n_entries, dim, s1);
+k_behz_tensor(const __grid_constant__ BehzC B, int base, const u64* __restrict__ A, u64 a_bstride,
+              const u64* __restrict__ S, u64 s_bstride, u64* __restrict__ D, u64 d_bstride, u32 n_entries, u32 dim,
+              int s1) {
+  k_behz_tensor_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, base, A, a_bstride, S, s_bstride, D,
+                     d_bstride, n_entries, dim, s1);
 }
 __global__ void __launch_bounds__(CT_NT)
-k_behz_floor(const __grid_constant__ BehzC B, const u64* __restrict__ Dq, u64 dq_bstride, const u64* __restrict__ Db, u64 db_bstride, u64* __restrict__ out, u64 out_bstride, u32 n_polys) {
-  k_behz_floor_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, Dq, dq_bstride, Db, db_bstride, out, out_bstride, n_polys);
+k_behz_floor(const __grid_constant__ BehzC B, const u64* __restrict__ Dq, u64 dq_bstride, const u64* __restrict__ Db,
+             u64 db_bstride, u64* __restrict__ out, u64 out_bstride, u32 n_polys) {
+  k_behz_floor_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, Dq, dq_bstride, Db, db_bstride, out,
+                    out_bstride, n_polys);
 }
 __global__ void __launch_bounds__(CT_NT)
-k_relin_digits(const __grid_constant__ BehzC B, const u64* __restrict__ prod, u64 p_bstride, u64* __restrict__ dig, u64 dig_bstride, u32 n_entries) {
-  k_relin_digits_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, prod, p_bstride, dig, dig_bstride, n_entries);
+k_relin_digits(const __grid_constant__ BehzC B, const u64* __restrict__ prod, u64 p_bstride, u64* __restrict__ dig,
+               u64 dig_bstride, u32 n_entries) {
+  k_relin_digits_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, prod, p_bstride, dig, dig_bstride,
+                      n_entries);
 }
 __global__ void __launch_bounds__(CT_NT)
-k_relin_mac(const __grid_constant__ BehzC B, const u64* __restrict__ dig, u64 dig_bstride, const u64* __restrict__ key, u64* __restrict__ acc, u64 acc_bstride, u32 n_entries) {
-  k_relin_mac_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, dig, dig_bstride, key, acc, acc_bstride, n_entries);
+k_relin_mac(const __grid_constant__ BehzC B, const u64* __restrict__ dig, u64 dig_bstride,
+            const u64* __restrict__ key, u64* __restrict__ acc, u64 acc_bstride, u32 n_entries) {
+  k_relin_mac_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, dig, dig_bstride, key, acc, acc_bstride,
+                   n_entries);
 }
 __global__ void __launch_bounds__(CT_NT)
-k_relin_finish(const __grid_constant__ BehzC B, const u64* __restrict__ prod, u64 p_bstride, const u64* __restrict__ acc, u64 acc_bstride, u64* __restrict__ X, u64 x_bstride, u32 n_entries) {
-  k_relin_finish_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, prod, p_bstride, acc, acc_bstride, X, x_bstride, n_entries);
+k_relin_finish(const __grid_constant__ BehzC B, const u64* __restrict__ prod, u64 p_bstride,
+               const u64* __restrict__ acc, u64 acc_bstride, u64* __restrict__ X, u64 x_bstride, u32 n_entries) {
+  k_relin_finish_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, prod, p_bstride, acc, acc_bstride, X,
+                      x_bstride, n_entries);
 }
 __global__ void __launch_bounds__(CT_NT)
-k_ct_reduce(const __grid_constant__ BehzC B, const u64* __restrict__ X, u64 x_bstride, u64* __restrict__ out, u64 out_bstride, u32 n_entries, u32 dim, u32 polys) {
-  k_ct_reduce_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, X, x_bstride, out, out_bstride, n_entries, dim, polys);
+k_ct_reduce(const __grid_constant__ BehzC B, const u64* __restrict__ X, u64 x_bstride, u64* __restrict__ out,
+            u64 out_bstride, u32 n_entries, u32 dim, u32 polys) {
+  k_ct_reduce_body(B, (u64)blockIdx.x * CT_NT + threadIdx.x, blockIdx.y, X, x_bstride, out, out_bstride, n_entries,
+                   dim, polys);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -136,8 +136,8 @@ __device__ __forceinline__ u64 relin_moddown_coeff(u64 acc_j, u64 last, u64 P, u
 // Kernel bodies of kernels_ctmul.cu: one call = one thread (idx = global thread index along x, y_ = batch index).
 // ------------------------------------------------------------------------------------------
 // steps (1)-(2): in [p][k][N] base q, coefficient form -> out [p][nB+1][N] base Bsk, coefficient form
-__device__ __forceinline__ void k_behz_extend_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ in, u64 in_bstride, u32 n_polys,
-              u64* __restrict__ out, u64 out_bstride) {
+__device__ __forceinline__ void k_behz_extend_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ in,
+    u64 in_bstride, u32 n_polys, u64* __restrict__ out, u64 out_bstride) {
   const u32 N = B.N;
   if (idx >= (u64)n_polys * N) return;
   const u32 n = (u32)idx & (N - 1);
@@ -152,8 +152,9 @@ __device__ __forceinline__ void k_behz_extend_body(const BehzC& B, u64 idx, u64 
 
 // step (4) in one base (base = 0: q, 1: Bsk), NTT form:
 //   A [e][s1][nm][N], S [i][2][nm][N], D [e][s1+1][nm][N];  entry e multiplies selection entry e % dim
-__device__ __forceinline__ void k_behz_tensor_body(const BehzC& B, u64 idx, u64 y_, int base, const u64* __restrict__ A, u64 a_bstride,
-              const u64* __restrict__ S, u64 s_bstride, u64* __restrict__ D, u64 d_bstride, u32 n_entries, u32 dim, int s1) {
+__device__ __forceinline__ void k_behz_tensor_body(const BehzC& B, u64 idx, u64 y_, int base,
+    const u64* __restrict__ A, u64 a_bstride, const u64* __restrict__ S, u64 s_bstride, u64* __restrict__ D,
+    u64 d_bstride, u32 n_entries, u32 dim, int s1) {
   const u32 N = B.N;
   const u32 nm = base ? (u32)B.nB + 1 : (u32)B.k;
   if (idx >= (u64)n_entries * nm * N) return;
@@ -172,8 +173,9 @@ __device__ __forceinline__ void k_behz_tensor_body(const BehzC& B, u64 idx, u64 
 }
 
 // steps (6)-(8): Dq [p][k][N], Db [p][nB+1][N] (coefficient form) -> out [p][k][N]
-__device__ __forceinline__ void k_behz_floor_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ Dq, u64 dq_bstride, const u64* __restrict__ Db,
-             u64 db_bstride, u64* __restrict__ out, u64 out_bstride, u32 n_polys) {
+__device__ __forceinline__ void k_behz_floor_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ Dq,
+    u64 dq_bstride, const u64* __restrict__ Db, u64 db_bstride, u64* __restrict__ out, u64 out_bstride,
+    u32 n_polys) {
   const u32 N = B.N;
   if (idx >= (u64)n_polys * N) return;
   const u32 n = (u32)idx & (N - 1);
@@ -190,8 +192,8 @@ __device__ __forceinline__ void k_behz_floor_body(const BehzC& B, u64 idx, u64 y
 
 // switch_key_inplace, step 1: third polynomial of product e (prod [e][3][k][N]) -> dig [e][J][I][N], digit J re-reduced
 // modulo key-level modulus I (I = k: the special prime); the forward NTT follows (launch_ntt_fwd, cycle k + 1)
-__device__ __forceinline__ void k_relin_digits_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ prod, u64 p_bstride, u64* __restrict__ dig,
-               u64 dig_bstride, u32 n_entries) {
+__device__ __forceinline__ void k_relin_digits_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ prod,
+    u64 p_bstride, u64* __restrict__ dig, u64 dig_bstride, u32 n_entries) {
   const u32 N = B.N;
   const u32 k = (u32)B.k, k1 = k + 1;
   if (idx >= (u64)n_entries * k * k1 * N) return;
@@ -207,8 +209,8 @@ __device__ __forceinline__ void k_relin_digits_body(const BehzC& B, u64 idx, u64
 }
 
 // step 2: acc [e][c][I][N] = sum_J dig[e][J][I] (.) key[J][c][I]   (NTT form; the inverse NTT follows)
-__device__ __forceinline__ void k_relin_mac_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ dig, u64 dig_bstride, const u64* __restrict__ key,
-            u64* __restrict__ acc, u64 acc_bstride, u32 n_entries) {
+__device__ __forceinline__ void k_relin_mac_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ dig,
+    u64 dig_bstride, const u64* __restrict__ key, u64* __restrict__ acc, u64 acc_bstride, u32 n_entries) {
   const u32 N = B.N;
   const u32 k = (u32)B.k, k1 = k + 1;
   if (idx >= (u64)n_entries * 2 * k1 * N) return;
@@ -226,8 +228,8 @@ __device__ __forceinline__ void k_relin_mac_body(const BehzC& B, u64 idx, u64 y_
 
 // step 3: mod-down by the special prime with rounding, added to the first two polynomials of the product:
 //   X [e][c][j][N] = prod[e][c][j] + (acc[e][c][j] - round-term(acc[e][c][k])) / P      (acc in coefficient form)
-__device__ __forceinline__ void k_relin_finish_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ prod, u64 p_bstride, const u64* __restrict__ acc,
-               u64 acc_bstride, u64* __restrict__ X, u64 x_bstride, u32 n_entries) {
+__device__ __forceinline__ void k_relin_finish_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ prod,
+    u64 p_bstride, const u64* __restrict__ acc, u64 acc_bstride, u64* __restrict__ X, u64 x_bstride, u32 n_entries) {
   const u32 N = B.N;
   const u32 k = (u32)B.k, k1 = k + 1;
   if (idx >= (u64)n_entries * 2 * k * N) return;
@@ -244,8 +246,8 @@ __device__ __forceinline__ void k_relin_finish_body(const BehzC& B, u64 idx, u64
 }
 
 // database.cpp:240-247: out [g][polys][k][N] = sum_{i < cnt(g)} X[g*dim + i][polys][k][N]  (mod q_j), cnt(g) = entries left
-__device__ __forceinline__ void k_ct_reduce_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ X, u64 x_bstride, u64* __restrict__ out,
-            u64 out_bstride, u32 n_entries, u32 dim, u32 polys) {
+__device__ __forceinline__ void k_ct_reduce_body(const BehzC& B, u64 idx, u64 y_, const u64* __restrict__ X,
+    u64 x_bstride, u64* __restrict__ out, u64 out_bstride, u32 n_entries, u32 dim, u32 polys) {
   const u32 N = B.N;
   const u32 k = (u32)B.k;
   const u32 n_groups = (n_entries + dim - 1) / dim;
