@@ -308,6 +308,38 @@ inline std::string SerializeGaloisKeys(const EncryptionParameters& ep, const Gal
   }
   return wire::SaveKSwitchKeys(K);
 }
+// SEALSerialize<RelinKeys> / SEALDeserialize<RelinKeys>: a KSwitchKeys object with ONE slot (RelinKeys::get_index(2) == 0)
+// holding the k digits of the key KeyGenerator::relin_keys() makes (client.cpp:49)
+inline std::string SerializeRelinKeys(const EncryptionParameters& ep, const RelinKeys& rk) {
+  const wire::SealParams sp = ToSealParams(ep);
+  const size_t N = ep.poly_modulus_degree, k = ep.coeff_modulus.size() - 1, per_digit = 2 * (k + 1) * N;
+  wire::KSwitchKeysData K;
+  K.parms_id = wire::key_parms_id(sp);
+  K.keys.resize(1);
+  K.keys[0].resize(rk.limbs.size() / per_digit);
+  for (size_t j = 0; j < K.keys[0].size(); ++j) {
+    auto& c = K.keys[0][j];
+    c.parms_id = K.parms_id;
+    c.is_ntt_form = true;
+    c.size = 2;
+    c.poly_modulus_degree = N;
+    c.coeff_modulus_size = k + 1;
+    c.limbs.assign(rk.limbs.begin() + j * per_digit, rk.limbs.begin() + (j + 1) * per_digit);
+  }
+  return wire::SaveKSwitchKeys(K);
+}
+inline StatusOr<RelinKeys> DeserializeRelinKeys(const EncryptionParameters& ep, const std::string& bytes) {
+  wire::KSwitchKeysData K;
+  std::string err;
+  if (!wire::LoadKSwitchKeys(bytes, ToSealParams(ep), &K, &err)) return InvalidArgumentError(err);
+  const size_t k = ep.coeff_modulus.size() - 1;
+  if (K.keys.size() != 1 || K.keys[0].size() != k)
+    return InvalidArgumentError("relinearization keys must hold exactly one key of k digits");
+  const size_t per_digit = 2 * ep.coeff_modulus.size() * (size_t)ep.poly_modulus_degree;
+  RelinKeys rk;
+  for (const auto& ct : K.keys[0]) rk.limbs.insert(rk.limbs.end(), ct.limbs.begin(), ct.limbs.begin() + per_digit);
+  return rk;
+}
 // SEALSerialize<Ciphertext> / SEALDeserialize<Ciphertext> for data-level ciphertexts [2][k][N]
 inline std::string SerializeCiphertext(const EncryptionParameters& ep, const Ciphertext& ct,
                                        const wire::parms_id_type* parms_id = nullptr) {
@@ -334,6 +366,42 @@ inline StatusOr<Ciphertext> DeserializeCiphertext(const EncryptionParameters& ep
   ct.limbs = std::move(d.limbs);
   ct.is_ntt_form = d.is_ntt_form;
   return ct;
+}
+
+// serialization.cpp:32-58: Ciphertexts message <-> vector<Ciphertext>
+inline StatusOr<std::vector<Ciphertext>> LoadCiphertexts(const EncryptionParameters& ep, const wire::CiphertextsMsg& input) {
+  std::vector<Ciphertext> out;
+  out.reserve(input.ct.size());
+  for (const auto& blob : input.ct) {
+    auto ct = DeserializeCiphertext(ep, blob);
+    if (!ct.ok()) return ct.status();
+    out.push_back(std::move(*ct));
+  }
+  return out;
+}
+inline Status SaveCiphertexts(const EncryptionParameters& ep, const std::vector<Ciphertext>& cts, wire::CiphertextsMsg* output) {
+  if (output == nullptr) return InvalidArgumentError("output nullptr");
+  for (const auto& ct : cts) output->ct.push_back(SerializeCiphertext(ep, ct));
+  return OkStatus();
+}
+// serialization.cpp:53-73: SaveRequest(cts) leaves both key fields empty, SaveRequest(cts, galois, relin) fills them
+inline Status SaveRequest(const EncryptionParameters& ep, const std::vector<std::vector<Ciphertext>>& cts,
+                          wire::RequestMsg* request) {
+  if (request == nullptr) return InvalidArgumentError("output nullptr");
+  for (const auto& q : cts) {
+    request->query.emplace_back();
+    Status st = SaveCiphertexts(ep, q, &request->query.back());
+    if (!st.ok()) return st;
+  }
+  return OkStatus();
+}
+inline Status SaveRequest(const EncryptionParameters& ep, const std::vector<std::vector<Ciphertext>>& cts,
+                          const GaloisKeys& galois_keys, const RelinKeys& relin_keys, wire::RequestMsg* request) {
+  Status st = SaveRequest(ep, cts, request);
+  if (!st.ok()) return st;
+  request->galois_keys = SerializeGaloisKeys(ep, galois_keys);
+  request->relin_keys = SerializeRelinKeys(ep, relin_keys);
+  return OkStatus();
 }
 
 namespace detail {

@@ -167,8 +167,74 @@ static int fingerprint_tests() {
   return 0;
 }
 
+// serialization_test.cpp:80-164 restated on raw limbs: SaveRequest with and without keys, the objects survive the trip
+static int serialization_tests() {
+  const pir::EncryptionParameters ep = pir::GenerateEncryptionParams(4096);
+  const size_t N = 4096, k = ep.coeff_modulus.size() - 1, key_limbs = k * 2 * (k + 1) * N;
+  std::mt19937_64 rng(5);
+  auto poly_limbs = [&](size_t polys, size_t n_mod, std::vector<uint64_t>& out) {
+    out.resize(polys * n_mod * N);
+    for (size_t p = 0; p < polys; ++p)
+      for (size_t j = 0; j < n_mod; ++j)
+        for (size_t n = 0; n < N; ++n) out[(p * n_mod + j) * N + n] = rng() % ep.coeff_modulus[j];
+  };
+  std::vector<std::vector<pir::Ciphertext>> cts(2, std::vector<pir::Ciphertext>(2));
+  for (auto& q : cts)
+    for (auto& ct : q) poly_limbs(2, k, ct.limbs);
+  pir::GaloisKeys gk;
+  gk.elts = pir::generate_galois_elts(N);
+  gk.limbs.resize(gk.elts.size() * key_limbs);
+  for (size_t e = 0; e < gk.elts.size() * k; ++e) {
+    std::vector<uint64_t> digit;
+    poly_limbs(2, k + 1, digit);
+    std::copy(digit.begin(), digit.end(), gk.limbs.begin() + e * digit.size());
+  }
+  pir::RelinKeys rk;
+  for (size_t j = 0; j < k; ++j) {
+    std::vector<uint64_t> digit;
+    poly_limbs(2, k + 1, digit);
+    rk.limbs.insert(rk.limbs.end(), digit.begin(), digit.end());
+  }
+  // TestRequestSerialization (:135-164): all three fields
+  pir::wire::RequestMsg m;
+  CHECK(pir::SaveRequest(ep, cts, gk, rk, &m).ok(), "SaveRequest");
+  pir::wire::RequestMsg back;
+  CHECK(pir::wire::Parse(pir::wire::Serialize(m), &back) && back.query.size() == 2 && back.query[1].ct.size() == 2,
+        "request parse");
+  for (size_t q = 0; q < 2; ++q) {
+    auto loaded = pir::LoadCiphertexts(ep, back.query[q]);
+    CHECK(loaded.ok() && loaded->size() == 2 && (*loaded)[0].limbs == cts[q][0].limbs && (*loaded)[1].limbs == cts[q][1].limbs,
+          "ciphertexts round trip");
+  }
+  auto gk2 = pir::DeserializeGaloisKeys(ep, back.galois_keys);
+  CHECK(gk2.ok() && gk2->elts.size() == gk.elts.size(), "galois keys round trip: has_key for every element");
+  for (size_t e = 0; e < gk.elts.size(); ++e) {  // returned in slot order
+    size_t at = 0;
+    while (at < gk2->elts.size() && gk2->elts[at] != gk.elts[e]) ++at;
+    CHECK(at < gk2->elts.size() && std::equal(gk.limbs.begin() + e * key_limbs, gk.limbs.begin() + (e + 1) * key_limbs,
+                                               gk2->limbs.begin() + at * key_limbs), "galois key limbs");
+  }
+  auto rk2 = pir::DeserializeRelinKeys(ep, back.relin_keys);
+  CHECK(rk2.ok() && rk2->limbs == rk.limbs, "relin keys round trip");
+  CHECK(!pir::DeserializeRelinKeys(ep, back.galois_keys).ok(), "a Galois key set is not a relinearization key");
+  CHECK(!pir::DeserializeRelinKeys(ep, back.relin_keys.substr(0, back.relin_keys.size() - 3)).ok(), "truncated relin keys");
+  // TestRequestSerialization_Shortcut (:115-132): no keys at all
+  pir::wire::RequestMsg sc;
+  CHECK(pir::SaveRequest(ep, cts, &sc).ok() && sc.galois_keys.empty() && sc.relin_keys.empty() && sc.query.size() == 2,
+        "SaveRequest shortcut");
+  CHECK(!pir::SaveRequest(ep, cts, nullptr).ok() && !pir::SaveCiphertexts(ep, cts[0], nullptr).ok(), "output nullptr");
+  // a size-3 ciphertext (ciphertext-multiplication reply without relinearization) serializes with its size
+  pir::Ciphertext three;
+  poly_limbs(3, k, three.limbs);
+  pir::wire::CiphertextData d;
+  std::string err;
+  CHECK(pir::wire::LoadCiphertext(pir::SerializeCiphertext(ep, three), (uint32_t)N, ep.coeff_modulus.data(), k, &d, &err) &&
+            d.size == 3 && d.limbs == three.limbs, "size-3 ciphertext round trip");
+  return 0;
+}
+
 int main() {
-  if (parameters_tests() || string_encoder_tests() || index_tests() || fingerprint_tests()) return 1;
+  if (parameters_tests() || string_encoder_tests() || index_tests() || fingerprint_tests() || serialization_tests()) return 1;
   // without a device the factories must fail loudly, never fall back (server.cpp:35-42 shape)
   auto p = *pir::CreatePIRParameters(10, 0, 1);
   auto db = pir::PIRDatabase::Create(p);
