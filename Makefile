@@ -57,6 +57,11 @@ build/ctmul_host_test: tests/cpp/ctmul_host_test.cpp $(HDRS) oracle/pir_oracle.h
 	@mkdir -p build
 	g++ -O2 -std=c++17 -march=x86-64-v3 -I/usr/local/cuda/include -Wno-attributes -o $@ tests/cpp/ctmul_host_test.cpp
 
+# the wire parsers on truncated / bit-flipped / length-inflated requests under AddressSanitizer + UBSan (CPU only)
+build/wire_fuzz_test: tests/cpp/wire_fuzz_test.cpp pir_b200/cpp/wire.hpp
+	@mkdir -p build
+	g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-sanitize-recover=all -fno-omit-frame-pointer -o $@ tests/cpp/wire_fuzz_test.cpp
+
 oracle:
 	$(MAKE) -C oracle
 

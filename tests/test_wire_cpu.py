@@ -511,6 +511,16 @@ def test_wire_end_to_end_against_the_oracle_cpp():
     assert out.returncode == 0 and "WIRE_TEST_OK" in out.stdout, out.stdout + out.stderr
 
 
+def test_wire_parsers_survive_malformed_requests_under_sanitizers():
+    """tests/cpp/wire_fuzz_test.cpp (AddressSanitizer + UBSan): truncated, bit-flipped, length-inflated and spliced
+    requests are rejected or parsed without out-of-bounds accesses, and the copy-free parsers of the device server's
+    wire path (ParseView, LoadCiphertextTo) agree with the object-building ones on every input."""
+    exe = os.path.join(ROOT, "build", "wire_fuzz_test")
+    subprocess.check_call(["make", "-C", ROOT, "build/wire_fuzz_test"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([exe, "1500"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "WIRE_FUZZ_TEST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # pir_b200/wire.py: the Python mirror's view of the same codec (host-side only, no GPU)
 # ---------------------------------------------------------------------------------------------------------------
