@@ -52,10 +52,11 @@ build/device_math_host_test: tests/cpp/device_math_host_test.cpp $(HDRS) oracle/
 	g++ -O2 -std=c++17 -march=x86-64-v3 -ffp-contract=off -I/usr/local/cuda/include -Wno-attributes -o $@ tests/cpp/device_math_host_test.cpp
 
 # the ciphertext-multiplication kernels' bodies (pirb_behz.cuh) and host setup compiled for the HOST: constants,
-# per-coefficient functions and a whole upper dimension, launch by launch, against the oracle
+# per-coefficient functions and a whole upper dimension, launch by launch, against the oracle — under AddressSanitizer +
+# UBSan with exactly-sized buffers, so an out-of-range index in a kernel body is a test failure
 build/ctmul_host_test: tests/cpp/ctmul_host_test.cpp $(HDRS) oracle/pir_oracle.hpp oracle/bfv_mul_oracle.hpp
 	@mkdir -p build
-	g++ -O2 -std=c++17 -march=x86-64-v3 -I/usr/local/cuda/include -Wno-attributes -o $@ tests/cpp/ctmul_host_test.cpp
+	g++ -O1 -g -std=c++17 -march=x86-64-v3 -fsanitize=address,undefined -fno-sanitize-recover=all -I/usr/local/cuda/include -Wno-attributes -o $@ tests/cpp/ctmul_host_test.cpp
 
 # the wire parsers on truncated / bit-flipped / length-inflated requests under AddressSanitizer + UBSan (CPU only)
 build/wire_fuzz_test: tests/cpp/wire_fuzz_test.cpp pir_b200/cpp/wire.hpp
