@@ -49,7 +49,7 @@ build/wire_test: tests/cpp/wire_test.cpp pir_b200/cpp/wire.hpp oracle/pir_oracle
 # the device arithmetic (pirb_device.cuh) compiled for the HOST and checked against 128-bit integers and the oracle
 build/device_math_host_test: tests/cpp/device_math_host_test.cpp $(HDRS) oracle/pir_oracle.hpp
 	@mkdir -p build
-	g++ -O2 -std=c++17 -march=x86-64-v3 -ffp-contract=off -I/usr/local/cuda/include -Wno-attributes -o $@ tests/cpp/device_math_host_test.cpp
+	g++ -O1 -g -std=c++17 -march=x86-64-v3 -ffp-contract=off -fsanitize=address,undefined -fno-sanitize-recover=all -I/usr/local/cuda/include -Wno-attributes -o $@ tests/cpp/device_math_host_test.cpp
 
 # the ciphertext-multiplication kernels' bodies (pirb_behz.cuh) and host setup compiled for the HOST: constants,
 # per-coefficient functions and a whole upper dimension, launch by launch, against the oracle — under AddressSanitizer +
